@@ -1,0 +1,121 @@
+"""Seeded synthetic inputs for the categorization hot path. Test/bench infrastructure.
+
+Genome pair generation follows the reference's scripts/read_generator.py:158-162 (uniform ACGT; the second
+haplotype is the first with per-base substitution probability `rate`, shift 1..3 mod 4). Read simulators
+(art, nanosim-h, simlord) are not installed, so reads are drawn directly: uniform start, strand flip
+p=0.5, substitution errors, constant quality.
+"""
+import os
+
+import numpy as np
+
+BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+COMP = np.array([3, 2, 1, 0], dtype=np.uint8)
+
+
+def random_genome(n, seed):
+    return np.random.default_rng(seed).integers(0, 4, size=n, dtype=np.uint8)
+
+
+def mutate(codes, rate, seed):
+    rng = np.random.default_rng(seed)
+    shift = (rng.random(codes.shape[0]) < rate).astype(np.uint8) * rng.integers(1, 4, size=codes.shape[0], dtype=np.uint8)
+    return ((codes + shift) % 4).astype(np.uint8)
+
+
+def to_ascii(codes):
+    return BASES[codes].tobytes().decode()
+
+
+def canonical_kmers(codes, k):
+    """All canonical k-mer values of a code array (uint64), in window order (KmerIterator semantics)."""
+    n = codes.shape[0] - k + 1
+    if n <= 0:
+        return np.zeros(0, dtype=np.uint64)
+    fwd = np.zeros(n, dtype=np.uint64)
+    rev = np.zeros(n, dtype=np.uint64)
+    c = codes.astype(np.uint64)
+    for j in range(k):
+        fwd |= c[j:j + n] << np.uint64(2 * (k - 1 - j))
+        rev |= (np.uint64(3) - c[j:j + n]) << np.uint64(2 * j)
+    return np.minimum(fwd, rev)
+
+
+def kmer_to_str(v, k):
+    return "".join("ACGT"[(int(v) >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def discriminative_kmers(haplotypes, k, mode="exactly_one"):
+    """Canonical k-mers present in exactly one haplotype (or absent from at least one: mode='not_all')."""
+    sets = [np.unique(canonical_kmers(h, k)) for h in haplotypes]
+    allk, counts = np.unique(np.concatenate(sets), return_counts=True)
+    if mode == "exactly_one":
+        return allk[counts == 1]
+    return allk[counts < len(haplotypes)]
+
+
+def sample_reads(codes, n_reads, length, seed, error_rate=0.0, length_sigma=0.0, min_len=1, max_len=None):
+    """Returns a list of code arrays. length_sigma > 0 => lognormal lengths with that sigma around `length`."""
+    rng = np.random.default_rng(seed)
+    G = codes.shape[0]
+    out = []
+    for _ in range(n_reads):
+        if length_sigma > 0:
+            L = int(rng.lognormal(np.log(length) - 0.5 * length_sigma ** 2, length_sigma))
+        else:
+            L = length
+        L = max(min_len, min(L, max_len or G, G))
+        s = int(rng.integers(0, G - L + 1))
+        r = codes[s:s + L].copy()
+        if error_rate > 0:
+            err = rng.random(L) < error_rate
+            r[err] = (r[err] + rng.integers(1, 4, size=int(err.sum()), dtype=np.uint8)) % 4
+        if rng.random() < 0.5:
+            r = COMP[r[::-1]]
+        out.append(r)
+    return out
+
+
+def write_fasta(path, reads, prefix="r", newline="\n"):
+    with open(path, "w", newline="") as f:
+        for i, r in enumerate(reads):
+            s = r if isinstance(r, str) else to_ascii(r)
+            f.write(f">{prefix}{i}{newline}{s}{newline}")
+
+
+def write_fastq(path, reads, prefix="r", newline="\n"):
+    with open(path, "w", newline="") as f:
+        for i, r in enumerate(reads):
+            s = r if isinstance(r, str) else to_ascii(r)
+            f.write(f"@{prefix}{i}{newline}{s}{newline}+{newline}{'I' * len(s)}{newline}")
+
+
+def write_kmers(path, values, k, newline="\n"):
+    with open(path, "w", newline="") as f:
+        for v in values:
+            f.write(kmer_to_str(v, k) + newline)
+
+
+def make_diploid_case(outdir, genome_size, divergence, k, read_len, coverage, seed, error_rate=0.0, fmt="fasta",
+                      length_sigma=0.0, kmer_subsample=1.0):
+    """Two haplotypes, one read file each, discriminative k-mer file. Returns (read_paths, kmer_path)."""
+    os.makedirs(outdir, exist_ok=True)
+    a = random_genome(genome_size, 1000 * seed)
+    b = mutate(a, divergence, 1000 * seed + 1)
+    paths = []
+    for i, h in enumerate((a, b)):
+        n_reads = max(1, int(coverage * genome_size / read_len))
+        reads = sample_reads(h, n_reads, read_len, 1000 * seed + 10 + i, error_rate=error_rate, length_sigma=length_sigma,
+                             min_len=min(50, genome_size))
+        p = os.path.join(outdir, f"hap{i}.{ 'fq' if fmt == 'fastq' else 'fa'}")
+        (write_fastq if fmt == "fastq" else write_fasta)(p, reads, prefix=f"h{i}_")
+        paths.append(p)
+    sdk = discriminative_kmers([a, b], k)
+    if kmer_subsample < 1.0:
+        rng = np.random.default_rng(1000 * seed + 99)
+        sdk = sdk[rng.random(sdk.shape[0]) < kmer_subsample]
+    # shuffle so that the file order is not the sorted order (ids must not depend on it)
+    rng = np.random.default_rng(1000 * seed + 98)
+    kp = os.path.join(outdir, f"{k}-mers.txt")
+    write_kmers(kp, rng.permutation(sdk), k)
+    return paths, kp
