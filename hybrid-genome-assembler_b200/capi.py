@@ -1,0 +1,220 @@
+"""ctypes binding of libhga_b200.so — one Python method per C-ABI entry point of include/hga_b200.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+
+
+class HgaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"hga_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _Hits(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_hits", C.c_uint64), ("row_off", u64p), ("kmer_id", u32p), ("pos", u32p)]
+
+
+class _Index(C.Structure):
+    _fields_ = [("n_kmers", C.c_uint64), ("n_entries", C.c_uint64), ("off", u64p), ("read_id", u32p)]
+
+
+class _Pairs(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("n_increments", C.c_uint64), ("x", u32p), ("y", u32p), ("score", u32p)]
+
+
+class _Selection(C.Structure):
+    _fields_ = [("n_directed", C.c_uint64), ("cut_score", C.c_uint64), ("n_selected", C.c_uint64), ("x", u32p), ("y", u32p), ("score", u32p)]
+
+
+class _Components(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("read_id_first", C.c_uint32), ("label", u32p), ("n_components", C.c_uint64),
+                ("comp_label", u32p), ("comp_size", u32p)]
+
+
+class Metrics(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("table_build_ms", "h2d_ms", "scan_ms", "index_ms", "pair_ms", "select_ms", "components_ms", "exchange_ms")] + \
+               [(n, C.c_uint64) for n in ("n_bases", "n_reads", "n_hits", "n_pairs", "n_increments", "n_selected", "n_components", "table_bytes",
+                                          "filter_bytes", "pair_retries", "heavy_pivots", "kernel_launches")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
+EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
+           "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
+           "hga_get_selection", "hga_components", "hga_get_components", "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
+
+
+def library_path():
+    return os.path.join(_HERE, "libhga_b200.so")
+
+
+def load_library():
+    """Loads the in-tree CUDA library. Fails loudly when it has not been built: there is no fallback."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise HgaError(-1, f"{path} is missing: run `python hybrid-genome-assembler_b200/build.py` (no CPU fallback exists)")
+        lib = C.CDLL(path)
+        lib.hga_last_error.restype = C.c_char_p
+        lib.hga_version.restype = C.c_char_p
+        lib.hga_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        lib.hga_destroy.argtypes = [C.c_void_p]
+        lib.hga_destroy.restype = None
+        lib.hga_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.hga_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
+        lib.hga_scan_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
+        lib.hga_get_hits.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Hits)]
+        lib.hga_build_index.argtypes = [C.c_void_p]
+        lib.hga_get_index.argtypes = [C.c_void_p, C.POINTER(_Index)]
+        lib.hga_pair_count.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        lib.hga_get_pairs.argtypes = [C.c_void_p, C.POINTER(_Pairs)]
+        lib.hga_select_edges.argtypes = [C.c_void_p, C.c_double, C.c_uint32]
+        lib.hga_get_selection.argtypes = [C.c_void_p, C.POINTER(_Selection)]
+        lib.hga_components.argtypes = [C.c_void_p, C.c_int]
+        lib.hga_get_components.argtypes = [C.c_void_p, C.POINTER(_Components)]
+        lib.hga_metrics.argtypes = [C.c_void_p, C.POINTER(Metrics)]
+        lib.hga_comm_unique_id.argtypes = [C.c_void_p]
+        lib.hga_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64]
+        lib.hga_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        lib.hga_host_free.argtypes = [C.c_void_p]
+        lib.hga_device_count.argtypes = [C.POINTER(C.c_int)]
+        _LIB = lib
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise HgaError(rc, load_library().hga_last_error().decode())
+
+
+def _arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(load_library().hga_device_count(C.byref(n)))
+    return n.value
+
+
+def comm_unique_id():
+    buf = (C.c_ubyte * 128)()
+    _check(load_library().hga_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Handle:
+    """One GPU-resident k-mer table + the stage results of the most recent run (hga_handle)."""
+
+    def __init__(self, kmers, k, device=0):
+        self.lib = load_library()
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        self.k = int(k)
+        self.n_kmers = int(kmers.shape[0])
+        self._h = C.c_void_p()
+        _check(self.lib.hga_create(int(device), self.k, kmers.ctypes.data_as(C.c_void_p), self.n_kmers, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.hga_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.lib.hga_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def comm_init(self, unique_id: bytes, rank, nranks, n_reads_total):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        _check(self.lib.hga_comm_init(self._h, buf, int(rank), int(nranks), int(n_reads_total)))
+
+    # -- stages ------------------------------------------------------------------------------------------
+    def scan(self, bases, read_off, read_id_base=1):
+        """bases: bytes / bytearray / uint8 array (host); read_off: uint64[n_reads+1]."""
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        n_reads = read_off.shape[0] - 1
+        if isinstance(bases, np.ndarray):
+            b = np.ascontiguousarray(bases, dtype=np.uint8)
+            ptr = b.ctypes.data_as(C.c_void_p)
+        else:
+            b = bases
+            ptr = C.cast(C.c_char_p(bytes(b)) if not isinstance(b, bytes) else C.c_char_p(b), C.c_void_p)
+        _check(self.lib.hga_scan(self._h, ptr, read_off.ctypes.data_as(C.c_void_p), n_reads, int(read_id_base)))
+
+    def scan_host_ptr(self, bases_ptr, read_off_ptr, n_reads, read_id_base=1):
+        _check(self.lib.hga_scan(self._h, C.c_void_p(bases_ptr), C.c_void_p(read_off_ptr), int(n_reads), int(read_id_base)))
+
+    def scan_device(self, d_bases_ptr, d_read_off_ptr, n_reads, n_bases, read_id_base=1):
+        _check(self.lib.hga_scan_device(self._h, C.c_void_p(d_bases_ptr), C.c_void_p(d_read_off_ptr), int(n_reads), int(n_bases), int(read_id_base)))
+
+    def get_hits(self, sorted_by_kmer_id=False):
+        out = _Hits()
+        _check(self.lib.hga_get_hits(self._h, 1 if sorted_by_kmer_id else 0, C.byref(out)))
+        return _arr(out.row_off, out.n_reads + 1, np.uint64), _arr(out.kmer_id, out.n_hits, np.uint32), _arr(out.pos, out.n_hits, np.uint32)
+
+    def build_index(self):
+        _check(self.lib.hga_build_index(self._h))
+
+    def get_index(self):
+        out = _Index()
+        _check(self.lib.hga_get_index(self._h, C.byref(out)))
+        return _arr(out.off, out.n_kmers + 1, np.uint64), _arr(out.read_id, out.n_entries, np.uint32)
+
+    def pair_count(self, min_score=1, pivots=None):
+        if pivots is None:
+            _check(self.lib.hga_pair_count(self._h, int(min_score), None, 0))
+        else:
+            pv = np.ascontiguousarray(pivots, dtype=np.uint32)
+            _check(self.lib.hga_pair_count(self._h, int(min_score), pv.ctypes.data_as(C.c_void_p), pv.shape[0]))
+
+    def get_pairs(self):
+        out = _Pairs()
+        _check(self.lib.hga_get_pairs(self._h, C.byref(out)))
+        n = out.n_pairs
+        return _arr(out.x, n, np.uint32), _arr(out.y, n, np.uint32), _arr(out.score, n, np.uint32), int(out.n_increments)
+
+    def select_edges(self, fraction=0.15, score_threshold=0):
+        _check(self.lib.hga_select_edges(self._h, float(fraction), int(score_threshold)))
+
+    def get_selection(self):
+        out = _Selection()
+        _check(self.lib.hga_get_selection(self._h, C.byref(out)))
+        n = out.n_selected
+        return dict(n_directed=int(out.n_directed), cut_score=int(out.cut_score), x=_arr(out.x, n, np.uint32), y=_arr(out.y, n, np.uint32),
+                    score=_arr(out.score, n, np.uint32))
+
+    def components(self, min_size=30):
+        _check(self.lib.hga_components(self._h, int(min_size)))
+
+    def get_components(self):
+        out = _Components()
+        _check(self.lib.hga_get_components(self._h, C.byref(out)))
+        return dict(read_id_first=int(out.read_id_first), label=_arr(out.label, out.n_reads, np.uint32),
+                    comp_label=_arr(out.comp_label, out.n_components, np.uint32), comp_size=_arr(out.comp_size, out.n_components, np.uint32))
+
+    def metrics(self):
+        m = Metrics()
+        _check(self.lib.hga_metrics(self._h, C.byref(m)))
+        return m.as_dict()

@@ -1,0 +1,151 @@
+/*
+ * hga_b200.h — C-ABI of the B200-native `categorization` hot path.
+ *
+ * The reference (matuszelenak/Hybrid-Genome-Assembler) has no FFI; the seam this library replaces is the set
+ * of protected stage functions of ReadClusteringEngine (paths relative to /root/reference/src):
+ *
+ *   hga_create           <- load_text_file_kmers' set + KmerIndex           read_clustering.cpp:18-33,
+ *                                                                           clustering/ReadClusteringEngine.cpp:237-241
+ *   hga_scan[_device]    <- construct_indices, per-read half                clustering/ReadClusteringEngine.cpp:246-277
+ *                           (KmerIterator semantics: common/KmerIterator.cpp:23-76)
+ *   hga_build_index      <- construct_indices, kmer_component_index half    clustering/ReadClusteringEngine.cpp:262-269,282-284
+ *   hga_pair_count       <- get_connections / get_all_connections           clustering/ReadClusteringEngine.cpp:301-339
+ *   hga_select_edges     <- the 15 % slice / --sc_score filter              clustering/ReadClusteringEngine.cpp:748-756
+ *   hga_components       <- union_find(edges, {}, min, -1)                  clustering/ReadClusteringEngine.cpp:424-489, call :763
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; hga_last_error() gives the message
+ *     (thread-local). The reference signals errors by uncaught C++ exceptions (std::terminate).
+ *   - plain pointers and sizes only. Inputs are caller-owned HOST buffers unless the name says _device.
+ *   - results stay in HBM between stages; hga_get_* copies them into library-owned pinned host buffers that
+ *     remain valid until the next call that produces the same result, or hga_destroy.
+ *   - read ids are 1-based and global (SequenceRecordIterator.h:82): row r of a scan has id read_id_base + r.
+ *   - kmer_id = index into the array given to hga_create (the reference's KmerID is an arbitrary bijection,
+ *     so parity is by k-mer VALUE).
+ *   - one handle per GPU; a handle is not thread-safe. There is NO CPU fallback: every entry point fails
+ *     with an error if no CUDA device is usable.
+ */
+#ifndef HGA_B200_H
+#define HGA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hga_handle hga_handle;
+
+#define HGA_OK 0
+#define HGA_E_CUDA 1        /* CUDA runtime / no device */
+#define HGA_E_ARG 2         /* bad argument (k > 32 mirrors KmerIterator.cpp:24-26) */
+#define HGA_E_STATE 3       /* stage called out of order */
+#define HGA_E_NOMEM 4
+#define HGA_E_OVERFLOW 5    /* a 32-bit pair score or entry count overflowed */
+#define HGA_E_NCCL 6
+#define HGA_E_DUPLICATE 7   /* duplicate k-mer handed to hga_create */
+
+const char *hga_last_error(void);
+/* library + build identification, e.g. "hga_b200 0.1 sm_100a" */
+const char *hga_version(void);
+int hga_device_count(int *count);
+
+/* Pinned host memory helpers (H2D from pinned buffers runs at PCIe speed). */
+int hga_host_alloc(void **ptr, size_t bytes);
+int hga_host_free(void *ptr);
+
+/* Table of canonical discriminative k-mers on `device` (open-addressing key table + blocked Bloom pre-filter,
+ * built by CUDA kernels). kmers must be canonical (min(forward, reverse-complement) in the 2-bit code
+ * A0 C1 G2 T3) and unique. 1 <= k <= 32. */
+int hga_create(int device, int k, const uint64_t *kmers, uint64_t n_kmers, hga_handle **out);
+void hga_destroy(hga_handle *h);
+/* Run every kernel of this handle on an existing CUDA stream (cudaStream_t passed as void*); NULL restores
+ * the handle's own stream. Lets a caller bracket stages with its own CUDA events. */
+int hga_set_stream(hga_handle *h, void *cuda_stream);
+
+/* Scan: 2-bit pack + canonical k-mer windows + membership -> hits in (read, position) order.
+ * bases  : the reads' sequence bytes back to back (no separators), ASCII as in the file
+ * read_off[n_reads+1] : byte offset of every read in `bases`
+ * Any byte other than 'A','C','G','T' follows the reference rule (code 0 on BOTH strands).
+ * hga_scan copies the host buffers to the GPU inside the call; hga_scan_device takes device pointers. */
+int hga_scan(hga_handle *h, const char *bases, const uint64_t *read_off, uint64_t n_reads, uint32_t read_id_base);
+int hga_scan_device(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases,
+                    uint32_t read_id_base);
+
+typedef struct {
+    uint64_t n_reads;          /* rows scanned */
+    uint64_t n_hits;           /* E */
+    const uint64_t *row_off;   /* n_reads + 1 */
+    const uint32_t *kmer_id;   /* E, position order inside a row (sorted by kmer_id if requested) */
+    const uint32_t *pos;       /* E, KmerIterator::position_in_sequence = window start + k */
+} hga_hits;
+/* sorted_by_kmer_id != 0: each row ordered by (kmer_id, pos) like ReadComponent::discriminative_kmer_ids */
+int hga_get_hits(hga_handle *h, int sorted_by_kmer_id, hga_hits *out);
+
+/* Inverted index by k-mer. With a communicator attached this includes the all-to-all by k-mer owner. */
+int hga_build_index(hga_handle *h);
+typedef struct {
+    uint64_t n_kmers;
+    uint64_t n_entries;
+    const uint64_t *off;       /* n_kmers + 1, indexed by kmer_id */
+    const uint32_t *read_id;   /* n_entries, ascending inside a list, one entry per occurrence */
+} hga_index;
+int hga_get_index(hga_handle *h, hga_index *out);
+
+/* score(x,y) = sum_k mult_x(k) * mult_y(k) for every unordered read pair sharing a k-mer.
+ * pivots == NULL: all reads (get_all_connections); else only pairs with at least one endpoint in pivots
+ * (get_connections over a component list). Pairs with score < min_score are dropped. */
+int hga_pair_count(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
+typedef struct {
+    uint64_t n_pairs;          /* unordered pairs, x < y, ordered by (x, y) */
+    uint64_t n_increments;     /* sum_k occ(k)*(occ(k)-1)/2 over the processed lists (work measure) */
+    const uint32_t *x, *y, *score;
+} hga_pairs;
+int hga_get_pairs(hga_handle *h, hga_pairs *out);
+
+typedef struct {
+    uint64_t n_directed;       /* n = (size_t)(2P * fraction), the reference's slice length */
+    uint64_t cut_score;        /* s*: score of the last directed edge inside the slice (0 if n == 0) */
+    uint64_t n_selected;       /* unordered edges selected under the canonical tie order */
+    const uint32_t *x, *y, *score;
+} hga_selection;
+/* score_threshold == 0: fraction slice under the canonical order (score desc, x asc, y asc);
+ * score_threshold  > 0: keep score > score_threshold (--sc_score). */
+int hga_select_edges(hga_handle *h, double fraction, uint32_t score_threshold);
+int hga_get_selection(hga_handle *h, hga_selection *out);
+
+typedef struct {
+    uint64_t n_reads;          /* labels cover read ids read_id_first .. read_id_first + n_reads - 1 */
+    uint32_t read_id_first;
+    const uint32_t *label;     /* smallest read id of the read's component (itself when isolated) */
+    uint64_t n_components;     /* components with size >= min_size */
+    const uint32_t *comp_label;/* their labels, ascending */
+    const uint32_t *comp_size;
+} hga_components_t;
+int hga_components(hga_handle *h, int min_size);
+int hga_get_components(hga_handle *h, hga_components_t *out);
+
+/* Per-stage device time (CUDA events on the handle's stream) and counters of the most recent run. */
+typedef struct {
+    double table_build_ms, h2d_ms, scan_ms, index_ms, pair_ms, select_ms, components_ms, exchange_ms;
+    uint64_t n_bases, n_reads, n_hits, n_pairs, n_increments, n_selected, n_components;
+    uint64_t table_bytes, filter_bytes, pair_retries, heavy_pivots;
+    uint64_t kernel_launches;  /* kernels of this library launched on this handle since creation */
+} hga_metrics_t;
+int hga_metrics(hga_handle *h, hga_metrics_t *out);
+
+/* Multi-GPU (one handle per rank/GPU). The 128-byte id comes from hga_comm_unique_id on rank 0 and is
+ * distributed by the caller (torch.distributed broadcast, a file, ...). After hga_comm_init:
+ *   hga_build_index   routes (kmer, read) incidences to the k-mer's owner rank (all-to-all),
+ *   hga_pair_count    reduces partial scores at the owner of x (all-to-all),
+ *   hga_select_edges  all-reduces the score histogram,
+ *   hga_components    iterates union-find with all-reduce(min) on the label array.
+ * n_reads_total = number of reads over all ranks (rows are global: rank shards are contiguous id ranges). */
+int hga_comm_unique_id(void *id128);
+int hga_comm_init(hga_handle *h, const void *id128, int rank, int nranks, uint64_t n_reads_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
