@@ -7,3 +7,4 @@ entry point raises HgaError unless a CUDA device is present.
 """
 from .capi import HgaError, Handle, library_path, load_library  # noqa: F401
 from .engine import ReadClusteringConfig, ReadClusteringEngine, load_text_file_kmers, SequenceRecords  # noqa: F401
+from . import capi, parallel  # noqa: F401,E402

@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
             for k, v in logs.items():
                 f.write(f"==== {k}\n{v}\n")
     if force or jobs or _stale(LIB, objs):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"], verbose)
+        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"], verbose)
     cli_src = os.path.join(CLI, "categorization.cpp")
     if os.path.exists(cli_src):
         cli_deps = [os.path.join(CLI, f) for f in os.listdir(CLI)] + headers

@@ -1,0 +1,60 @@
+"""GPU: the CUDA path through the C-ABI against the committed golden vectors of the real reference."""
+import numpy as np
+import pytest
+
+import compare
+import golden_util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_util.CASES)
+def test_cuda_vs_reference_golden(name):
+    import hga_b200
+    c = golden_util.load_case(name)
+    ref = c["ref"]
+    with hga_b200.Handle(c["kmers"], c["k"]) as h:
+        h.scan(c["bases"], c["seq_off"])
+        row_off, kid, pos = h.get_hits()
+        compare.check_hits(ref, row_off, kid, pos, c["kmers"])
+        h.build_index()
+        inv_off, inv_read = h.get_index()
+        compare.check_index(ref, inv_off, inv_read, c["kmers"])
+        h.pair_count(min_score=1)
+        x, y, s, _ = h.get_pairs()
+        ux, uy, us = compare.undirected(ref["conn_x"], ref["conn_y"], ref["conn_score"])
+        assert np.array_equal(x, ux) and np.array_equal(y, uy) and np.array_equal(s.astype(np.uint64), us)
+        compare.check_directed_symmetric(ref["conn_x"], ref["conn_y"], ref["conn_score"])
+        h.select_edges(fraction=c["fraction"])
+        sel = h.get_selection()
+        assert sel["n_directed"] == ref["cut_n"] and sel["cut_score"] == ref["cut_score"]
+        n = ref["cut_n"]
+        want = {(min(a, b), max(a, b), sc) for a, b, sc in zip(ref["conn_x"][:n].tolist(), ref["conn_y"][:n].tolist(), ref["conn_score"][:n].tolist())}
+        assert set(zip(sel["x"].tolist(), sel["y"].tolist(), sel["score"].tolist())) == want
+        h.components(min_size=c["min_size"])
+        comp = h.get_components()
+        got = sorted(tuple(sorted(int(v) for v in (np.nonzero(comp["label"] == r)[0] + comp["read_id_first"]))) for r in comp["comp_label"])
+        assert got == compare.components_partition(ref["comp_off"], ref["comp_read"])
+
+
+def test_engine_mirror_on_golden():
+    """the reference-shaped Python interface (construct_indices / get_all_connections / scaffold_components)"""
+    import hga_b200
+    c = golden_util.load_case("config1_mini")
+    ref = c["ref"]
+
+    class _Reader:
+        bases, seq_off = c["bases"], c["seq_off"]
+        n_reads = len(c["seq_off"]) - 1
+
+    eng = hga_b200.ReadClusteringEngine(_Reader(), hga_b200.ReadClusteringConfig())
+    eng.construct_indices(c["kmers"], c["k"])
+    x, y, s = eng.get_all_connections(1)
+    assert np.array_equal(x, ref["conn_x"]) and np.array_equal(y, ref["conn_y"]) and np.array_equal(s, ref["conn_score"])
+    comps = eng.scaffold_components()
+    assert sorted(tuple(cc.tolist()) for cc in comps) == compare.components_partition(ref["comp_off"], ref["comp_read"])
+    ids = eng.component_ids()[:7]
+    gx, gy, gs = eng.get_connections(ids, 20)
+    m = np.isin(ref["conn_x"], ids) & (ref["conn_score"] >= 20)
+    assert np.array_equal(gx, ref["conn_x"][m]) and np.array_equal(gy, ref["conn_y"][m]) and np.array_equal(gs, ref["conn_score"][m])
+    eng.close()
