@@ -166,6 +166,10 @@ int hga_scan(hga_handle *h, const char *bases, const uint64_t *read_off, uint64_
     const uint64_t n_bases = read_off[n_reads];
     if (read_off[0] != 0) { hga_set_error("hga_scan: read_off[0] must be 0"); return HGA_E_ARG; }
     if (n_bases && !bases) { hga_set_error("hga_scan: bases is NULL"); return HGA_E_ARG; }
+    for (uint64_t i = 0; i < n_reads; i++) {
+        if (read_off[i + 1] < read_off[i]) { hga_set_error("hga_scan: read_off is not monotone at read %llu", (unsigned long long) i); return HGA_E_ARG; }
+        if (read_off[i + 1] - read_off[i] >= (1ull << 30)) { hga_set_error("hga_scan: read %llu is longer than 2^30 bases", (unsigned long long) i); return HGA_E_ARG; }
+    }
     HGA_TRY(h->d_bases.ensure(n_bases + 64));
     HGA_TRY(h->d_read_off.ensure((n_reads + 1) * 8));
     {
