@@ -426,6 +426,9 @@ def main():
             "scan_gbases_per_s": total_bases_all / (scan_ms * 1e-3) / 1e9,
             "pairs_per_s": pairs_total / (pair_ms * 1e-3) if pair_ms > 0 else None,
             "increments_per_s": incr_total / (pair_ms * 1e-3) if pair_ms > 0 else None,
+            "diagnostics": {"filter_candidates_per_base": m["n_candidates"] / max(1, m["n_bases"]), "table_overflow_keys": m["table_overflow_keys"],
+                            "table_bytes": m["table_bytes"], "filter_bytes": m["filter_bytes"], "pair_mid_rows": m["mid_pivots"],
+                            "pair_heavy_rows": m["heavy_pivots"], "exchange_ms": m["exchange_ms"]},
             "roofline": {"kernel": "scan_probe_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_base": 1.0 + 8.0 * hpb,
                          "note": "achieved = (1 + 8*hits/base) B/base x bases per GPU / scan stage time (CUDA events on the launch stream, includes the 1/64 sampling pre-pass)"},

@@ -1,0 +1,204 @@
+// `categorization` — drop-in command line for the hot path of the reference executable of the same name
+// (/root/reference/src/read_clustering.cpp:35-85): same positional read files, same option names and defaults
+// (:41-58, ReadClusteringEngine.h:138-148), same per-file meta blocks, "<stage> took <ms>ms" lines (common/Utils.h:17-35)
+// and the same output layout: <dir>/#<component id>.fa, records re-emitted in input order (export_components,
+// clustering/ReadClusteringEngine.cpp:804-826).
+//
+// The arithmetic (scan -> membership -> incidence -> pair counting -> edge selection -> components) runs on the GPU
+// behind include/hga_b200.h; there is no CPU path. What is exported are the SCAFFOLD components (union_find at :763):
+// the reference's later host stages (merge_components, tails + spectral clustering, core enrichment)
+// are outside this hot path and not part of this build; --spectral is accepted and reported as unsupported.
+//
+// Extra, test-only switches: --parse-only (print the record stream and meta data, no GPU), --dump-kmers (print the
+// canonical k-mer values of the --kmers file, no GPU), --device N.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <iostream>
+#include <map>
+
+#include "hga_b200.h"
+#include "hga_host.h"
+
+namespace {
+
+struct Config {                                     // ReadClusteringConfig, ReadClusteringEngine.h:138-148
+    int scaffold_component_min_size = 30;
+    int scaffold_component_max_size = -1;
+    double scaffold_forming_fraction = 0.15;
+    uint64_t scaffold_forming_score = 0;
+    uint64_t enrichment_connections_min_score = 20;
+    uint64_t tail_amplification_min_score = 40;
+    int threads = 1;
+    int spectral_dims = 16;
+    bool force_spectral = false;
+};
+
+void usage() {
+    std::cout << "Options:\n"
+                 "  -h [ --help ]             Help screen\n"
+                 "  --read_paths arg          Path to file with reads (FASTA or FASTQ)\n"
+                 "  -k [ --kmers ] arg        Path to text file with kmers\n"
+                 "  -o [ --output ] arg       Path to folder with exported clusters\n"
+                 "  --sc_max_size arg         Maximum size for a scaffold component\n"
+                 "  --sc_min_size arg         Minimum size for a scaffold component\n"
+                 "  --sc_fraction arg         Minimum score for a scaffold component forming connection\n"
+                 "  --sc_score arg            Minimum score for a scaffold component forming connection\n"
+                 "  --tail_amplification arg  Minimal score for tail amplifying connections\n"
+                 "  --core_enrichment arg     Minimal score for connections enriching core components\n"
+                 "  --spectral_dims arg       Number of dimensions for spectral embedding\n"
+                 "  -s [ --spectral ]         Forces the usage of spectral clustering on the entire dataset\n"
+                 "  -d [ --debug ]            Debug flag. Treat read files as separate haplotype reads.\n"
+                 "  -t [ --threads ] arg      Number of threads to use\n";
+}
+
+struct Timer {
+    const char *label;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Timer(const char *l) : label(l) {}
+    void done() {
+        const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        std::cout << label << " took " << ms << "ms\n";               // Utils.h:17-35
+    }
+};
+
+void check(int rc, const char *what) {
+    if (rc != HGA_OK) {
+        std::cerr << "categorization: " << what << " failed (" << rc << "): " << hga_last_error() << "\n";
+        std::exit(2);
+    }
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    std::vector<std::string> read_paths;
+    std::string kmer_path, output_folder_path;
+    Config config;
+    bool debug = false, parse_only = false, dump_kmers = false;
+    int device = 0;
+
+    auto need = [&](int &i) -> const char * {
+        if (i + 1 >= argc) throw std::invalid_argument(std::string("the required argument for option '") + argv[i] + "' is missing");
+        return argv[++i];
+    };
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        if (a == "-h" || a == "--help") { usage(); return 0; }
+        else if (a == "-k" || a == "--kmers") kmer_path = need(i);
+        else if (a == "-o" || a == "--output") output_folder_path = need(i);
+        else if (a == "--read_paths") read_paths.push_back(need(i));
+        else if (a == "--sc_max_size") config.scaffold_component_max_size = std::atoi(need(i));
+        else if (a == "--sc_min_size") config.scaffold_component_min_size = std::atoi(need(i));
+        else if (a == "--sc_fraction") config.scaffold_forming_fraction = std::atof(need(i));
+        else if (a == "--sc_score") config.scaffold_forming_score = std::strtoull(need(i), nullptr, 10);
+        else if (a == "--tail_amplification") config.tail_amplification_min_score = std::strtoull(need(i), nullptr, 10);
+        else if (a == "--core_enrichment") config.enrichment_connections_min_score = std::strtoull(need(i), nullptr, 10);
+        else if (a == "--spectral_dims") config.spectral_dims = std::atoi(need(i));
+        else if (a == "-s" || a == "--spectral") config.force_spectral = true;
+        else if (a == "-d" || a == "--debug") debug = true;
+        else if (a == "-t" || a == "--threads") config.threads = std::atoi(need(i));
+        else if (a == "--parse-only") parse_only = true;
+        else if (a == "--dump-kmers") dump_kmers = true;
+        else if (a == "--device") device = std::atoi(need(i));
+        else if (a.size() > 1 && a[0] == '-') throw std::invalid_argument("unrecognised option '" + a + "'");
+        else read_paths.push_back(a);
+    }
+    (void) debug;   // haplotype annotation / plots are debug output of the reference, not part of the hot path
+
+    if (kmer_path.empty() && !parse_only) throw std::invalid_argument("You need to specify path to kmers");
+    if (dump_kmers) {
+        const hga_host::KmerSet ks = hga_host::load_text_file_kmers(kmer_path);
+        std::cout << "#K " << ks.k << " " << ks.kmers.size() << "\n";
+        for (uint64_t v : ks.kmers) std::cout << v << "\n";
+        return 0;
+    }
+    if (read_paths.empty()) throw std::invalid_argument("You need to specify paths to read files");
+
+    hga_host::KmerSet ks;
+    if (!parse_only) ks = hga_host::load_text_file_kmers(kmer_path);
+    hga_host::SequenceRecords reads(read_paths);
+    if (parse_only) {
+        for (const auto &m : reads.file_meta)
+            std::cout << "#META " << m.filename << " " << m.records << " " << m.total_bases << " " << m.avg_read_length << " " << m.max_read_length << " "
+                      << m.min_read_length << "\n";
+        const auto &m = reads.meta;
+        std::cout << "#AGG " << m.filename << " " << m.records << " " << m.total_bases << " " << m.avg_read_length << " " << m.max_read_length << " "
+                  << m.min_read_length << "\n";
+        for (size_t i = 0; i < reads.n_reads(); i++)
+            std::cout << (i + 1) << "\t" << reads.headers[i] << "\t" << reads.bases.substr(reads.seq_off[i], reads.seq_off[i + 1] - reads.seq_off[i]) << "\t"
+                      << reads.qualities[i] << "\n";
+        return 0;
+    }
+    for (const auto &m : reads.file_meta) std::cout << m.repr();
+    if (output_folder_path.empty()) output_folder_path = "./" + reads.meta.filename + "_clusters/";
+    if (config.force_spectral) {
+        std::cerr << "categorization: --spectral (spectral clustering of the whole data set, lib/clustering) is a host stage outside the GPU hot path "
+                     "and is not part of this build\n";
+        return 3;
+    }
+    if (config.scaffold_component_max_size != -1) {
+        std::cerr << "categorization: --sc_max_size needs the order-dependent sequential union_find and is not supported on the GPU path\n";
+        return 3;
+    }
+
+    hga_handle *h = nullptr;
+    {
+        Timer t("Index construction");               // table build + scan + inverted index = construct_indices (:234-299)
+        check(hga_create(device, ks.k, ks.kmers.data(), ks.kmers.size(), &h), "hga_create");
+        check(hga_scan(h, reads.bases.data(), reads.seq_off.data(), reads.n_reads(), 1), "hga_scan");
+        check(hga_build_index(h), "hga_build_index");
+        t.done();
+    }
+    {
+        Timer t("Calculation of connections between reads");
+        if (config.scaffold_forming_score > 0) {
+            // pivots = components with at least sc_score discriminative k-mers (:750-752)
+            hga_hits hits;
+            check(hga_get_hits(h, 0, &hits), "hga_get_hits");
+            std::vector<uint32_t> pivots;
+            for (uint64_t r = 0; r < hits.n_reads; r++)
+                if (hits.row_off[r + 1] - hits.row_off[r] >= config.scaffold_forming_score) pivots.push_back((uint32_t) (r + 1));
+            check(hga_pair_count(h, (uint32_t) config.scaffold_forming_score, pivots.data(), pivots.size()), "hga_pair_count");
+            check(hga_select_edges(h, 0.0, (uint32_t) config.scaffold_forming_score), "hga_select_edges");
+        } else {
+            check(hga_pair_count(h, 1, nullptr, 0), "hga_pair_count");
+            check(hga_select_edges(h, config.scaffold_forming_fraction, 0), "hga_select_edges");
+        }
+        t.done();
+    }
+    hga_components_t comp;
+    {
+        Timer t("Union-find");
+        check(hga_components(h, config.scaffold_component_min_size), "hga_components");
+        check(hga_get_components(h, &comp), "hga_get_components");
+        t.done();
+    }
+
+    // export_components (:804-826): one file per component, records in input order; reads of no component are dropped
+    std::filesystem::remove_all(output_folder_path);
+    std::filesystem::create_directories(output_folder_path);
+    std::map<uint32_t, std::ofstream> files;
+    for (uint64_t c = 0; c < comp.n_components; c++)
+        files[comp.comp_label[c]] = std::ofstream(output_folder_path + "/#" + std::to_string(comp.comp_label[c]) + ".fa", std::ios::binary);
+    for (uint64_t r = 0; r < comp.n_reads; r++) {
+        auto it = files.find(comp.label[r]);
+        if (it != files.end()) it->second << reads.fastx_string(r) << std::endl;
+    }
+    for (auto &f : files) f.second.close();
+    std::cout << "Exported " << comp.n_components << " components\n";
+
+    hga_metrics_t m;
+    if (hga_metrics(h, &m) == HGA_OK) {
+        std::fprintf(stderr,
+                     "hga_b200: %llu reads, %llu bases, %llu hits, %llu pairs, %llu selected edges, %llu components | GPU ms: table %.2f h2d %.2f scan %.2f "
+                     "index %.2f pairs %.2f select %.2f components %.2f\n",
+                     (unsigned long long) m.n_reads, (unsigned long long) m.n_bases, (unsigned long long) m.n_hits, (unsigned long long) m.n_pairs,
+                     (unsigned long long) m.n_selected, (unsigned long long) m.n_components, m.table_build_ms, m.h2d_ms, m.scan_ms, m.index_ms, m.pair_ms,
+                     m.select_ms, m.components_ms);
+    }
+    hga_destroy(h);
+    return 0;
+}

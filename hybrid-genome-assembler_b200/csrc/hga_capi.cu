@@ -33,7 +33,7 @@ __global__ void low32_kernel(const uint64_t *__restrict__ key, uint64_t n, uint3
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) out[i] = (uint32_t) key[i];
 }
 
-__global__ void kid_list_len_kernel(const uint32_t *__restrict__ kid_slot, const uint64_t *__restrict__ inv_off, uint64_t n_kmers, unsigned long long *len) {
+__global__ void kid_list_len_kernel(const uint32_t *__restrict__ kid_slot, const uint32_t *__restrict__ inv_off, uint64_t n_kmers, unsigned long long *len) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i <= n_kmers; i += (uint64_t) gridDim.x * blockDim.x) {
         if (i == n_kmers) { len[i] = 0; continue; }
         const uint32_t s = kid_slot[i];
@@ -41,7 +41,7 @@ __global__ void kid_list_len_kernel(const uint32_t *__restrict__ kid_slot, const
     }
 }
 
-__global__ void kid_list_copy_kernel(const uint32_t *__restrict__ kid_slot, const uint64_t *__restrict__ inv_off, const uint32_t *__restrict__ inv_row,
+__global__ void kid_list_copy_kernel(const uint32_t *__restrict__ kid_slot, const uint32_t *__restrict__ inv_off, const uint32_t *__restrict__ inv_row,
                                      const unsigned long long *__restrict__ out_off, uint64_t n_kmers, uint32_t first_id, uint32_t *out) {
     const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
     const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
@@ -114,9 +114,14 @@ int hga_create(int device, int k, const uint64_t *kmers, uint64_t n_kmers, hga_h
     hga_handle *h = new hga_handle();
     memset(&h->metrics, 0, sizeof(h->metrics));
     h->device = device; h->k = k; h->n_kmers = n_kmers; h->sm_count = prop.multiProcessorCount;
+    {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess && v > 0) h->l2_persist_max = (size_t) v;
+        cudaGetLastError();
+    }
     cudaError_t e1 = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-    cudaError_t e2 = cudaEventCreate(&h->ev0), e3 = cudaEventCreate(&h->ev1);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { hga_set_error("stream/event creation failed"); delete h; return HGA_E_CUDA; }
+    cudaError_t e2 = cudaEventCreate(&h->ev0), e3 = cudaEventCreate(&h->ev1), e4 = cudaEventCreate(&h->ev2), e5 = cudaEventCreate(&h->ev3);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) { hga_set_error("stream/event creation failed"); delete h; return HGA_E_CUDA; }
     h->stream = h->own_stream;
     int rc = hga_table_build(h, kmers);
     if (rc != HGA_OK) { hga_destroy(h); return rc; }
@@ -130,9 +135,9 @@ void hga_destroy(hga_handle *h) {
     cudaDeviceSynchronize();
     hga_comm_destroy(h);
     DevBuf *dev[] = {&h->d_keys, &h->d_slot_kid, &h->d_kid_slot, &h->d_filter, &h->d_bases, &h->d_read_off, &h->d_row_off, &h->d_hit_slot, &h->d_hit_pos,
-                     &h->d_tile_state, &h->d_scan_scalars, &h->d_x_row_off, &h->d_x_slot, &h->d_x_row, &h->d_inv_off, &h->d_inv_row, &h->d_sort_a,
+                     &h->d_tile_state, &h->d_tile_dir, &h->d_scan_scalars, &h->d_x_slot, &h->d_x_row, &h->d_inv_off, &h->d_inv_row, &h->d_sort_a,
                      &h->d_sort_b, &h->d_sort_tmp, &h->d_pair_key, &h->d_pair_score, &h->d_pair_key2, &h->d_pair_score2, &h->d_pair_scalars,
-                     &h->d_heavy_list, &h->d_heavy_tab, &h->d_pivot_flag, &h->d_hist, &h->d_sel_key, &h->d_sel_score, &h->d_sel_scalars, &h->d_parent,
+                     &h->d_heavy_list, &h->d_mid_list, &h->d_heavy_tab, &h->d_pivot_flag, &h->d_hist, &h->d_sel_key, &h->d_sel_score, &h->d_sel_scalars, &h->d_parent,
                      &h->d_comp_size, &h->d_comp_label, &h->d_comp_scalars, &h->d_export_a, &h->d_export_b, &h->d_export_c};
     for (DevBuf *b : dev) b->release();
     PinBuf *pin[] = {&h->h_row_off, &h->h_kid, &h->h_pos, &h->h_inv_off, &h->h_inv_read, &h->h_px, &h->h_py, &h->h_ps, &h->h_sx, &h->h_sy, &h->h_ss,
@@ -140,6 +145,8 @@ void hga_destroy(hga_handle *h) {
     for (PinBuf *b : pin) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -238,12 +245,12 @@ int hga_get_index(hga_handle *h, hga_index *out) {
     HGA_TRY(h->d_export_a.ensure((K + 2) * 8 * 2));
     HGA_TRY(h->d_export_b.ensure((E + 1) * 4));
     unsigned long long *len = h->d_export_a.as<unsigned long long>(), *off = len + (K + 2);
-    kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(h->table.kid_slot, h->d_inv_off.as<uint64_t>(), K, len);
+    kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(h->table.kid_slot, h->d_inv_off.as<uint32_t>(), K, len);
     size_t tmp = 0;
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, off, K + 1, h->stream));
     HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, len, off, K + 1, h->stream));
-    if (K) kid_list_copy_kernel<<<grid_for(h, K * 32), 256, 0, h->stream>>>(h->table.kid_slot, h->d_inv_off.as<uint64_t>(), h->d_inv_row.as<uint32_t>(), off, K,
+    if (K) kid_list_copy_kernel<<<grid_for(h, K * 32), 256, 0, h->stream>>>(h->table.kid_slot, h->d_inv_off.as<uint32_t>(), h->d_inv_row.as<uint32_t>(), off, K,
                                                                           h->inc_row_first_id, h->d_export_b.as<uint32_t>());
     h->metrics.kernel_launches += 4;
     HGA_CUDA(cudaGetLastError());

@@ -22,13 +22,13 @@ __global__ void expand_rows_kernel(const uint64_t *__restrict__ row_off, uint64_
 }
 
 // inv_off[s] = first position whose key is >= s (keys sorted ascending)
-__global__ void run_offsets_kernel(const uint32_t *__restrict__ keys, uint64_t n, uint32_t n_slots, uint64_t *__restrict__ inv_off) {
+__global__ void run_offsets_kernel(const uint32_t *__restrict__ keys, uint64_t n, uint32_t n_slots, uint32_t *__restrict__ inv_off) {
     uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
     for (; i <= n; i += stride) {
         const uint32_t cur = (i < n) ? keys[i] : n_slots;          // sentinel closes the tail
         const int64_t prev = (i == 0) ? -1 : (int64_t) keys[i - 1];
-        for (int64_t s = prev + 1; s <= (int64_t) cur; s++) inv_off[s] = i;
+        for (int64_t s = prev + 1; s <= (int64_t) cur; s++) inv_off[s] = (uint32_t) i;
     }
 }
 
@@ -39,51 +39,48 @@ int hga_index_run(hga_handle *h) {
     h->have_index = h->have_pairs = h->have_selection = h->have_components = false;
     const uint32_t n_slots = h->table.n_slots;
 
-    uint32_t *d_rows = nullptr;
     if (h->comm && hga_comm_size(h) > 1) {
-        HGA_TRY(hga_comm_exchange_incidence(h));   // fills inc_* and d_x_row
-        d_rows = h->d_x_row.as<uint32_t>();
-    } else {
-        h->inc_rows = h->n_reads;
-        h->inc_row_first_id = h->read_id_base;
-        h->inc_entries = h->n_hits;
-        h->inc_row_off = h->d_row_off.as<uint64_t>();
-        h->inc_slot = h->d_hit_slot.as<uint32_t>();
+        // sharded reads: all-to-all by slot owner + all-gather into a replicated global index (hga_comm.cu)
+        StageTimer timer(h, &h->metrics.index_ms);
+        HGA_TRY(hga_comm_build_global_index(h));
+        timer.stop();
+        h->have_index = true;
+        return HGA_OK;
     }
+    h->inc_rows = h->n_reads;
+    h->pair_rows = h->n_reads; h->pair_row_base = 0;
+    h->inc_row_first_id = h->read_id_base;
+    h->inc_entries = h->n_hits;
     const uint64_t E = h->inc_entries;
     if (E >= (1ull << 32)) { hga_set_error("incidence of %llu entries exceeds the 32-bit per-GPU limit", (unsigned long long) E); return HGA_E_OVERFLOW; }
 
     StageTimer timer(h, &h->metrics.index_ms);
-    HGA_TRY(h->d_inv_off.ensure(((size_t) n_slots + 2) * 8));
+    HGA_TRY(h->d_inv_off.ensure(((size_t) n_slots + 2) * 4));
     HGA_TRY(h->d_inv_row.ensure((E + 1) * 4));
     HGA_TRY(h->d_sort_a.ensure((E + 1) * 4));     // sorted keys
-    uint64_t *inv_off = h->d_inv_off.as<uint64_t>();
+    uint32_t *inv_off = h->d_inv_off.as<uint32_t>();
 
     if (E > 0) {
-        if (!d_rows) {
-            HGA_TRY(h->d_sort_b.ensure((E + 1) * 4));
-            d_rows = h->d_sort_b.as<uint32_t>();
-            const int blocks = (int) std::min<uint64_t>((h->inc_rows * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
-            expand_rows_kernel<<<blocks, 256, 0, h->stream>>>(h->inc_row_off, h->inc_rows, d_rows);
-            h->metrics.kernel_launches++;
-            HGA_CUDA(cudaGetLastError());
-        }
-        size_t tmp_bytes = 0;
-        const int end_bit = (int) std::max<uint32_t>(h->table.slot_bits, 1);
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->inc_slot, h->d_sort_a.as<uint32_t>(), d_rows, h->d_inv_row.as<uint32_t>(), E, 0,
-                                                 end_bit, h->stream));
-        HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp_bytes, h->inc_slot, h->d_sort_a.as<uint32_t>(), d_rows,
-                                                 h->d_inv_row.as<uint32_t>(), E, 0, end_bit, h->stream));
-        h->metrics.kernel_launches += (uint64_t) (end_bit + 7) / 8 + 2;   // CUB: histogram + onesweep passes
-    }
-    if (E == 0) {
-        HGA_CUDA(cudaMemsetAsync(inv_off, 0, ((size_t) n_slots + 1) * 8, h->stream));
-    } else {
-        const int blocks = (int) std::min<uint64_t>((E + 256) / 256, (uint64_t) h->sm_count * 16);
-        run_offsets_kernel<<<blocks, 256, 0, h->stream>>>(h->d_sort_a.as<uint32_t>(), E, n_slots, inv_off);
+        HGA_TRY(h->d_sort_b.ensure((E + 1) * 4));
+        uint32_t *d_rows = h->d_sort_b.as<uint32_t>();
+        const int blocks = (int) std::min<uint64_t>((h->inc_rows * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
+        expand_rows_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->inc_rows, d_rows);
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        const int end_bit = (int) std::max<uint32_t>(h->table.slot_bits, 1);
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->d_hit_slot.as<uint32_t>(), h->d_sort_a.as<uint32_t>(), d_rows, h->d_inv_row.as<uint32_t>(), E, 0,
+                                                 end_bit, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp_bytes, h->d_hit_slot.as<uint32_t>(), h->d_sort_a.as<uint32_t>(), d_rows,
+                                                 h->d_inv_row.as<uint32_t>(), E, 0, end_bit, h->stream));
+        h->metrics.kernel_launches += (uint64_t) (end_bit + 7) / 8 + 2;   // CUB: histogram + onesweep passes
+        const int oblocks = (int) std::min<uint64_t>((E + 256) / 256, (uint64_t) h->sm_count * 16);
+        run_offsets_kernel<<<oblocks, 256, 0, h->stream>>>(h->d_sort_a.as<uint32_t>(), E, n_slots, inv_off);
+        h->metrics.kernel_launches++;
+        HGA_CUDA(cudaGetLastError());
+    } else {
+        HGA_CUDA(cudaMemsetAsync(inv_off, 0, ((size_t) n_slots + 1) * 4, h->stream));
     }
     timer.stop();
     h->have_index = true;

@@ -79,43 +79,97 @@ struct PinBuf {
 
 // ------------------------------------------------------------------------------------------------
 // k-mer membership structures (device)
-//   key table : groups of 4 x u64 canonical k-mers (one 32 B sector), group-wise linear probing, load <= 0.5.
-//               The internal k-mer id ("slot") is the index of the key in this table; slot_kid maps it back
-//               to the caller's kmer_id.
-//   filter    : blocked Bloom filter, one 64-bit word per k-mer, 4 bits (2 per 32-bit half). Sized to stay
-//               L2-resident; consulted before the key table so that non-members cost one 8 B probe.
+//
+// Every canonical k-mer gets a 32-bit LOCALITY hash B that is shared by most consecutive windows of a read:
+// B = rehash of the minimum, over the W central m-mers of the k-mer, of the hashed canonical m-mer (a strand-
+// symmetric minimizer). Runs of ~(W + 1) / 2 consecutive windows share B, so their probes fall into the same
+// 32 B sector / 128 B bucket and coalesce inside a warp. m is chosen from the size of the set: the number of
+// distinct m-mers (4^m / 2) must be well above the number of keys, otherwise unrelated loci share a minimizer
+// VALUE and pile into the same block (4^m / 2 >= 3 n), and W = k - m + 1 <= HGA_MIN_W. m <= 16 so that m-mers
+// fit 32 bits. For k < HGA_MIN_K_FOR_MIN there is no room for minimizers and B is a plain hash of the k-mer.
+//
+//   filter    : blocked Bloom filter; block = 32 B (8 words) selected by B, word + 2 bits inside the block
+//               selected by an independent hash of the k-mer. Sized to stay L2-resident; consulted first so
+//               that a non-member costs one 4 B probe that its neighbours share.
+//   key table : buckets of 16 x u64 keys (one 128 B line) selected by B; inside a bucket the probe sequence starts
+//               at a slot picked by the k-mer hash and wraps around the bucket before it moves to the next
+//               bucket, for at most HGA_CHAIN_BUCKETS buckets (load factor 1/3, so a lookup usually ends on the
+//               first or second slot). Keys that find no room there go to a plain open-addressing overflow
+//               table hashed by k-mer. The internal k-mer id ("slot") is the index of the key in the (main | overflow) key
+//               array; slot_kid maps it back to the caller's kmer_id.
 // ------------------------------------------------------------------------------------------------
+#define HGA_MIN_W 8
+#define HGA_MIN_K_FOR_MIN 12
+#define HGA_BUCKET_SLOTS 16      // one 128 B line of u64 keys
+#define HGA_CHAIN_BUCKETS 4      // a key lives within this many buckets of its home bucket, else in the overflow region
+#define HGA_CHAIN_SLOTS (HGA_BUCKET_SLOTS * HGA_CHAIN_BUCKETS)
+
+struct KmerGeom {
+    int k = 0;
+    int use_min = 0;      // 1: B from the minimizer, 0: B from the k-mer hash
+    int m = 0;            // m-mer length (<= 16)
+    int W = 0;            // m-mers the minimum is taken over (2 .. HGA_MIN_W)
+    int skip = 0;         // m-mers skipped at each end of the window (> 0 only when k - m + 1 > HGA_MIN_W)
+    uint32_t mmask = 0;   // 2m low bits
+    int rc_shift = 0;     // 2 (k - m): the reverse-complement k-mer's first m-mer
+};
+
 struct KmerTable {
-    uint64_t *keys = nullptr;       // n_groups * 4
-    uint32_t *slot_kid = nullptr;   // n_groups * 4
+    uint64_t *keys = nullptr;       // n_slots (main region, then overflow region)
+    uint32_t *slot_kid = nullptr;   // n_slots
     uint32_t *kid_slot = nullptr;   // n_kmers
-    uint64_t *filter = nullptr;     // n_words
-    uint32_t n_groups = 0;
-    uint32_t n_words = 0;
-    uint32_t n_slots = 0;
+    uint32_t *filter = nullptr;     // n_blocks * 8 words
+    uint32_t n_buckets = 0;         // main region: (n_buckets + HGA_CHAIN_BUCKETS) * HGA_BUCKET_SLOTS slots
+    uint32_t n_main = 0;            // slots in the main region
+    uint32_t n_over = 0;            // slots in the overflow region (0: none; else a power of two)
+    uint32_t n_blocks = 0;
+    uint32_t n_slots = 0;           // n_main + n_over
     uint32_t slot_bits = 0;         // ceil(log2(n_slots))
+    KmerGeom geom;
 };
 
 #define HGA_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
-#define HGA_HASH_MULT 0x9E3779B97F4A7C15ull
+#define HGA_C1 0x9E3779B1u
+#define HGA_C2 0x85EBCA77u
+#define HGA_C3 0xC2B2AE3Du
+#define HGA_C4 0x27D4EB2Fu
 
-struct KmerHash {
-    uint32_t hi;     // selects filter word and home group
-    uint32_t lo;     // selects the bits inside the filter word
-};
-
-__host__ __device__ __forceinline__ KmerHash hga_hash(uint64_t kmer) {
-    uint64_t t = kmer * HGA_HASH_MULT;
-    KmerHash h;
-    h.hi = (uint32_t) (t >> 32);
-    h.lo = (uint32_t) t;
-    return h;
+static inline KmerGeom hga_make_geom(int k, uint64_t n_kmers) {
+    KmerGeom g;
+    g.k = k;
+    if (k < HGA_MIN_K_FOR_MIN) return g;
+    g.use_min = 1;
+    int m = 4;
+    while (m < 16 && (1ull << (2 * m - 1)) < 3 * n_kmers) m++;      // 4^m / 2 >= 3 n
+    if (m < k - HGA_MIN_W + 1) m = k - HGA_MIN_W + 1;                // W <= HGA_MIN_W where k leaves room
+    if (m > 16) m = 16;
+    if (m > k - 1) m = k - 1;                                         // W >= 2
+    int W = k - m + 1;
+    if (W > HGA_MIN_W) W = ((k - m + 1 - HGA_MIN_W) % 2 == 0) ? HGA_MIN_W : HGA_MIN_W - 1;   // centred: strand symmetric
+    g.m = m; g.W = W;
+    g.skip = (k - m + 1 - W) / 2;
+    g.mmask = (m == 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1);
+    g.rc_shift = 2 * (k - m);
+    return g;
 }
 
-// 2 bits in each 32-bit half of the filter word, taken from the top 20 bits of h.lo
-__host__ __device__ __forceinline__ void hga_filter_mask(uint32_t lo, uint32_t &m0, uint32_t &m1) {
-    m0 = (1u << ((lo >> 27) & 31)) | (1u << ((lo >> 22) & 31));
-    m1 = (1u << ((lo >> 17) & 31)) | (1u << ((lo >> 12) & 31));
+// hash of the k-mer that picks the word and the two bits inside a filter block (independent of B)
+__host__ __device__ __forceinline__ uint32_t hga_bits_hash(uint64_t kmer) {
+    return ((uint32_t) kmer ^ ((uint32_t) (kmer >> 32) * HGA_C3)) * HGA_C1;
+}
+__host__ __device__ __forceinline__ uint32_t hga_bits_word(uint32_t h) { return h >> 29; }
+__host__ __device__ __forceinline__ uint32_t hga_bits_mask(uint32_t h) { return (1u << ((h >> 24) & 31)) | (1u << ((h >> 19) & 31)); }
+// first slot of the probe sequence inside a bucket, and the j-th slot of the sequence (relative to the home bucket)
+__host__ __device__ __forceinline__ uint32_t hga_bits_start(uint32_t h) { return (h >> 15) & (HGA_BUCKET_SLOTS - 1); }
+__host__ __device__ __forceinline__ uint32_t hga_chain_slot(uint32_t start, uint32_t j) {
+    return (j & ~(uint32_t) (HGA_BUCKET_SLOTS - 1)) | ((start + j) & (HGA_BUCKET_SLOTS - 1));
+}
+
+// plain k-mer hash: B for small k, and the overflow table's home position
+__host__ __device__ __forceinline__ uint32_t hga_plain_hash(uint64_t kmer) {
+    uint32_t h = (uint32_t) kmer * HGA_C2 + (uint32_t) (kmer >> 32) * HGA_C1;
+    h ^= h >> 16;
+    return h * HGA_C3;
 }
 
 __host__ __device__ __forceinline__ uint32_t hga_scale(uint32_t h, uint32_t n) {
@@ -124,6 +178,41 @@ __host__ __device__ __forceinline__ uint32_t hga_scale(uint32_t h, uint32_t n) {
 #else
     return (uint32_t) (((uint64_t) h * n) >> 32);
 #endif
+}
+
+// reverse complement of an m-mer held in the low 2m bits (codes A0 C1 G2 T3)
+__host__ __device__ __forceinline__ uint32_t hga_revcomp32(uint32_t x, int m) {
+#ifdef __CUDA_ARCH__
+    x = __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    x = (x >> 16) | (x << 16);
+#endif
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);   // bits reversed -> 2-bit groups reversed
+    return (~x) >> (32 - 2 * m);
+}
+
+__host__ __device__ __forceinline__ uint32_t hga_mmer_hash(uint32_t fwd_m, uint32_t rc_m) {
+    return (fwd_m < rc_m ? fwd_m : rc_m) * HGA_C1;
+}
+// the minimum of 8 hashes is biased towards small values; the multiply carries its low bits up into the bits hga_scale uses
+__host__ __device__ __forceinline__ uint32_t hga_locality_from_min(uint32_t gmin) { return gmin * HGA_C2; }
+
+// B computed from the k-mer VALUE alone (table build; scan windows that contain a non-ACGT byte, whose two
+// strands are not reverse complements of each other)
+__host__ __device__ __forceinline__ uint32_t hga_locality_hash(uint64_t kmer, const KmerGeom &g) {
+    if (!g.use_min) return hga_plain_hash(kmer);
+    uint32_t gmin = 0xFFFFFFFFu;
+    for (int o = 0; o < g.W; o++) {
+        const int sh = 2 * (g.k - g.m - g.skip - o);
+        const uint32_t fm = (uint32_t) (kmer >> sh) & g.mmask;
+        const uint32_t h = hga_mmer_hash(fm, hga_revcomp32(fm, g.m));
+        gmin = h < gmin ? h : gmin;
+    }
+    return hga_locality_from_min(gmin);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -137,8 +226,9 @@ struct hga_handle {
     uint64_t n_kmers = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // stage timer, nested (exchange) timer
     int sm_count = 148;
+    size_t l2_persist_max = 0;            // cudaDevAttrMaxPersistingL2CacheSize
 
     // table
     KmerTable table;
@@ -150,19 +240,17 @@ struct hga_handle {
     DevBuf d_bases, d_read_off;           // staging for hga_scan (host entry)
     DevBuf d_row_off;                     // u64[n_reads+1]
     DevBuf d_hit_slot, d_hit_pos;         // u32[E]
-    DevBuf d_tile_state, d_scan_scalars;
+    DevBuf d_tile_state, d_tile_dir, d_scan_scalars;
     bool have_scan = false;
 
-    // incidence the pair counter works on (local rows for 1 GPU; global rows x owned k-mers with a comm)
-    uint64_t inc_rows = 0;                // number of rows in the incidence
+    // row space of the inverted index, pairs and components (this GPU's reads; ALL reads with a communicator)
+    uint64_t inc_rows = 0;                // number of rows
     uint32_t inc_row_first_id = 1;        // read id of row 0
-    uint64_t inc_entries = 0;
-    uint64_t *inc_row_off = nullptr;      // u64[inc_rows+1]  (aliases d_row_off or d_x_row_off)
-    uint32_t *inc_slot = nullptr;         // u32[inc_entries] (aliases d_hit_slot or d_x_slot)
-    DevBuf d_x_row_off, d_x_slot, d_x_row;   // exchanged incidence (multi-GPU)
+    uint64_t inc_entries = 0;             // entries of the inverted index
+    DevBuf d_x_slot, d_x_row;             // exchange staging (multi-GPU)
 
     // inverted index
-    DevBuf d_inv_off;                     // u64[n_slots+1]
+    DevBuf d_inv_off;                     // u32[n_slots+1] (the incidence of one GPU has < 2^32 entries)
     DevBuf d_inv_row;                     // u32[inc_entries]: ROW numbers (0-based), ascending inside a list
     DevBuf d_sort_a, d_sort_b, d_sort_tmp;
     bool have_index = false;
@@ -170,8 +258,10 @@ struct hga_handle {
     // pairs
     uint64_t n_pairs = 0, n_increments = 0;
     DevBuf d_pair_key, d_pair_score;      // u64 key = (x_row << 32 | y_row), u32 score; sorted by key
-    DevBuf d_pair_key2, d_pair_score2, d_pair_scalars, d_heavy_list, d_heavy_tab, d_pivot_flag;
+    DevBuf d_pair_key2, d_pair_score2, d_pair_scalars, d_heavy_list, d_mid_list, d_heavy_tab, d_pivot_flag;
     uint64_t pair_capacity = 0;
+    uint64_t pair_rows = 0;               // pivot rows held by this GPU (rows of d_row_off / d_hit_slot)
+    uint32_t pair_row_base = 0;           // global row number of local row 0
     bool have_pairs = false;
     uint32_t pair_min_score = 1;
 
@@ -203,8 +293,9 @@ int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold);
 int hga_cc_run(hga_handle *h, int min_size);
 
 // multi-GPU hooks (hga_comm.cu); all are no-ops / never called without a communicator
-int hga_comm_exchange_incidence(hga_handle *h);
-int hga_comm_reduce_pairs(hga_handle *h);
+int hga_comm_build_global_index(hga_handle *h);
+int hga_comm_allgather_u64(hga_handle *h, uint64_t mine, std::vector<uint64_t> &all);
+int hga_comm_allgatherv(hga_handle *h, const void *d_mine, void *d_all, const std::vector<uint64_t> &counts, int elem_bytes);
 int hga_comm_allreduce_u64_sum(hga_handle *h, uint64_t *d_buf, size_t n);
 int hga_comm_allreduce_u32_min(hga_handle *h, uint32_t *d_buf, size_t n);
 int hga_comm_allreduce_u32_max(hga_handle *h, uint32_t *d_buf, size_t n);
@@ -221,12 +312,15 @@ static inline uint32_t hga_ceil_log2(uint64_t n) {
 struct StageTimer {
     hga_handle *h;
     double *slot;
-    StageTimer(hga_handle *hh, double *s) : h(hh), slot(s) { cudaEventRecord(h->ev0, h->stream); }
+    cudaEvent_t a, b;
+    StageTimer(hga_handle *hh, double *s, bool nested = false) : h(hh), slot(s), a(nested ? hh->ev2 : hh->ev0), b(nested ? hh->ev3 : hh->ev1) {
+        cudaEventRecord(a, h->stream);
+    }
     void stop() {
-        cudaEventRecord(h->ev1, h->stream);
-        cudaEventSynchronize(h->ev1);
+        cudaEventRecord(b, h->stream);
+        cudaEventSynchronize(b);
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        cudaEventElapsedTime(&ms, a, b);
         *slot = ms;
     }
 };

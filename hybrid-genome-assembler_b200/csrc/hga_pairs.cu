@@ -3,12 +3,19 @@
 // Replaces ReadClusteringEngine::get_connections / get_all_connections
 // (clustering/ReadClusteringEngine.cpp:301-339): per pivot, the reference walks the pivot's k-mer id list
 // (duplicates included) and every entry of each k-mer's inverted list (duplicates included) and does
-// ++count[candidate] in a tsl::robin_map. This is a sparse integer A * A^T; here it is row-wise Gustavson:
-//   * one CTA per pivot row, a shared-memory open-addressing accumulator sized from the row's work,
-//   * one warp per incidence entry streams that k-mer's inverted list with coalesced loads,
-//   * every unordered pair is produced once (candidate > pivot), not twice as in the reference,
-//   * rows whose partner set does not fit shared memory go to a second kernel with a per-CTA table in HBM.
-// Output: (key = min_row << 32 | max_row, score) appended through one atomic cursor per row, then one
+// ++count[candidate] in a tsl::robin_map. This is a sparse integer A * A^T; here it is row-wise Gustavson in
+// three tiers:
+//   1. pair_count_warp_kernel: one WARP per pivot row, a per-warp shared-memory open-addressing accumulator
+//      (<= 1024 partners). Each LANE owns one incidence entry at a time and walks that k-mer's inverted list
+//      itself, so a warp has 32 independent list walks (and their random offset look-ups) in flight; a lane that
+//      finishes a list picks up the row's next entry without waiting for the others, and the offsets of its next
+//      list are prefetched while it walks the current one. Lists are sorted by row, so with all rows as pivots
+//      the walk runs from the END of the list and stops at the first row <= pivot: only the half of every list
+//      that can produce a (pivot < partner) pair is read, and every unordered pair is produced exactly once.
+//      Lists longer than PW_LONG are walked by the whole warp with coalesced loads.
+//   2. pair_count_kernel: rows whose partner set overflowed tier 1; one CTA per row, 4096-entry accumulator.
+//   3. pair_count_heavy_kernel: rows that overflow tier 2; per-CTA accumulator in HBM.
+// Output: (key = min_row << 32 | max_row, score) appended through one atomic cursor bump per row, then one
 // radix sort by key puts the pairs in the canonical (x asc, y asc) order that the tie rule of
 // hga_select_edges needs.
 #include "hga_internal.cuh"
@@ -20,6 +27,16 @@
 #define PC_CMAX 4096
 #define PC_EMPTY 0xFFFFFFFFu
 #define HV_THREADS 256
+#define PW_THREADS 128
+#define PW_WARPS (PW_THREADS / 32)
+#define PW_CMAX 1024
+#define PW_LONG 96
+#define PW_DEFER 32
+
+// which (pivot x, candidate y) combinations a pivot accumulates
+#define PAIR_MODE_TAIL 0     // every row is a pivot, one GPU: y > x (walk list tails only)
+#define PAIR_MODE_SUBSET 1   // pivot subset: pair (pivot, non-pivot), or ordered pivot pair
+#define PAIR_MODE_PARITY 2   // every row is a pivot somewhere (multi-GPU shards): the endpoint chosen by the parity of x + y
 
 struct PairScalars {
     unsigned long long ticket;
@@ -27,6 +44,8 @@ struct PairScalars {
     unsigned long long heavy_count;
     unsigned long long heavy_ticket;
     unsigned long long increments;
+    unsigned long long mid_count;
+    unsigned long long mid_ticket;
     unsigned int overflow;
     unsigned int pad;
 };
@@ -37,25 +56,29 @@ struct PairParams {
     const uint64_t *row_off;
     const uint32_t *row_slot;
     uint64_t n_rows;
-    const uint64_t *inv_off;
-    const uint32_t *inv_row;
-    const uint32_t *pivot_rows;     // nullptr: every row is a pivot
-    const uint8_t *pivot_flag;      // nullptr when every row is a pivot
+    uint32_t row_base;              // global row number of local row 0 (multi-GPU: rows of this rank's shard)
+    const uint32_t *inv_off;
+    const uint32_t *inv_row;        // global row numbers
+    const uint32_t *pivot_rows;     // nullptr: every local row is a pivot
+    const uint8_t *pivot_flag;      // SUBSET mode only
     uint64_t n_pivots;
+    int mode;
     uint32_t min_score;
     uint64_t *out_key;
     uint32_t *out_score;
     uint64_t capacity;
+    uint32_t *mid_list;
     uint32_t *heavy_list;
     uint32_t *heavy_tab;            // per-CTA tables of heavy_cap (key,val) pairs
     uint32_t heavy_cap;             // power of two
     PairScalars *sc;
 };
 
-__device__ __forceinline__ bool keep_candidate(uint32_t x, uint32_t y, const uint8_t *pivot_flag) {
+__device__ __forceinline__ bool keep_candidate(uint32_t x, uint32_t y, int mode, const uint8_t *pivot_flag) {
     if (y == x) return false;                         // :317 erase(pivot)
-    if (pivot_flag == nullptr) return y > x;          // all rows are pivots: count each unordered pair once
-    return !pivot_flag[y] || y > x;                   // pivot subset: pair (pivot, non-pivot) or ordered pivot pair
+    if (mode == PAIR_MODE_TAIL) return y > x;         // all rows are pivots: count each unordered pair once
+    if (mode == PAIR_MODE_SUBSET) return !pivot_flag[y] || y > x;
+    return ((x ^ y) & 1u) ? (y < x) : (y > x);        // PARITY: exactly one endpoint of every pair accepts the other
 }
 
 __device__ __forceinline__ uint32_t hash_row(uint32_t y) { return y * 2654435761u; }
@@ -90,6 +113,133 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_red,
     return base + incl - v;
 }
 
+// ---- tier 1 ---------------------------------------------------------------------------------------------------
+struct WarpAcc {
+    uint32_t key[PW_CMAX];
+    uint32_t val[PW_CMAX];
+    uint2 defer[PW_DEFER];          // long lists: [lo, hi)
+    uint32_t distinct, overflow, n_defer, pad;
+};
+
+// ++count[y]; most calls find y already present: one plain read, one shared-memory atomic add
+__device__ __forceinline__ void acc_add(WarpAcc &A, uint32_t y, uint32_t cmask, int cshift, uint32_t limit) {
+    uint32_t h = hash_row(y) >> cshift;
+    for (;;) {
+        uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&A.key[h]);
+        if (cur == PC_EMPTY) {
+            cur = atomicCAS(&A.key[h], PC_EMPTY, y);
+            if (cur == PC_EMPTY) { if (atomicAdd(&A.distinct, 1u) >= limit) A.overflow = 1; cur = y; }
+        }
+        if (cur == y) { atomicAdd(&A.val[h], 1u); return; }
+        if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) return;
+        h = (h + 1) & cmask;
+    }
+}
+
+__global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(PairParams p) {
+    __shared__ WarpAcc s_acc[PW_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpAcc &A = s_acc[warp];
+    const bool tail = p.mode == PAIR_MODE_TAIL;
+
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&p.sc->ticket, 1ull);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= p.n_pivots) break;
+        const uint32_t xl = p.pivot_rows ? p.pivot_rows[t] : (uint32_t) t;     // local row
+        const uint32_t x = xl + p.row_base;                                     // global row
+        const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
+        if (a == b) continue;
+
+        uint32_t C = 64;
+        while (C < PW_CMAX && C < 4 * (b - a)) C <<= 1;
+        for (bool retry = false;; retry = true) {
+            if (retry) C = PW_CMAX;
+            const uint32_t cmask = C - 1, limit = (C / 4) * 3;
+            const int cshift = 32 - (31 - __clz(C));
+            for (uint32_t i = lane; i < C; i += 32) { A.key[i] = PC_EMPTY; A.val[i] = 0; }
+            if (lane == 0) { A.distinct = 0; A.overflow = 0; A.n_defer = 0; }
+            __syncwarp();
+
+            // every lane: one list at a time, the next list's bounds prefetched
+            uint64_t j = a + lane;
+            uint32_t cur_lo = 0, cur_i = 0, n_lo = 0, n_hi = 0;
+            bool have_next = j < b;
+            if (have_next) { const uint32_t slot = __ldg(&p.row_slot[j]); n_lo = __ldg(&p.inv_off[slot]); n_hi = __ldg(&p.inv_off[slot + 1]); }
+            while (__any_sync(0xFFFFFFFFu, have_next || cur_i > cur_lo)) {
+                if (cur_i > cur_lo) {
+                    const uint32_t y = __ldg(&p.inv_row[--cur_i]);
+                    if (tail && y <= x) cur_i = cur_lo;                      // ascending list: nothing further down can be > x
+                    else if (keep_candidate(x, y, p.mode, p.pivot_flag)) acc_add(A, y, cmask, cshift, limit);
+                } else if (have_next) {
+                    cur_lo = n_lo; cur_i = n_hi;
+                    if (cur_i - cur_lo > PW_LONG) {                           // long list: leave it to the whole warp
+                        const uint32_t at = atomicAdd(&A.n_defer, 1u);
+                        if (at < PW_DEFER) { A.defer[at] = make_uint2(cur_lo, cur_i); cur_i = cur_lo; }
+                    }
+                    j += 32;
+                    have_next = j < b;
+                    if (have_next) { const uint32_t slot = __ldg(&p.row_slot[j]); n_lo = __ldg(&p.inv_off[slot]); n_hi = __ldg(&p.inv_off[slot + 1]); }
+                }
+                if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) { cur_i = cur_lo; have_next = false; }
+            }
+            __syncwarp();
+            const uint32_t nd = min(*reinterpret_cast<volatile uint32_t *>(&A.n_defer), (uint32_t) PW_DEFER);
+            for (uint32_t d = 0; d < nd && !*reinterpret_cast<volatile uint32_t *>(&A.overflow); d++) {
+                const uint2 r = A.defer[d];
+                for (int64_t i = (int64_t) r.y - 1 - lane;; i -= 32) {
+                    bool go = i >= (int64_t) r.x;
+                    if (go) {
+                        const uint32_t y = __ldg(&p.inv_row[i]);
+                        if (tail && y <= x) go = false;
+                        else if (keep_candidate(x, y, p.mode, p.pivot_flag)) acc_add(A, y, cmask, cshift, limit);
+                    }
+                    if (!__any_sync(0xFFFFFFFFu, go)) break;
+                }
+            }
+            __syncwarp();
+            if (!*reinterpret_cast<volatile uint32_t *>(&A.overflow)) {
+                // flush: entries with score >= min_score
+                uint32_t total = 0;
+                for (uint32_t i0 = 0; i0 < C; i0 += 32) {
+                    const bool ok = A.key[i0 + lane] != PC_EMPTY && A.val[i0 + lane] >= p.min_score;
+                    total += __popc(__ballot_sync(0xFFFFFFFFu, ok));
+                }
+                if (total) {
+                    unsigned long long base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd(&p.sc->cursor, (unsigned long long) total);
+                        if (base + total > p.capacity) p.sc->overflow = 1;
+                    }
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base + total <= p.capacity) {
+                        uint32_t off = 0;
+                        for (uint32_t i0 = 0; i0 < C; i0 += 32) {
+                            const uint32_t y = A.key[i0 + lane], v = A.val[i0 + lane];
+                            const bool ok = y != PC_EMPTY && v >= p.min_score;
+                            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+                            if (ok) {
+                                const uint64_t at = base + off + __popc(bal & ((1u << lane) - 1));
+                                p.out_key[at] = ((uint64_t) min(x, y) << 32) | max(x, y);
+                                p.out_score[at] = v;
+                            }
+                            off += __popc(bal);
+                        }
+                    }
+                }
+                break;
+            }
+            if (C == PW_CMAX) {      // more partners than a warp accumulator holds: tier 2
+                if (lane == 0) p.mid_list[atomicAdd(&p.sc->mid_count, 1ull)] = xl;
+                break;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- tier 2 ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PC_THREADS) pair_count_kernel(PairParams p) {
     __shared__ uint32_t s_key[PC_CMAX];
     __shared__ uint32_t s_val[PC_CMAX];
@@ -100,14 +250,16 @@ __global__ void __launch_bounds__(PC_THREADS) pair_count_kernel(PairParams p) {
     __shared__ volatile uint32_t s_overflow;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t n_mid = p.sc->mid_count;
 
     for (;;) {
-        if (tid == 0) { s_ticket = atomicAdd(&p.sc->ticket, 1ull); s_distinct = 0; s_overflow = 0; }
+        if (tid == 0) { s_ticket = atomicAdd(&p.sc->mid_ticket, 1ull); s_distinct = 0; s_overflow = 0; }
         __syncthreads();
         const uint64_t t = s_ticket;
-        if (t >= p.n_pivots) break;
-        const uint32_t x = p.pivot_rows ? p.pivot_rows[t] : (uint32_t) t;
-        const uint64_t a = p.row_off[x], b = p.row_off[x + 1];
+        if (t >= n_mid) break;
+        const uint32_t xl = p.mid_list[t];
+        const uint32_t x = xl + p.row_base;
+        const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         if (a == b) { __syncthreads(); continue; }
 
         // pass A: total list length W bounds the number of distinct partners
@@ -128,10 +280,10 @@ __global__ void __launch_bounds__(PC_THREADS) pair_count_kernel(PairParams p) {
         // pass B: warp per incidence entry, lanes over the inverted list
         for (uint64_t j = a + warp; j < b && !s_overflow; j += PC_WARPS) {
             const uint32_t slot = __ldg(&p.row_slot[j]);
-            const uint64_t lo = __ldg(&p.inv_off[slot]), hi = __ldg(&p.inv_off[slot + 1]);
-            for (uint64_t i = lo + lane; i < hi; i += 32) {
+            const uint32_t lo = __ldg(&p.inv_off[slot]), hi = __ldg(&p.inv_off[slot + 1]);
+            for (uint32_t i = lo + lane; i < hi; i += 32) {
                 const uint32_t y = __ldg(&p.inv_row[i]);
-                if (!keep_candidate(x, y, p.pivot_flag)) continue;
+                if (!keep_candidate(x, y, p.mode, p.pivot_flag)) continue;
                 uint32_t hsh = hash_row(y) >> (32 - cbits);
                 for (;;) {
                     const uint32_t old = atomicCAS(&s_key[hsh], PC_EMPTY, y);
@@ -148,7 +300,7 @@ __global__ void __launch_bounds__(PC_THREADS) pair_count_kernel(PairParams p) {
         if (s_overflow) {
             if (tid == 0) {
                 const unsigned long long hi = atomicAdd(&p.sc->heavy_count, 1ull);
-                p.heavy_list[hi] = x;
+                p.heavy_list[hi] = xl;
             }
             __syncthreads();
             continue;
@@ -196,16 +348,17 @@ __global__ void __launch_bounds__(HV_THREADS) pair_count_heavy_kernel(PairParams
         __syncthreads();
         const uint64_t t = s_ticket;
         if (t >= n_heavy) break;
-        const uint32_t x = p.heavy_list[t];
-        const uint64_t a = p.row_off[x], b = p.row_off[x + 1];
+        const uint32_t xl = p.heavy_list[t];
+        const uint32_t x = xl + p.row_base;
+        const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         for (uint32_t i = tid; i < p.heavy_cap; i += HV_THREADS) { tab_key[i] = PC_EMPTY; tab_val[i] = 0; }
         __syncthreads();
         for (uint64_t j = a + warp; j < b; j += HV_THREADS / 32) {
             const uint32_t slot = __ldg(&p.row_slot[j]);
-            const uint64_t lo = __ldg(&p.inv_off[slot]), hi = __ldg(&p.inv_off[slot + 1]);
-            for (uint64_t i = lo + lane; i < hi; i += 32) {
+            const uint32_t lo = __ldg(&p.inv_off[slot]), hi = __ldg(&p.inv_off[slot + 1]);
+            for (uint32_t i = lo + lane; i < hi; i += 32) {
                 const uint32_t y = __ldg(&p.inv_row[i]);
-                if (!keep_candidate(x, y, p.pivot_flag)) continue;
+                if (!keep_candidate(x, y, p.mode, p.pivot_flag)) continue;
                 uint32_t hsh = hash_row(y) >> (32 - cbits);
                 for (;;) {
                     const uint32_t old = atomicCAS(&tab_key[hsh], PC_EMPTY, y);
@@ -241,7 +394,7 @@ __global__ void __launch_bounds__(HV_THREADS) pair_count_heavy_kernel(PairParams
 }
 
 // work measure: sum over k-mers of occ*(occ-1)/2
-__global__ void increments_kernel(const uint64_t *__restrict__ inv_off, uint32_t n_slots, unsigned long long *out) {
+__global__ void increments_kernel(const uint32_t *__restrict__ inv_off, uint32_t n_slots, unsigned long long *out) {
     unsigned long long acc = 0;
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
         const unsigned long long len = inv_off[i + 1] - inv_off[i];
@@ -262,18 +415,24 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     if (!h->have_index) { hga_set_error("hga_pair_count: no index (call hga_build_index)"); return HGA_E_STATE; }
     h->have_pairs = h->have_selection = h->have_components = false;
     const bool multi = h->comm && hga_comm_size(h) > 1;
-    const uint64_t n_rows = h->inc_rows;
+    const uint64_t n_rows = h->pair_rows;         // pivot rows live on this GPU (all rows without a communicator)
     h->pair_min_score = min_score;
+    if (multi && pivots) { hga_set_error("hga_pair_count: pivot subsets are not supported with a communicator"); return HGA_E_ARG; }
 
     HGA_TRY(h->d_pair_scalars.ensure(sizeof(PairScalars)));
     PairScalars *d_sc = h->d_pair_scalars.as<PairScalars>();
     HGA_TRY(h->d_heavy_list.ensure((n_rows + 1) * 4));
+    HGA_TRY(h->d_mid_list.ensure((n_rows + 1) * 4));
 
     PairParams p;
-    p.row_off = h->inc_row_off; p.row_slot = h->inc_slot; p.n_rows = n_rows;
-    p.inv_off = h->d_inv_off.as<uint64_t>(); p.inv_row = h->d_inv_row.as<uint32_t>();
+    memset(&p, 0, sizeof(p));
+    p.row_off = h->d_row_off.as<uint64_t>(); p.row_slot = h->d_hit_slot.as<uint32_t>(); p.n_rows = n_rows;
+    p.row_base = h->pair_row_base;
+    p.inv_off = h->d_inv_off.as<uint32_t>(); p.inv_row = h->d_inv_row.as<uint32_t>();
     p.pivot_rows = nullptr; p.pivot_flag = nullptr; p.n_pivots = n_rows;
-    p.min_score = multi ? 1u : min_score;     // partial scores are thresholded after the cross-rank reduction
+    p.mode = multi ? PAIR_MODE_PARITY : PAIR_MODE_TAIL;
+    p.min_score = min_score;
+    p.mid_list = h->d_mid_list.as<uint32_t>();
     p.heavy_list = h->d_heavy_list.as<uint32_t>();
     p.heavy_tab = nullptr; p.heavy_cap = 0;
     p.sc = d_sc;
@@ -300,14 +459,17 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
         p.pivot_rows = d_pivots.as<uint32_t>();
         p.pivot_flag = h->d_pivot_flag.as<uint8_t>();
         p.n_pivots = n_pivots;
+        p.mode = PAIR_MODE_SUBSET;
     }
 
     StageTimer timer(h, &h->metrics.pair_ms);
     uint64_t capacity = std::max<uint64_t>(h->pair_capacity, std::max<uint64_t>(64 * n_rows, 1ull << 20));
-    int occ = 0;
-    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_count_kernel, PC_THREADS, 0));
-    if (occ < 1) occ = 1;
-    const int grid = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) h->sm_count * occ, p.n_pivots));
+    int occ_w = 0, occ_c = 0;
+    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel, PW_THREADS, 0));
+    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pair_count_kernel, PC_THREADS, 0));
+    if (occ_w < 1) occ_w = 1;
+    if (occ_c < 1) occ_c = 1;
+    const int grid_w = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) h->sm_count * occ_w, (p.n_pivots + PW_WARPS - 1) / PW_WARPS));
 
     PairScalars sc;
     h->metrics.pair_retries = 0;
@@ -317,15 +479,23 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
         p.out_key = h->d_pair_key.as<uint64_t>(); p.out_score = h->d_pair_score.as<uint32_t>(); p.capacity = capacity;
         HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(PairScalars), h->stream));
         if (p.n_pivots) {
-            pair_count_kernel<<<grid, PC_THREADS, 0, h->stream>>>(p);
+            pair_count_warp_kernel<<<grid_w, PW_THREADS, 0, h->stream>>>(p);
             h->metrics.kernel_launches++;
             HGA_CUDA(cudaGetLastError());
         }
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
+        if (sc.mid_count) {
+            const int grid_c = (int) std::min<uint64_t>(sc.mid_count, (uint64_t) h->sm_count * occ_c);
+            pair_count_kernel<<<grid_c, PC_THREADS, 0, h->stream>>>(p);
+            h->metrics.kernel_launches++;
+            HGA_CUDA(cudaGetLastError());
+            HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+        }
         if (sc.heavy_count) {
             uint32_t cap = 1024;
-            while (cap < 2 * n_rows && cap < (1u << 30)) cap <<= 1;
+            while (cap < 2 * h->inc_rows && cap < (1u << 30)) cap <<= 1;
             uint64_t budget = 4ull << 30;
             int hgrid = (int) std::min<uint64_t>(sc.heavy_count, (uint64_t) h->sm_count);
             while (hgrid > 1 && (uint64_t) hgrid * cap * 8 > budget) hgrid--;
@@ -338,6 +508,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
             HGA_CUDA(cudaStreamSynchronize(h->stream));
         }
         h->metrics.heavy_pivots = sc.heavy_count;
+        h->metrics.mid_pivots = sc.mid_count;
         if (!sc.overflow) break;
         if (attempt >= 1) { hga_set_error("pair_count: output overflow after exact resize (internal error)"); return HGA_E_OVERFLOW; }
         capacity = sc.cursor;
@@ -350,7 +521,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     HGA_TRY(h->d_pair_key2.ensure((P + 1) * 8));
     HGA_TRY(h->d_pair_score2.ensure((P + 1) * 4));
     if (P > 0) {
-        const int row_bits = (int) std::max<uint32_t>(hga_ceil_log2(n_rows + 1), 1);
+        const int row_bits = (int) std::max<uint32_t>(hga_ceil_log2(h->inc_rows + 1), 1);
         size_t tmp_bytes = 0;
         HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->d_pair_key.as<uint64_t>(), h->d_pair_key2.as<uint64_t>(),
                                                  h->d_pair_score.as<uint32_t>(), h->d_pair_score2.as<uint32_t>(), P, 0, 32 + row_bits, h->stream));
@@ -365,13 +536,12 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
 
     {   // work measure
         HGA_CUDA(cudaMemsetAsync(&d_sc->increments, 0, 8, h->stream));
-        increments_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_inv_off.as<uint64_t>(), h->table.n_slots, &d_sc->increments);
+        increments_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_inv_off.as<uint32_t>(), h->table.n_slots, &d_sc->increments);
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         h->n_increments = sc.increments;
     }
-    if (multi) HGA_TRY(hga_comm_reduce_pairs(h));   // all-to-all of partial scores + reduce by key + min_score filter
     timer.stop();
     h->metrics.n_pairs = h->n_pairs; h->metrics.n_increments = h->n_increments;
     h->have_pairs = true;

@@ -96,6 +96,35 @@ __global__ void write_selected_kernel(const uint64_t *__restrict__ key, const ui
     }
 }
 
+// keys of the pairs whose score equals the cut, in (x, y) order (tie_base = exclusive scan of the chunk tie counts)
+__global__ void write_ties_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ score, uint64_t n, uint32_t cut,
+                                  const unsigned long long *__restrict__ tie_base, uint64_t *out_key) {
+    __shared__ uint32_t s_t[SEL_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t) blockIdx.x * SEL_CHUNK;
+    unsigned long long out = tie_base[blockIdx.x];
+    for (uint32_t c = 0; c < SEL_CHUNK; c += SEL_THREADS) {
+        const uint64_t g = base + c + threadIdx.x;
+        const bool tie = g < n && score[g] == cut;
+        const uint32_t tb = __ballot_sync(0xFFFFFFFFu, tie);
+        if (lane == 0) s_t[warp] = __popc(tb);
+        __syncthreads();
+        uint32_t prefix = __popc(tb & ((1u << lane) - 1)), total = 0;
+        for (int i = 0; i < SEL_THREADS / 32; i++) { if (i < warp) prefix += s_t[i]; total += s_t[i]; }
+        if (tie) out_key[out + prefix] = key[g];
+        out += total;
+        __syncthreads();
+    }
+}
+
+// number of entries of the ascending array that are <= limit
+__global__ void count_le_kernel(const uint64_t *__restrict__ sorted, uint64_t n, const uint64_t *limit, unsigned long long *out) {
+    const uint64_t lim = *limit;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (sorted[mid] <= lim) lo = mid + 1; else hi = mid; }
+    *out = lo;
+}
+
 }  // namespace
 
 int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold) {
@@ -173,19 +202,33 @@ int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold) {
         HGA_CUDA(cudaMemsetAsync(blk_ties + nb, 0, 8, h->stream));
         HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp_bytes, blk_ties, tie_base, nb + 1, h->stream));
         unsigned long long tie_offset = 0;
-        if (multi) {
-            // ties held by lower ranks precede ours in (x, y) order: x ranges are ordered by rank
+        if (multi && quota > 0) {
+            // The canonical order interleaves the ranks' pairs, so the global quota of tied pairs is turned into a local
+            // one: gather every rank's tie keys, find the quota-th smallest, count the local ties up to it.
             unsigned long long my_ties = 0;
             HGA_CUDA(cudaMemcpyAsync(&my_ties, tie_base + nb, 8, cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
-            const int G = hga_comm_size(h), me = hga_comm_rank(h);
-            std::vector<unsigned long long> all(G, 0);
-            all[me] = my_ties;
-            HGA_CUDA(cudaMemcpyAsync(d_hist, all.data(), G * 8, cudaMemcpyHostToDevice, h->stream));
-            HGA_TRY(hga_comm_allreduce_u64_sum(h, (uint64_t *) d_hist, G));
-            HGA_CUDA(cudaMemcpyAsync(all.data(), d_hist, G * 8, cudaMemcpyDeviceToHost, h->stream));
+            std::vector<uint64_t> counts;
+            HGA_TRY(hga_comm_allgather_u64(h, my_ties, counts));
+            uint64_t T = 0;
+            for (uint64_t c : counts) T += c;
+            if (quota > T) { hga_set_error("select: tie quota beyond the number of ties (internal error)"); return HGA_E_STATE; }
+            HGA_TRY(h->d_sel_key.ensure((my_ties + 1) * 8));
+            HGA_TRY(h->d_export_a.ensure((T + 1) * 8 * 2 + 64));
+            uint64_t *d_mine = h->d_sel_key.as<uint64_t>(), *d_all = h->d_export_a.as<uint64_t>(), *d_all_sorted = d_all + (T + 1);
+            write_ties_kernel<<<(unsigned) nb, SEL_THREADS, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), h->d_pair_score.as<uint32_t>(), P, (uint32_t) cut, tie_base, d_mine);
+            HGA_CUDA(cudaGetLastError());
+            HGA_TRY(hga_comm_allgatherv(h, d_mine, d_all, counts, 8));
+            size_t tb2 = 0;
+            HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb2, d_all, d_all_sorted, T, 0, 64, h->stream));
+            HGA_TRY(h->d_sort_tmp.ensure(std::max(tb2, tmp_bytes) + 16));
+            HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, tb2, d_all, d_all_sorted, T, 0, 64, h->stream));
+            count_le_kernel<<<1, 1, 0, h->stream>>>(d_mine, my_ties, d_all_sorted + (quota - 1), d_hist);
+            h->metrics.kernel_launches += 12;
+            unsigned long long local_quota = 0;
+            HGA_CUDA(cudaMemcpyAsync(&local_quota, d_hist, 8, cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
-            for (int g = 0; g < me; g++) tie_offset += all[g];
+            quota = local_quota;
         }
         chunk_selected_kernel<<<(unsigned) ((nb + 255) / 256), 256, 0, h->stream>>>(blk_ties, tie_base, blk_above, nb, tie_offset, quota, blk_sel);
         HGA_CUDA(cudaMemsetAsync(blk_sel + nb, 0, 8, h->stream));

@@ -132,6 +132,9 @@ typedef struct {
     uint64_t n_bases, n_reads, n_hits, n_pairs, n_increments, n_selected, n_components;
     uint64_t table_bytes, filter_bytes, pair_retries, heavy_pivots;
     uint64_t kernel_launches;  /* kernels of this library launched on this handle since creation */
+    uint64_t table_overflow_keys; /* keys that did not fit their locality chain (stored in the overflow region) */
+    uint64_t mid_pivots;       /* pivot rows whose partner set overflowed the per-warp accumulator (tier 2) */
+    uint64_t n_candidates;     /* windows that passed the membership filter in the last scan (hits + false positives) */
 } hga_metrics_t;
 int hga_metrics(hga_handle *h, hga_metrics_t *out);
 

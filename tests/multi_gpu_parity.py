@@ -1,0 +1,107 @@
+"""Multi-GPU parity check (one process per GPU, launched by torchrun; see tests/test_multi_gpu.py):
+every rank scans its contiguous shard of the reads, the ranks exchange the inverted index over NCCL, and the union of
+the ranks' results is compared with the oracle run on the whole input. Bit-exact: hits, replicated inverted index,
+pair scores, cut (n, s*), selected edge set, components.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu_parity.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import hga_b200
+    from hga_b200 import parallel
+    import datagen
+    import oracle_lib
+    import compare
+
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    for case, (k, gsize, n_reads, rlen, sigma, err, min_size) in enumerate([(19, 60000, 500, 1500, 0.5, 0.03, 5), (15, 20000, 3000, 150, 0.0, 0.005, 10)]):
+        a = datagen.random_genome(gsize, 700 + case)
+        b = datagen.mutate(a, 0.02, 800 + case)
+        reads = datagen.sample_reads(a, n_reads, rlen, 11 + case, error_rate=err, length_sigma=sigma, max_len=gsize) + \
+            datagen.sample_reads(b, n_reads, rlen, 21 + case, error_rate=err, length_sigma=sigma, max_len=gsize)
+        reads.insert(7, np.zeros(0, dtype=np.uint8))            # an empty read inside a shard
+        seqs = [datagen.to_ascii(r).encode() for r in reads]
+        lens = np.array([len(s) for s in seqs], dtype=np.int64)
+        kmers = datagen.discriminative_kmers([a, b], k)
+        bounds = parallel.shard_bounds(lens, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        bases = b"".join(seqs[lo:hi])
+        off = np.zeros(hi - lo + 1, dtype=np.uint64)
+        np.cumsum(lens[lo:hi], out=off[1:])
+
+        h = hga_b200.Handle(kmers, k, device=local)
+        uid = parallel.broadcast_unique_id(dist, rank, hga_b200.capi.comm_unique_id)
+        h.comm_init(uid, rank, world, len(seqs))
+        h.scan(bases, off, read_id_base=lo + 1)
+        row_off, kid, pos = h.get_hits()
+        h.build_index()
+        inv_off, inv_read = h.get_index()
+        h.pair_count(min_score=1)
+        x, y, s, _ = h.get_pairs()
+        h.select_edges(fraction=0.15)
+        sel = h.get_selection()
+        h.components(min_size=min_size)
+        comp = h.get_components()
+        m = h.metrics()
+        h.close()
+
+        mine = dict(row_off=row_off, kid=kid, pos=pos, x=x, y=y, s=s, sx=sel["x"], sy=sel["y"], ss=sel["score"], n_directed=sel["n_directed"],
+                    cut=sel["cut_score"], label=comp["label"], comp_label=comp["comp_label"], comp_size=comp["comp_size"], inv_off=inv_off,
+                    inv_read=inv_read, exchange_ms=m["exchange_ms"])
+        box = [None] * world
+        dist.all_gather_object(box, mine)
+        if rank == 0:
+            orc = oracle_lib.load()
+            allb = b"".join(seqs)
+            alloff = np.zeros(len(seqs) + 1, dtype=np.uint64)
+            np.cumsum(lens, out=alloff[1:])
+            ref = orc.run(allb, alloff, k, kmers, fraction=0.15, min_size=min_size)
+            ro = ref["row_off"].astype(np.int64)
+            for r, res in enumerate(box):
+                a0, a1 = bounds[r], bounds[r + 1]
+                assert np.array_equal(res["row_off"].astype(np.int64), ro[a0:a1 + 1] - ro[a0]), f"case {case}: row offsets of rank {r} differ"
+                assert np.array_equal(res["kid"], ref["hit_kid"][ro[a0]:ro[a1]]) and np.array_equal(res["pos"], ref["hit_pos"][ro[a0]:ro[a1]]), f"hits of rank {r} differ"
+                assert np.array_equal(res["inv_off"], ref["inv_off"]) and np.array_equal(res["inv_read"], ref["inv_read"]), f"replicated index on rank {r} differs"
+            ux, uy, us = compare.undirected(*ref["conn"])
+            gx = np.concatenate([r["x"] for r in box]); gy = np.concatenate([r["y"] for r in box]); gs = np.concatenate([r["s"] for r in box])
+            o = np.lexsort((gy, gx))
+            assert np.array_equal(gx[o], ux) and np.array_equal(gy[o], uy) and np.array_equal(gs[o].astype(np.uint64), us), f"case {case}: pair scores differ"
+            for r in box:
+                assert r["n_directed"] == ref["cut_n"] and r["cut"] == ref["cut_score"], f"case {case}: cut differs"
+            got = set()
+            for r in box:
+                got |= set(zip(r["sx"].tolist(), r["sy"].tolist(), r["ss"].tolist()))
+            want = set()
+            cx, cy, cs = ref["conn"]
+            for p, q, w in zip(cx[:ref["cut_n"]].tolist(), cy[:ref["cut_n"]].tolist(), cs[:ref["cut_n"]].tolist()):
+                want.add((min(p, q), max(p, q), w))
+            assert got == want, f"case {case}: selected edge set differs ({len(got)} vs {len(want)})"
+            assert sum(len(r["sx"]) for r in box) == len(want), "an edge was selected on two ranks"
+            co, cm, _, _, _ = ref["comp"]
+            wantc = compare.components_partition(co, cm)
+            for r in box:
+                label = r["label"]
+                gotc = sorted(tuple(sorted(int(v) for v in (np.nonzero(label == c)[0] + 1))) for c in r["comp_label"])
+                assert gotc == wantc, f"case {case}: components differ"
+            print(f"multi-GPU parity ok: case {case}, {world} ranks, {len(seqs)} reads, {len(ux)} pairs, {len(want)} selected, {len(wantc)} components, "
+                  f"exchange {max(r['exchange_ms'] for r in box):.3f} ms")
+        dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
