@@ -91,10 +91,19 @@ def read_plan(torch, dev, genome_size, n_reads_per_hap, mean_len, seed):
     return lens, starts, flip, hap
 
 
-def synth_reads(torch, dev, haps, lens, starts, flip, hap, lo, hi, error, seed):
-    """ASCII bytes of reads [lo, hi) back to back + their offsets (uint64-compatible int64)"""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed + 13 + lo)
+def _mix64(torch, x):
+    """murmur3 finaliser on int64 tensors (wrapping arithmetic, logical shifts emulated)"""
+    x = x ^ ((x >> 33) & 0x7FFFFFFF)
+    x = x * -49064778989728563          # 0xff51afd7ed558ccd
+    x = x ^ ((x >> 33) & 0x7FFFFFFF)
+    x = x * -4265267296055464877        # 0xc4ceb9fe1a85ec53
+    return x ^ ((x >> 33) & 0x7FFFFFFF)
+
+
+def synth_reads(torch, dev, haps, lens, starts, flip, hap, lo, hi, error, seed, base0=0):
+    """ASCII bytes of reads [lo, hi) back to back + their offsets (uint64-compatible int64). Substitution errors are a
+    function of the GLOBAL base index (base0 = index of the shard's first base), so the data does not depend on how the
+    reads are sharded over ranks."""
     L = lens[lo:hi]
     off = torch.zeros(hi - lo + 1, dtype=torch.int64, device=dev)
     torch.cumsum(L, 0, out=off[1:])
@@ -120,9 +129,11 @@ def synth_reads(torch, dev, haps, lens, starts, flip, hap, lo, hi, error, seed):
         code = genome.view(-1)[hap[gr] * G + src]
         code = torch.where(fl, 3 - code, code)
         if error > 0:
-            e = torch.rand(b1 - b0, device=dev, generator=g) < error
-            sh = torch.randint(1, 4, (b1 - b0,), dtype=torch.uint8, device=dev, generator=g)
+            hsh = _mix64(torch, torch.arange(b0, b1, device=dev, dtype=torch.int64) + (base0 + seed * 1000003))
+            e = (hsh & 0xFFFFFF).to(torch.float32) < error * float(1 << 24)
+            sh = (((hsh >> 24) & 0xFFFF) % 3 + 1).to(torch.uint8)
             code = torch.where(e, (code + sh) % 4, code)
+            del hsh, e, sh
         out[b0:b1] = lut[code.to(torch.int64)]
         del rid, j, gr, fl, src, code
         r0 = r1
@@ -291,7 +302,8 @@ def main():
         bounds.append(int(torch.searchsorted(csum, total_bases_all * r // world).item()))
     bounds.append(n_reads_total)
     lo, hi = bounds[rank], bounds[rank + 1]
-    d_bases, d_off, n_bases = synth_reads(torch, dev, list(haps), lens, starts, flip, hap, lo, hi, args.error, args.seed)
+    base0 = int(csum[lo - 1]) if lo > 0 else 0
+    d_bases, d_off, n_bases = synth_reads(torch, dev, list(haps), lens, starts, flip, hap, lo, hi, args.error, args.seed, base0)
     n_reads = hi - lo
     del haps
     torch.cuda.empty_cache()

@@ -33,10 +33,11 @@ __global__ void low32_kernel(const uint64_t *__restrict__ key, uint64_t n, uint3
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) out[i] = (uint32_t) key[i];
 }
 
+// kid_slot == nullptr: the index is already keyed by kmer_id
 __global__ void kid_list_len_kernel(const uint32_t *__restrict__ kid_slot, const uint32_t *__restrict__ inv_off, uint64_t n_kmers, unsigned long long *len) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i <= n_kmers; i += (uint64_t) gridDim.x * blockDim.x) {
         if (i == n_kmers) { len[i] = 0; continue; }
-        const uint32_t s = kid_slot[i];
+        const uint32_t s = kid_slot ? kid_slot[i] : (uint32_t) i;
         len[i] = inv_off[s + 1] - inv_off[s];
     }
 }
@@ -47,7 +48,7 @@ __global__ void kid_list_copy_kernel(const uint32_t *__restrict__ kid_slot, cons
     const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint64_t kid = w; kid < n_kmers; kid += warps) {
-        const uint32_t s = kid_slot[kid];
+        const uint32_t s = kid_slot ? kid_slot[kid] : (uint32_t) kid;
         const uint64_t a = inv_off[s], b = inv_off[s + 1], o = out_off[kid];
         for (uint64_t i = lane; i < b - a; i += 32) out[o + i] = inv_row[a + i] + first_id;
     }
@@ -120,6 +121,7 @@ int hga_create(int device, int k, const uint64_t *kmers, uint64_t n_kmers, hga_h
         cudaGetLastError();
     }
     cudaError_t e1 = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { h->copy_stream = nullptr; cudaGetLastError(); }
     cudaError_t e2 = cudaEventCreate(&h->ev0), e3 = cudaEventCreate(&h->ev1), e4 = cudaEventCreate(&h->ev2), e5 = cudaEventCreate(&h->ev3);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) { hga_set_error("stream/event creation failed"); delete h; return HGA_E_CUDA; }
     h->stream = h->own_stream;
@@ -135,7 +137,7 @@ void hga_destroy(hga_handle *h) {
     cudaDeviceSynchronize();
     hga_comm_destroy(h);
     DevBuf *dev[] = {&h->d_keys, &h->d_slot_kid, &h->d_kid_slot, &h->d_filter, &h->d_bases, &h->d_read_off, &h->d_row_off, &h->d_hit_slot, &h->d_hit_pos,
-                     &h->d_tile_state, &h->d_tile_dir, &h->d_scan_scalars, &h->d_x_slot, &h->d_x_row, &h->d_inv_off, &h->d_inv_row, &h->d_sort_a,
+                     &h->d_tile_state, &h->d_tile_dir, &h->d_scan_scalars, &h->d_x_slot, &h->d_x_row, &h->d_hit_kid, &h->d_g_kid, &h->d_g_row_off, &h->d_inv_off, &h->d_inv_row, &h->d_sort_a,
                      &h->d_sort_b, &h->d_sort_tmp, &h->d_pair_key, &h->d_pair_score, &h->d_pair_key2, &h->d_pair_score2, &h->d_pair_scalars,
                      &h->d_heavy_list, &h->d_mid_list, &h->d_heavy_tab, &h->d_pivot_flag, &h->d_hist, &h->d_sel_key, &h->d_sel_score, &h->d_sel_scalars, &h->d_parent,
                      &h->d_comp_size, &h->d_comp_label, &h->d_comp_scalars, &h->d_export_a, &h->d_export_b, &h->d_export_c};
@@ -148,6 +150,7 @@ void hga_destroy(hga_handle *h) {
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
 }
 
@@ -163,7 +166,7 @@ int hga_scan_device(hga_handle *h, const char *d_bases, const uint64_t *d_read_o
     if (((uintptr_t) d_bases & 15) != 0) { hga_set_error("hga_scan_device: d_bases must be 16-byte aligned"); return HGA_E_ARG; }
     HGA_TRY(use_device(h));
     h->read_id_base = read_id_base;
-    return hga_scan_run(h, d_bases, d_read_off, n_reads, n_bases);
+    return hga_scan_run(h, d_bases, d_read_off, n_reads, n_bases, nullptr);
 }
 
 int hga_scan(hga_handle *h, const char *bases, const uint64_t *read_off, uint64_t n_reads, uint32_t read_id_base) {
@@ -179,14 +182,10 @@ int hga_scan(hga_handle *h, const char *bases, const uint64_t *read_off, uint64_
     }
     HGA_TRY(h->d_bases.ensure(n_bases + 64));
     HGA_TRY(h->d_read_off.ensure((n_reads + 1) * 8));
-    {
-        StageTimer t(h, &h->metrics.h2d_ms);
-        if (n_bases) HGA_CUDA(cudaMemcpyAsync(h->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, h->stream));
-        HGA_CUDA(cudaMemcpyAsync(h->d_read_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-        t.stop();
-    }
+    h->metrics.h2d_ms = 0;
+    HGA_CUDA(cudaMemcpyAsync(h->d_read_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, h->stream));
     h->read_id_base = read_id_base;
-    return hga_scan_run(h, h->d_bases.as<char>(), h->d_read_off.as<uint64_t>(), n_reads, n_bases);
+    return hga_scan_run(h, h->d_bases.as<char>(), h->d_read_off.as<uint64_t>(), n_reads, n_bases, bases);
 }
 
 int hga_get_hits(hga_handle *h, int sorted_by_kmer_id, hga_hits *out) {
@@ -245,12 +244,13 @@ int hga_get_index(hga_handle *h, hga_index *out) {
     HGA_TRY(h->d_export_a.ensure((K + 2) * 8 * 2));
     HGA_TRY(h->d_export_b.ensure((E + 1) * 4));
     unsigned long long *len = h->d_export_a.as<unsigned long long>(), *off = len + (K + 2);
-    kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(h->table.kid_slot, h->d_inv_off.as<uint32_t>(), K, len);
+    const uint32_t *kid_slot = h->index_by_kid ? nullptr : h->table.kid_slot;
+    kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(kid_slot, h->d_inv_off.as<uint32_t>(), K, len);
     size_t tmp = 0;
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, off, K + 1, h->stream));
     HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, len, off, K + 1, h->stream));
-    if (K) kid_list_copy_kernel<<<grid_for(h, K * 32), 256, 0, h->stream>>>(h->table.kid_slot, h->d_inv_off.as<uint32_t>(), h->d_inv_row.as<uint32_t>(), off, K,
+    if (K) kid_list_copy_kernel<<<grid_for(h, K * 32), 256, 0, h->stream>>>(kid_slot, h->d_inv_off.as<uint32_t>(), h->d_inv_row.as<uint32_t>(), off, K,
                                                                           h->inc_row_first_id, h->d_export_b.as<uint32_t>());
     h->metrics.kernel_launches += 4;
     HGA_CUDA(cudaGetLastError());

@@ -3,15 +3,19 @@
 // The reference has no distributed path; SURVEY.md §8(e) defines this one. Reads shard by contiguous read-id ranges
 // (each rank scans its own shard against a replicated k-mer table). The only data that has to cross ranks for the
 // sparse A * A^T is the inverted index:
-//   1. every rank sorts its local (slot, global row) incidences by slot; slot ranges are owned by ranks
-//      (owner = slot / ceil(n_slots / G); slots are hash positions, so the ranges are balanced);
-//   2. ALL-TO-ALL (grouped ncclSend / ncclRecv): each owner receives its slot range from every rank, in rank order,
-//      which is also global row order, so one stable sort by slot gives the owner's lists with rows ascending;
+//   1. every rank translates its hits from table slots (which differ between ranks: every rank builds its own table
+//      with atomics) to the caller's kmer_id, and sorts its local (kmer_id, global row) incidences by kmer_id;
+//      kmer_id ranges are owned by ranks (owner = kmer_id / ceil(K / G));
+//   2. ALL-TO-ALL (grouped ncclSend / ncclRecv): each owner receives its kmer_id range from every rank, in rank order,
+//      which is also global row order, so one stable sort by kmer_id gives the owner's lists with rows ascending;
 //   3. ALL-GATHER (grouped ncclBroadcast, one root per rank): the per-owner CSR pieces are concatenated in owner
-//      order into a REPLICATED global inverted index (slot ranges are contiguous, so concatenation is the index);
-//   4. every rank then counts pairs for the pivot rows of its own shard against the replicated index, choosing the
-//      pivot endpoint of a pair by the parity of x + y: every unordered pair is produced exactly once, on exactly one
-//      rank, with its FINAL score, and the load is balanced without a second exchange.
+//      order into a REPLICATED global inverted index (kmer_id ranges are contiguous, so concatenation is the index);
+//   4. ALL-GATHER of the by-read incidence (kmer_id per hit + row offsets): with both sides of A * A^T replicated, rank r
+//      counts pairs for the pivot rows r, r + G, r + 2G, ... with the single-GPU rule (partner > pivot, list tails
+//      only): every unordered pair is produced exactly once, on exactly one rank, with its FINAL score; interleaving
+//      balances the ranks (a contiguous shard of early rows would carry most of the y > x work), and no partial
+//      scores ever cross the links. (A first version kept pivots on their shard and chose the endpoint by the parity
+//      of x + y: balanced too, but it walks whole lists and was no faster on 2 GPUs than one GPU alone.)
 // Edge selection needs two small all-reduces (score histograms) and an all-gather of the tie keys; components
 // iterate union-find with all-reduce(min) over the replicated label array.
 //
@@ -80,6 +84,14 @@ int load_nccl() {
             return HGA_E_NCCL;                                                                                          \
         }                                                                                                               \
     } while (0)
+
+__global__ void slots_to_kids_kernel2(const uint32_t *__restrict__ slot, const uint32_t *__restrict__ slot_kid, uint64_t n, uint32_t *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) out[i] = slot_kid[slot[i]];
+}
+
+__global__ void shift_u64_kernel(const uint64_t *__restrict__ in, uint64_t n, uint64_t add, uint64_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) out[i] = in[i] + add;
+}
 
 __global__ void global_rows_kernel(const uint64_t *__restrict__ row_off, uint64_t n_rows, uint32_t row_base, uint32_t *__restrict__ out_row) {
     const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
@@ -171,7 +183,7 @@ int hga_comm_allgatherv(hga_handle *h, const void *d_mine, void *d_all, const st
 // (rows are global row numbers = read id - 1) and h->inc_* describe it.
 int hga_comm_build_global_index(hga_handle *h) {
     const int G = h->comm->size, me = h->comm->rank;
-    const uint32_t n_slots = h->table.n_slots;
+    const uint32_t n_slots = (uint32_t) h->n_kmers;    // lists of the exchanged index: one per kmer_id
     const uint64_t E_loc = h->n_hits;
     const uint64_t per_rank = ((uint64_t) n_slots + G - 1) / G;
     const uint32_t row_base = h->read_id_base - 1;
@@ -181,15 +193,19 @@ int hga_comm_build_global_index(hga_handle *h) {
     HGA_TRY(h->d_sort_a.ensure((E_loc + 1) * 4));      // sorted slots
     HGA_TRY(h->d_sort_b.ensure((E_loc + 1) * 4));      // global rows, unsorted
     HGA_TRY(h->d_x_row.ensure((E_loc + 1) * 4));       // global rows, sorted
-    const int end_bit = (int) std::max<uint32_t>(h->table.slot_bits, 1);
+    const int end_bit = (int) std::max<uint32_t>(hga_ceil_log2(h->n_kmers + 1), 1);
+    HGA_TRY(h->d_hit_kid.ensure((E_loc + 1) * 4));
     if (E_loc) {
+        slots_to_kids_kernel2<<<(int) std::min<uint64_t>((E_loc + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(
+            h->d_hit_slot.as<uint32_t>(), h->table.slot_kid, E_loc, h->d_hit_kid.as<uint32_t>());
+        h->metrics.kernel_launches++;
         const int blocks = (int) std::min<uint64_t>((h->n_reads * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
         global_rows_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->n_reads, row_base, h->d_sort_b.as<uint32_t>());
         size_t tmp = 0;
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->d_hit_slot.as<uint32_t>(), h->d_sort_a.as<uint32_t>(), h->d_sort_b.as<uint32_t>(),
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->d_hit_kid.as<uint32_t>(), h->d_sort_a.as<uint32_t>(), h->d_sort_b.as<uint32_t>(),
                                                  h->d_x_row.as<uint32_t>(), E_loc, 0, end_bit, h->stream));
         HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp, h->d_hit_slot.as<uint32_t>(), h->d_sort_a.as<uint32_t>(), h->d_sort_b.as<uint32_t>(),
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp, h->d_hit_kid.as<uint32_t>(), h->d_sort_a.as<uint32_t>(), h->d_sort_b.as<uint32_t>(),
                                                  h->d_x_row.as<uint32_t>(), E_loc, 0, end_bit, h->stream));
         h->metrics.kernel_launches += (uint64_t) (end_bit + 7) / 8 + 3;
     }
@@ -250,6 +266,7 @@ int hga_comm_build_global_index(hga_handle *h) {
     HGA_TRY(h->d_inv_off.ensure(((size_t) per_rank * G + 2) * 4));
     HGA_TRY(h->d_inv_row.ensure((E_total + 1) * 4));
     uint32_t *inv_off = h->d_inv_off.as<uint32_t>(), *inv_row = h->d_inv_row.as<uint32_t>();
+    HGA_CUDA(cudaMemsetAsync(inv_off, 0, ((size_t) per_rank * G + 2) * 4, h->stream));
     uint64_t my_base = 0;
     for (int g = 0; g < me; g++) my_base += own_cnt[g];
     const uint64_t first = (uint64_t) me * per_rank;
@@ -278,8 +295,38 @@ int hga_comm_build_global_index(hga_handle *h) {
     h->inc_rows = h->n_reads_total;
     h->inc_row_first_id = 1;
     h->inc_entries = E_total;
-    h->pair_rows = h->n_reads;
-    h->pair_row_base = row_base;
+    // 4. replicated by-read incidence
+    {
+        StageTimer gt(h, &h->metrics.exchange_ms, true);
+        std::vector<uint64_t> hit_cnt, row_cnt;
+        HGA_TRY(hga_comm_allgather_u64(h, E_loc, hit_cnt));
+        HGA_TRY(hga_comm_allgather_u64(h, h->n_reads, row_cnt));
+        uint64_t hit_base = 0, n_rows_all = 0;
+        for (int g = 0; g < me; g++) hit_base += hit_cnt[g];
+        for (int g = 0; g < G; g++) n_rows_all += row_cnt[g];
+        uint64_t rows_before = 0;
+        for (int g = 0; g < me; g++) rows_before += row_cnt[g];
+        if (rows_before != row_base) { hga_set_error("hga_build_index: shards must be contiguous read-id ranges in rank order (rank %d starts at row %u, expected %llu)", me, row_base, (unsigned long long) rows_before); return HGA_E_ARG; }
+        if (n_rows_all != h->n_reads_total) { hga_set_error("hga_build_index: the ranks scanned %llu reads, hga_comm_init said %llu", (unsigned long long) n_rows_all, (unsigned long long) h->n_reads_total); return HGA_E_ARG; }
+        HGA_TRY(h->d_g_kid.ensure((E_total + 1) * 4));
+        HGA_TRY(h->d_g_row_off.ensure((n_rows_all + 2) * 8));
+        HGA_TRY(h->d_x_slot.ensure((h->n_reads + 2) * 8));          // my row offsets, shifted to global positions
+        shift_u64_kernel<<<(int) std::min<uint64_t>((h->n_reads + 256) / 256, 2048), 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->n_reads, hit_base,
+                                                                                                     h->d_x_slot.as<uint64_t>());
+        h->metrics.kernel_launches++;
+        HGA_CUDA(cudaGetLastError());
+        HGA_TRY(hga_comm_allgatherv(h, h->d_hit_kid.p, h->d_g_kid.p, hit_cnt, 4));
+        HGA_TRY(hga_comm_allgatherv(h, h->d_x_slot.p, h->d_g_row_off.p, row_cnt, 8));
+        const uint64_t e_total = E_total;
+        HGA_CUDA(cudaMemcpyAsync(h->d_g_row_off.as<uint64_t>() + n_rows_all, &e_total, 8, cudaMemcpyHostToDevice, h->stream));
+        const double first_ms = h->metrics.exchange_ms;
+        gt.stop();
+        h->metrics.exchange_ms += first_ms;
+    }
+    h->pair_rows = h->n_reads_total;
+    h->pair_pivot_mul = (uint32_t) G; h->pair_pivot_add = (uint32_t) me;
+    h->index_by_kid = true;
+    h->index_keys = n_slots;
     return HGA_OK;
 }
 

@@ -48,7 +48,8 @@ int hga_index_run(hga_handle *h) {
         return HGA_OK;
     }
     h->inc_rows = h->n_reads;
-    h->pair_rows = h->n_reads; h->pair_row_base = 0;
+    h->pair_rows = h->n_reads; h->pair_pivot_mul = 1; h->pair_pivot_add = 0;
+    h->index_by_kid = false; h->index_keys = n_slots;
     h->inc_row_first_id = h->read_id_base;
     h->inc_entries = h->n_hits;
     const uint64_t E = h->inc_entries;

@@ -92,9 +92,9 @@ struct PinBuf {
 //               selected by an independent hash of the k-mer. Sized to stay L2-resident; consulted first so
 //               that a non-member costs one 4 B probe that its neighbours share.
 //   key table : buckets of 16 x u64 keys (one 128 B line) selected by B; inside a bucket the probe sequence starts
-//               at a slot picked by the k-mer hash and wraps around the bucket before it moves to the next
-//               bucket, for at most HGA_CHAIN_BUCKETS buckets (load factor 1/3, so a lookup usually ends on the
-//               first or second slot). Keys that find no room there go to a plain open-addressing overflow
+//               in the 4-slot sector (32 B) picked by the k-mer hash, goes round the bucket's sectors, then moves to
+//               the next bucket, for at most HGA_CHAIN_BUCKETS buckets (load factor 1/3: a lookup usually ends
+//               after one 32 B load). Keys that find no room there go to a plain open-addressing overflow
 //               table hashed by k-mer. The internal k-mer id ("slot") is the index of the key in the (main | overflow) key
 //               array; slot_kid maps it back to the caller's kmer_id.
 // ------------------------------------------------------------------------------------------------
@@ -159,10 +159,15 @@ __host__ __device__ __forceinline__ uint32_t hga_bits_hash(uint64_t kmer) {
 }
 __host__ __device__ __forceinline__ uint32_t hga_bits_word(uint32_t h) { return h >> 29; }
 __host__ __device__ __forceinline__ uint32_t hga_bits_mask(uint32_t h) { return (1u << ((h >> 24) & 31)) | (1u << ((h >> 19) & 31)); }
-// first slot of the probe sequence inside a bucket, and the j-th slot of the sequence (relative to the home bucket)
-__host__ __device__ __forceinline__ uint32_t hga_bits_start(uint32_t h) { return (h >> 15) & (HGA_BUCKET_SLOTS - 1); }
-__host__ __device__ __forceinline__ uint32_t hga_chain_slot(uint32_t start, uint32_t j) {
-    return (j & ~(uint32_t) (HGA_BUCKET_SLOTS - 1)) | ((start + j) & (HGA_BUCKET_SLOTS - 1));
+// Probe order of a key: the 4-slot SECTOR (32 B) of its home bucket picked by the k-mer hash, then the bucket's other three
+// sectors in cyclic order, then the next bucket the same way. A lookup therefore usually ends after ONE 32 B load.
+#define HGA_SECTOR_SLOTS 4
+__host__ __device__ __forceinline__ uint32_t hga_bits_sector(uint32_t h) { return (h >> 15) & (HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1); }
+// slot (relative to the home bucket) of the j-th probe, j = 0 .. HGA_CHAIN_SLOTS - 1
+__host__ __device__ __forceinline__ uint32_t hga_chain_slot(uint32_t sector, uint32_t j) {
+    const uint32_t in_bucket = j & (HGA_BUCKET_SLOTS - 1);
+    const uint32_t sec = (sector + in_bucket / HGA_SECTOR_SLOTS) & (HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1);
+    return (j & ~(uint32_t) (HGA_BUCKET_SLOTS - 1)) | (sec * HGA_SECTOR_SLOTS) | (in_bucket & (HGA_SECTOR_SLOTS - 1));
 }
 
 // plain k-mer hash: B for small k, and the overflow table's home position
@@ -225,6 +230,7 @@ struct hga_handle {
     int k = 0;
     uint64_t n_kmers = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D of the bases, overlapped with the scan (hga_scan)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // stage timer, nested (exchange) timer
     int sm_count = 148;
@@ -248,6 +254,10 @@ struct hga_handle {
     uint32_t inc_row_first_id = 1;        // read id of row 0
     uint64_t inc_entries = 0;             // entries of the inverted index
     DevBuf d_x_slot, d_x_row;             // exchange staging (multi-GPU)
+    DevBuf d_hit_kid;                     // multi-GPU: hits keyed by the caller's kmer_id (slots differ between ranks: the table is built with atomics)
+    DevBuf d_g_kid, d_g_row_off;          // multi-GPU: replicated by-read incidence of ALL reads (kmer_id per hit, u64 row offsets)
+    bool index_by_kid = false;            // the inverted index is keyed by kmer_id (multi-GPU) instead of table slot
+    uint32_t index_keys = 0;              // number of lists in the inverted index: n_slots, or n_kmers when keyed by kmer_id
 
     // inverted index
     DevBuf d_inv_off;                     // u32[n_slots+1] (the incidence of one GPU has < 2^32 entries)
@@ -260,8 +270,8 @@ struct hga_handle {
     DevBuf d_pair_key, d_pair_score;      // u64 key = (x_row << 32 | y_row), u32 score; sorted by key
     DevBuf d_pair_key2, d_pair_score2, d_pair_scalars, d_heavy_list, d_mid_list, d_heavy_tab, d_pivot_flag;
     uint64_t pair_capacity = 0;
-    uint64_t pair_rows = 0;               // pivot rows held by this GPU (rows of d_row_off / d_hit_slot)
-    uint32_t pair_row_base = 0;           // global row number of local row 0
+    uint64_t pair_rows = 0;               // rows of the by-read incidence the pair counter walks (all reads with a communicator)
+    uint32_t pair_pivot_mul = 1, pair_pivot_add = 0;   // pivot rows of this GPU: add, add + mul, ... (rank, rank + G, ...)
     bool have_pairs = false;
     uint32_t pair_min_score = 1;
 
@@ -286,7 +296,8 @@ struct hga_handle {
 
 // stage launchers (each in its own .cu)
 int hga_table_build(hga_handle *h, const uint64_t *host_kmers);
-int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases);
+// h_bases != nullptr: the bases are still on the host; the run copies them (in chunks, overlapped with the scan when large)
+int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, const char *h_bases);
 int hga_index_run(hga_handle *h);
 int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
 int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold);

@@ -11,8 +11,10 @@
 //      finishes a list picks up the row's next entry without waiting for the others, and the offsets of its next
 //      list are prefetched while it walks the current one. Lists are sorted by row, so with all rows as pivots
 //      the walk runs from the END of the list and stops at the first row <= pivot: only the half of every list
-//      that can produce a (pivot < partner) pair is read, and every unordered pair is produced exactly once.
-//      Lists longer than PW_LONG are walked by the whole warp with coalesced loads.
+//      that can produce a (pivot < partner) pair is read (four entries per aligned 16 B load), and every unordered
+//      pair is produced exactly once. Lists longer than PW_LONG are walked by the whole warp with coalesced loads.
+//      (Merging equal candidates of a step with __match_any_sync so that the update is a plain read-modify-write was
+//      measured 5 % SLOWER than the shared-memory atomics and dropped.)
 //   2. pair_count_kernel: rows whose partner set overflowed tier 1; one CTA per row, 4096-entry accumulator.
 //   3. pair_count_heavy_kernel: rows that overflow tier 2; per-CTA accumulator in HBM.
 // Output: (key = min_row << 32 | max_row, score) appended through one atomic cursor bump per row, then one
@@ -34,9 +36,8 @@
 #define PW_DEFER 32
 
 // which (pivot x, candidate y) combinations a pivot accumulates
-#define PAIR_MODE_TAIL 0     // every row is a pivot, one GPU: y > x (walk list tails only)
+#define PAIR_MODE_TAIL 0     // every row is a pivot (on some GPU): y > x (walk list tails only)
 #define PAIR_MODE_SUBSET 1   // pivot subset: pair (pivot, non-pivot), or ordered pivot pair
-#define PAIR_MODE_PARITY 2   // every row is a pivot somewhere (multi-GPU shards): the endpoint chosen by the parity of x + y
 
 struct PairScalars {
     unsigned long long ticket;
@@ -56,7 +57,7 @@ struct PairParams {
     const uint64_t *row_off;
     const uint32_t *row_slot;
     uint64_t n_rows;
-    uint32_t row_base;              // global row number of local row 0 (multi-GPU: rows of this rank's shard)
+    uint32_t pivot_mul, pivot_add;  // all-rows mode: pivot t is row t * pivot_mul + pivot_add (multi-GPU: rank, rank + G, ...)
     const uint32_t *inv_off;
     const uint32_t *inv_row;        // global row numbers
     const uint32_t *pivot_rows;     // nullptr: every local row is a pivot
@@ -77,8 +78,7 @@ struct PairParams {
 __device__ __forceinline__ bool keep_candidate(uint32_t x, uint32_t y, int mode, const uint8_t *pivot_flag) {
     if (y == x) return false;                         // :317 erase(pivot)
     if (mode == PAIR_MODE_TAIL) return y > x;         // all rows are pivots: count each unordered pair once
-    if (mode == PAIR_MODE_SUBSET) return !pivot_flag[y] || y > x;
-    return ((x ^ y) & 1u) ? (y < x) : (y > x);        // PARITY: exactly one endpoint of every pair accepts the other
+    return !pivot_flag[y] || y > x;
 }
 
 __device__ __forceinline__ uint32_t hash_row(uint32_t y) { return y * 2654435761u; }
@@ -121,8 +121,8 @@ struct WarpAcc {
     uint32_t distinct, overflow, n_defer, pad;
 };
 
-// ++count[y]; most calls find y already present: one plain read, one shared-memory atomic add
-__device__ __forceinline__ void acc_add(WarpAcc &A, uint32_t y, uint32_t cmask, int cshift, uint32_t limit) {
+// ++count[y] with shared-memory atomics; most calls find y already present: one plain read, one atomic add
+__device__ __forceinline__ void acc_add(WarpAcc &A, uint32_t y, uint32_t c, uint32_t cmask, int cshift, uint32_t limit) {
     uint32_t h = hash_row(y) >> cshift;
     for (;;) {
         uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&A.key[h]);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void acc_add(WarpAcc &A, uint32_t y, uint32_t cmask, 
             cur = atomicCAS(&A.key[h], PC_EMPTY, y);
             if (cur == PC_EMPTY) { if (atomicAdd(&A.distinct, 1u) >= limit) A.overflow = 1; cur = y; }
         }
-        if (cur == y) { atomicAdd(&A.val[h], 1u); return; }
+        if (cur == y) { atomicAdd(&A.val[h], c); return; }
         if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) return;
         h = (h + 1) & cmask;
     }
@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(PairParams 
         if (lane == 0) t = atomicAdd(&p.sc->ticket, 1ull);
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
         if (t >= p.n_pivots) break;
-        const uint32_t xl = p.pivot_rows ? p.pivot_rows[t] : (uint32_t) t;     // local row
-        const uint32_t x = xl + p.row_base;                                     // global row
+        const uint32_t x = p.pivot_rows ? p.pivot_rows[t] : (uint32_t) t * p.pivot_mul + p.pivot_add;
+        const uint32_t xl = x;
         const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         if (a == b) continue;
 
@@ -162,27 +162,42 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(PairParams 
             if (lane == 0) { A.distinct = 0; A.overflow = 0; A.n_defer = 0; }
             __syncwarp();
 
-            // every lane: one list at a time, the next list's bounds prefetched
+            // every lane: one list at a time, two lists ahead in flight: the bounds of list j + 64 are being loaded while the
+            // last 16 B chunk of list j + 32 (bounds known by now) is prefetched into L2 and list j is walked
             uint64_t j = a + lane;
-            uint32_t cur_lo = 0, cur_i = 0, n_lo = 0, n_hi = 0;
-            bool have_next = j < b;
-            if (have_next) { const uint32_t slot = __ldg(&p.row_slot[j]); n_lo = __ldg(&p.inv_off[slot]); n_hi = __ldg(&p.inv_off[slot + 1]); }
-            while (__any_sync(0xFFFFFFFFu, have_next || cur_i > cur_lo)) {
+            uint32_t cur_lo = 0, cur_i = 0, n1_lo = 0, n1_hi = 0, n2_lo = 0, n2_hi = 0;
+            bool have1 = j < b, have2 = j + 32 < b;
+            if (have1) { const uint32_t slot = __ldg(&p.row_slot[j]); n1_lo = __ldg(&p.inv_off[slot]); n1_hi = __ldg(&p.inv_off[slot + 1]); }
+            if (have2) { const uint32_t slot = __ldg(&p.row_slot[j + 32]); n2_lo = __ldg(&p.inv_off[slot]); n2_hi = __ldg(&p.inv_off[slot + 1]); }
+            while (__any_sync(0xFFFFFFFFu, have1 || cur_i > cur_lo)) {
                 if (cur_i > cur_lo) {
-                    const uint32_t y = __ldg(&p.inv_row[--cur_i]);
-                    if (tail && y <= x) cur_i = cur_lo;                      // ascending list: nothing further down can be > x
-                    else if (keep_candidate(x, y, p.mode, p.pivot_flag)) acc_add(A, y, cmask, cshift, limit);
-                } else if (have_next) {
-                    cur_lo = n_lo; cur_i = n_hi;
+                    // four list entries per step (one aligned 16 B load), walked from the end of the list
+                    const uint32_t q = (cur_i - 1) >> 2, cb = q << 2;
+                    const uint4 c = __ldg(reinterpret_cast<const uint4 *>(p.inv_row) + q);
+                    const uint32_t ys[4] = {c.x, c.y, c.z, c.w};
+                    #pragma unroll
+                    for (int e = 3; e >= 0; e--) {
+                        const uint32_t idx = cb + e;
+                        if (idx < cur_i && idx >= cur_lo) {
+                            const uint32_t yy = ys[e];
+                            if (tail && yy <= x) cur_i = cur_lo;                  // ascending list: nothing further down can be > x
+                            else if (keep_candidate(x, yy, p.mode, p.pivot_flag)) acc_add(A, yy, 1u, cmask, cshift, limit);
+                        }
+                    }
+                    if (cur_i > cur_lo) cur_i = max(cb, cur_lo);
+                } else if (have1) {
+                    cur_lo = n1_lo; cur_i = n1_hi;
                     if (cur_i - cur_lo > PW_LONG) {                           // long list: leave it to the whole warp
                         const uint32_t at = atomicAdd(&A.n_defer, 1u);
                         if (at < PW_DEFER) { A.defer[at] = make_uint2(cur_lo, cur_i); cur_i = cur_lo; }
                     }
                     j += 32;
-                    have_next = j < b;
-                    if (have_next) { const uint32_t slot = __ldg(&p.row_slot[j]); n_lo = __ldg(&p.inv_off[slot]); n_hi = __ldg(&p.inv_off[slot + 1]); }
+                    have1 = have2; n1_lo = n2_lo; n1_hi = n2_hi;
+                    if (have1 && n1_hi > n1_lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.inv_row + (((size_t) n1_hi - 1) & ~(size_t) 3)));
+                    have2 = j + 32 < b;
+                    if (have2) { const uint32_t slot = __ldg(&p.row_slot[j + 32]); n2_lo = __ldg(&p.inv_off[slot]); n2_hi = __ldg(&p.inv_off[slot + 1]); }
                 }
-                if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) { cur_i = cur_lo; have_next = false; }
+                if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) { cur_i = cur_lo; have1 = false; }
             }
             __syncwarp();
             const uint32_t nd = min(*reinterpret_cast<volatile uint32_t *>(&A.n_defer), (uint32_t) PW_DEFER);
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(PairParams 
                     if (go) {
                         const uint32_t y = __ldg(&p.inv_row[i]);
                         if (tail && y <= x) go = false;
-                        else if (keep_candidate(x, y, p.mode, p.pivot_flag)) acc_add(A, y, cmask, cshift, limit);
+                        else if (keep_candidate(x, y, p.mode, p.pivot_flag)) acc_add(A, y, 1u, cmask, cshift, limit);
                     }
                     if (!__any_sync(0xFFFFFFFFu, go)) break;
                 }
@@ -258,7 +273,7 @@ __global__ void __launch_bounds__(PC_THREADS) pair_count_kernel(PairParams p) {
         const uint64_t t = s_ticket;
         if (t >= n_mid) break;
         const uint32_t xl = p.mid_list[t];
-        const uint32_t x = xl + p.row_base;
+        const uint32_t x = xl;
         const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         if (a == b) { __syncthreads(); continue; }
 
@@ -349,7 +364,7 @@ __global__ void __launch_bounds__(HV_THREADS) pair_count_heavy_kernel(PairParams
         const uint64_t t = s_ticket;
         if (t >= n_heavy) break;
         const uint32_t xl = p.heavy_list[t];
-        const uint32_t x = xl + p.row_base;
+        const uint32_t x = xl;
         const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         for (uint32_t i = tid; i < p.heavy_cap; i += HV_THREADS) { tab_key[i] = PC_EMPTY; tab_val[i] = 0; }
         __syncthreads();
@@ -415,7 +430,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     if (!h->have_index) { hga_set_error("hga_pair_count: no index (call hga_build_index)"); return HGA_E_STATE; }
     h->have_pairs = h->have_selection = h->have_components = false;
     const bool multi = h->comm && hga_comm_size(h) > 1;
-    const uint64_t n_rows = h->pair_rows;         // pivot rows live on this GPU (all rows without a communicator)
+    const uint64_t n_rows = h->pair_rows;         // rows of the by-read incidence (all reads with a communicator)
     h->pair_min_score = min_score;
     if (multi && pivots) { hga_set_error("hga_pair_count: pivot subsets are not supported with a communicator"); return HGA_E_ARG; }
 
@@ -426,11 +441,16 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
 
     PairParams p;
     memset(&p, 0, sizeof(p));
-    p.row_off = h->d_row_off.as<uint64_t>(); p.row_slot = h->d_hit_slot.as<uint32_t>(); p.n_rows = n_rows;
-    p.row_base = h->pair_row_base;
+    p.n_rows = n_rows;
+    // multi-GPU: the replicated incidence of all reads, keyed by kmer_id like the exchanged index; this GPU's pivots are
+    // the rows rank, rank + G, ... (interleaved: every GPU sees the same mix of early and late rows, and y > x halves the walks)
+    p.row_off = multi ? h->d_g_row_off.as<uint64_t>() : h->d_row_off.as<uint64_t>();
+    p.row_slot = multi ? h->d_g_kid.as<uint32_t>() : h->d_hit_slot.as<uint32_t>();
+    p.pivot_mul = h->pair_pivot_mul; p.pivot_add = h->pair_pivot_add;
     p.inv_off = h->d_inv_off.as<uint32_t>(); p.inv_row = h->d_inv_row.as<uint32_t>();
-    p.pivot_rows = nullptr; p.pivot_flag = nullptr; p.n_pivots = n_rows;
-    p.mode = multi ? PAIR_MODE_PARITY : PAIR_MODE_TAIL;
+    p.pivot_rows = nullptr; p.pivot_flag = nullptr;
+    p.n_pivots = n_rows > h->pair_pivot_add ? (n_rows - h->pair_pivot_add + h->pair_pivot_mul - 1) / h->pair_pivot_mul : 0;
+    p.mode = PAIR_MODE_TAIL;
     p.min_score = min_score;
     p.mid_list = h->d_mid_list.as<uint32_t>();
     p.heavy_list = h->d_heavy_list.as<uint32_t>();
@@ -536,7 +556,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
 
     {   // work measure
         HGA_CUDA(cudaMemsetAsync(&d_sc->increments, 0, 8, h->stream));
-        increments_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_inv_off.as<uint32_t>(), h->table.n_slots, &d_sc->increments);
+        increments_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_inv_off.as<uint32_t>(), h->index_keys, &d_sc->increments);
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));

@@ -64,8 +64,9 @@ struct ScanParams {
     unsigned long long *tile_tmp_off; // where the tile's segment starts in the temporary arrays
     uint32_t *tile_cnt;               // hits of the tile
     ScanScalars *scalars;
-    uint64_t n_tiles;
-    uint64_t tile_stride;             // > 0: sampling mode (count only, tile = ticket * stride)
+    uint64_t n_tiles;                 // tickets of this launch
+    uint64_t tile_begin;              // first tile of this launch (chunked launches while the bases are still arriving)
+    uint64_t tile_stride;             // > 0: sampling mode (count only, tile = tile_begin + ticket * stride)
     int diag;                         // HGA_SCAN_DIAG timing experiments (results are WRONG when set): 1 = no key probes, 2 = no filter probes
 };
 
@@ -100,6 +101,29 @@ __device__ __forceinline__ uint64_t find_read(const uint64_t *__restrict__ read_
 __device__ __forceinline__ int clamp_local(uint64_t glob, uint64_t tile_start) {
     const int64_t d = (int64_t) glob - (int64_t) tile_start;
     return (int) max((int64_t) -(1 << 30), min((int64_t) (1 << 30), d));
+}
+
+// L2 eviction policies: the filter is the one structure every window touches (keep it: evict_last); key-table sectors are
+// touched once per candidate and must not push it out (evict_first). The base stream uses ld.global.cs, the hits st.global.cs.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ldg_u32_policy(const uint32_t *a, uint64_t pol) {
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ ulonglong2 ldg_u64x2_policy(const ulonglong2 *a, uint64_t pol) {
+    ulonglong2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
+    return v;
 }
 
 // shared memory of one warp
@@ -190,27 +214,23 @@ __device__ __noinline__ uint32_t drain_queue(uint32_t head, uint32_t n, uint32_t
             extract_window(T.fwd, T.rc, e, k, c.kmask, fwd, rc);
             const unsigned long long key = fwd < rc ? fwd : rc;                       // KmerIterator.cpp:69
             if (qe.y & 0x8000u) B = hga_locality_hash(key, t.geom);
-            // The key, if present, sits in its home bucket unless that bucket is full. All 16 slots of the bucket (one
-            // 128 B line, prefetched into L2 when the candidate was queued) are loaded at once: one memory round trip
-            // instead of one per probed slot.
+            // Probe order = insertion order (hga_chain_slot): the 32 B sector picked by the k-mer hash first (the line was
+            // prefetched into L2 when the candidate was queued), then the other sectors of the bucket, then the next
+            // bucket. One sector = two 16 B loads; a sector with an empty slot and no match closes the search.
             const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS;
+            const uint32_t sec0 = hga_bits_sector(hga_bits_hash(key));
+            const uint64_t pol_first = l2_policy_evict_first();
             bool open = true;             // chain not yet closed by an empty slot or a match
             #pragma unroll 1
-            for (uint32_t c0 = 0; c0 < HGA_CHAIN_BUCKETS && open; c0++) {
-                const ulonglong2 *bk = reinterpret_cast<const ulonglong2 *>(t.keys + home + c0 * HGA_BUCKET_SLOTS);
-                ulonglong2 v[HGA_BUCKET_SLOTS / 2];
-                #pragma unroll
-                for (int j = 0; j < HGA_BUCKET_SLOTS / 2; j++) v[j] = __ldg(bk + j);
-                uint32_t found = 0xFFFFFFFFu;
-                bool has_empty = false;
-                #pragma unroll
-                for (int j = 0; j < HGA_BUCKET_SLOTS / 2; j++) {
-                    if (v[j].x == key) found = 2 * j;
-                    if (v[j].y == key) found = 2 * j + 1;
-                    has_empty |= (v[j].x == HGA_EMPTY_KEY) | (v[j].y == HGA_EMPTY_KEY);
-                }
-                if (found != 0xFFFFFFFFu) { slot = home + c0 * HGA_BUCKET_SLOTS + found; open = false; }
-                else if (has_empty) open = false;
+            for (uint32_t j = 0; j < HGA_CHAIN_SLOTS && open; j += HGA_SECTOR_SLOTS) {
+                const uint32_t off = hga_chain_slot(sec0, j);
+                const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(t.keys + home + off);
+                const ulonglong2 a = ldg_u64x2_policy(sp, pol_first), b = ldg_u64x2_policy(sp + 1, pol_first);
+                if (a.x == key) { slot = home + off; open = false; }
+                else if (a.y == key) { slot = home + off + 1; open = false; }
+                else if (b.x == key) { slot = home + off + 2; open = false; }
+                else if (b.y == key) { slot = home + off + 3; open = false; }
+                else if (a.x == HGA_EMPTY_KEY || a.y == HGA_EMPTY_KEY || b.x == HGA_EMPTY_KEY || b.y == HGA_EMPTY_KEY) open = false;
             }
             if (open && t.n_over) {       // chain full: the key, if present, lives in the overflow region
                 const uint32_t mask = t.n_over - 1;
@@ -262,10 +282,14 @@ __device__ __forceinline__ uint32_t scan_tile_windows(const TileCtx &c, int lane
         (void) window_min<W ? W : 2>(hga_mmer_hash((uint32_t) fwd & geo.mmask, (uint32_t) (rc >> geo.rc_shift)), ms, skip, lane);
     }
     uint32_t F0 = pf[0], R0 = pr[0];
+    const uint64_t pol_last = l2_policy_evict_last();
 
+    // (Requesting the filter words one group ahead of testing them was tried: no gain - the probes are bound by L1 wavefront
+    // throughput, ~10 distinct lines per warp load, not by their latency - and the extra live registers spilled around the
+    // drain call.)
     #pragma unroll 1
     for (int s0 = 0; s0 < SCAN_STEPS; s0 += SCAN_UNROLL, pf += 2 * SCAN_UNROLL, pr += 2 * SCAN_UNROLL, pe += SCAN_UNROLL) {
-        uint32_t msk[SCAN_UNROLL], fw[SCAN_UNROLL], Bv[SCAN_UNROLL];
+        uint32_t msk[SCAN_UNROLL], fw[SCAN_UNROLL], Bv[SCAN_UNROLL], sec[SCAN_UNROLL];
         bool exc[SCAN_UNROLL];
         #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u++) {
@@ -280,7 +304,8 @@ __device__ __forceinline__ uint32_t scan_tile_windows(const TileCtx &c, int lane
             if (EXC && W) exc[u] = (__funnelshift_r(pe[u], pe[u + 1], oe) & kbits) != 0;
             const uint32_t hb = hga_bits_hash(canon);
             msk[u] = hga_bits_mask(hb);
-            fw[u] = diag2 ? 0u : __ldg(filter + ((hga_scale(Bv[u], n_blocks) << 3) | hga_bits_word(hb)));
+            sec[u] = hga_bits_sector(hb) * HGA_SECTOR_SLOTS;
+            fw[u] = diag2 ? 0u : ldg_u32_policy(filter + ((hga_scale(Bv[u], n_blocks) << 3) | hga_bits_word(hb)), pol_last);
         }
         #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u++) {
@@ -288,8 +313,8 @@ __device__ __forceinline__ uint32_t scan_tile_windows(const TileCtx &c, int lane
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
             if (pass) {
                 T.q[(q_tail + __popc(bal & lane_lt)) & (SCAN_Q - 1)] = make_uint2(Bv[u], (uint32_t) (lane + 32 * (s0 + u)) | (exc[u] ? 0x8000u : 0u));
-                // start the key bucket's trip from HBM now; the drain that reads it runs a few steps later
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(keys + (size_t) hga_scale(Bv[u], n_buckets) * HGA_BUCKET_SLOTS));
+                // start the key sector's trip from HBM now; the drain that reads it runs a few steps later
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(keys + (size_t) hga_scale(Bv[u], n_buckets) * HGA_BUCKET_SLOTS + sec[u]));
             }
             q_tail += __popc(bal);
         }
@@ -320,7 +345,8 @@ __device__ __forceinline__ uint32_t scan_tile_dispatch(const TileCtx &c, int lan
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS, 6) scan_probe_kernel(ScanParams p) {
+template<int MIN_CTAS>
+__global__ void __launch_bounds__(SCAN_THREADS, MIN_CTAS) scan_probe_kernel(ScanParams p) {
     __shared__ WarpTile s_tiles[SCAN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpTile &T = s_tiles[warp];
@@ -336,7 +362,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 6) scan_probe_kernel(ScanParams 
         if (lane == 0) ticket = atomicAdd(&p.scalars->ticket, 1ull);
         ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
         if (ticket >= p.n_tiles) break;
-        const uint64_t tile = p.tile_stride ? ticket * p.tile_stride : ticket;
+        const uint64_t tile = p.tile_begin + (p.tile_stride ? ticket * p.tile_stride : ticket);
         const uint64_t tile_start = tile * SCAN_TILE;
         const int n_loc = (int) min((uint64_t) SCAN_TILE, p.n_bases - tile_start);      // window ends in this tile
 
@@ -462,7 +488,7 @@ __global__ void scan_fix_rows_kernel(const uint64_t *__restrict__ read_off, uint
     }
 }
 
-int launch_scan(hga_handle *h, const ScanParams &p, int grid, size_t smem, bool persist) {
+int launch_scan(hga_handle *h, const ScanParams &p, int grid, size_t smem, bool persist, int min_ctas) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SCAN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
@@ -481,14 +507,15 @@ int launch_scan(hga_handle *h, const ScanParams &p, int grid, size_t smem, bool 
         n_attr = 1;
     }
     cfg.attrs = attr; cfg.numAttrs = n_attr;
-    HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel, p));
+    if (min_ctas >= 6) HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<6>, p));
+    else HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<5>, p));
     h->metrics.kernel_launches++;
     return HGA_OK;
 }
 
 }  // namespace
 
-int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases) {
+int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, const char *h_bases) {
     h->have_scan = h->have_index = h->have_pairs = h->have_selection = h->have_components = false;
     h->n_reads = n_reads; h->n_bases = n_bases; h->n_hits = 0;
     if (n_reads >= (1ull << 32) - 1) { hga_set_error("hga_scan: more than 2^32-2 reads per GPU"); return HGA_E_ARG; }
@@ -514,7 +541,10 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
 
     int occ = 0;
     const size_t smem = 0;
-    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel, SCAN_THREADS, smem));
+    int min_ctas = 6;   // register budget of the kernel variant: 6 CTAs/SM (<= 85 registers) or 5 (<= 102)
+    if (const char *e = getenv("HGA_SCAN_MIN_CTAS")) min_ctas = atoi(e);
+    if (min_ctas >= 6) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<6>, SCAN_THREADS, smem));
+    else HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<5>, SCAN_THREADS, smem));
     if (occ < 1) occ = 1;
     const int grid_full = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, std::max<uint64_t>((n_tiles + SCAN_WARPS - 1) / SCAN_WARPS, 1));
 
@@ -530,12 +560,75 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     StageTimer timer(h, &h->metrics.scan_ms);
     ScanScalars sc;
     memset(&sc, 0, sizeof(sc));
-    uint64_t capacity = 0;
+    uint64_t capacity = 0, E = 0;
+    // Host source (hga_scan): the bases travel in chunks on a second stream and every chunk is scanned as soon as it has
+    // landed (a tile only needs bases at or before its own end, so chunk c can run while chunk c + 1 is in flight).
+    const uint64_t chunk_tiles = (256ull << 20) / SCAN_TILE;                      // ~256 MB of bases per chunk
+    const bool pipelined = h_bases != nullptr && n_tiles > 2 * chunk_tiles && h->copy_stream != nullptr;
+    if (h_bases != nullptr && !pipelined && n_bases) {
+        StageTimer t(h, &h->metrics.h2d_ms, true);
+        HGA_CUDA(cudaMemcpyAsync(const_cast<char *>(d_bases), h_bases, n_bases, cudaMemcpyHostToDevice, h->stream));
+        t.stop();
+    }
     if (n_tiles > 0) {
         scan_tile_dir_kernel<<<(int) std::min<uint64_t>((n_tiles + 256) / 256, (uint64_t) h->sm_count * 8), 256, 0, h->stream>>>(d_read_off, n_reads, n_tiles,
                                                                                                                                h->d_tile_dir.as<uint2>());
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaGetLastError());
+    }
+    bool done = false;
+    if (pipelined) {
+        const uint64_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+        std::vector<cudaEvent_t> landed(n_chunks, nullptr);
+        auto chunk_bytes = [&](uint64_t c, uint64_t &lo, uint64_t &hi) { lo = c * chunk_tiles * SCAN_TILE; hi = std::min<uint64_t>(n_bases, (c + 1) * chunk_tiles * SCAN_TILE); };
+        cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+        HGA_CUDA(cudaEventCreate(&ev_begin)); HGA_CUDA(cudaEventCreate(&ev_end));
+        HGA_CUDA(cudaEventRecord(ev_begin, h->stream));
+        HGA_CUDA(cudaStreamWaitEvent(h->copy_stream, ev_begin, 0));               // the destination buffer was (re)allocated on h->stream
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            uint64_t lo, hi;
+            chunk_bytes(c, lo, hi);
+            HGA_CUDA(cudaMemcpyAsync(const_cast<char *>(d_bases) + lo, h_bases + lo, hi - lo, cudaMemcpyHostToDevice, h->copy_stream));
+            HGA_CUDA(cudaEventCreateWithFlags(&landed[c], cudaEventDisableTiming));
+            HGA_CUDA(cudaEventRecord(landed[c], h->copy_stream));
+        }
+        HGA_CUDA(cudaEventRecord(ev_end, h->copy_stream));
+        // capacity from a count-only sample of the first chunk (1 tile in 16)
+        HGA_CUDA(cudaStreamWaitEvent(h->stream, landed[0], 0));
+        {
+            const uint64_t stride = 16, n_sample = (chunk_tiles + stride - 1) / stride;
+            HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
+            ScanParams ps = p;
+            ps.tile_stride = stride; ps.n_tiles = n_sample; ps.tile_begin = 0; ps.capacity = 0;
+            HGA_TRY(launch_scan(h, ps, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (n_sample + SCAN_WARPS - 1) / SCAN_WARPS), smem, persist, min_ctas));
+            HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            const double est = (double) sc.total * (double) n_tiles / (double) n_sample;
+            capacity = std::min<uint64_t>(n_bases, (uint64_t) (est * 1.15) + (1ull << 20));
+        }
+        HGA_TRY(h->d_sort_a.ensure((capacity + 1) * 4));
+        HGA_TRY(h->d_sort_b.ensure((capacity + 1) * 4));
+        p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_sort_b.as<uint32_t>();
+        p.capacity = capacity; p.tile_stride = 0;
+        HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            HGA_CUDA(cudaStreamWaitEvent(h->stream, landed[c], 0));
+            p.tile_begin = c * chunk_tiles; p.n_tiles = std::min<uint64_t>(chunk_tiles, n_tiles - p.tile_begin);
+            HGA_CUDA(cudaMemsetAsync(&d_sc->ticket, 0, 8, h->stream));
+            HGA_TRY(launch_scan(h, p, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (p.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS), smem, persist, min_ctas));
+        }
+        HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->copy_stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        h->metrics.h2d_ms = ms;
+        for (cudaEvent_t e : landed) cudaEventDestroy(e);
+        cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
+        E = sc.total;
+        p.tile_begin = 0;
+        if (!sc.overflow) done = true; else capacity = E;     // the bases are resident now: one plain rerun with the exact size
+    } else if (n_tiles > 0) {
         // capacity of the hit arrays: exact upper bound for small inputs, otherwise estimated from a strided
         // count-only sample (1 tile in 64)
         const uint64_t small_limit = 32ull << 20;
@@ -548,7 +641,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             ScanParams ps = p;
             ps.tile_stride = stride; ps.n_tiles = n_sample; ps.capacity = 0;
             const int grid_s = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (n_sample + SCAN_WARPS - 1) / SCAN_WARPS);
-            HGA_TRY(launch_scan(h, ps, grid_s, smem, persist));
+            HGA_TRY(launch_scan(h, ps, grid_s, smem, persist, min_ctas));
             HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             const double est = (double) sc.total * (double) n_tiles / (double) n_sample;
@@ -557,14 +650,13 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         }
     }
 
-    uint64_t E = 0;
-    for (int attempt = 0; attempt < 2 && n_tiles > 0; attempt++) {
+    for (int attempt = 0; attempt < 2 && n_tiles > 0 && !done; attempt++) {
         HGA_TRY(h->d_sort_a.ensure((capacity + 1) * 4));      // temporaries (reused by the index sort later)
         HGA_TRY(h->d_sort_b.ensure((capacity + 1) * 4));
         p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_sort_b.as<uint32_t>();
-        p.capacity = capacity; p.n_tiles = n_tiles; p.tile_stride = 0;
+        p.capacity = capacity; p.n_tiles = n_tiles; p.tile_begin = 0; p.tile_stride = 0;
         HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
-        HGA_TRY(launch_scan(h, p, grid_full, smem, persist));
+        HGA_TRY(launch_scan(h, p, grid_full, smem, persist, min_ctas));
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         E = sc.total;

@@ -18,7 +18,7 @@ __global__ void table_insert_main_kernel(const uint64_t *__restrict__ kmers, uin
         const uint32_t B = hga_locality_hash(key, t.geom);
         const uint32_t hb = hga_bits_hash(key);
         atomicOr(&t.filter[(size_t) hga_scale(B, t.n_blocks) * 8 + hga_bits_word(hb)], hga_bits_mask(hb));
-        const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS, start = hga_bits_start(hb);
+        const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS, start = hga_bits_sector(hb);
         bool done = false;
         for (uint32_t j = 0; j < HGA_CHAIN_SLOTS && !done; j++) {
             const uint32_t slot = home + hga_chain_slot(start, j);

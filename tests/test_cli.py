@@ -1,0 +1,70 @@
+"""The C++ host `categorization` (hybrid-genome-assembler_b200/cli): record / k-mer loaders against the golden fixtures from
+the real reference (CPU), and the whole executable against the oracle's scaffold components (GPU)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import datagen
+import golden_util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "hybrid-genome-assembler_b200", "categorization")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    if not os.path.exists(EXE):
+        import importlib
+        importlib.import_module("hybrid-genome-assembler_b200.build").build()
+    assert os.path.exists(EXE)
+    return EXE
+
+
+@pytest.mark.parametrize("tag,files", [("fq", ["records_a.fq"]), ("fq_fq", ["records_a.fq", "records_c.fq"]), ("fa", ["records_b.fa"])])
+def test_cli_record_stream_matches_reference(exe, tag, files):
+    out = subprocess.run([exe, "--parse-only"] + [os.path.join(golden_util.GOLDEN, f) for f in files], capture_output=True, text=True, check=True).stdout
+    with open(os.path.join(golden_util.GOLDEN, f"records_{tag}.expected.txt")) as f:
+        assert out == f.read()
+
+
+def test_cli_kmer_loader_matches_reference(exe):
+    z = np.load(os.path.join(golden_util.GOLDEN, "kmers_fixture.npz"))
+    out = subprocess.run([exe, "--dump-kmers", "--kmers", os.path.join(golden_util.GOLDEN, "kmers_fixture.txt")], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert out[0] == f"#K {int(z['k'])} {len(z['kmers'])}"
+    assert [int(v) for v in out[1:] if v] == [int(v) for v in z["kmers"]]
+
+
+def test_cli_errors(exe, tmp_path):
+    bad = tmp_path / "bad.txt"
+    bad.write_text("hello\nworld\n")
+    r = subprocess.run([exe, "--parse-only", str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "Unrecognized file format" in r.stderr
+    r = subprocess.run([exe, str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "You need to specify path to kmers" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_components(exe, oracle, tmp_path):
+    paths, kp = datagen.make_diploid_case(str(tmp_path / "c"), genome_size=30000, divergence=0.03, k=19, read_len=1200, coverage=12, seed=5,
+                                          error_rate=0.01, fmt="fastq", length_sigma=0.3)
+    outdir = str(tmp_path / "out")
+    r = subprocess.run([exe] + paths + ["--kmers", kp, "-o", outdir, "--sc_min_size", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for label in ("Index construction took", "Calculation of connections between reads took", "Union-find took", "Exported"):
+        assert label in r.stdout
+    rc, reads = oracle.load_reads(paths)
+    kmers, k = oracle.load_kmers(kp)
+    ref = oracle.run(reads["seq"], reads["seq_off"], k, kmers, fraction=0.15, min_size=5)
+    co, cm, _, _, _ = ref["comp"]
+    co = co.astype(np.int64)
+    hdr_off = reads["hdr_off"].astype(np.int64)
+    want = sorted(sorted(reads["hdr"][hdr_off[i - 1]:hdr_off[i]].decode() for i in cm[co[c]:co[c + 1]]) for c in range(len(co) - 1))
+    got = []
+    for f in sorted(os.listdir(outdir)):
+        assert f.startswith("#") and f.endswith(".fa")
+        lines = open(os.path.join(outdir, f)).read().split("\n")
+        got.append(sorted(l[1:] for l in lines[0::4] if l))      # FASTQ records: 4 lines each
+    assert sorted(got) == want
+    assert f"Exported {len(want)} components" in r.stdout
