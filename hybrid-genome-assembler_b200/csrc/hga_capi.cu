@@ -33,22 +33,22 @@ __global__ void low32_kernel(const uint64_t *__restrict__ key, uint64_t n, uint3
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) out[i] = (uint32_t) key[i];
 }
 
-// kid_slot == nullptr: the index is already keyed by kmer_id
-__global__ void kid_list_len_kernel(const uint32_t *__restrict__ kid_slot, const uint32_t *__restrict__ inv_off, uint64_t n_kmers, unsigned long long *len) {
+// kid_slot == nullptr: the index is keyed by the multi-GPU index key kmer_id + kmer_id / key_div
+__global__ void kid_list_len_kernel(const uint32_t *__restrict__ kid_slot, uint32_t key_div, const uint32_t *__restrict__ inv_off, uint64_t n_kmers, unsigned long long *len) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i <= n_kmers; i += (uint64_t) gridDim.x * blockDim.x) {
         if (i == n_kmers) { len[i] = 0; continue; }
-        const uint32_t s = kid_slot ? kid_slot[i] : (uint32_t) i;
+        const uint32_t s = kid_slot ? kid_slot[i] : (uint32_t) i + (uint32_t) i / key_div;
         len[i] = inv_off[s + 1] - inv_off[s];
     }
 }
 
-__global__ void kid_list_copy_kernel(const uint32_t *__restrict__ kid_slot, const uint32_t *__restrict__ inv_off, const uint32_t *__restrict__ inv_row,
+__global__ void kid_list_copy_kernel(const uint32_t *__restrict__ kid_slot, uint32_t key_div, const uint32_t *__restrict__ inv_off, const uint32_t *__restrict__ inv_row,
                                      const unsigned long long *__restrict__ out_off, uint64_t n_kmers, uint32_t first_id, uint32_t *out) {
     const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
     const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint64_t kid = w; kid < n_kmers; kid += warps) {
-        const uint32_t s = kid_slot ? kid_slot[kid] : (uint32_t) kid;
+        const uint32_t s = kid_slot ? kid_slot[kid] : (uint32_t) kid + (uint32_t) kid / key_div;
         const uint64_t a = inv_off[s], b = inv_off[s + 1], o = out_off[kid];
         for (uint64_t i = lane; i < b - a; i += 32) out[o + i] = inv_row[a + i] + first_id;
     }
@@ -245,12 +245,12 @@ int hga_get_index(hga_handle *h, hga_index *out) {
     HGA_TRY(h->d_export_b.ensure((E + 1) * 4));
     unsigned long long *len = h->d_export_a.as<unsigned long long>(), *off = len + (K + 2);
     const uint32_t *kid_slot = h->index_by_kid ? nullptr : h->table.kid_slot;
-    kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(kid_slot, h->d_inv_off.as<uint32_t>(), K, len);
+    kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(kid_slot, h->index_key_div, h->d_inv_off.as<uint32_t>(), K, len);
     size_t tmp = 0;
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, off, K + 1, h->stream));
     HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, len, off, K + 1, h->stream));
-    if (K) kid_list_copy_kernel<<<grid_for(h, K * 32), 256, 0, h->stream>>>(kid_slot, h->d_inv_off.as<uint32_t>(), h->d_inv_row.as<uint32_t>(), off, K,
+    if (K) kid_list_copy_kernel<<<grid_for(h, K * 32), 256, 0, h->stream>>>(kid_slot, h->index_key_div, h->d_inv_off.as<uint32_t>(), h->d_inv_row.as<uint32_t>(), off, K,
                                                                           h->inc_row_first_id, h->d_export_b.as<uint32_t>());
     h->metrics.kernel_launches += 4;
     HGA_CUDA(cudaGetLastError());

@@ -255,9 +255,10 @@ struct hga_handle {
     uint64_t inc_entries = 0;             // entries of the inverted index
     DevBuf d_x_slot, d_x_row;             // exchange staging (multi-GPU)
     DevBuf d_hit_kid;                     // multi-GPU: hits keyed by the caller's kmer_id (slots differ between ranks: the table is built with atomics)
-    DevBuf d_g_kid, d_g_row_off;          // multi-GPU: replicated by-read incidence of ALL reads (kmer_id per hit, u64 row offsets)
+    DevBuf d_g_kid, d_g_row_off;          // multi-GPU: by-read incidence of this rank's pivot rows (index key per hit, u64 row offsets)
     bool index_by_kid = false;            // the inverted index is keyed by kmer_id (multi-GPU) instead of table slot
-    uint32_t index_keys = 0;              // number of lists in the inverted index: n_slots, or n_kmers when keyed by kmer_id
+    uint32_t index_keys = 0;              // number of lists in the inverted index: n_slots, or the index-key space when keyed by kmer_id
+    uint32_t index_key_div = 0;           // multi-GPU: index key of kmer_id = kmer_id + kmer_id / index_key_div (one unused key closes every owner's range)
 
     // inverted index
     DevBuf d_inv_off;                     // u32[n_slots+1] (the incidence of one GPU has < 2^32 entries)
@@ -270,8 +271,8 @@ struct hga_handle {
     DevBuf d_pair_key, d_pair_score;      // u64 key = (x_row << 32 | y_row), u32 score; sorted by key
     DevBuf d_pair_key2, d_pair_score2, d_pair_scalars, d_heavy_list, d_mid_list, d_heavy_tab, d_pivot_flag;
     uint64_t pair_capacity = 0;
-    uint64_t pair_rows = 0;               // rows of the by-read incidence the pair counter walks (all reads with a communicator)
-    uint32_t pair_pivot_mul = 1, pair_pivot_add = 0;   // pivot rows of this GPU: add, add + mul, ... (rank, rank + G, ...)
+    uint64_t pair_rows = 0;               // rows of the by-read incidence the pair counter walks (this rank's pivots with a communicator)
+    uint32_t pair_pivot_mul = 1, pair_pivot_add = 0;   // local row t is global row t * mul + add (rank, rank + G, ...)
     bool have_pairs = false;
     uint32_t pair_min_score = 1;
 

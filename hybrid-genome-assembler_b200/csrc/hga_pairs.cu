@@ -147,8 +147,9 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(PairParams 
         if (lane == 0) t = atomicAdd(&p.sc->ticket, 1ull);
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
         if (t >= p.n_pivots) break;
+        // x: global row (what the inverted lists hold); xl: row of the by-read incidence on this GPU
         const uint32_t x = p.pivot_rows ? p.pivot_rows[t] : (uint32_t) t * p.pivot_mul + p.pivot_add;
-        const uint32_t xl = x;
+        const uint32_t xl = p.pivot_rows ? x : (uint32_t) t;
         const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         if (a == b) continue;
 
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(PC_THREADS) pair_count_kernel(PairParams p) {
         const uint64_t t = s_ticket;
         if (t >= n_mid) break;
         const uint32_t xl = p.mid_list[t];
-        const uint32_t x = xl;
+        const uint32_t x = xl * p.pivot_mul + p.pivot_add;
         const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         if (a == b) { __syncthreads(); continue; }
 
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(HV_THREADS) pair_count_heavy_kernel(PairParams
         const uint64_t t = s_ticket;
         if (t >= n_heavy) break;
         const uint32_t xl = p.heavy_list[t];
-        const uint32_t x = xl;
+        const uint32_t x = xl * p.pivot_mul + p.pivot_add;
         const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         for (uint32_t i = tid; i < p.heavy_cap; i += HV_THREADS) { tab_key[i] = PC_EMPTY; tab_val[i] = 0; }
         __syncthreads();
@@ -408,10 +409,12 @@ __global__ void __launch_bounds__(HV_THREADS) pair_count_heavy_kernel(PairParams
     }
 }
 
-// work measure: sum over k-mers of occ*(occ-1)/2
-__global__ void increments_kernel(const uint32_t *__restrict__ inv_off, uint32_t n_slots, unsigned long long *out) {
+// work measure: sum over lists of occ*(occ-1)/2. key_div > 0: keys with key % (key_div + 1) == key_div are the unused
+// closing keys of the multi-GPU key space (their "list" is the padding of an owner's row segment)
+__global__ void increments_kernel(const uint32_t *__restrict__ inv_off, uint32_t n_slots, uint32_t key_div, unsigned long long *out) {
     unsigned long long acc = 0;
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
+        if (key_div && i % (key_div + 1) == key_div) continue;
         const unsigned long long len = inv_off[i + 1] - inv_off[i];
         acc += len * (len - (len ? 1 : 0)) / 2;
     }
@@ -449,7 +452,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     p.pivot_mul = h->pair_pivot_mul; p.pivot_add = h->pair_pivot_add;
     p.inv_off = h->d_inv_off.as<uint32_t>(); p.inv_row = h->d_inv_row.as<uint32_t>();
     p.pivot_rows = nullptr; p.pivot_flag = nullptr;
-    p.n_pivots = n_rows > h->pair_pivot_add ? (n_rows - h->pair_pivot_add + h->pair_pivot_mul - 1) / h->pair_pivot_mul : 0;
+    p.n_pivots = n_rows;
     p.mode = PAIR_MODE_TAIL;
     p.min_score = min_score;
     p.mid_list = h->d_mid_list.as<uint32_t>();
@@ -556,7 +559,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
 
     {   // work measure
         HGA_CUDA(cudaMemsetAsync(&d_sc->increments, 0, 8, h->stream));
-        increments_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_inv_off.as<uint32_t>(), h->index_keys, &d_sc->increments);
+        increments_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_inv_off.as<uint32_t>(), h->index_keys, h->index_by_kid ? h->index_key_div : 0u, &d_sc->increments);
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));

@@ -284,6 +284,8 @@ __device__ __forceinline__ uint32_t scan_tile_windows(const TileCtx &c, int lane
     uint32_t F0 = pf[0], R0 = pr[0];
     const uint64_t pol_last = l2_policy_evict_last();
 
+    // (Fetching the next tile's bytes one tile ahead with cp.async was tried: slower, -5 % at 2 Gbases and -14 % at 10 Gbases:
+    // cp.async has no evict-first path, so the base stream displaced the filter from L2.)
     // (Requesting the filter words one group ahead of testing them was tried: no gain - the probes are bound by L1 wavefront
     // throughput, ~10 distinct lines per warp load, not by their latency - and the extra live registers spilled around the
     // drain call.)
@@ -507,7 +509,8 @@ int launch_scan(hga_handle *h, const ScanParams &p, int grid, size_t smem, bool 
         n_attr = 1;
     }
     cfg.attrs = attr; cfg.numAttrs = n_attr;
-    if (min_ctas >= 6) HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<6>, p));
+    if (min_ctas >= 7) HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<7>, p));
+    else if (min_ctas == 6) HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<6>, p));
     else HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<5>, p));
     h->metrics.kernel_launches++;
     return HGA_OK;
@@ -543,7 +546,8 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     const size_t smem = 0;
     int min_ctas = 6;   // register budget of the kernel variant: 6 CTAs/SM (<= 85 registers) or 5 (<= 102)
     if (const char *e = getenv("HGA_SCAN_MIN_CTAS")) min_ctas = atoi(e);
-    if (min_ctas >= 6) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<6>, SCAN_THREADS, smem));
+    if (min_ctas >= 7) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<7>, SCAN_THREADS, smem));
+    else if (min_ctas == 6) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<6>, SCAN_THREADS, smem));
     else HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<5>, SCAN_THREADS, smem));
     if (occ < 1) occ = 1;
     const int grid_full = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, std::max<uint64_t>((n_tiles + SCAN_WARPS - 1) / SCAN_WARPS, 1));
