@@ -567,7 +567,9 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     uint64_t capacity = 0, E = 0;
     // Host source (hga_scan): the bases travel in chunks on a second stream and every chunk is scanned as soon as it has
     // landed (a tile only needs bases at or before its own end, so chunk c can run while chunk c + 1 is in flight).
-    const uint64_t chunk_tiles = (256ull << 20) / SCAN_TILE;                      // ~256 MB of bases per chunk
+    uint64_t chunk_mb = 256;                                                      // bases per chunk; HGA_SCAN_CHUNK_MB lets the tests reach this path with small inputs
+    if (const char *e = getenv("HGA_SCAN_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));
+    const uint64_t chunk_tiles = (chunk_mb << 20) / SCAN_TILE;
     const bool pipelined = h_bases != nullptr && n_tiles > 2 * chunk_tiles && h->copy_stream != nullptr;
     if (h_bases != nullptr && !pipelined && n_bases) {
         StageTimer t(h, &h->metrics.h2d_ms, true);

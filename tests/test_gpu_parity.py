@@ -213,3 +213,24 @@ def test_errors():
     with hga_b200.Handle(np.array([1], dtype=np.uint64), 5) as h:
         with pytest.raises(hga_b200.HgaError):
             h.build_index()                                       # stage out of order
+
+
+def test_host_scan_pipelined_chunks(oracle, monkeypatch):
+    """hga_scan with host buffers copies the bases in chunks on a second stream and scans every chunk as it lands; with
+    HGA_SCAN_CHUNK_MB=1 a 3 MB input takes that path (tiles at chunk seams need the previous chunk's last bases)"""
+    import hga_b200
+    monkeypatch.setenv("HGA_SCAN_CHUNK_MB", "1")
+    a = datagen.random_genome(150000, 77)
+    b = datagen.mutate(a, 0.02, 78)
+    reads = datagen.sample_reads(a, 210, 7800, 5, error_rate=0.05, length_sigma=0.5, max_len=60000) + \
+        datagen.sample_reads(b, 210, 7800, 6, error_rate=0.05, length_sigma=0.5, max_len=60000)
+    bases, off = _pack([datagen.to_ascii(r) for r in reads])
+    assert len(bases) > 2 * (1 << 20) + 4096
+    kmers = datagen.discriminative_kmers([a, b], 19)
+    ref_ro, ref_kid, ref_pos = oracle.scan(bases, off, 19, kmers)
+    with hga_b200.Handle(kmers, 19) as h:
+        h.scan(bases, off)
+        row_off, kid, pos = h.get_hits()
+        m = h.metrics()
+    assert np.array_equal(row_off, ref_ro) and np.array_equal(kid, ref_kid) and np.array_equal(pos, ref_pos)
+    assert m["h2d_ms"] > 0
