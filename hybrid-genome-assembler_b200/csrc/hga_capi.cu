@@ -115,11 +115,6 @@ int hga_create(int device, int k, const uint64_t *kmers, uint64_t n_kmers, hga_h
     hga_handle *h = new hga_handle();
     memset(&h->metrics, 0, sizeof(h->metrics));
     h->device = device; h->k = k; h->n_kmers = n_kmers; h->sm_count = prop.multiProcessorCount;
-    {
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess && v > 0) h->l2_persist_max = (size_t) v;
-        cudaGetLastError();
-    }
     cudaError_t e1 = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { h->copy_stream = nullptr; cudaGetLastError(); }
     cudaError_t e2 = cudaEventCreate(&h->ev0), e3 = cudaEventCreate(&h->ev1), e4 = cudaEventCreate(&h->ev2), e5 = cudaEventCreate(&h->ev3);

@@ -136,16 +136,6 @@ __global__ void unpack_records_kernel(const uint64_t *__restrict__ rec, uint64_t
     }
 }
 
-__global__ void global_rows_kernel(const uint64_t *__restrict__ row_off, uint64_t n_rows, uint32_t row_base, uint32_t *__restrict__ out_row) {
-    const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
-    const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    for (uint64_t r = w; r < n_rows; r += warps) {
-        const uint64_t a = row_off[r], b = row_off[r + 1];
-        for (uint64_t i = a + lane; i < b; i += 32) out_row[i] = (uint32_t) r + row_base;
-    }
-}
-
 // bound[g] = first position of the partitioned records whose owner is >= g, g = 0 .. G
 __global__ void owner_bounds_kernel(const uint8_t *__restrict__ sorted_owner, uint64_t n, int G, unsigned long long *bound) {
     const int g = threadIdx.x;

@@ -234,7 +234,6 @@ struct hga_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // stage timer, nested (exchange) timer
     int sm_count = 148;
-    size_t l2_persist_max = 0;            // cudaDevAttrMaxPersistingL2CacheSize
 
     // table
     KmerTable table;

@@ -67,7 +67,7 @@ struct ScanParams {
     uint64_t n_tiles;                 // tickets of this launch
     uint64_t tile_begin;              // first tile of this launch (chunked launches while the bases are still arriving)
     uint64_t tile_stride;             // > 0: sampling mode (count only, tile = tile_begin + ticket * stride)
-    int diag;                         // HGA_SCAN_DIAG timing experiments (results are WRONG when set): 1 = no key probes, 2 = no filter probes
+    int diag;                         // HGA_SCAN_DIAG timing experiments (results are WRONG when set): 1 = no key probes, 2 = no filter probes, 4 = no key-sector prefetch
 };
 
 // 4 ASCII bytes (little-endian in w, lowest address = first base) -> forward codes (8 bits, first base most
@@ -124,6 +124,39 @@ __device__ __forceinline__ ulonglong2 ldg_u64x2_policy(const ulonglong2 *a, uint
     ulonglong2 v;
     asm("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
     return v;
+}
+
+// Key-table lookup: slot of `key` or 0xFFFFFFFF. Probe order = insertion order (hga_chain_slot): the 32 B sector picked by
+// the k-mer hash first (the line was prefetched into L2 when the candidate was queued), then the other sectors of the
+// bucket, then the next bucket. One sector = two 16 B loads; a sector with an empty slot and no match closes the search.
+__device__ __forceinline__ uint32_t probe_key(const KmerTable &t, unsigned long long key, uint32_t B) {
+    uint32_t slot = 0xFFFFFFFFu;
+    const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS;
+    const uint32_t sec0 = hga_bits_sector(hga_bits_hash(key));
+    const uint64_t pol_first = l2_policy_evict_first();
+    bool open = true;             // chain not yet closed by an empty slot or a match
+    #pragma unroll 1
+    for (uint32_t j = 0; j < HGA_CHAIN_SLOTS && open; j += HGA_SECTOR_SLOTS) {
+        const uint32_t off = hga_chain_slot(sec0, j);
+        const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(t.keys + home + off);
+        const ulonglong2 a = ldg_u64x2_policy(sp, pol_first), b = ldg_u64x2_policy(sp + 1, pol_first);
+        if (a.x == key) { slot = home + off; open = false; }
+        else if (a.y == key) { slot = home + off + 1; open = false; }
+        else if (b.x == key) { slot = home + off + 2; open = false; }
+        else if (b.y == key) { slot = home + off + 3; open = false; }
+        else if (a.x == HGA_EMPTY_KEY || a.y == HGA_EMPTY_KEY || b.x == HGA_EMPTY_KEY || b.y == HGA_EMPTY_KEY) open = false;
+    }
+    if (open && t.n_over) {       // chain full: the key, if present, lives in the overflow region
+        const uint32_t mask = t.n_over - 1;
+        uint32_t q = hga_plain_hash(key) & mask;
+        for (;;) {
+            const unsigned long long a = __ldg(t.keys + t.n_main + q);
+            if (a == key) { slot = t.n_main + q; break; }
+            if (a == HGA_EMPTY_KEY) break;
+            q = (q + 1) & mask;
+        }
+    }
+    return slot;
 }
 
 // shared memory of one warp
@@ -197,11 +230,16 @@ __device__ __forceinline__ int read_start_of(const TileCtx &c, int e) {
 }
 
 // n (<= 32) queued candidates starting at ring position head: re-extract the k-mer, check the window against the
-// read boundaries, probe the key table; hits are appended to the staging area in position order
-__device__ __noinline__ uint32_t drain_queue(uint32_t head, uint32_t n, uint32_t st_count, const TileCtx &c, int lane) {
-    const KmerTable &t = c.p->t;
-    WarpTile &T = *c.T;
+// read boundaries, probe the key table; hits are appended to the staging area in position order. A real call (the
+// window loop stays small); everything it needs comes in registers, nothing through local memory.
+__device__ __noinline__ uint32_t drain_queue(uint32_t head, uint32_t n, uint32_t st_count, int lane, WarpTile *Tp, const ScanParams *pp,
+                                             uint64_t tile_start, uint64_t r_lo, uint64_t r_hi, uint32_t n_bnd, int n_loc) {
+    TileCtx c;
+    c.p = pp; c.T = Tp; c.tile_start = tile_start; c.r_lo = r_lo; c.r_hi = r_hi; c.n_bnd = n_bnd; c.n_loc = n_loc;
+    const KmerTable &t = pp->t;
+    WarpTile &T = *Tp;
     const int k = t.geom.k;
+    c.kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
     uint32_t slot = 0xFFFFFFFFu, widx = 0;
     if ((uint32_t) lane < n) {
         const uint2 qe = T.q[(head + lane) & (SCAN_Q - 1)];
@@ -209,39 +247,12 @@ __device__ __noinline__ uint32_t drain_queue(uint32_t head, uint32_t n, uint32_t
         widx = qe.y & 0x7FFFu;
         const int e = (int) widx;
         const int start = read_start_of(c, e);
-        if (e < c.n_loc && e - start + 1 >= k && !(c.p->diag & 1)) {
+        if (e < c.n_loc && e - start + 1 >= k && !(pp->diag & 1)) {
             unsigned long long fwd, rc;
             extract_window(T.fwd, T.rc, e, k, c.kmask, fwd, rc);
             const unsigned long long key = fwd < rc ? fwd : rc;                       // KmerIterator.cpp:69
             if (qe.y & 0x8000u) B = hga_locality_hash(key, t.geom);
-            // Probe order = insertion order (hga_chain_slot): the 32 B sector picked by the k-mer hash first (the line was
-            // prefetched into L2 when the candidate was queued), then the other sectors of the bucket, then the next
-            // bucket. One sector = two 16 B loads; a sector with an empty slot and no match closes the search.
-            const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS;
-            const uint32_t sec0 = hga_bits_sector(hga_bits_hash(key));
-            const uint64_t pol_first = l2_policy_evict_first();
-            bool open = true;             // chain not yet closed by an empty slot or a match
-            #pragma unroll 1
-            for (uint32_t j = 0; j < HGA_CHAIN_SLOTS && open; j += HGA_SECTOR_SLOTS) {
-                const uint32_t off = hga_chain_slot(sec0, j);
-                const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(t.keys + home + off);
-                const ulonglong2 a = ldg_u64x2_policy(sp, pol_first), b = ldg_u64x2_policy(sp + 1, pol_first);
-                if (a.x == key) { slot = home + off; open = false; }
-                else if (a.y == key) { slot = home + off + 1; open = false; }
-                else if (b.x == key) { slot = home + off + 2; open = false; }
-                else if (b.y == key) { slot = home + off + 3; open = false; }
-                else if (a.x == HGA_EMPTY_KEY || a.y == HGA_EMPTY_KEY || b.x == HGA_EMPTY_KEY || b.y == HGA_EMPTY_KEY) open = false;
-            }
-            if (open && t.n_over) {       // chain full: the key, if present, lives in the overflow region
-                const uint32_t mask = t.n_over - 1;
-                uint32_t q = hga_plain_hash(key) & mask;
-                for (;;) {
-                    const unsigned long long a = __ldg(t.keys + t.n_main + q);
-                    if (a == key) { slot = t.n_main + q; break; }
-                    if (a == HGA_EMPTY_KEY) break;
-                    q = (q + 1) & mask;
-                }
-            }
+            slot = probe_key(t, key, B);
         }
     }
     const bool hit = slot != 0xFFFFFFFFu;
@@ -266,7 +277,7 @@ __device__ __forceinline__ uint32_t scan_tile_windows(const TileCtx &c, int lane
     const uint32_t *filter = p.t.filter;
     const uint32_t n_blocks = p.t.n_blocks, n_buckets = p.t.n_buckets;
     const uint64_t *keys = p.t.keys;
-    const bool diag2 = (p.diag & 2) != 0;
+    const bool diag2 = (p.diag & 2) != 0, diag4 = (p.diag & 4) != 0;
     const int skip = W ? geo.skip : 0;
     // staged coordinates (0 = tile_start - SCAN_HALO) of this lane's first window; every step moves 32 bases = 2 words,
     // so the bit offset inside the word is loop invariant and consecutive steps share a word
@@ -316,18 +327,18 @@ __device__ __forceinline__ uint32_t scan_tile_windows(const TileCtx &c, int lane
             if (pass) {
                 T.q[(q_tail + __popc(bal & lane_lt)) & (SCAN_Q - 1)] = make_uint2(Bv[u], (uint32_t) (lane + 32 * (s0 + u)) | (exc[u] ? 0x8000u : 0u));
                 // start the key sector's trip from HBM now; the drain that reads it runs a few steps later
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(keys + (size_t) hga_scale(Bv[u], n_buckets) * HGA_BUCKET_SLOTS + sec[u]));
+                if (!diag4) asm volatile("prefetch.global.L2 [%0];" :: "l"(keys + (size_t) hga_scale(Bv[u], n_buckets) * HGA_BUCKET_SLOTS + sec[u]));
             }
             q_tail += __popc(bal);
         }
         __syncwarp();
         while (q_tail - q_head >= 32) {
-            st_count = drain_queue(q_head, 32, st_count, c, lane);
+            st_count = drain_queue(q_head, 32, st_count, lane, c.T, c.p, c.tile_start, c.r_lo, c.r_hi, c.n_bnd, c.n_loc);
             q_head += 32;
         }
         __syncwarp();
     }
-    if (q_tail != q_head) st_count = drain_queue(q_head, q_tail - q_head, st_count, c, lane);
+    if (q_tail != q_head) st_count = drain_queue(q_head, q_tail - q_head, st_count, lane, c.T, c.p, c.tile_start, c.r_lo, c.r_hi, c.n_bnd, c.n_loc);
     n_cand += q_tail;
     return st_count;
 }
@@ -348,7 +359,7 @@ __device__ __forceinline__ uint32_t scan_tile_dispatch(const TileCtx &c, int lan
 }
 
 template<int MIN_CTAS>
-__global__ void __launch_bounds__(SCAN_THREADS, MIN_CTAS) scan_probe_kernel(ScanParams p) {
+__global__ void __launch_bounds__(SCAN_THREADS, MIN_CTAS) scan_probe_kernel(const __grid_constant__ ScanParams p) {
     __shared__ WarpTile s_tiles[SCAN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpTile &T = s_tiles[warp];
@@ -490,28 +501,10 @@ __global__ void scan_fix_rows_kernel(const uint64_t *__restrict__ read_off, uint
     }
 }
 
-int launch_scan(hga_handle *h, const ScanParams &p, int grid, size_t smem, bool persist, int min_ctas) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SCAN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
-    cudaLaunchAttribute attr[1];
-    int n_attr = 0;
-    const size_t fbytes = (size_t) p.t.n_blocks * 32;
-    if (persist && h->l2_persist_max > 0 && fbytes > 0) {
-        // keep the filter resident in L2 while the base stream and the hit lists pass through
-        memset(&attr[0], 0, sizeof(attr[0]));
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = (void *) p.t.filter;
-        attr[0].val.accessPolicyWindow.num_bytes = fbytes;
-        attr[0].val.accessPolicyWindow.hitRatio = fbytes <= h->l2_persist_max ? 1.0f : (float) ((double) h->l2_persist_max / (double) fbytes);
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        n_attr = 1;
-    }
-    cfg.attrs = attr; cfg.numAttrs = n_attr;
-    if (min_ctas >= 7) HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<7>, p));
-    else if (min_ctas == 6) HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<6>, p));
-    else HGA_CUDA(cudaLaunchKernelEx(&cfg, scan_probe_kernel<5>, p));
+int launch_scan(hga_handle *h, const ScanParams &p, int grid, int min_ctas) {
+    if (min_ctas >= 6) scan_probe_kernel<6><<<grid, SCAN_THREADS, 0, h->stream>>>(p);
+    else scan_probe_kernel<5><<<grid, SCAN_THREADS, 0, h->stream>>>(p);
+    HGA_CUDA(cudaGetLastError());
     h->metrics.kernel_launches++;
     return HGA_OK;
 }
@@ -543,23 +536,12 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     if (const char *e = getenv("HGA_SCAN_DIAG")) p.diag = atoi(e);
 
     int occ = 0;
-    const size_t smem = 0;
     int min_ctas = 6;   // register budget of the kernel variant: 6 CTAs/SM (<= 85 registers) or 5 (<= 102)
     if (const char *e = getenv("HGA_SCAN_MIN_CTAS")) min_ctas = atoi(e);
-    if (min_ctas >= 7) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<7>, SCAN_THREADS, smem));
-    else if (min_ctas == 6) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<6>, SCAN_THREADS, smem));
-    else HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<5>, SCAN_THREADS, smem));
+    if (min_ctas >= 6) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<6>, SCAN_THREADS, 0));
+    else HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<5>, SCAN_THREADS, 0));
     if (occ < 1) occ = 1;
     const int grid_full = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, std::max<uint64_t>((n_tiles + SCAN_WARPS - 1) / SCAN_WARPS, 1));
-
-    bool persist = false;   // measured on B200: an L2 access-policy window on the filter does not pay (profiles/)
-    if (const char *e = getenv("HGA_L2_PERSIST")) persist = atoi(e) != 0;
-    const size_t fbytes = (size_t) h->table.n_blocks * 32;
-    if (persist && h->l2_persist_max > 0 && n_tiles > 0) {
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(h->l2_persist_max, fbytes)) != cudaSuccess) { cudaGetLastError(); persist = false; }
-    } else {
-        persist = false;
-    }
 
     StageTimer timer(h, &h->metrics.scan_ms);
     ScanScalars sc;
@@ -606,7 +588,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
             ScanParams ps = p;
             ps.tile_stride = stride; ps.n_tiles = n_sample; ps.tile_begin = 0; ps.capacity = 0;
-            HGA_TRY(launch_scan(h, ps, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (n_sample + SCAN_WARPS - 1) / SCAN_WARPS), smem, persist, min_ctas));
+            HGA_TRY(launch_scan(h, ps, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (n_sample + SCAN_WARPS - 1) / SCAN_WARPS), min_ctas));
             HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             const double est = (double) sc.total * (double) n_tiles / (double) n_sample;
@@ -621,7 +603,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             HGA_CUDA(cudaStreamWaitEvent(h->stream, landed[c], 0));
             p.tile_begin = c * chunk_tiles; p.n_tiles = std::min<uint64_t>(chunk_tiles, n_tiles - p.tile_begin);
             HGA_CUDA(cudaMemsetAsync(&d_sc->ticket, 0, 8, h->stream));
-            HGA_TRY(launch_scan(h, p, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (p.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS), smem, persist, min_ctas));
+            HGA_TRY(launch_scan(h, p, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (p.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS), min_ctas));
         }
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
@@ -647,7 +629,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             ScanParams ps = p;
             ps.tile_stride = stride; ps.n_tiles = n_sample; ps.capacity = 0;
             const int grid_s = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (n_sample + SCAN_WARPS - 1) / SCAN_WARPS);
-            HGA_TRY(launch_scan(h, ps, grid_s, smem, persist, min_ctas));
+            HGA_TRY(launch_scan(h, ps, grid_s, min_ctas));
             HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             const double est = (double) sc.total * (double) n_tiles / (double) n_sample;
@@ -662,7 +644,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_sort_b.as<uint32_t>();
         p.capacity = capacity; p.n_tiles = n_tiles; p.tile_begin = 0; p.tile_stride = 0;
         HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
-        HGA_TRY(launch_scan(h, p, grid_full, smem, persist, min_ctas));
+        HGA_TRY(launch_scan(h, p, grid_full, min_ctas));
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         E = sc.total;
@@ -690,10 +672,6 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         HGA_CUDA(cudaMemsetAsync(p.row_off, 0, (n_reads + 1) * 8, h->stream));
     }
     timer.stop();
-    if (persist) {
-        cudaCtxResetPersistingL2Cache();
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
-    }
     h->n_hits = E;
     h->metrics.n_bases = n_bases; h->metrics.n_reads = n_reads; h->metrics.n_hits = E; h->metrics.n_candidates = sc.candidates;
     h->have_scan = true;
