@@ -230,9 +230,8 @@ __device__ __forceinline__ int read_start_of(const TileCtx &c, int e) {
 }
 
 // n (<= 32) queued candidates starting at ring position head: re-extract the k-mer, check the window against the
-// read boundaries, probe the key table; hits are appended to the staging area in position order. A real call (the
-// window loop stays small); everything it needs comes in registers, nothing through local memory.
-__device__ __noinline__ uint32_t drain_queue(uint32_t head, uint32_t n, uint32_t st_count, int lane, WarpTile *Tp, const ScanParams *pp,
+// read boundaries, probe the key table; hits are appended to the staging area in position order
+__device__ __forceinline__ uint32_t drain_queue(uint32_t head, uint32_t n, uint32_t st_count, int lane, WarpTile *Tp, const ScanParams *pp,
                                              uint64_t tile_start, uint64_t r_lo, uint64_t r_hi, uint32_t n_bnd, int n_loc) {
     TileCtx c;
     c.p = pp; c.T = Tp; c.tile_start = tile_start; c.r_lo = r_lo; c.r_hi = r_hi; c.n_bnd = n_bnd; c.n_loc = n_loc;
@@ -358,8 +357,10 @@ __device__ __forceinline__ uint32_t scan_tile_dispatch(const TileCtx &c, int lan
     }
 }
 
-template<int MIN_CTAS>
-__global__ void __launch_bounds__(SCAN_THREADS, MIN_CTAS) scan_probe_kernel(const __grid_constant__ ScanParams p) {
+// 63 registers, 30.9 KB of shared memory per CTA: 7 CTAs = 28 independent warps per SM. The parameters are __grid_constant__ and
+// every helper is inlined so that NOTHING lives in local memory: a by-value parameter struct whose address is taken, and a
+// tile context handed to a non-inlined drain function, cost 26 % of the scan time when they did (r1y / r1z / r2a).
+__global__ void __launch_bounds__(SCAN_THREADS, 7) scan_probe_kernel(const __grid_constant__ ScanParams p) {
     __shared__ WarpTile s_tiles[SCAN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpTile &T = s_tiles[warp];
@@ -501,9 +502,8 @@ __global__ void scan_fix_rows_kernel(const uint64_t *__restrict__ read_off, uint
     }
 }
 
-int launch_scan(hga_handle *h, const ScanParams &p, int grid, int min_ctas) {
-    if (min_ctas >= 6) scan_probe_kernel<6><<<grid, SCAN_THREADS, 0, h->stream>>>(p);
-    else scan_probe_kernel<5><<<grid, SCAN_THREADS, 0, h->stream>>>(p);
+int launch_scan(hga_handle *h, const ScanParams &p, int grid) {
+    scan_probe_kernel<<<grid, SCAN_THREADS, 0, h->stream>>>(p);
     HGA_CUDA(cudaGetLastError());
     h->metrics.kernel_launches++;
     return HGA_OK;
@@ -536,10 +536,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     if (const char *e = getenv("HGA_SCAN_DIAG")) p.diag = atoi(e);
 
     int occ = 0;
-    int min_ctas = 6;   // register budget of the kernel variant: 6 CTAs/SM (<= 85 registers) or 5 (<= 102)
-    if (const char *e = getenv("HGA_SCAN_MIN_CTAS")) min_ctas = atoi(e);
-    if (min_ctas >= 6) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<6>, SCAN_THREADS, 0));
-    else HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<5>, SCAN_THREADS, 0));
+    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel, SCAN_THREADS, 0));
     if (occ < 1) occ = 1;
     const int grid_full = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, std::max<uint64_t>((n_tiles + SCAN_WARPS - 1) / SCAN_WARPS, 1));
 
@@ -588,7 +585,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
             ScanParams ps = p;
             ps.tile_stride = stride; ps.n_tiles = n_sample; ps.tile_begin = 0; ps.capacity = 0;
-            HGA_TRY(launch_scan(h, ps, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (n_sample + SCAN_WARPS - 1) / SCAN_WARPS), min_ctas));
+            HGA_TRY(launch_scan(h, ps, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (n_sample + SCAN_WARPS - 1) / SCAN_WARPS)));
             HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             const double est = (double) sc.total * (double) n_tiles / (double) n_sample;
@@ -603,7 +600,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             HGA_CUDA(cudaStreamWaitEvent(h->stream, landed[c], 0));
             p.tile_begin = c * chunk_tiles; p.n_tiles = std::min<uint64_t>(chunk_tiles, n_tiles - p.tile_begin);
             HGA_CUDA(cudaMemsetAsync(&d_sc->ticket, 0, 8, h->stream));
-            HGA_TRY(launch_scan(h, p, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (p.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS), min_ctas));
+            HGA_TRY(launch_scan(h, p, (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (p.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS)));
         }
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
@@ -629,7 +626,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             ScanParams ps = p;
             ps.tile_stride = stride; ps.n_tiles = n_sample; ps.capacity = 0;
             const int grid_s = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, (n_sample + SCAN_WARPS - 1) / SCAN_WARPS);
-            HGA_TRY(launch_scan(h, ps, grid_s, min_ctas));
+            HGA_TRY(launch_scan(h, ps, grid_s));
             HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             const double est = (double) sc.total * (double) n_tiles / (double) n_sample;
@@ -644,7 +641,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_sort_b.as<uint32_t>();
         p.capacity = capacity; p.n_tiles = n_tiles; p.tile_begin = 0; p.tile_stride = 0;
         HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
-        HGA_TRY(launch_scan(h, p, grid_full, min_ctas));
+        HGA_TRY(launch_scan(h, p, grid_full));
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         E = sc.total;
