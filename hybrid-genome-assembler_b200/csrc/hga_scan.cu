@@ -296,6 +296,8 @@ __device__ __forceinline__ uint32_t scan_tile_windows(const TileCtx &c, int lane
 
     // (Fetching the next tile's bytes one tile ahead with cp.async was tried: slower, -5 % at 2 Gbases and -14 % at 10 Gbases:
     // cp.async has no evict-first path, so the base stream displaced the filter from L2.)
+    // (Splitting the drain into "request the key sector now, compare when the queue has filled again" was tried as well: no gain,
+    // r2c: 13.7 vs 13.2 ms at 2 Gbases, 76.4 vs 75.7 ms at 10 Gbases.)
     // (Requesting the filter words one group ahead of testing them was tried: no gain - the probes are bound by L1 wavefront
     // throughput, ~10 distinct lines per warp load, not by their latency - and the extra live registers spilled around the
     // drain call.)
