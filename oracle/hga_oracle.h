@@ -61,6 +61,20 @@ int orc_union_find(uint64_t n_edges, const uint32_t *ex, const uint32_t *ey, con
                    uint32_t **tree_y);
 void orc_free(void *p);
 
+/* SURVEY §8f-1 — engine state after the scaffold stage: merge_components (:349-422), get_connections on the merged
+ * state (:301-333), get_component_ids (:727-735). Component ids are read ids (1-based). */
+typedef struct orc_engine orc_engine;
+orc_engine *orc_engine_new(const uint64_t *row_off, const uint32_t *hit_kid, uint64_t n_reads, uint64_t n_kmers, const uint64_t *inv_off,
+                           const uint32_t *inv_read);
+void orc_engine_free(orc_engine *e);
+int orc_engine_merge(orc_engine *e, uint64_t n_comp, const uint64_t *comp_off, const uint32_t *comp_member, uint32_t *merged_ids);
+uint64_t orc_engine_ids(const orc_engine *e, uint64_t min_size, uint32_t *out);
+uint64_t orc_engine_component_kmers(const orc_engine *e, uint32_t id, uint32_t *out);
+uint64_t orc_engine_component_reads(const orc_engine *e, uint32_t id, uint32_t *out);
+uint64_t orc_engine_index_list(const orc_engine *e, uint64_t kmer_id, uint32_t *out);
+int orc_engine_connections(const orc_engine *e, const uint32_t *pivots, uint64_t n_pivots, uint64_t min_score, uint64_t *n_conn, uint32_t **cx,
+                           uint32_t **cy, uint64_t **cs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,8 @@
 //   construct_indices                 clustering/ReadClusteringEngine.cpp:234-299
 //   get_all_connections               clustering/ReadClusteringEngine.cpp:301-339
 //   union_find                        clustering/ReadClusteringEngine.cpp:424-489
+//   merge_components (--enrich)       clustering/ReadClusteringEngine.cpp:349-422
+//   get_connections  (--enrich)       clustering/ReadClusteringEngine.cpp:301-333  (pivots = the merged cores)
 // Restated here because read_clustering.cpp cannot be compiled (boost::program_options is absent):
 //   load_text_file_kmers              read_clustering.cpp:18-33   (7 lines, uses the real KmerIterator)
 //   the 15 % cut                      clustering/ReadClusteringEngine.cpp:754-755
@@ -93,7 +95,7 @@ public:
     Probe(SequenceRecordIterator &it, ReadClusteringConfig cfg) : ReadClusteringEngine(it, cfg) {}
 
     int run(std::unordered_set<Kmer> &kmers, int k, const std::string &out, bool do_dump, double fraction, int min_size,
-            ConnectionScore min_score, int stop_after) {
+            ConnectionScore min_score, int stop_after, ConnectionScore enrich_min = 0) {
         // KmerID assignment order = iteration order of the very same unordered_set object (.cpp:237-241)
         std::vector<Kmer> id2kmer;
         for (auto kmer : kmers) id2kmer.push_back(kmer);
@@ -213,6 +215,99 @@ public:
             dump(out, "tree_x.u32", tree_x);
             dump(out, "tree_y.u32", tree_y);
         }
+        if (enrich_min == 0) { fclose(meta); return 0; }
+
+        // ---- merge of the scaffold components + enrichment, all real reference code --------------------
+        // run_clustering :764 (merge_components), :785-794 (get_connections over the cores, restricted union_find,
+        // merge_components). The tail / spectral block (:768-777) is skipped, which is the reference's own path when it finds
+        // no strong tail connections (:771) or at most two scaffold components (:768).
+        std::vector<Component> scaffold_components;
+        for (auto &p : comps) scaffold_components.push_back(p.first);
+        t0 = now_ms();
+        auto scaffold_ids = merge_components(scaffold_components);
+        double t_merge = now_ms() - t0;
+        std::vector<ComponentID> core_ids;
+        for (auto p : component_index) if (p.second->size() >= (uint64_t) min_size) core_ids.push_back(p.first);
+        std::sort(core_ids.begin(), core_ids.end());
+        fprintf(meta, "merged_scaffolds=%zu\ncores=%zu\nmerge_ms=%.3f\n", scaffold_ids.size(), core_ids.size(), t_merge);
+        if (do_dump) {
+            // merged cores: survivor id, k-mer VALUES of the merged list (sorted), member reads (sorted)
+            std::vector<uint32_t> core_id, core_read;
+            std::vector<uint64_t> core_kmer_off{0}, core_kmer, core_read_off{0};
+            for (auto id : core_ids) {
+                core_id.push_back(id);
+                std::vector<uint64_t> vals;
+                for (KmerID kid : component_index[id]->discriminative_kmer_ids) vals.push_back(id2kmer[kid]);
+                std::sort(vals.begin(), vals.end());
+                core_kmer.insert(core_kmer.end(), vals.begin(), vals.end());
+                core_kmer_off.push_back(core_kmer.size());
+                auto reads = component_index[id]->contained_read_ids;
+                std::sort(reads.begin(), reads.end());
+                core_read.insert(core_read.end(), reads.begin(), reads.end());
+                core_read_off.push_back(core_read.size());
+            }
+            dump(out, "core_id.u32", core_id);
+            dump(out, "core_kmer_off.u64", core_kmer_off);
+            dump(out, "core_kmer.u64", core_kmer);
+            dump(out, "core_read_off.u64", core_read_off);
+            dump(out, "core_read.u32", core_read);
+            // the purged inverted index, ordered by k-mer value (the reference's purge loop, :395-419)
+            std::vector<std::pair<uint64_t, KmerID>> order;
+            for (KmerID i = 0; i < id2kmer.size(); i++) order.push_back({id2kmer[i], i});
+            std::sort(order.begin(), order.end());
+            std::vector<uint64_t> inv_off{0};
+            std::vector<uint32_t> inv_read;
+            for (auto &o : order) {
+                for (auto r : kmer_component_index[o.second]) inv_read.push_back(r);
+                inv_off.push_back(inv_read.size());
+            }
+            dump(out, "purged_off.u64", inv_off);
+            dump(out, "purged_read.u32", inv_read);
+        }
+
+        t0 = now_ms();
+        auto econn = get_connections(core_ids, enrich_min);
+        double t_econn = now_ms() - t0;
+        std::sort(econn.begin(), econn.end(), canonical_less);
+        fprintf(meta, "enrichment_connections=%zu\nenrichment_connections_ms=%.3f\n", econn.size(), t_econn);
+        if (do_dump) {
+            std::vector<uint32_t> cx, cy;
+            std::vector<uint64_t> cs;
+            for (auto &c : econn) { cx.push_back(c.component_x_id); cy.push_back(c.component_y_id); cs.push_back(c.score); }
+            dump(out, "econn_x.u32", cx);
+            dump(out, "econn_y.u32", cy);
+            dump(out, "econn_score.u64", cs);
+        }
+        std::set<ComponentID> core_set(core_ids.begin(), core_ids.end());
+        auto enriched = union_find(econn, core_set, 2, -1);
+        std::vector<Component> enriched_components;
+        for (auto &p : enriched) enriched_components.push_back(p.first);
+        merge_components(enriched_components);
+        std::vector<ComponentID> final_ids;
+        for (auto p : component_index) if (p.second->size() >= (uint64_t) min_size) final_ids.push_back(p.first);
+        std::sort(final_ids.begin(), final_ids.end());
+        fprintf(meta, "final_components=%zu\n", final_ids.size());
+        if (do_dump) {
+            // final components ordered by their smallest member
+            std::vector<std::pair<uint32_t, ComponentID>> forder;
+            for (auto id : final_ids) {
+                auto &r = component_index[id]->contained_read_ids;
+                forder.push_back({*std::min_element(r.begin(), r.end()), id});
+            }
+            std::sort(forder.begin(), forder.end());
+            std::vector<uint32_t> final_id, final_read;
+            std::vector<uint64_t> final_off{0};
+            for (auto &o : forder) {
+                final_id.push_back(o.second);
+                auto reads = component_index[o.second]->contained_read_ids;
+                std::sort(reads.begin(), reads.end());
+                final_read.insert(final_read.end(), reads.begin(), reads.end());
+                final_off.push_back(final_read.size());
+            }
+            dump(out, "final_id.u32", final_id);
+            dump(out, "final_off.u64", final_off);
+            dump(out, "final_read.u32", final_read);
+        }
         fclose(meta);
         return 0;
     }
@@ -224,7 +319,7 @@ int usage() {
             "ref_driver canon <kmer file> <out dir>\n"
             "ref_driver records <out dir> <reads...>\n"
             "ref_driver run --kmers F --out DIR [--threads T] [--fraction 0.15] [--min-size 30] [--min-score 1]\n"
-            "               [--no-dump] [--stop-after 1|2] <reads...>\n");
+            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] <reads...>\n");
     return 2;
 }
 
@@ -279,6 +374,7 @@ int main(int argc, char **argv) {
     int min_size = config.scaffold_component_min_size;
     ConnectionScore min_score = 1;
     int stop_after = 0;
+    ConnectionScore enrich_min = 0;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) exit(usage()); return argv[++i]; };
@@ -289,6 +385,7 @@ int main(int argc, char **argv) {
         else if (a == "--min-size") min_size = std::stoi(next());
         else if (a == "--min-score") min_score = std::stoul(next());
         else if (a == "--stop-after") stop_after = std::stoi(next());
+        else if (a == "--enrich") enrich_min = std::stoul(next());
         else if (a == "--no-dump") do_dump = false;
         else paths.push_back(a);
     }
@@ -302,7 +399,7 @@ int main(int argc, char **argv) {
     reader.show_progress = false;
     double t_meta = now_ms() - t0;
     Probe engine(reader, config);
-    int rc = engine.run(kk.first, kk.second, out, do_dump, fraction, min_size, min_score, stop_after);
+    int rc = engine.run(kk.first, kk.second, out, do_dump, fraction, min_size, min_score, stop_after, enrich_min);
     FILE *meta = fopen((out + "/meta.txt").c_str(), "a");
     fprintf(meta, "kmer_load_ms=%.3f\nmeta_pass_ms=%.3f\nthreads=%d\n", t_load, t_meta, config.threads);
     fclose(meta);

@@ -58,3 +58,23 @@ def tree_edges(tree_off, tx, ty):
         e = sorted((min(int(a), int(b)), max(int(a), int(b))) for a, b in zip(tx[tree_off[i]:tree_off[i + 1]], ty[tree_off[i]:tree_off[i + 1]]))
         out.append(tuple(e))
     return sorted(out)
+
+
+def check_enrichment(ref, e, kmers_sorted):
+    """Oracle.enrich-style result (oracle_lib.enrich / the CUDA path's mirror of it) against a ref_driver --enrich dump."""
+    kmers_sorted = np.asarray(kmers_sorted, dtype=np.uint64)
+    assert np.array_equal(e["core_id"], ref["core_id"]), "core (merged scaffold) survivor ids differ"
+    if "core_kmers" in e:
+        ck = np.concatenate([np.sort(kmers_sorted[np.asarray(c, dtype=np.int64)]) for c in e["core_kmers"]]) if len(e["core_kmers"]) else np.zeros(0, np.uint64)
+        assert np.array_equal(ck, ref["core_kmer"]), "merged k-mer lists differ"
+        assert np.array_equal(np.cumsum([0] + [len(c) for c in e["core_kmers"]]).astype(np.uint64), ref["core_kmer_off"])
+    cr = np.concatenate(e["core_reads"]) if len(e["core_reads"]) else np.zeros(0, np.uint32)
+    assert np.array_equal(cr, ref["core_read"]), "core members differ"
+    if "purged_off" in e:
+        assert np.array_equal(e["purged_off"], ref["purged_off"]) and np.array_equal(e["purged_read"], ref["purged_read"]), "purged inverted index differs"
+    ex, ey, es = e["econn"]
+    assert np.array_equal(ex, ref["econn_x"]) and np.array_equal(ey, ref["econn_y"]) and np.array_equal(es, ref["econn_score"]), "enrichment connections differ"
+    assert np.array_equal(e["final_id"], ref["final_id"]), "final component ids differ"
+    fr = np.concatenate(e["final_reads"]) if len(e["final_reads"]) else np.zeros(0, np.uint32)
+    assert np.array_equal(fr, ref["final_read"]), "final components differ"
+    assert np.array_equal(np.cumsum([0] + [len(c) for c in e["final_reads"]]).astype(np.uint64), ref["final_off"])

@@ -144,6 +144,93 @@ class Oracle:
                     comp=comp)
 
 
+class Engine:
+    """Mutable engine state after the scaffold stage: merge_components / get_connections / get_component_ids."""
+
+    def __init__(self, orc, row_off, hit_kid, n_kmers, inv_off, inv_read):
+        self.lib = orc.lib
+        self.lib.orc_engine_new.restype = C.c_void_p
+        for f in ("orc_engine_ids", "orc_engine_component_kmers", "orc_engine_component_reads", "orc_engine_index_list"):
+            getattr(self.lib, f).restype = C.c_uint64
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint64); hit_kid = np.ascontiguousarray(hit_kid, dtype=np.uint32)
+        inv_off = np.ascontiguousarray(inv_off, dtype=np.uint64); inv_read = np.ascontiguousarray(inv_read, dtype=np.uint32)
+        self.n_reads = row_off.shape[0] - 1
+        self.n_kmers = n_kmers
+        self.h = C.c_void_p(self.lib.orc_engine_new(row_off.ctypes.data_as(u64p), hit_kid.ctypes.data_as(u32p), C.c_uint64(self.n_reads), C.c_uint64(n_kmers),
+                                                    inv_off.ctypes.data_as(u64p), inv_read.ctypes.data_as(u32p)))
+
+    def close(self):
+        if self.h:
+            self.lib.orc_engine_free(self.h)
+            self.h = None
+
+    def merge(self, comp_off, comp_member):
+        comp_off = np.ascontiguousarray(comp_off, dtype=np.uint64); comp_member = np.ascontiguousarray(comp_member, dtype=np.uint32)
+        n = comp_off.shape[0] - 1
+        ids = np.zeros(max(n, 1), dtype=np.uint32)
+        self.lib.orc_engine_merge(self.h, C.c_uint64(n), comp_off.ctypes.data_as(u64p), comp_member.ctypes.data_as(u32p), ids.ctypes.data_as(u32p))
+        return ids[:n]
+
+    def ids(self, min_size):
+        out = np.zeros(self.n_reads + 1, dtype=np.uint32)
+        n = self.lib.orc_engine_ids(self.h, C.c_uint64(min_size), out.ctypes.data_as(u32p))
+        return out[:n].copy()
+
+    def _list(self, fn, key, ktype):
+        n = getattr(self.lib, fn)(self.h, ktype(key), None)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        getattr(self.lib, fn)(self.h, ktype(key), out.ctypes.data_as(u32p))
+        return out[:n]
+
+    def component_kmers(self, cid):
+        return self._list("orc_engine_component_kmers", int(cid), C.c_uint32)
+
+    def component_reads(self, cid):
+        return self._list("orc_engine_component_reads", int(cid), C.c_uint32)
+
+    def index_list(self, kmer_id):
+        return self._list("orc_engine_index_list", int(kmer_id), C.c_uint64)
+
+    def index(self):
+        lists = [self.index_list(k) for k in range(self.n_kmers)]
+        off = np.zeros(self.n_kmers + 1, dtype=np.uint64)
+        np.cumsum([len(l) for l in lists], out=off[1:])
+        return off, (np.concatenate(lists) if lists else np.zeros(0, dtype=np.uint32)).astype(np.uint32)
+
+    def connections(self, pivots, min_score):
+        pivots = np.ascontiguousarray(pivots, dtype=np.uint32)
+        n = C.c_uint64(); cx = u32p(); cy = u32p(); cs = u64p()
+        self.lib.orc_engine_connections(self.h, pivots.ctypes.data_as(u32p), C.c_uint64(pivots.shape[0]), C.c_uint64(min_score), C.byref(n), C.byref(cx),
+                                        C.byref(cy), C.byref(cs))
+        out = (_np(cx, n.value, np.uint32), _np(cy, n.value, np.uint32), _np(cs, n.value, np.uint64))
+        for p in (cx, cy, cs):
+            self.lib.orc_free(p)
+        return out
+
+
+def enrich(orc, res, n_kmers, min_size=30, enrich_min=20):
+    """run_clustering :764 and :785-794 on the result of Oracle.run (tail / spectral block skipped: the reference's own path
+    when it has at most two scaffold components or no strong tail connection). Returns a dict mirroring ref_driver --enrich."""
+    co, cm = res["comp"][0], res["comp"][1]
+    eng = Engine(orc, res["row_off"], res["hit_kid"], n_kmers, res["inv_off"], res["inv_read"])
+    try:
+        eng.merge(co, cm)
+        cores = eng.ids(min_size)
+        core_kmers = [eng.component_kmers(c) for c in cores]
+        core_reads = [np.sort(eng.component_reads(c)) for c in cores]
+        purged_off, purged_read = eng.index()
+        ex, ey, es = orc.canonical_sort(*eng.connections(cores, enrich_min))
+        eo, em, _, _, _ = orc.union_find(ex, ey, min_size=2, max_size=-1, restricted=cores)
+        eng.merge(eo, em)
+        final = eng.ids(min_size)
+        final_reads = [np.sort(eng.component_reads(c)) for c in final]
+    finally:
+        eng.close()
+    order = np.argsort([int(r[0]) for r in final_reads], kind="stable") if len(final) else []
+    return dict(core_id=cores, core_kmers=core_kmers, core_reads=core_reads, purged_off=purged_off, purged_read=purged_read,
+                econn=(ex, ey, es), final_id=np.array([final[i] for i in order], dtype=np.uint32), final_reads=[final_reads[i] for i in order])
+
+
 _cached = None
 
 

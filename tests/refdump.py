@@ -10,11 +10,13 @@ _FILES = {
     "readlen_read": "u32", "readlen_len": "u32", "inv_kmer": "u64", "inv_off": "u64", "inv_read": "u32",
     "conn_x": "u32", "conn_y": "u32", "conn_score": "u64", "comp_off": "u64", "comp_read": "u32", "comp_root": "u32",
     "tree_off": "u64", "tree_x": "u32", "tree_y": "u32",
+    "core_id": "u32", "core_kmer_off": "u64", "core_kmer": "u64", "core_read_off": "u64", "core_read": "u32", "purged_off": "u64", "purged_read": "u32",
+    "econn_x": "u32", "econn_y": "u32", "econn_score": "u64", "final_id": "u32", "final_off": "u64", "final_read": "u32",
 }
 _DT = {"u32": np.uint32, "u64": np.uint64}
 
 
-def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None):
+def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0):
     tmp = None
     if outdir is None:
         tmp = tempfile.TemporaryDirectory()
@@ -25,6 +27,8 @@ def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score
         cmd.append("--no-dump")
     if stop_after:
         cmd += ["--stop-after", str(stop_after)]
+    if enrich:
+        cmd += ["--enrich", str(enrich)]
     cmd += list(read_paths)
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     out = {}

@@ -54,9 +54,9 @@ def test_load_kmers_matches_ref(oracle, ref_driver, tmp_path):
     assert k == kr == 19 and np.array_equal(a, b)
 
 
-def _full_compare(oracle, ref_driver, paths, kp, fraction=0.15, min_size=30, threads=1):
+def _full_compare(oracle, ref_driver, paths, kp, fraction=0.15, min_size=30, threads=1, enrich=0):
     reads, kmers, k = _load_case(oracle, paths, kp)
-    ref = refdump.run_ref(ref_driver, paths, kp, fraction=fraction, min_size=min_size, threads=threads)
+    ref = refdump.run_ref(ref_driver, paths, kp, fraction=fraction, min_size=min_size, threads=threads, enrich=enrich)
     res = oracle.run(reads["seq"], reads["seq_off"], k, kmers, fraction=fraction, min_size=min_size)
     assert ref["k"] == k and ref["n_kmers"] == kmers.shape[0] and ref["n_reads"] == reads["n_reads"]
     compare.check_hits(ref, res["row_off"], res["hit_kid"], res["hit_pos"], kmers)
@@ -70,6 +70,9 @@ def _full_compare(oracle, ref_driver, paths, kp, fraction=0.15, min_size=30, thr
     # root = element [0] of each component (ReadClusteringEngine.cpp:366)
     roots = sorted(int(cm[int(o)]) for o in co[:-1])
     assert roots == sorted(int(r) for r in ref["comp_root"])
+    if enrich:
+        import oracle_lib
+        compare.check_enrichment(ref, oracle_lib.enrich(oracle, res, kmers.shape[0], min_size=min_size, enrich_min=enrich), kmers)
     return ref, res
 
 
@@ -104,6 +107,25 @@ def test_long_reads_k_sweep(oracle, ref_driver, tmp_path, k):
     paths, kp = datagen.make_diploid_case(str(tmp_path), genome_size=30000, divergence=0.02, k=k, read_len=2000, coverage=12, seed=k,
                                           error_rate=0.05, length_sigma=0.5)
     _full_compare(oracle, ref_driver, paths, kp, min_size=3)
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_merge_and_enrichment_short_reads(oracle, ref_driver, tmp_path, threads):
+    # merge_components (unique union, index purge with its truncation quirk), get_connections over the merged
+    # cores, restricted union-find, second merge: all stages against the real reference
+    paths, kp = datagen.make_diploid_case(str(tmp_path), genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=7,
+                                          error_rate=0.005, fmt="fastq")
+    ref, _ = _full_compare(oracle, ref_driver, paths, kp, threads=threads, enrich=20)
+    assert ref["cores"] > 10 and ref["enrichment_connections"] > 100 and ref["final_components"] == ref["cores"]
+
+
+@pytest.mark.parametrize("enrich,min_size", [(20, 5), (3, 3)])
+def test_merge_and_enrichment_long_reads(oracle, ref_driver, tmp_path, enrich, min_size):
+    # long noisy reads: k-mers occur several times per read, so the survivor keeps stale entries (quirk i)
+    paths, kp = datagen.make_diploid_case(str(tmp_path), genome_size=30000, divergence=0.02, k=15, read_len=2000, coverage=12, seed=21,
+                                          error_rate=0.05, length_sigma=0.5)
+    ref, _ = _full_compare(oracle, ref_driver, paths, kp, min_size=min_size, enrich=enrich)
+    assert ref["cores"] >= 1
 
 
 def test_non_acgt_and_crlf(oracle, ref_driver, tmp_path):
