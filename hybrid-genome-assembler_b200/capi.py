@@ -38,10 +38,22 @@ class _Components(C.Structure):
                 ("comp_label", u32p), ("comp_size", u32p)]
 
 
+class _Enrichment(C.Structure):
+    _fields_ = [("n_cores", C.c_uint64), ("core_id", u32p), ("core_off", u64p), ("core_read", u32p),
+                ("n_connections", C.c_uint64), ("conn_x", u32p), ("conn_y", u32p), ("conn_score", u32p),
+                ("n_final", C.c_uint64), ("final_id", u32p), ("final_off", u64p), ("final_read", u32p),
+                ("n_reads", C.c_uint64), ("read_id_first", C.c_uint32), ("assignment", u32p)]
+
+
+class _CoreKmers(C.Structure):
+    _fields_ = [("n_cores", C.c_uint64), ("off", u64p), ("kmer_id", u32p)]
+
+
 class Metrics(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("table_build_ms", "h2d_ms", "scan_ms", "index_ms", "pair_ms", "select_ms", "components_ms", "exchange_ms")] + \
                [(n, C.c_uint64) for n in ("n_bases", "n_reads", "n_hits", "n_pairs", "n_increments", "n_selected", "n_components", "table_bytes",
-                                          "filter_bytes", "pair_retries", "heavy_pivots", "kernel_launches", "table_overflow_keys", "mid_pivots", "n_candidates")]
+                                          "filter_bytes", "pair_retries", "heavy_pivots", "kernel_launches", "table_overflow_keys", "mid_pivots", "n_candidates")] + \
+               [("enrich_ms", C.c_double)] + [(n, C.c_uint64) for n in ("n_cores", "n_enrich_connections", "n_final_components")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -50,7 +62,8 @@ class Metrics(C.Structure):
 # every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
-           "hga_get_selection", "hga_components", "hga_get_components", "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
+           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers",
+           "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
 
 
 def library_path():
@@ -82,6 +95,10 @@ def load_library():
         lib.hga_get_selection.argtypes = [C.c_void_p, C.POINTER(_Selection)]
         lib.hga_components.argtypes = [C.c_void_p, C.c_int]
         lib.hga_get_components.argtypes = [C.c_void_p, C.POINTER(_Components)]
+        lib.hga_enrich.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        lib.hga_get_enrichment.argtypes = [C.c_void_p, C.POINTER(_Enrichment)]
+        lib.hga_get_purged_index.argtypes = [C.c_void_p, C.POINTER(_Index)]
+        lib.hga_get_core_kmers.argtypes = [C.c_void_p, C.POINTER(_CoreKmers)]
         lib.hga_metrics.argtypes = [C.c_void_p, C.POINTER(Metrics)]
         lib.hga_comm_unique_id.argtypes = [C.c_void_p]
         lib.hga_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64]
@@ -213,6 +230,31 @@ class Handle:
         _check(self.lib.hga_get_components(self._h, C.byref(out)))
         return dict(read_id_first=int(out.read_id_first), label=_arr(out.label, out.n_reads, np.uint32),
                     comp_label=_arr(out.comp_label, out.n_components, np.uint32), comp_size=_arr(out.comp_size, out.n_components, np.uint32))
+
+    def enrich(self, min_size=30, enrichment_min_score=20):
+        _check(self.lib.hga_enrich(self._h, int(min_size), int(enrichment_min_score)))
+
+    def get_enrichment(self):
+        out = _Enrichment()
+        _check(self.lib.hga_get_enrichment(self._h, C.byref(out)))
+        nc, nf = out.n_cores, out.n_final
+        core_off = _arr(out.core_off, nc + 1, np.uint64); final_off = _arr(out.final_off, nf + 1, np.uint64)
+        return dict(core_id=_arr(out.core_id, nc, np.uint32), core_off=core_off, core_read=_arr(out.core_read, int(core_off[-1]) if nc else 0, np.uint32),
+                    conn_x=_arr(out.conn_x, out.n_connections, np.uint32), conn_y=_arr(out.conn_y, out.n_connections, np.uint32),
+                    conn_score=_arr(out.conn_score, out.n_connections, np.uint32),
+                    final_id=_arr(out.final_id, nf, np.uint32), final_off=final_off, final_read=_arr(out.final_read, int(final_off[-1]) if nf else 0, np.uint32),
+                    read_id_first=int(out.read_id_first), assignment=_arr(out.assignment, out.n_reads, np.uint32))
+
+    def get_purged_index(self):
+        out = _Index()
+        _check(self.lib.hga_get_purged_index(self._h, C.byref(out)))
+        return _arr(out.off, out.n_kmers + 1, np.uint64), _arr(out.read_id, out.n_entries, np.uint32)
+
+    def get_core_kmers(self):
+        out = _CoreKmers()
+        _check(self.lib.hga_get_core_kmers(self._h, C.byref(out)))
+        off = _arr(out.off, out.n_cores + 1, np.uint64)
+        return off, _arr(out.kmer_id, int(off[-1]), np.uint32)
 
     def metrics(self):
         m = Metrics()

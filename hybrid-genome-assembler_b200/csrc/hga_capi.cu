@@ -135,7 +135,8 @@ void hga_destroy(hga_handle *h) {
                      &h->d_tile_state, &h->d_tile_dir, &h->d_scan_scalars, &h->d_x_slot, &h->d_x_row, &h->d_hit_kid, &h->d_g_kid, &h->d_g_row_off, &h->d_inv_off, &h->d_inv_row, &h->d_sort_a,
                      &h->d_sort_b, &h->d_sort_tmp, &h->d_pair_key, &h->d_pair_score, &h->d_pair_key2, &h->d_pair_score2, &h->d_pair_scalars,
                      &h->d_heavy_list, &h->d_mid_list, &h->d_heavy_tab, &h->d_pivot_flag, &h->d_hist, &h->d_sel_key, &h->d_sel_score, &h->d_sel_scalars, &h->d_parent,
-                     &h->d_comp_size, &h->d_comp_label, &h->d_comp_scalars, &h->d_export_a, &h->d_export_b, &h->d_export_c};
+                     &h->d_comp_size, &h->d_comp_label, &h->d_comp_scalars, &h->d_export_a, &h->d_export_b, &h->d_export_c, &h->d_enr_core_of,
+                     &h->d_enr_surv, &h->d_enr_R, &h->d_enr_scalars, &h->d_enr_keys, &h->d_enr_keys2, &h->d_enr_core_koff, &h->d_purged_off, &h->d_purged_row};
     for (DevBuf *b : dev) b->release();
     PinBuf *pin[] = {&h->h_row_off, &h->h_kid, &h->h_pos, &h->h_inv_off, &h->h_inv_read, &h->h_px, &h->h_py, &h->h_ps, &h->h_sx, &h->h_sy, &h->h_ss,
                      &h->h_label, &h->h_clabel, &h->h_csize, &h->h_scalars};
@@ -231,21 +232,19 @@ int hga_build_index(hga_handle *h) {
     return hga_index_run(h);
 }
 
-int hga_get_index(hga_handle *h, hga_index *out) {
-    if (!h || !out) { hga_set_error("NULL argument"); return HGA_E_ARG; }
-    if (!h->have_index) { hga_set_error("hga_get_index: no index"); return HGA_E_STATE; }
-    HGA_TRY(use_device(h));
-    const uint64_t K = h->n_kmers, E = h->inc_entries;
+// CSR by table slot (off u32[n_slots + 1], rows) -> CSR by the caller's kmer_id with read ids, in the pinned export buffers
+static int export_index(hga_handle *h, const uint32_t *d_off, const uint32_t *d_row, uint64_t E, hga_index *out) {
+    const uint64_t K = h->n_kmers;
     HGA_TRY(h->d_export_a.ensure((K + 2) * 8 * 2));
     HGA_TRY(h->d_export_b.ensure((E + 1) * 4));
     unsigned long long *len = h->d_export_a.as<unsigned long long>(), *off = len + (K + 2);
     const uint32_t *kid_slot = h->index_by_kid ? nullptr : h->table.kid_slot;
-    kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(kid_slot, h->index_key_div, h->d_inv_off.as<uint32_t>(), K, len);
+    kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(kid_slot, h->index_key_div, d_off, K, len);
     size_t tmp = 0;
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, off, K + 1, h->stream));
     HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, len, off, K + 1, h->stream));
-    if (K) kid_list_copy_kernel<<<grid_for(h, K * 32), 256, 0, h->stream>>>(kid_slot, h->index_key_div, h->d_inv_off.as<uint32_t>(), h->d_inv_row.as<uint32_t>(), off, K,
+    if (K) kid_list_copy_kernel<<<grid_for(h, K * 32), 256, 0, h->stream>>>(kid_slot, h->index_key_div, d_off, d_row, off, K,
                                                                           h->inc_row_first_id, h->d_export_b.as<uint32_t>());
     h->metrics.kernel_launches += 4;
     HGA_CUDA(cudaGetLastError());
@@ -256,6 +255,59 @@ int hga_get_index(hga_handle *h, hga_index *out) {
     HGA_CUDA(cudaStreamSynchronize(h->stream));
     out->n_kmers = K; out->n_entries = h->h_inv_off.as<uint64_t>()[K];
     out->off = h->h_inv_off.as<uint64_t>(); out->read_id = h->h_inv_read.as<uint32_t>();
+    return HGA_OK;
+}
+
+int hga_get_index(hga_handle *h, hga_index *out) {
+    if (!h || !out) { hga_set_error("NULL argument"); return HGA_E_ARG; }
+    if (!h->have_index) { hga_set_error("hga_get_index: no index"); return HGA_E_STATE; }
+    HGA_TRY(use_device(h));
+    return export_index(h, h->d_inv_off.as<uint32_t>(), h->d_inv_row.as<uint32_t>(), h->inc_entries, out);
+}
+
+int hga_enrich(hga_handle *h, int min_size, uint32_t enrichment_min_score) {
+    if (!h) { hga_set_error("NULL handle"); return HGA_E_ARG; }
+    HGA_TRY(use_device(h));
+    return hga_enrich_run(h, min_size, enrichment_min_score);
+}
+
+int hga_get_enrichment(hga_handle *h, hga_enrichment_t *out) {
+    if (!h || !out) { hga_set_error("NULL argument"); return HGA_E_ARG; }
+    if (!h->have_enrichment) { hga_set_error("hga_get_enrichment: no enrichment result"); return HGA_E_STATE; }
+    const EnrichResult &r = h->enrich;
+    out->n_cores = r.core_id.size(); out->core_id = r.core_id.data(); out->core_off = r.core_off.data(); out->core_read = r.core_read.data();
+    out->n_connections = r.conn_x.size(); out->conn_x = r.conn_x.data(); out->conn_y = r.conn_y.data(); out->conn_score = r.conn_score.data();
+    out->n_final = r.final_id.size(); out->final_id = r.final_id.data(); out->final_off = r.final_off.data(); out->final_read = r.final_read.data();
+    out->n_reads = r.assignment.size(); out->read_id_first = h->inc_row_first_id; out->assignment = r.assignment.data();
+    return HGA_OK;
+}
+
+int hga_get_purged_index(hga_handle *h, hga_index *out) {
+    if (!h || !out) { hga_set_error("NULL argument"); return HGA_E_ARG; }
+    if (!h->have_enrichment) { hga_set_error("hga_get_purged_index: no enrichment result"); return HGA_E_STATE; }
+    HGA_TRY(use_device(h));
+    return export_index(h, h->d_purged_off.as<uint32_t>(), h->d_purged_row.as<uint32_t>(), h->n_purged, out);
+}
+
+int hga_get_core_kmers(hga_handle *h, hga_core_kmers_t *out) {
+    if (!h || !out) { hga_set_error("NULL argument"); return HGA_E_ARG; }
+    if (!h->have_enrichment) { hga_set_error("hga_get_core_kmers: no enrichment result"); return HGA_E_STATE; }
+    HGA_TRY(use_device(h));
+    const uint64_t n = h->n_core_kmers, C = h->enrich.core_id.size();
+    HGA_TRY(h->d_export_a.ensure((n + 1) * 4 * 2));
+    uint32_t *d_slot = h->d_export_a.as<uint32_t>(), *d_kid = d_slot + (n + 1);
+    HGA_TRY(h->h_kid.ensure((n + 1) * 4));
+    HGA_TRY(h->h_row_off.ensure((C + 2) * 8));
+    if (n) {
+        low32_kernel<<<grid_for(h, n), 256, 0, h->stream>>>(h->d_enr_keys.as<uint64_t>(), n, d_slot);
+        slots_to_kids_kernel<<<grid_for(h, n), 256, 0, h->stream>>>(d_slot, h->table.slot_kid, n, d_kid);
+        h->metrics.kernel_launches += 2;
+        HGA_CUDA(cudaGetLastError());
+        HGA_CUDA(cudaMemcpyAsync(h->h_kid.p, d_kid, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    HGA_CUDA(cudaMemcpyAsync(h->h_row_off.p, h->d_enr_core_koff.p, (C + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    HGA_CUDA(cudaStreamSynchronize(h->stream));
+    out->n_cores = C; out->off = h->h_row_off.as<uint64_t>(); out->kmer_id = h->h_kid.as<uint32_t>();
     return HGA_OK;
 }
 

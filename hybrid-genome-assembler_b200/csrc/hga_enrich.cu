@@ -1,0 +1,412 @@
+// enrich: merge of the scaffold components, enrichment connections, restricted union-find, final merge.
+//
+// Replaces, in ReadClusteringEngine::run_clustering (clustering/ReadClusteringEngine.cpp):
+//   :763-764  union_find(...) roots + merge_components(scaffold_components)      (merge_components: :349-422)
+//   :785-794  get_connections(core_component_ids, enrichment_connections_min_score), union_find(conns, restricted = cores,
+//             2, -1), merge_components, get_component_ids(scaffold_component_min_size)
+// The tail / spectral block in between (:768-777) is SURVEY §8f-2 and not part of this stage: what runs here is the reference's
+// own path when it has at most two scaffold components or finds no strong tail connection.
+//
+// What the reference's merge does to the engine state, restated as data-parallel rules (oracle: orc_engine_merge):
+//   * the survivor of a component (element [0] = the root the sequential union_find ended with) receives the sorted UNIQUE
+//     union U_c of its members' k-mer id lists (:379, merge_n_vectors(unique = true));
+//   * every k-mer gets a removal list: each non-surviving member once per occurrence, the survivor ONCE if the k-mer is in
+//     U_c (:385-389). The purge (:395-419) is a two-pointer walk that STOPS when the removal list is exhausted and keeps only
+//     what it has copied so far. With R(k) = the largest removed id of k-mer k, the new list is therefore
+//         { e in list(k) : e < R(k), e in no core, or e a survivor and not the first of its copies }
+//     (entries >= R(k) are dropped whoever they belong to; a survivor holding the k-mer m times keeps m - 1 stale entries);
+//     k-mers no merged component holds are untouched.
+//   * enrichment score(c, y) = sum over k in U_c of the copies of y in the purged list of k, y != survivor(c) (:311-317).
+// The survivor ids matter (they enter R(k)), and they depend on the order the sequential union_find saw the edges in: the
+// roots are replayed on the host over the selected edges in the canonical order (score desc, x asc, y asc), union by size with
+// ties to y's root (:459-466) - O(M alpha), a few hundred ms for the 14 M selected edges of config 4. Everything proportional to
+// the incidence (E) runs on the GPU:
+//   enr_hit_keys_kernel      (core, slot) key per hit + member part of R(k)                       8 E B written
+//   CUB radix sort + unique  U_c for every core at once
+//   enr_survivor_max_kernel  survivor part of R(k)
+//   enr_purge_kernel         count / fill passes over the inverted index -> purged CSR           2 x 4 E B read, <= 4 E written
+//   enr_emit_kernel          (core, partner row) per (k in U_c, entry of purged list(k)), then radix sort + run-length encode
+//   enr_filter_kernel        score >= min, partner != survivor
+// The connection list that comes out is small (cores x partners); its canonical order, the restricted union-find over it and the
+// final membership are host code (sequential in the reference as well).
+#include "hga_internal.cuh"
+
+#include <algorithm>
+#include <numeric>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+namespace {
+
+inline int grid_for(const hga_handle *h, uint64_t n, int per_block = 256) {
+    return (int) std::max<uint64_t>(1, std::min<uint64_t>((n + per_block - 1) / per_block, (uint64_t) h->sm_count * 16));
+}
+
+// one warp per row: key = core << 32 | slot for hits of rows that belong to a core (n_cores << 32 otherwise: sorts last);
+// R[slot] = max(row + 1) over the core members that hold the k-mer
+__global__ void enr_hit_keys_kernel(const uint64_t *__restrict__ row_off, const uint32_t *__restrict__ hit_slot, uint64_t n_rows,
+                                    const int32_t *__restrict__ core_of, uint32_t n_cores, uint64_t *__restrict__ keys, uint32_t *R) {
+    const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t r = w; r < n_rows; r += warps) {
+        const uint64_t a = row_off[r], b = row_off[r + 1];
+        const int32_t c = core_of[r];
+        for (uint64_t i = a + lane; i < b; i += 32) {
+            if (c >= 0) {
+                const uint32_t slot = hit_slot[i];
+                keys[i] = ((uint64_t) (uint32_t) c << 32) | slot;
+                atomicMax(&R[slot], (uint32_t) r + 1);
+            } else {
+                keys[i] = (uint64_t) n_cores << 32;
+            }
+        }
+    }
+}
+
+// the survivor is scheduled for removal from every k-mer of its union, whether it holds the k-mer itself or not
+__global__ void enr_survivor_max_kernel(const uint64_t *__restrict__ ukeys, uint64_t n, const uint32_t *__restrict__ surv_row, uint32_t *R) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t k = ukeys[i];
+        atomicMax(&R[(uint32_t) k], surv_row[k >> 32] + 1);
+    }
+}
+
+// first position of every core's run in the sorted unique keys
+__global__ void enr_core_bounds_kernel(const uint64_t *__restrict__ ukeys, uint64_t n, uint32_t n_cores, unsigned long long *core_koff) {
+    for (uint64_t c = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; c <= n_cores; c += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t want = c << 32;
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (ukeys[mid] < want) lo = mid + 1; else hi = mid; }
+        core_koff[c] = lo;
+    }
+}
+
+// The purge of one inverted list. FILL = false: count the surviving entries; FILL = true: write them at out_off[slot].
+template<bool FILL>
+__global__ void enr_purge_kernel(const uint32_t *__restrict__ inv_off, const uint32_t *__restrict__ inv_row, uint32_t n_slots,
+                                 const uint32_t *__restrict__ R, const int32_t *__restrict__ core_of, const uint32_t *__restrict__ surv_row,
+                                 uint32_t *__restrict__ cnt, const uint32_t *__restrict__ out_off, uint32_t *__restrict__ out_row) {
+    for (uint64_t s = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t lo = inv_off[s], hi = inv_off[s + 1];
+        uint32_t n = 0;
+        uint32_t w = FILL ? out_off[s] : 0;
+        if (lo != hi) {
+            const uint32_t r1 = R[s];                 // largest removed row + 1; 0: no merged component holds this k-mer
+            if (r1 == 0) {
+                n = hi - lo;
+                if (FILL) for (uint32_t i = lo; i < hi; i++) out_row[w++] = inv_row[i];
+            } else {
+                uint32_t prev = 0xFFFFFFFFu;
+                for (uint32_t i = lo; i < hi; i++) {
+                    const uint32_t e = inv_row[i];
+                    if (e + 1 >= r1) break;           // the walk ends with the removal list: e >= R(k) is dropped (ascending list)
+                    const int32_t c = core_of[e];
+                    const bool keep = c < 0 || (surv_row[c] == e && prev == e);   // stale copies of a survivor stay
+                    prev = e;
+                    if (keep) { n++; if (FILL) out_row[w++] = e; }
+                }
+            }
+        }
+        if (!FILL) cnt[s] = n;
+    }
+}
+
+__global__ void enr_emit_len_kernel(const uint64_t *__restrict__ ukeys, uint64_t n, const uint32_t *__restrict__ p_off, unsigned long long *len) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t slot = (uint32_t) ukeys[i];
+        len[i] = p_off[slot + 1] - p_off[slot];
+    }
+}
+
+// (core, partner row) for every entry of the purged list of every k-mer of every core
+__global__ void enr_emit_kernel(const uint64_t *__restrict__ ukeys, uint64_t n, const uint32_t *__restrict__ p_off, const uint32_t *__restrict__ p_row,
+                                const unsigned long long *__restrict__ at, uint64_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t k = ukeys[i];
+        const uint32_t slot = (uint32_t) k;
+        const uint64_t hi_bits = k & 0xFFFFFFFF00000000ull;
+        unsigned long long w = at[i];
+        for (uint32_t j = p_off[slot]; j < p_off[slot + 1]; j++) out[w++] = hi_bits | p_row[j];
+    }
+}
+
+// :317 erase(pivot), :320 score >= min_score
+__global__ void enr_filter_kernel(const uint64_t *__restrict__ run_key, const uint32_t *__restrict__ run_len, uint64_t n_runs, const uint32_t *__restrict__ surv_row,
+                                  uint32_t min_score, uint32_t first_id, uint32_t *cx, uint32_t *cy, uint32_t *cs, unsigned long long *count) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_runs; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t k = run_key[i];
+        const uint32_t s = surv_row[k >> 32], y = (uint32_t) k, v = run_len[i];
+        if (y != s && v >= min_score) {
+            const unsigned long long w = atomicAdd(count, 1ull);
+            cx[w] = s + first_id; cy[w] = y + first_id; cs[w] = v;
+        }
+    }
+}
+
+__global__ void enr_key_rows_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *x, uint32_t *y) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        x[i] = (uint32_t) (keys[i] >> 32); y[i] = (uint32_t) keys[i];
+    }
+}
+
+uint32_t dsu_find(std::vector<uint32_t> &parent, uint32_t v) {
+    uint32_t r = v;
+    while (parent[r] != r) r = parent[r];
+    while (parent[v] != r) { const uint32_t nx = parent[v]; parent[v] = r; v = nx; }
+    return r;
+}
+
+struct Conn { uint32_t x, y, s; };
+
+}  // namespace
+
+int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
+    if (!h->have_selection || !h->have_index || !h->have_scan) { hga_set_error("hga_enrich: needs hga_scan, hga_build_index and hga_select_edges"); return HGA_E_STATE; }
+    if (h->comm && hga_comm_size(h) > 1) { hga_set_error("hga_enrich: not available with a communicator yet (single GPU only)"); return HGA_E_STATE; }
+    if (min_size < 2) { hga_set_error("hga_enrich: min_size must be >= 2 (a core is a merged component)"); return HGA_E_ARG; }
+    h->have_enrichment = false;
+    EnrichResult &res = h->enrich;
+    res = EnrichResult();
+    const uint64_t n = h->inc_rows, M = h->n_selected, E = h->n_hits;
+    const uint32_t first_id = h->inc_row_first_id;
+    const uint32_t n_slots = h->index_keys;
+    StageTimer timer(h, &h->metrics.enrich_ms);
+
+    // ---- 1. roots of the sequential union_find (:453-478) over the selected edges in canonical order ----------------------
+    std::vector<uint32_t> ex(M), ey(M);
+    if (M) {
+        // the selection is stored in (x, y) order; a stable descending sort by score gives (score desc, x asc, y asc)
+        HGA_TRY(h->d_export_a.ensure((M + 1) * 8));
+        HGA_TRY(h->d_export_b.ensure((M + 1) * 4 * 3));
+        uint64_t *d_key = h->d_export_a.as<uint64_t>();
+        uint32_t *d_score = h->d_export_b.as<uint32_t>(), *d_x = d_score + (M + 1), *d_y = d_x + (M + 1);
+        size_t tmp = 0;
+        HGA_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, h->d_sel_score.as<uint32_t>(), d_score, h->d_sel_key.as<uint64_t>(), d_key, M, 0, 32, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+        HGA_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp.p, tmp, h->d_sel_score.as<uint32_t>(), d_score, h->d_sel_key.as<uint64_t>(), d_key, M, 0, 32, h->stream));
+        enr_key_rows_kernel<<<grid_for(h, M), 256, 0, h->stream>>>(d_key, M, d_x, d_y);
+        h->metrics.kernel_launches += 6;
+        HGA_CUDA(cudaGetLastError());
+        HGA_CUDA(cudaMemcpyAsync(ex.data(), d_x, M * 4, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaMemcpyAsync(ey.data(), d_y, M * 4, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    std::vector<uint32_t> parent(n + 1), size(n + 1, 1);
+    std::vector<uint8_t> touched(n + 1, 0);
+    std::iota(parent.begin(), parent.end(), 0u);
+    for (uint64_t i = 0; i < M; i++) {
+        // the reference's list holds (x, y) and (y, x) back to back; the second is a no-op after the first
+        const uint32_t x = ex[i], y = ey[i];
+        touched[x] = touched[y] = 1;                                                           // :427-431
+        const uint32_t px = dsu_find(parent, x), py = dsu_find(parent, y);                     // :453-454
+        if (px == py) continue;                                                                // :455
+        const uint32_t bigger = size[px] > size[py] ? px : py, smaller = bigger == px ? py : px;   // :459-466 (ties: y's root)
+        parent[smaller] = bigger;                                                              // :468-470
+        size[bigger] += size[smaller];                                                         // :471
+    }
+    // cores = components with >= min_size vertices (:482-486), identified by their root = element [0] = the survivor (:366)
+    std::vector<int32_t> core_of(n + 1, -1);
+    std::vector<uint32_t> surv_row;
+    for (uint64_t r = 0; r < n; r++)
+        if (touched[r] && parent[r] == r && size[r] >= (uint32_t) min_size) { core_of[r] = (int32_t) surv_row.size(); surv_row.push_back((uint32_t) r); }
+    const uint32_t C = (uint32_t) surv_row.size();
+    for (uint64_t r = 0; r < n; r++)
+        if (touched[r] && parent[r] != r) core_of[r] = core_of[dsu_find(parent, (uint32_t) r)];
+    res.core_id.resize(C);
+    res.core_off.assign(C + 1, 0);
+    for (uint32_t c = 0; c < C; c++) { res.core_id[c] = surv_row[c] + first_id; res.core_off[c + 1] = size[surv_row[c]]; }
+    for (uint32_t c = 0; c < C; c++) res.core_off[c + 1] += res.core_off[c];
+    res.core_read.resize(res.core_off[C]);
+    {
+        std::vector<uint64_t> cur(res.core_off.begin(), res.core_off.end() - 1);
+        for (uint64_t r = 0; r < n; r++) if (core_of[r] >= 0) res.core_read[cur[core_of[r]]++] = (uint32_t) r + first_id;
+    }
+
+    // ---- 2. GPU: unions, removal bounds, purged index ----------------------------------------------------------------------
+    HGA_TRY(h->d_enr_core_of.ensure((n + 1) * 4));
+    HGA_TRY(h->d_enr_surv.ensure(((size_t) C + 1) * 4));
+    HGA_TRY(h->d_enr_R.ensure(((size_t) n_slots + 1) * 4));
+    HGA_TRY(h->d_enr_scalars.ensure(64));
+    int32_t *d_core_of = h->d_enr_core_of.as<int32_t>();
+    uint32_t *d_surv = h->d_enr_surv.as<uint32_t>(), *d_R = h->d_enr_R.as<uint32_t>();
+    unsigned long long *d_count = h->d_enr_scalars.as<unsigned long long>();
+    HGA_CUDA(cudaMemcpyAsync(d_core_of, core_of.data(), (n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    if (C) HGA_CUDA(cudaMemcpyAsync(d_surv, surv_row.data(), (size_t) C * 4, cudaMemcpyHostToDevice, h->stream));
+    HGA_CUDA(cudaMemsetAsync(d_R, 0, ((size_t) n_slots + 1) * 4, h->stream));
+
+    uint64_t n_u = 0;
+    HGA_TRY(h->d_enr_keys.ensure((E + 1) * 8));
+    HGA_TRY(h->d_enr_keys2.ensure((E + 1) * 8));
+    uint64_t *d_keys = h->d_enr_keys.as<uint64_t>(), *d_ukeys = h->d_enr_keys2.as<uint64_t>();
+    if (E && C) {
+        enr_hit_keys_kernel<<<grid_for(h, n * 32), 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->d_hit_slot.as<uint32_t>(), n, d_core_of, C, d_keys, d_R);
+        const int bits = 32 + (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) C + 1), 1);
+        size_t tmp = 0, tmp2 = 0;
+        HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_keys, d_ukeys, E, 0, bits, h->stream));
+        HGA_CUDA(cub::DeviceSelect::Unique(nullptr, tmp2, d_ukeys, d_keys, d_count, E, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(std::max(tmp, tmp2) + 16));
+        HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, tmp, d_keys, d_ukeys, E, 0, bits, h->stream));
+        HGA_CUDA(cub::DeviceSelect::Unique(h->d_sort_tmp.p, tmp2, d_ukeys, d_keys, d_count, E, h->stream));   // unique keys back in d_keys
+        h->metrics.kernel_launches += (uint64_t) (bits + 7) / 8 + 4;
+        HGA_CUDA(cudaGetLastError());
+        unsigned long long nu = 0;
+        HGA_CUDA(cudaMemcpyAsync(&nu, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+        if (nu) {   // the filler key (hits of rows outside every core) sorts last
+            uint64_t last = 0;
+            HGA_CUDA(cudaMemcpy(&last, d_keys + (nu - 1), 8, cudaMemcpyDeviceToHost));
+            if (last == ((uint64_t) C << 32)) nu--;
+        }
+        n_u = nu;
+    }
+    const uint64_t *d_u = d_keys;      // sorted unique (core, slot)
+    HGA_TRY(h->d_enr_core_koff.ensure(((size_t) C + 2) * 8));
+    unsigned long long *d_core_koff = h->d_enr_core_koff.as<unsigned long long>();
+    enr_core_bounds_kernel<<<grid_for(h, (uint64_t) C + 1), 256, 0, h->stream>>>(d_u, n_u, C, d_core_koff);
+    if (n_u) enr_survivor_max_kernel<<<grid_for(h, n_u), 256, 0, h->stream>>>(d_u, n_u, d_surv, d_R);
+    h->metrics.kernel_launches += 2;
+
+    HGA_TRY(h->d_purged_off.ensure(((size_t) n_slots + 2) * 4 * 2));
+    uint32_t *d_cnt = h->d_purged_off.as<uint32_t>() + (n_slots + 2), *d_poff = h->d_purged_off.as<uint32_t>();
+    const uint32_t *inv_off = h->d_inv_off.as<uint32_t>(), *inv_row = h->d_inv_row.as<uint32_t>();
+    enr_purge_kernel<false><<<grid_for(h, n_slots), 256, 0, h->stream>>>(inv_off, inv_row, n_slots, d_R, d_core_of, d_surv, d_cnt, nullptr, nullptr);
+    HGA_CUDA(cudaMemsetAsync(d_cnt + n_slots, 0, 4, h->stream));
+    {
+        size_t tmp = 0;
+        HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_cnt, d_poff, (uint64_t) n_slots + 1, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+        HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, d_cnt, d_poff, (uint64_t) n_slots + 1, h->stream));
+    }
+    uint32_t n_purged = 0;
+    HGA_CUDA(cudaMemcpyAsync(&n_purged, d_poff + n_slots, 4, cudaMemcpyDeviceToHost, h->stream));
+    HGA_CUDA(cudaStreamSynchronize(h->stream));
+    HGA_TRY(h->d_purged_row.ensure(((size_t) n_purged + 1) * 4));
+    uint32_t *d_prow = h->d_purged_row.as<uint32_t>();
+    enr_purge_kernel<true><<<grid_for(h, n_slots), 256, 0, h->stream>>>(inv_off, inv_row, n_slots, d_R, d_core_of, d_surv, nullptr, d_poff, d_prow);
+    h->metrics.kernel_launches += 4;
+    HGA_CUDA(cudaGetLastError());
+    h->n_purged = n_purged;
+    h->n_core_kmers = n_u;
+
+    // ---- 3. GPU: enrichment connections = run lengths of the sorted (core, partner) emissions ------------------------------
+    std::vector<Conn> conns;
+    if (n_u) {
+        HGA_TRY(h->d_export_a.ensure((n_u + 2) * 8 * 2));
+        unsigned long long *d_len = h->d_export_a.as<unsigned long long>(), *d_at = d_len + (n_u + 2);
+        enr_emit_len_kernel<<<grid_for(h, n_u), 256, 0, h->stream>>>(d_u, n_u, d_poff, d_len);
+        HGA_CUDA(cudaMemsetAsync(d_len + n_u, 0, 8, h->stream));
+        size_t tmp = 0;
+        HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_len, d_at, n_u + 1, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+        HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, d_len, d_at, n_u + 1, h->stream));
+        unsigned long long n_emit = 0;
+        HGA_CUDA(cudaMemcpyAsync(&n_emit, d_at + n_u, 8, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+        h->metrics.kernel_launches += 3;
+        if (n_emit) {
+            HGA_TRY(h->d_enr_keys2.ensure((n_emit + 1) * 8));          // d_ukeys is free again (the unique keys live in d_keys)
+            HGA_TRY(h->d_export_b.ensure((n_emit + 1) * 8));
+            HGA_TRY(h->d_export_c.ensure((n_emit + 1) * 4 * 4));
+            uint64_t *d_emit = h->d_enr_keys2.as<uint64_t>(), *d_sorted = h->d_export_b.as<uint64_t>();
+            enr_emit_kernel<<<grid_for(h, n_u), 256, 0, h->stream>>>(d_u, n_u, d_poff, d_prow, d_at, d_emit);
+            const int bits = 32 + (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) C + 1), 1);
+            size_t t1 = 0, t2 = 0;
+            uint32_t *d_run_len = h->d_export_c.as<uint32_t>();
+            HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, t1, d_emit, d_sorted, n_emit, 0, bits, h->stream));
+            HGA_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, t2, d_sorted, d_emit, d_run_len, d_count, n_emit, h->stream));
+            HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
+            HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, t1, d_emit, d_sorted, n_emit, 0, bits, h->stream));
+            HGA_CUDA(cub::DeviceRunLengthEncode::Encode(h->d_sort_tmp.p, t2, d_sorted, d_emit, d_run_len, d_count, n_emit, h->stream));   // run keys in d_emit
+            unsigned long long n_runs = 0;
+            HGA_CUDA(cudaMemcpyAsync(&n_runs, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            uint32_t *d_cx = d_run_len + (n_emit + 1), *d_cy = d_cx + (n_emit + 1), *d_cs = d_cy + (n_emit + 1);
+            HGA_CUDA(cudaMemsetAsync(d_count, 0, 8, h->stream));
+            enr_filter_kernel<<<grid_for(h, n_runs), 256, 0, h->stream>>>(d_emit, d_run_len, n_runs, d_surv, min_score, first_id, d_cx, d_cy, d_cs, d_count);
+            h->metrics.kernel_launches += (uint64_t) (bits + 7) / 8 + 6;
+            HGA_CUDA(cudaGetLastError());
+            unsigned long long n_conn = 0;
+            HGA_CUDA(cudaMemcpyAsync(&n_conn, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            std::vector<uint32_t> cx(n_conn), cy(n_conn), cs(n_conn);
+            if (n_conn) {
+                HGA_CUDA(cudaMemcpyAsync(cx.data(), d_cx, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
+                HGA_CUDA(cudaMemcpyAsync(cy.data(), d_cy, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
+                HGA_CUDA(cudaMemcpyAsync(cs.data(), d_cs, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
+                HGA_CUDA(cudaStreamSynchronize(h->stream));
+            }
+            conns.resize(n_conn);
+            for (uint64_t i = 0; i < n_conn; i++) conns[i] = {cx[i], cy[i], cs[i]};
+        }
+    }
+
+    // ---- 4. host: canonical order, restricted union_find (:424-489 with restricted = cores, min 2, max -1), final merge -----
+    std::sort(conns.begin(), conns.end(), [](const Conn &a, const Conn &b) {
+        if (a.s != b.s) return a.s > b.s;
+        const uint32_t amin = std::min(a.x, a.y), amax = std::max(a.x, a.y), bmin = std::min(b.x, b.y), bmax = std::max(b.x, b.y);
+        if (amin != bmin) return amin < bmin;
+        if (amax != bmax) return amax < bmax;
+        return a.x < b.x;
+    });
+    res.conn_x.resize(conns.size()); res.conn_y.resize(conns.size()); res.conn_score.resize(conns.size());
+    for (size_t i = 0; i < conns.size(); i++) { res.conn_x[i] = conns[i].x; res.conn_y[i] = conns[i].y; res.conn_score[i] = conns[i].s; }
+
+    std::iota(parent.begin(), parent.end(), 0u);
+    std::fill(size.begin(), size.end(), 1u);
+    std::vector<uint8_t> restricted(n + 1, 0), affected(n + 1, 0);
+    for (uint32_t c = 0; c < C; c++) restricted[surv_row[c]] = 1;
+    for (const Conn &cn : conns) {
+        const uint32_t x = cn.x - first_id, y = cn.y - first_id;
+        affected[x] = affected[y] = 1;
+        const uint32_t px = dsu_find(parent, x), py = dsu_find(parent, y);
+        if (px == py) continue;
+        if (restricted[px] && restricted[py]) continue;                                        // :456
+        const uint32_t bigger = size[px] > size[py] ? px : py, smaller = bigger == px ? py : px;
+        parent[smaller] = bigger;
+        size[bigger] += size[smaller];
+        restricted[bigger] |= restricted[smaller];                                             // :478
+    }
+    // final id of every read: the root of its enrichment component when that has >= 2 vertices (union_find's min_size = 2),
+    // otherwise the id it had; a core's members follow their survivor. get_component_ids keeps ids with >= min_size reads.
+    std::vector<uint32_t> final_of(n + 1, 0xFFFFFFFFu);    // row -> final survivor row
+    for (uint64_t r = 0; r < n; r++) {
+        uint32_t v;
+        if (core_of[r] >= 0) v = surv_row[core_of[r]];
+        else if (affected[r]) v = (uint32_t) r;
+        else continue;
+        if (affected[v]) v = dsu_find(parent, v);
+        final_of[r] = v;
+    }
+    std::vector<uint32_t> fcount(n + 1, 0);
+    for (uint64_t r = 0; r < n; r++) if (final_of[r] != 0xFFFFFFFFu) fcount[final_of[r]]++;
+    // components ordered by their smallest member
+    std::vector<uint32_t> order_of(n + 1, 0xFFFFFFFFu);
+    uint32_t n_final = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        const uint32_t f = final_of[r];
+        if (f == 0xFFFFFFFFu || fcount[f] < (uint32_t) min_size) continue;
+        if (order_of[f] == 0xFFFFFFFFu) { order_of[f] = n_final++; res.final_id.push_back(f + first_id); res.final_off.push_back(fcount[f]); }
+    }
+    {
+        uint64_t acc = 0;
+        for (auto &v : res.final_off) { const uint64_t c = v; v = acc; acc += c; }
+        res.final_off.push_back(acc);
+        res.final_read.resize(acc);
+        std::vector<uint64_t> cur(res.final_off.begin(), res.final_off.end() - 1);
+        res.assignment.assign(n, 0);
+        for (uint64_t r = 0; r < n; r++) {
+            const uint32_t f = final_of[r];
+            if (f == 0xFFFFFFFFu || order_of[f] == 0xFFFFFFFFu) continue;
+            res.final_read[cur[order_of[f]]++] = (uint32_t) r + first_id;
+            res.assignment[r] = f + first_id;
+        }
+    }
+    timer.stop();
+    h->metrics.n_cores = C; h->metrics.n_enrich_connections = conns.size(); h->metrics.n_final_components = n_final;
+    h->have_enrichment = true;
+    return HGA_OK;
+}

@@ -225,6 +225,15 @@ __host__ __device__ __forceinline__ uint32_t hga_locality_hash(uint64_t kmer, co
 // ------------------------------------------------------------------------------------------------
 struct hga_comm;   // NCCL state, hga_comm.cu
 
+// host-side result of hga_enrich (small: cores, enrichment connections, final membership)
+struct EnrichResult {
+    std::vector<uint32_t> core_id, core_read;           // survivor ids ascending; members ascending inside a core
+    std::vector<uint64_t> core_off;
+    std::vector<uint32_t> conn_x, conn_y, conn_score;   // directed (core survivor -> partner), canonical order
+    std::vector<uint32_t> final_id, final_read, assignment;
+    std::vector<uint64_t> final_off;
+};
+
 struct hga_handle {
     int device = 0;
     int k = 0;
@@ -285,6 +294,12 @@ struct hga_handle {
     uint64_t n_components = 0;
     bool have_components = false;
 
+    // merge + enrichment (hga_enrich.cu)
+    DevBuf d_enr_core_of, d_enr_surv, d_enr_R, d_enr_scalars, d_enr_keys, d_enr_keys2, d_enr_core_koff, d_purged_off, d_purged_row;
+    uint64_t n_purged = 0, n_core_kmers = 0;
+    EnrichResult enrich;
+    bool have_enrichment = false;
+
     // host mirrors for hga_get_*
     PinBuf h_row_off, h_kid, h_pos, h_inv_off, h_inv_read, h_px, h_py, h_ps, h_sx, h_sy, h_ss, h_label, h_clabel, h_csize, h_scalars;
     DevBuf d_export_a, d_export_b, d_export_c;
@@ -302,6 +317,7 @@ int hga_index_run(hga_handle *h);
 int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
 int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold);
 int hga_cc_run(hga_handle *h, int min_size);
+int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score);
 
 // multi-GPU hooks (hga_comm.cu); all are no-ops / never called without a communicator
 int hga_comm_build_global_index(hga_handle *h);

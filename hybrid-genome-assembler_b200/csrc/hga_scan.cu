@@ -514,7 +514,7 @@ int launch_scan(hga_handle *h, const ScanParams &p, int grid) {
 }  // namespace
 
 int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, const char *h_bases) {
-    h->have_scan = h->have_index = h->have_pairs = h->have_selection = h->have_components = false;
+    h->have_scan = h->have_index = h->have_pairs = h->have_selection = h->have_components = h->have_enrichment = false;
     h->n_reads = n_reads; h->n_bases = n_bases; h->n_hits = 0;
     if (n_reads >= (1ull << 32) - 1) { hga_set_error("hga_scan: more than 2^32-2 reads per GPU"); return HGA_E_ARG; }
     HGA_TRY(h->d_row_off.ensure((n_reads + 1) * 8));

@@ -12,6 +12,8 @@
  *   hga_pair_count       <- get_connections / get_all_connections           clustering/ReadClusteringEngine.cpp:301-339
  *   hga_select_edges     <- the 15 % slice / --sc_score filter              clustering/ReadClusteringEngine.cpp:748-756
  *   hga_components       <- union_find(edges, {}, min, -1)                  clustering/ReadClusteringEngine.cpp:424-489, call :763
+ *   hga_enrich           <- merge_components(scaffolds), get_connections(cores, min), union_find(conns, cores, 2, -1),
+ *                           merge_components, get_component_ids             clustering/ReadClusteringEngine.cpp:349-422, :764, :785-794
  *
  * Conventions
  *   - every function returns 0 on success, non-zero on failure; hga_last_error() gives the message
@@ -126,6 +128,40 @@ typedef struct {
 int hga_components(hga_handle *h, int min_size);
 int hga_get_components(hga_handle *h, hga_components_t *out);
 
+/* Merge of the scaffold components + enrichment: everything run_clustering does after the scaffold union_find
+ * EXCEPT the tail / spectral block (:768-777), i.e. the reference's path when it has at most two scaffold components or no strong
+ * tail connection. Needs hga_scan, hga_build_index and hga_select_edges on this handle (single GPU).
+ *   cores          : the components of the selected edges with >= min_size reads, identified by the SURVIVOR the reference's
+ *                    sequential union_find would end with under the canonical edge order (element [0], :366)
+ *   purged index   : kmer_component_index after merge_components (:395-419), including its truncation at the largest removed id
+ *   connections    : get_connections(cores, enrichment_min_score) on the merged state, directed core -> partner, canonical order
+ *   final          : components after union_find(connections, restricted = cores, 2, -1) + merge; id = surviving component id */
+int hga_enrich(hga_handle *h, int min_size, uint32_t enrichment_min_score);
+typedef struct {
+    uint64_t n_cores;
+    const uint32_t *core_id;       /* n_cores, ascending */
+    const uint64_t *core_off;      /* n_cores + 1 */
+    const uint32_t *core_read;     /* member read ids, ascending inside a core */
+    uint64_t n_connections;
+    const uint32_t *conn_x, *conn_y, *conn_score;
+    uint64_t n_final;
+    const uint32_t *final_id;      /* ordered by the smallest member */
+    const uint64_t *final_off;     /* n_final + 1 */
+    const uint32_t *final_read;    /* ascending inside a component */
+    uint64_t n_reads;              /* assignment covers read ids read_id_first .. read_id_first + n_reads - 1 */
+    uint32_t read_id_first;
+    const uint32_t *assignment;    /* final component id of the read, 0 = in no exported component */
+} hga_enrichment_t;
+int hga_get_enrichment(hga_handle *h, hga_enrichment_t *out);
+/* the purged inverted index (same layout as hga_get_index) and the merged k-mer id list of every core (off[n_cores + 1]) */
+int hga_get_purged_index(hga_handle *h, hga_index *out);
+typedef struct {
+    uint64_t n_cores;
+    const uint64_t *off;
+    const uint32_t *kmer_id;       /* unique inside a core, unordered */
+} hga_core_kmers_t;
+int hga_get_core_kmers(hga_handle *h, hga_core_kmers_t *out);
+
 /* Per-stage device time (CUDA events on the handle's stream) and counters of the most recent run. */
 typedef struct {
     double table_build_ms, h2d_ms, scan_ms, index_ms, pair_ms, select_ms, components_ms, exchange_ms;
@@ -135,6 +171,8 @@ typedef struct {
     uint64_t table_overflow_keys; /* keys that did not fit their locality chain (stored in the overflow region) */
     uint64_t mid_pivots;       /* pivot rows whose partner set overflowed the per-warp accumulator (tier 2) */
     uint64_t n_candidates;     /* windows that passed the membership filter in the last scan (hits + false positives) */
+    double enrich_ms;          /* hga_enrich, host replay of the union_find roots included */
+    uint64_t n_cores, n_enrich_connections, n_final_components;
 } hga_metrics_t;
 int hga_metrics(hga_handle *h, hga_metrics_t *out);
 

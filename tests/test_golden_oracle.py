@@ -52,3 +52,16 @@ def test_hot_path_golden(oracle, name):
     assert compare.components_partition(co, cm) == compare.components_partition(ref["comp_off"], ref["comp_read"])
     assert compare.tree_edges(to, tx, ty) == compare.tree_edges(ref["tree_off"], ref["tree_x"], ref["tree_y"])
     assert len(compare.components_partition(co, cm)) == ref["scaffold_components"]
+
+
+@pytest.mark.parametrize("name", golden_util.ENRICH_CASES)
+def test_merge_enrichment_golden(oracle, name):
+    """merge_components + enrichment + final merge against the dump of the real reference"""
+    import oracle_lib
+    c = golden_util.load_case(name)
+    ref = c["ref"]
+    res = oracle.run(c["bases"], c["seq_off"], c["k"], c["kmers"], fraction=c["fraction"], min_size=c["min_size"])
+    assert res["cut_n"] == ref["cut_n"] and res["cut_score"] == ref["cut_score"]
+    e = oracle_lib.enrich(oracle, res, len(c["kmers"]), min_size=c["min_size"], enrich_min=c["enrich"])
+    compare.check_enrichment(ref, e, c["kmers"])
+    assert len(e["final_id"]) == ref["final_components"] and ref["cores"] >= 2

@@ -58,3 +58,41 @@ def test_engine_mirror_on_golden():
     m = np.isin(ref["conn_x"], ids) & (ref["conn_score"] >= 20)
     assert np.array_equal(gx, ref["conn_x"][m]) and np.array_equal(gy, ref["conn_y"][m]) and np.array_equal(gs, ref["conn_score"][m])
     eng.close()
+
+
+def _gpu_enrichment(h, min_size, enrich_min):
+    """hga_enrich result in the shape compare.check_enrichment expects"""
+    h.enrich(min_size=min_size, enrichment_min_score=enrich_min)
+    e = h.get_enrichment()
+    ko, kk = h.get_core_kmers()
+    po, pr = h.get_purged_index()
+    co = e["core_off"].astype(np.int64); fo = e["final_off"].astype(np.int64); ko = ko.astype(np.int64)
+    return dict(core_id=e["core_id"], core_kmers=[kk[ko[i]:ko[i + 1]] for i in range(len(ko) - 1)],
+                core_reads=[e["core_read"][co[i]:co[i + 1]] for i in range(len(co) - 1)], purged_off=po, purged_read=pr,
+                econn=(e["conn_x"], e["conn_y"], e["conn_score"].astype(np.uint64)), final_id=e["final_id"],
+                final_reads=[e["final_read"][fo[i]:fo[i + 1]] for i in range(len(fo) - 1)], assignment=e["assignment"], read_id_first=e["read_id_first"])
+
+
+@pytest.mark.parametrize("name", golden_util.ENRICH_CASES)
+def test_cuda_merge_enrichment_vs_reference_golden(name):
+    """SURVEY §8f-1 through the C-ABI: cores (reference survivor ids), merged k-mer lists, purged index, enrichment connections,
+    final components, against the dump of the real reference"""
+    import hga_b200
+    c = golden_util.load_case(name)
+    ref = c["ref"]
+    with hga_b200.Handle(c["kmers"], c["k"]) as h:
+        h.scan(c["bases"], c["seq_off"])
+        h.build_index()
+        h.pair_count(min_score=1)
+        h.select_edges(fraction=c["fraction"])
+        sel = h.get_selection()
+        assert sel["n_directed"] == ref["cut_n"] and sel["cut_score"] == ref["cut_score"]
+        e = _gpu_enrichment(h, c["min_size"], c["enrich"])
+        compare.check_enrichment(ref, e, c["kmers"])
+        # assignment = final membership
+        a = e["assignment"]
+        for fid, reads in zip(e["final_id"], e["final_reads"]):
+            assert np.all(a[reads - e["read_id_first"]] == fid)
+        assert int((a != 0).sum()) == sum(len(r) for r in e["final_reads"])
+        m = h.metrics()
+        assert m["n_cores"] == ref["cores"] and m["n_final_components"] == ref["final_components"]

@@ -234,3 +234,48 @@ def test_host_scan_pipelined_chunks(oracle, monkeypatch):
         m = h.metrics()
     assert np.array_equal(row_off, ref_ro) and np.array_equal(kid, ref_kid) and np.array_equal(pos, ref_pos)
     assert m["h2d_ms"] > 0
+
+
+@pytest.mark.parametrize("case", ["short", "long", "long_low_threshold", "no_cores"])
+def test_merge_and_enrichment(oracle, case):
+    """SURVEY §8f-1 (hga_enrich) against the C restatement of merge_components / get_connections / restricted union_find"""
+    import hga_b200
+    import oracle_lib
+    from test_gpu_golden import _gpu_enrichment
+    if case == "short":
+        a = datagen.random_genome(30000, 41); b = datagen.mutate(a, 0.03, 42); k = 19; min_size, enrich_min = 30, 20
+        reads = datagen.sample_reads(a, 6000, 150, 43, error_rate=0.005) + datagen.sample_reads(b, 6000, 150, 44, error_rate=0.005)
+    elif case == "no_cores":
+        a = datagen.random_genome(5000, 45); b = datagen.mutate(a, 0.03, 46); k = 19; min_size, enrich_min = 30, 20
+        reads = datagen.sample_reads(a, 60, 150, 47) + datagen.sample_reads(b, 60, 150, 48)
+    else:
+        a = datagen.random_genome(60000, 51); b = datagen.mutate(a, 0.02, 52); k = 15
+        min_size, enrich_min = (5, 20) if case == "long" else (3, 2)
+        reads = datagen.sample_reads(a, 350, 2000, 53, error_rate=0.05, length_sigma=0.5) + datagen.sample_reads(b, 350, 2000, 54, error_rate=0.05, length_sigma=0.5)
+    bases, off = _pack([datagen.to_ascii(r) for r in reads])
+    kmers = datagen.discriminative_kmers([a, b], k)
+    res = oracle.run(bases, off, k, kmers, min_size=min_size)
+    want = oracle_lib.enrich(oracle, res, len(kmers), min_size=min_size, enrich_min=enrich_min)
+    with hga_b200.Handle(kmers, k) as h:
+        h.scan(bases, off)
+        h.build_index()
+        h.pair_count(min_score=1)
+        h.select_edges(fraction=0.15)
+        got = _gpu_enrichment(h, min_size, enrich_min)
+    assert np.array_equal(got["core_id"], want["core_id"])
+    assert len(got["core_kmers"]) == len(want["core_kmers"])
+    for g, w in zip(got["core_kmers"], want["core_kmers"]):
+        assert np.array_equal(np.sort(g), w)
+    for g, w in zip(got["core_reads"], want["core_reads"]):
+        assert np.array_equal(g, w)
+    assert np.array_equal(got["purged_off"], want["purged_off"]) and np.array_equal(got["purged_read"], want["purged_read"])
+    for g, w in zip(got["econn"], want["econn"]):
+        assert np.array_equal(g, w)
+    assert np.array_equal(got["final_id"], want["final_id"])
+    assert len(got["final_reads"]) == len(want["final_reads"])
+    for g, w in zip(got["final_reads"], want["final_reads"]):
+        assert np.array_equal(g, w)
+    if case == "no_cores":
+        assert len(want["core_id"]) == 0 and len(got["final_id"]) == 0
+    else:
+        assert len(want["core_id"]) >= 2 and len(want["econn"][0]) > 0
