@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-mbp", type=float, default=0.25, help="haplotype size of the CPU-baseline sample (same generator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-enrich", action="store_true")
     return ap.parse_args()
 
 
@@ -386,6 +387,18 @@ def main():
         del hb, ho
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- SURVEY §8f-1 stage, reported beside the headline (not part of `value`): merge of the scaffold components + enrichment
+    enrich = None
+    if world == 1 and not args.no_enrich:
+        step_device()
+        h.enrich(min_size=30, enrichment_min_score=20)
+        t0 = time.perf_counter()
+        h.enrich(min_size=30, enrichment_min_score=20)
+        me = h.metrics()
+        enrich = {"ms": me["enrich_ms"], "wall_ms": (time.perf_counter() - t0) * 1e3, "cores": me["n_cores"], "connections": me["n_enrich_connections"],
+                  "final_components": me["n_final_components"],
+                  "note": "hga_enrich after the timed steps: host replay of the union_find roots + GPU merge / purge / enrichment connections + host restricted union_find"}
+
     # gather per-rank stage numbers (max over ranks)
     def maxr(v):
         if world == 1:
@@ -427,9 +440,9 @@ def main():
         # algorithmic bytes of the fused pack+scan kernel: 1 B/base ASCII read + 8 B per hit written
         scan_bytes_per_rank = (1.0 + 8.0 * hpb) * (total_bases_all / world)
         achieved = scan_bytes_per_rank / (scan_ms * 1e-3) / 1e9
-        # measured DRAM traffic of the scan kernel for the default workload on one GPU (ncu, profiles/r01w_scan_dram_isolation.md)
+        # measured DRAM traffic of the scan kernel for the default workload on one GPU (ncu --set full, profiles/r02b_scan_pair_ncu_full.csv)
         default_cfg = (args.genome_mbp, args.coverage, args.mean_len, args.divergence, args.error, args.seed) == (100.0, 50.0, 10000.0, 0.01, 0.05, 4000)
-        traffic_gb = 205.1 if (default_cfg and world == 1) else None
+        traffic_gb = 119.7 if (default_cfg and world == 1) else None
         ms_per_step = ms_total / args.steps
         line = {
             "metric": METRIC, "value": total_bases_all / (ms_per_step * 1e-3) / 1e9, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
@@ -446,12 +459,14 @@ def main():
                             "table_bytes": m["table_bytes"], "filter_bytes": m["filter_bytes"], "pair_mid_rows": m["mid_pivots"],
                             "pair_heavy_rows": m["heavy_pivots"], "exchange_ms": m["exchange_ms"]},
             "roofline": {"kernel": "scan_probe_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic_gb, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu capture profiles/r01w, same workload)",
+                         "traffic": traffic_gb, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu capture profiles/r02b, same workload)",
                          "algorithmic_gb_per_launch": scan_bytes_per_rank / 1e9, "peak_source": peak_src, "bytes_per_base": 1.0 + 8.0 * hpb,
                          "note": "achieved = (1 + 8*hits/base) B/base x bases per GPU / scan stage time (CUDA events on the launch stream; the stage also "
                                  "holds the 1/64 sampling pre-pass, the segment reorder and the row fix-up, so the kernel alone is slightly faster)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
         }
+        if enrich:
+            line["enrich"] = enrich
         if cpu:
             line["cpu_baseline"] = {"value": cpu["bases"] / (cpu["hot_ms"] * 1e-3) / 1e9, "unit": "Gbases/s", "cores": cpu["cores"], "kind": "reference",
                                     "sample": cpu["sample"], "scan_gbases_per_s": cpu["bases"] / (cpu["index_ms"] * 1e-3) / 1e9,

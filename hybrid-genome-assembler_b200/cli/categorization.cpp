@@ -5,12 +5,16 @@
 // clustering/ReadClusteringEngine.cpp:804-826).
 //
 // The arithmetic (scan -> membership -> incidence -> pair counting -> edge selection -> components) runs on the GPU
-// behind include/hga_b200.h; there is no CPU path. What is exported are the SCAFFOLD components (union_find at :763):
-// the reference's later host stages (merge_components, tails + spectral clustering, core enrichment)
-// are outside this hot path and not part of this build; --spectral is accepted and reported as unsupported.
+// behind include/hga_b200.h; there is no CPU path. After the scaffold components (union_find at :763) the run continues
+// with the merge of the scaffold components and the core enrichment (hga_enrich; run_clustering :764, :785-794) and exports
+// the final components under the surviving component ids, like the reference. The tail / spectral block in between
+// (:768-777, SURVEY.md §8f-2: spanning-tree tails, tail amplification, spectral clustering of the scaffold components) is
+// NOT built: with more than two scaffold components the run says so on stderr and goes on the way the reference does when
+// it finds no strong tail connection (:771), i.e. every scaffold component becomes a core. --spectral is reported as
+// unsupported.
 //
-// Extra, test-only switches: --parse-only (print the record stream and meta data, no GPU), --dump-kmers (print the
-// canonical k-mer values of the --kmers file, no GPU), --device N.
+// Extra switches: --scaffolds-only (stop after union_find and export the scaffold components), --parse-only (print the
+// record stream and meta data, no GPU), --dump-kmers (print the canonical k-mer values of the --kmers file, no GPU), --device N.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -77,7 +81,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> read_paths;
     std::string kmer_path, output_folder_path;
     Config config;
-    bool debug = false, parse_only = false, dump_kmers = false;
+    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false;
     int device = 0;
 
     auto need = [&](int &i) -> const char * {
@@ -102,6 +106,7 @@ int main(int argc, char **argv) {
         else if (a == "-t" || a == "--threads") config.threads = std::atoi(need(i));
         else if (a == "--parse-only") parse_only = true;
         else if (a == "--dump-kmers") dump_kmers = true;
+        else if (a == "--scaffolds-only") scaffolds_only = true;
         else if (a == "--device") device = std::atoi(need(i));
         else if (a.size() > 1 && a[0] == '-') throw std::invalid_argument("unrecognised option '" + a + "'");
         else read_paths.push_back(a);
@@ -181,23 +186,48 @@ int main(int argc, char **argv) {
     std::filesystem::remove_all(output_folder_path);
     std::filesystem::create_directories(output_folder_path);
     std::map<uint32_t, std::ofstream> files;
-    for (uint64_t c = 0; c < comp.n_components; c++)
-        files[comp.comp_label[c]] = std::ofstream(output_folder_path + "/#" + std::to_string(comp.comp_label[c]) + ".fa", std::ios::binary);
-    for (uint64_t r = 0; r < comp.n_reads; r++) {
-        auto it = files.find(comp.label[r]);
-        if (it != files.end()) it->second << reads.fastx_string(r) << std::endl;
+    if (scaffolds_only) {
+        for (uint64_t c = 0; c < comp.n_components; c++)
+            files[comp.comp_label[c]] = std::ofstream(output_folder_path + "/#" + std::to_string(comp.comp_label[c]) + ".fa", std::ios::binary);
+        for (uint64_t r = 0; r < comp.n_reads; r++) {
+            auto it = files.find(comp.label[r]);
+            if (it != files.end()) it->second << reads.fastx_string(r) << std::endl;
+        }
+        for (auto &f : files) f.second.close();
+        std::cout << "Exported " << comp.n_components << " components\n";
+    } else {
+        if (comp.n_components > 2)
+            std::cerr << "categorization: " << comp.n_components << " scaffold components; the tail / spectral merge of scaffold components "
+                         "(ReadClusteringEngine.cpp:768-777) is not part of this build: every scaffold component becomes a core, as in the reference "
+                         "when it finds no strong tail connection\n";
+        hga_enrichment_t fin;
+        {
+            // the reference times these separately ("Merging of initial components", "Calculation of enrichment connections",
+            // "Merging into core components"); here they are one library call
+            Timer t("Merging of initial components, calculation of enrichment connections and merging into core components");
+            check(hga_enrich(h, config.scaffold_component_min_size, (uint32_t) config.enrichment_connections_min_score), "hga_enrich");
+            check(hga_get_enrichment(h, &fin), "hga_get_enrichment");
+            t.done();
+        }
+        for (uint64_t c = 0; c < fin.n_final; c++)
+            files[fin.final_id[c]] = std::ofstream(output_folder_path + "/#" + std::to_string(fin.final_id[c]) + ".fa", std::ios::binary);
+        for (uint64_t r = 0; r < fin.n_reads; r++) {
+            if (fin.assignment[r] == 0) continue;
+            files[fin.assignment[r]] << reads.fastx_string(r) << std::endl;
+        }
+        for (auto &f : files) f.second.close();
+        std::cout << "Exported " << fin.n_final << " components\n";
     }
-    for (auto &f : files) f.second.close();
-    std::cout << "Exported " << comp.n_components << " components\n";
 
     hga_metrics_t m;
     if (hga_metrics(h, &m) == HGA_OK) {
         std::fprintf(stderr,
                      "hga_b200: %llu reads, %llu bases, %llu hits, %llu pairs, %llu selected edges, %llu components | GPU ms: table %.2f h2d %.2f scan %.2f "
-                     "index %.2f pairs %.2f select %.2f components %.2f\n",
+                     "index %.2f pairs %.2f select %.2f components %.2f enrich %.2f (%llu cores, %llu enrichment connections, %llu final components)\n",
                      (unsigned long long) m.n_reads, (unsigned long long) m.n_bases, (unsigned long long) m.n_hits, (unsigned long long) m.n_pairs,
                      (unsigned long long) m.n_selected, (unsigned long long) m.n_components, m.table_build_ms, m.h2d_ms, m.scan_ms, m.index_ms, m.pair_ms,
-                     m.select_ms, m.components_ms);
+                     m.select_ms, m.components_ms, m.enrich_ms, (unsigned long long) m.n_cores, (unsigned long long) m.n_enrich_connections,
+                     (unsigned long long) m.n_final_components);
     }
     hga_destroy(h);
     return 0;

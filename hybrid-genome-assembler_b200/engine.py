@@ -5,7 +5,8 @@ Names, argument meaning and error behaviour follow the reference (paths relative
   SequenceRecords           common/SequenceRecordIterator.{h,cpp}  (record rules, 1-based global ReadID, MetaData)
   ReadClusteringConfig      clustering/ReadClusteringEngine.h:138-148
   ReadClusteringEngine      clustering/ReadClusteringEngine.h:150-199: construct_indices, get_connections,
-                            get_all_connections, union_find, and the hot first third of run_clustering (:699-765)
+                            get_all_connections, union_find, run_clustering (:699-802) without its tail / spectral block
+                            (:768-777), export_components (:804-826)
 
 All arithmetic on reads happens in libhga_b200.so on the GPU; this module only parses files, owns the handle and
 shapes results. It never touches oracle/.
@@ -272,6 +273,38 @@ class ReadClusteringEngine:
         for root in comp["comp_label"]:
             out.append((np.nonzero(label == root)[0] + comp["read_id_first"]).astype(np.uint32))
         return out
+
+
+    # run_clustering(discriminative_kmers, k) — .cpp:699-802. Returns the final component ids; their members are in
+    # self.final_components (id -> ascending read ids). The tail / spectral merge of scaffold components (:768-777) is not
+    # built: every scaffold component becomes a core, which is the reference's own path when it finds no strong tail connection.
+    def run_clustering(self, discriminative_kmers, k):
+        cfg = self.config
+        if cfg.force_spectral:
+            raise NotImplementedError("--spectral (lib/clustering) is not part of this build")
+        self.construct_indices(discriminative_kmers, k)
+        self.scaffold_components()
+        self.handle.enrich(min_size=cfg.scaffold_component_min_size, enrichment_min_score=cfg.enrichment_connections_min_score)
+        e = self.handle.get_enrichment()
+        off = e["final_off"].astype(np.int64)
+        self.final_components = {int(fid): e["final_read"][off[i]:off[i + 1]] for i, fid in enumerate(e["final_id"])}
+        self.assignment = e["assignment"]
+        return [int(v) for v in e["final_id"]]
+
+    # export_components(component_ids, directory_path) — .cpp:804-826
+    def export_components(self, component_ids, directory_path):
+        import shutil
+        shutil.rmtree(directory_path, ignore_errors=True)
+        os.makedirs(directory_path)
+        wanted = set(int(c) for c in component_ids)
+        files = {c: open(os.path.join(directory_path, f"#{c}.fa"), "wb") for c in wanted}
+        for rid in range(1, self.reader.n_reads + 1):
+            c = int(self.assignment[rid - 1])
+            if c in wanted:
+                files[c].write(self.reader.fastx_string(rid) + b"\n")
+        for f in files.values():
+            f.close()
+        print(f"Exported {len(wanted)} components")
 
 
 def _canonical_sort(x, y, s):

@@ -50,7 +50,7 @@ def test_cli_end_to_end_components(exe, oracle, tmp_path):
     paths, kp = datagen.make_diploid_case(str(tmp_path / "c"), genome_size=30000, divergence=0.03, k=19, read_len=1200, coverage=12, seed=5,
                                           error_rate=0.01, fmt="fastq", length_sigma=0.3)
     outdir = str(tmp_path / "out")
-    r = subprocess.run([exe] + paths + ["--kmers", kp, "-o", outdir, "--sc_min_size", "5"], capture_output=True, text=True)
+    r = subprocess.run([exe] + paths + ["--kmers", kp, "-o", outdir, "--sc_min_size", "5", "--scaffolds-only"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     for label in ("Index construction took", "Calculation of connections between reads took", "Union-find took", "Exported"):
         assert label in r.stdout
@@ -67,4 +67,28 @@ def test_cli_end_to_end_components(exe, oracle, tmp_path):
         lines = open(os.path.join(outdir, f)).read().split("\n")
         got.append(sorted(l[1:] for l in lines[0::4] if l))      # FASTQ records: 4 lines each
     assert sorted(got) == want
+    assert f"Exported {len(want)} components" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_final_components(exe, oracle, tmp_path):
+    """default run: scaffold components -> merge -> enrichment -> export under the surviving component ids"""
+    import oracle_lib
+    paths, kp = datagen.make_diploid_case(str(tmp_path / "c"), genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=9,
+                                          error_rate=0.005, fmt="fastq")
+    outdir = str(tmp_path / "out")
+    r = subprocess.run([exe] + paths + ["--kmers", kp, "-o", outdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Merging of initial components" in r.stdout and "Union-find took" in r.stdout
+    rc, reads = oracle.load_reads(paths)
+    kmers, k = oracle.load_kmers(kp)
+    res = oracle.run(reads["seq"], reads["seq_off"], k, kmers, fraction=0.15, min_size=30)
+    e = oracle_lib.enrich(oracle, res, len(kmers), min_size=30, enrich_min=20)
+    assert len(e["final_id"]) > 2 and "scaffold components; the tail / spectral merge" in r.stderr
+    hdr_off = reads["hdr_off"].astype(np.int64)
+    want = {f"#{int(fid)}.fa": [reads["hdr"][hdr_off[i - 1]:hdr_off[i]].decode() for i in members] for fid, members in zip(e["final_id"], e["final_reads"])}
+    assert sorted(os.listdir(outdir)) == sorted(want)
+    for f, hdrs in want.items():
+        lines = open(os.path.join(outdir, f)).read().split("\n")
+        assert [l[1:] for l in lines[0::4] if l] == hdrs           # input order = ascending read id
     assert f"Exported {len(want)} components" in r.stdout

@@ -96,3 +96,32 @@ def test_cuda_merge_enrichment_vs_reference_golden(name):
         assert int((a != 0).sum()) == sum(len(r) for r in e["final_reads"])
         m = h.metrics()
         assert m["n_cores"] == ref["cores"] and m["n_final_components"] == ref["final_components"]
+
+
+def test_engine_mirror_run_clustering(tmp_path):
+    """reference-shaped run_clustering + export_components against the golden final components"""
+    import hga_b200
+    c = golden_util.load_case("enrich_short")
+    ref = c["ref"]
+
+    class _Reader(hga_b200.SequenceRecords):
+        def __init__(self):
+            self.bases, self.seq_off = c["bases"], c["seq_off"]
+            n = len(c["seq_off"]) - 1
+            self.headers = [b"r%d" % i for i in range(n)]
+            self.qualities = [b""] * n
+
+    eng = hga_b200.ReadClusteringEngine(_Reader(), hga_b200.ReadClusteringConfig(scaffold_component_min_size=c["min_size"],
+                                                                                 enrichment_connections_min_score=c["enrich"]))
+    ids = eng.run_clustering(c["kmers"], c["k"])
+    assert ids == [int(v) for v in ref["final_id"]]
+    fo = ref["final_off"].astype(np.int64)
+    for i, fid in enumerate(ids):
+        assert np.array_equal(eng.final_components[fid], ref["final_read"][fo[i]:fo[i + 1]])
+    out = str(tmp_path / "clusters")
+    eng.export_components(ids, out)
+    import os
+    assert sorted(os.listdir(out)) == sorted(f"#{i}.fa" for i in ids)
+    first = open(os.path.join(out, f"#{ids[0]}.fa"), "rb").read().split(b"\n")
+    assert first[0] == b">r%d" % (int(ref["final_read"][0]) - 1)
+    eng.close()
