@@ -19,9 +19,10 @@
 //   * enrichment score(c, y) = sum over k in U_c of the copies of y in the purged list of k, y != survivor(c) (:311-317).
 // The survivor ids matter (they enter R(k)), and they depend on the order the sequential union_find saw the edges in: the
 // roots are replayed on the host over the selected edges in the canonical order (score desc, x asc, y asc), union by size with
-// ties to y's root (:459-466) - O(M alpha), a few hundred ms for the 14 M selected edges of config 4. Everything proportional to
-// the incidence (E) runs on the GPU:
-//   enr_hit_keys_kernel      (core, slot) key per hit + member part of R(k)                       8 E B written
+// ties to y's root (:459-466), after the GPU has dropped the edges whose endpoints were already connected. Everything
+// proportional to the incidence (E) runs on the GPU:
+//   enr_edge_filter/hook     the ~N of M selected edges that can still join two components (the host replays only those)
+//   enr_list_cores_kernel    (core, slot) candidates, one per run of same-core entries of a list, + member part of R(k)
 //   CUB radix sort + unique  U_c for every core at once
 //   enr_survivor_max_kernel  survivor part of R(k)
 //   enr_purge_kernel         count / fill passes over the inverted index -> purged CSR           2 x 4 E B read, <= 4 E written
@@ -32,6 +33,7 @@
 #include "hga_internal.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -45,24 +47,65 @@ inline int grid_for(const hga_handle *h, uint64_t n, int per_block = 256) {
     return (int) std::max<uint64_t>(1, std::min<uint64_t>((n + per_block - 1) / per_block, (uint64_t) h->sm_count * 16));
 }
 
-// one warp per row: key = core << 32 | slot for hits of rows that belong to a core (n_cores << 32 otherwise: sorts last);
-// R[slot] = max(row + 1) over the core members that hold the k-mer
-__global__ void enr_hit_keys_kernel(const uint64_t *__restrict__ row_off, const uint32_t *__restrict__ hit_slot, uint64_t n_rows,
-                                    const int32_t *__restrict__ core_of, uint32_t n_cores, uint64_t *__restrict__ keys, uint32_t *R) {
-    const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
-    const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    for (uint64_t r = w; r < n_rows; r += warps) {
-        const uint64_t a = row_off[r], b = row_off[r + 1];
-        const int32_t c = core_of[r];
-        for (uint64_t i = a + lane; i < b; i += 32) {
-            if (c >= 0) {
-                const uint32_t slot = hit_slot[i];
-                keys[i] = ((uint64_t) (uint32_t) c << 32) | slot;
-                atomicMax(&R[slot], (uint32_t) r + 1);
-            } else {
-                keys[i] = (uint64_t) n_cores << 32;
-            }
+// (core, slot) candidates from the inverted index: one thread per list; a run of consecutive entries of the same core yields ONE
+// candidate (a discriminative k-mer's reads mostly come from one haplotype, hence one core: ~1 candidate per list instead of
+// one per hit), the radix sort + unique that follows removes the rest. FILL = false also leaves the member part of R(k): the
+// list is ascending, so the last entry that belongs to a core is the largest removed member.
+template<bool FILL>
+__global__ void enr_list_cores_kernel(const uint32_t *__restrict__ inv_off, const uint32_t *__restrict__ inv_row, uint32_t n_slots,
+                                      const int32_t *__restrict__ core_of, uint32_t *__restrict__ cnt, const unsigned long long *__restrict__ out_off,
+                                      uint64_t *__restrict__ out, uint32_t *__restrict__ R) {
+    for (uint64_t s = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t lo = inv_off[s], hi = inv_off[s + 1];
+        uint32_t n = 0, last1 = 0;
+        unsigned long long w = FILL ? out_off[s] : 0;
+        int32_t prev = -1;
+        for (uint32_t i = lo; i < hi; i++) {
+            const uint32_t e = inv_row[i];
+            const int32_t c = core_of[e];
+            if (c < 0) continue;
+            last1 = e + 1;
+            if (c != prev) { n++; if (FILL) out[w++] = ((uint64_t) (uint32_t) c << 32) | s; }
+            prev = c;
+        }
+        if (!FILL) { cnt[s] = n; R[s] = last1; }
+    }
+}
+
+// ---- union_find roots: the edges that can still join two components ---------------------------------------------------------
+__device__ __forceinline__ uint32_t enr_find(uint32_t *parent, uint32_t v) {
+    uint32_t p = parent[v];
+    while (p != v) {
+        const uint32_t gp = parent[p];
+        if (gp != p) parent[v] = gp;     // path halving (benign race: only ever points further up)
+        v = p; p = gp;
+    }
+    return v;
+}
+
+__global__ void enr_iota_kernel(uint32_t *parent, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) parent[i] = (uint32_t) i;
+}
+
+// flag[i] = the endpoints of edge i are not connected by the edges of the EARLIER batches (parent is not modified apart from
+// path halving, so an edge never sees the unions of its own batch)
+__global__ void enr_edge_filter_kernel(const uint64_t *__restrict__ key, uint64_t lo, uint64_t hi, uint32_t *parent, uint8_t *__restrict__ flag) {
+    for (uint64_t i = lo + blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < hi; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t kk = key[i];
+        flag[i] = enr_find(parent, (uint32_t) (kk >> 32)) != enr_find(parent, (uint32_t) kk);
+    }
+}
+
+__global__ void enr_edge_hook_kernel(const uint64_t *__restrict__ key, uint64_t lo, uint64_t hi, uint32_t *parent, const uint8_t *__restrict__ flag) {
+    for (uint64_t i = lo + blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < hi; i += (uint64_t) gridDim.x * blockDim.x) {
+        if (!flag[i]) continue;
+        const uint64_t kk = key[i];
+        uint32_t a = (uint32_t) (kk >> 32), b = (uint32_t) kk;
+        for (;;) {
+            a = enr_find(parent, a); b = enr_find(parent, b);
+            if (a == b) break;
+            const uint32_t top = max(a, b), bot = min(a, b);
+            if (atomicCAS(&parent[top], top, bot) == top) break;
         }
     }
 }
@@ -162,6 +205,21 @@ uint32_t dsu_find(std::vector<uint32_t> &parent, uint32_t v) {
 
 struct Conn { uint32_t x, y, s; };
 
+// HGA_ENRICH_TIMING=1: wall time of every phase on stderr (synchronises the stream at each mark)
+struct PhaseClock {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    PhaseClock(cudaStream_t s) : on(getenv("HGA_ENRICH_TIMING") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "hga_enrich: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 }  // namespace
 
 int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
@@ -175,30 +233,59 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
     const uint32_t first_id = h->inc_row_first_id;
     const uint32_t n_slots = h->index_keys;
     StageTimer timer(h, &h->metrics.enrich_ms);
+    PhaseClock pc(h->stream);
+    HGA_TRY(h->d_enr_scalars.ensure(64));
+    unsigned long long *d_count = h->d_enr_scalars.as<unsigned long long>();
 
     // ---- 1. roots of the sequential union_find (:453-478) over the selected edges in canonical order ----------------------
-    std::vector<uint32_t> ex(M), ey(M);
+    // Only an edge whose endpoints are not yet connected by the edges before it changes the union_find state; every other edge
+    // is a no-op in the sequential loop (:455). The GPU walks the canonical list in batches of doubling size and keeps the edges
+    // whose endpoints are not connected by the EARLIER batches (a superset of the state-changing edges, ~N of the M edges); the
+    // host replays those, in order.
+    uint64_t M2 = 0;
+    const uint32_t *ex = nullptr, *ey = nullptr;
     if (M) {
         // the selection is stored in (x, y) order; a stable descending sort by score gives (score desc, x asc, y asc)
-        HGA_TRY(h->d_export_a.ensure((M + 1) * 8));
+        HGA_TRY(h->d_export_a.ensure((M + 1) * 8 * 2));
         HGA_TRY(h->d_export_b.ensure((M + 1) * 4 * 3));
-        uint64_t *d_key = h->d_export_a.as<uint64_t>();
+        HGA_TRY(h->d_export_c.ensure(M + 64));
+        HGA_TRY(h->d_enr_parent.ensure((n + 1) * 4));
+        uint64_t *d_key = h->d_export_a.as<uint64_t>(), *d_kept = d_key + (M + 1);
         uint32_t *d_score = h->d_export_b.as<uint32_t>(), *d_x = d_score + (M + 1), *d_y = d_x + (M + 1);
-        size_t tmp = 0;
+        uint8_t *d_flag = h->d_export_c.as<uint8_t>();
+        uint32_t *d_par = h->d_enr_parent.as<uint32_t>();
+        size_t tmp = 0, tmp2 = 0;
         HGA_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, h->d_sel_score.as<uint32_t>(), d_score, h->d_sel_key.as<uint64_t>(), d_key, M, 0, 32, h->stream));
-        HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+        HGA_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp2, d_key, d_flag, d_kept, d_count, M, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(std::max(tmp, tmp2) + 16));
         HGA_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp.p, tmp, h->d_sel_score.as<uint32_t>(), d_score, h->d_sel_key.as<uint64_t>(), d_key, M, 0, 32, h->stream));
-        enr_key_rows_kernel<<<grid_for(h, M), 256, 0, h->stream>>>(d_key, M, d_x, d_y);
+        enr_iota_kernel<<<grid_for(h, n), 256, 0, h->stream>>>(d_par, n);
         h->metrics.kernel_launches += 6;
-        HGA_CUDA(cudaGetLastError());
-        HGA_CUDA(cudaMemcpyAsync(ex.data(), d_x, M * 4, cudaMemcpyDeviceToHost, h->stream));
-        HGA_CUDA(cudaMemcpyAsync(ey.data(), d_y, M * 4, cudaMemcpyDeviceToHost, h->stream));
+        for (uint64_t lo = 0, batch = 1 << 16; lo < M; lo += batch, batch *= 2) {
+            const uint64_t hi = std::min(M, lo + batch);
+            enr_edge_filter_kernel<<<grid_for(h, hi - lo), 256, 0, h->stream>>>(d_key, lo, hi, d_par, d_flag);
+            enr_edge_hook_kernel<<<grid_for(h, hi - lo), 256, 0, h->stream>>>(d_key, lo, hi, d_par, d_flag);
+            h->metrics.kernel_launches += 2;
+        }
+        HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, tmp2, d_key, d_flag, d_kept, d_count, M, h->stream));
+        unsigned long long kept = 0;
+        HGA_CUDA(cudaMemcpyAsync(&kept, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
+        M2 = kept;
+        enr_key_rows_kernel<<<grid_for(h, M2), 256, 0, h->stream>>>(d_kept, M2, d_x, d_y);
+        h->metrics.kernel_launches += 3;
+        HGA_CUDA(cudaGetLastError());
+        HGA_TRY(h->h_sx.ensure((M2 + 1) * 4)); HGA_TRY(h->h_sy.ensure((M2 + 1) * 4));
+        HGA_CUDA(cudaMemcpyAsync(h->h_sx.p, d_x, M2 * 4, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaMemcpyAsync(h->h_sy.p, d_y, M2 * 4, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+        ex = h->h_sx.as<uint32_t>(); ey = h->h_sy.as<uint32_t>();
     }
+    pc.mark("selection sort + D2H");
     std::vector<uint32_t> parent(n + 1), size(n + 1, 1);
     std::vector<uint8_t> touched(n + 1, 0);
     std::iota(parent.begin(), parent.end(), 0u);
-    for (uint64_t i = 0; i < M; i++) {
+    for (uint64_t i = 0; i < M2; i++) {
         // the reference's list holds (x, y) and (y, x) back to back; the second is a no-op after the first
         const uint32_t x = ex[i], y = ey[i];
         touched[x] = touched[y] = 1;                                                           // :427-431
@@ -226,43 +313,57 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
         for (uint64_t r = 0; r < n; r++) if (core_of[r] >= 0) res.core_read[cur[core_of[r]]++] = (uint32_t) r + first_id;
     }
 
+    pc.mark("host root replay + cores");
     // ---- 2. GPU: unions, removal bounds, purged index ----------------------------------------------------------------------
     HGA_TRY(h->d_enr_core_of.ensure((n + 1) * 4));
     HGA_TRY(h->d_enr_surv.ensure(((size_t) C + 1) * 4));
     HGA_TRY(h->d_enr_R.ensure(((size_t) n_slots + 1) * 4));
-    HGA_TRY(h->d_enr_scalars.ensure(64));
     int32_t *d_core_of = h->d_enr_core_of.as<int32_t>();
     uint32_t *d_surv = h->d_enr_surv.as<uint32_t>(), *d_R = h->d_enr_R.as<uint32_t>();
-    unsigned long long *d_count = h->d_enr_scalars.as<unsigned long long>();
     HGA_CUDA(cudaMemcpyAsync(d_core_of, core_of.data(), (n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     if (C) HGA_CUDA(cudaMemcpyAsync(d_surv, surv_row.data(), (size_t) C * 4, cudaMemcpyHostToDevice, h->stream));
     HGA_CUDA(cudaMemsetAsync(d_R, 0, ((size_t) n_slots + 1) * 4, h->stream));
 
+    const uint32_t *inv_off = h->d_inv_off.as<uint32_t>(), *inv_row = h->d_inv_row.as<uint32_t>();
     uint64_t n_u = 0;
-    HGA_TRY(h->d_enr_keys.ensure((E + 1) * 8));
-    HGA_TRY(h->d_enr_keys2.ensure((E + 1) * 8));
-    uint64_t *d_keys = h->d_enr_keys.as<uint64_t>(), *d_ukeys = h->d_enr_keys2.as<uint64_t>();
+    HGA_TRY(h->d_purged_off.ensure(((size_t) n_slots + 2) * 4 * 2));
+    uint32_t *d_cnt = h->d_purged_off.as<uint32_t>() + (n_slots + 2), *d_poff = h->d_purged_off.as<uint32_t>();
+    HGA_TRY(h->d_enr_keys.ensure(64));
     if (E && C) {
-        enr_hit_keys_kernel<<<grid_for(h, n * 32), 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->d_hit_slot.as<uint32_t>(), n, d_core_of, C, d_keys, d_R);
-        const int bits = 32 + (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) C + 1), 1);
-        size_t tmp = 0, tmp2 = 0;
-        HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_keys, d_ukeys, E, 0, bits, h->stream));
-        HGA_CUDA(cub::DeviceSelect::Unique(nullptr, tmp2, d_ukeys, d_keys, d_count, E, h->stream));
-        HGA_TRY(h->d_sort_tmp.ensure(std::max(tmp, tmp2) + 16));
-        HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, tmp, d_keys, d_ukeys, E, 0, bits, h->stream));
-        HGA_CUDA(cub::DeviceSelect::Unique(h->d_sort_tmp.p, tmp2, d_ukeys, d_keys, d_count, E, h->stream));   // unique keys back in d_keys
-        h->metrics.kernel_launches += (uint64_t) (bits + 7) / 8 + 4;
-        HGA_CUDA(cudaGetLastError());
-        unsigned long long nu = 0;
-        HGA_CUDA(cudaMemcpyAsync(&nu, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+        HGA_TRY(h->d_export_a.ensure(((size_t) n_slots + 2) * 8));
+        unsigned long long *d_cand_off = h->d_export_a.as<unsigned long long>();
+        enr_list_cores_kernel<false><<<grid_for(h, n_slots), 256, 0, h->stream>>>(inv_off, inv_row, n_slots, d_core_of, d_cnt, nullptr, nullptr, d_R);
+        HGA_CUDA(cudaMemsetAsync(d_cnt + n_slots, 0, 4, h->stream));
+        size_t tmp = 0;
+        HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_cnt, d_cand_off, (uint64_t) n_slots + 1, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+        HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, d_cnt, d_cand_off, (uint64_t) n_slots + 1, h->stream));
+        unsigned long long n_cand = 0;
+        HGA_CUDA(cudaMemcpyAsync(&n_cand, d_cand_off + n_slots, 8, cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
-        if (nu) {   // the filler key (hits of rows outside every core) sorts last
-            uint64_t last = 0;
-            HGA_CUDA(cudaMemcpy(&last, d_keys + (nu - 1), 8, cudaMemcpyDeviceToHost));
-            if (last == ((uint64_t) C << 32)) nu--;
+        HGA_TRY(h->d_enr_keys.ensure((n_cand + 1) * 8));
+        HGA_TRY(h->d_enr_keys2.ensure((n_cand + 1) * 8));
+        uint64_t *d_keys = h->d_enr_keys.as<uint64_t>(), *d_sorted = h->d_enr_keys2.as<uint64_t>();
+        h->metrics.kernel_launches += 3;
+        if (n_cand) {
+            enr_list_cores_kernel<true><<<grid_for(h, n_slots), 256, 0, h->stream>>>(inv_off, inv_row, n_slots, d_core_of, nullptr, d_cand_off, d_keys, nullptr);
+            const int bits = 32 + (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) C), 1);
+            size_t t1 = 0, t2 = 0;
+            HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, t1, d_keys, d_sorted, n_cand, 0, bits, h->stream));
+            HGA_CUDA(cub::DeviceSelect::Unique(nullptr, t2, d_sorted, d_keys, d_count, n_cand, h->stream));
+            HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
+            HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, t1, d_keys, d_sorted, n_cand, 0, bits, h->stream));
+            HGA_CUDA(cub::DeviceSelect::Unique(h->d_sort_tmp.p, t2, d_sorted, d_keys, d_count, n_cand, h->stream));   // unique keys back in d_keys
+            h->metrics.kernel_launches += (uint64_t) (bits + 7) / 8 + 4;
+            HGA_CUDA(cudaGetLastError());
+            unsigned long long nu = 0;
+            HGA_CUDA(cudaMemcpyAsync(&nu, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            n_u = nu;
         }
-        n_u = nu;
     }
+    const uint64_t *d_keys = h->d_enr_keys.as<uint64_t>();
+    pc.mark("core k-mer unions");
     const uint64_t *d_u = d_keys;      // sorted unique (core, slot)
     HGA_TRY(h->d_enr_core_koff.ensure(((size_t) C + 2) * 8));
     unsigned long long *d_core_koff = h->d_enr_core_koff.as<unsigned long long>();
@@ -270,9 +371,6 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
     if (n_u) enr_survivor_max_kernel<<<grid_for(h, n_u), 256, 0, h->stream>>>(d_u, n_u, d_surv, d_R);
     h->metrics.kernel_launches += 2;
 
-    HGA_TRY(h->d_purged_off.ensure(((size_t) n_slots + 2) * 4 * 2));
-    uint32_t *d_cnt = h->d_purged_off.as<uint32_t>() + (n_slots + 2), *d_poff = h->d_purged_off.as<uint32_t>();
-    const uint32_t *inv_off = h->d_inv_off.as<uint32_t>(), *inv_row = h->d_inv_row.as<uint32_t>();
     enr_purge_kernel<false><<<grid_for(h, n_slots), 256, 0, h->stream>>>(inv_off, inv_row, n_slots, d_R, d_core_of, d_surv, d_cnt, nullptr, nullptr);
     HGA_CUDA(cudaMemsetAsync(d_cnt + n_slots, 0, 4, h->stream));
     {
@@ -292,6 +390,7 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
     h->n_purged = n_purged;
     h->n_core_kmers = n_u;
 
+    pc.mark("purge");
     // ---- 3. GPU: enrichment connections = run lengths of the sorted (core, partner) emissions ------------------------------
     std::vector<Conn> conns;
     if (n_u) {
@@ -308,7 +407,7 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         h->metrics.kernel_launches += 3;
         if (n_emit) {
-            HGA_TRY(h->d_enr_keys2.ensure((n_emit + 1) * 8));          // d_ukeys is free again (the unique keys live in d_keys)
+            HGA_TRY(h->d_enr_keys2.ensure((n_emit + 1) * 8));          // free again (the unique keys live in d_enr_keys)
             HGA_TRY(h->d_export_b.ensure((n_emit + 1) * 8));
             HGA_TRY(h->d_export_c.ensure((n_emit + 1) * 4 * 4));
             uint64_t *d_emit = h->d_enr_keys2.as<uint64_t>(), *d_sorted = h->d_export_b.as<uint64_t>();
@@ -343,6 +442,7 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
             for (uint64_t i = 0; i < n_conn; i++) conns[i] = {cx[i], cy[i], cs[i]};
         }
     }
+    pc.mark("enrichment connections");
 
     // ---- 4. host: canonical order, restricted union_find (:424-489 with restricted = cores, min 2, max -1), final merge -----
     std::sort(conns.begin(), conns.end(), [](const Conn &a, const Conn &b) {
@@ -405,6 +505,7 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
             res.assignment[r] = f + first_id;
         }
     }
+    pc.mark("host restricted union-find");
     timer.stop();
     h->metrics.n_cores = C; h->metrics.n_enrich_connections = conns.size(); h->metrics.n_final_components = n_final;
     h->have_enrichment = true;

@@ -295,7 +295,7 @@ struct hga_handle {
     bool have_components = false;
 
     // merge + enrichment (hga_enrich.cu)
-    DevBuf d_enr_core_of, d_enr_surv, d_enr_R, d_enr_scalars, d_enr_keys, d_enr_keys2, d_enr_core_koff, d_purged_off, d_purged_row;
+    DevBuf d_enr_parent, d_enr_core_of, d_enr_surv, d_enr_R, d_enr_scalars, d_enr_keys, d_enr_keys2, d_enr_core_koff, d_purged_off, d_purged_row;
     uint64_t n_purged = 0, n_core_kmers = 0;
     EnrichResult enrich;
     bool have_enrichment = false;
