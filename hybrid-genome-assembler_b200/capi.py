@@ -60,7 +60,7 @@ class Metrics(C.Structure):
 
 
 # every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
-EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
+EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_init", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
            "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers",
            "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]

@@ -13,7 +13,8 @@
 // it finds no strong tail connection (:771), i.e. every scaffold component becomes a core. --spectral is reported as
 // unsupported.
 //
-// Extra switches: --scaffolds-only (stop after union_find and export the scaffold components), --parse-only (print the
+// Extra switches: --scaffolds-only (stop after union_find and export the scaffold components), --load-only (load the k-mers and
+// the reads, print the meta data and the load time, no GPU), --parse-only (print the
 // record stream and meta data, no GPU), --dump-kmers (print the canonical k-mer values of the --kmers file, no GPU), --device N.
 #include <chrono>
 #include <cstdio>
@@ -22,6 +23,7 @@
 #include <filesystem>
 #include <iostream>
 #include <map>
+#include <thread>
 
 #include "hga_b200.h"
 #include "hga_host.h"
@@ -81,7 +83,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> read_paths;
     std::string kmer_path, output_folder_path;
     Config config;
-    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false;
+    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false;
     int device = 0;
 
     auto need = [&](int &i) -> const char * {
@@ -107,13 +109,14 @@ int main(int argc, char **argv) {
         else if (a == "--parse-only") parse_only = true;
         else if (a == "--dump-kmers") dump_kmers = true;
         else if (a == "--scaffolds-only") scaffolds_only = true;
+        else if (a == "--load-only") load_only = true;
         else if (a == "--device") device = std::atoi(need(i));
         else if (a.size() > 1 && a[0] == '-') throw std::invalid_argument("unrecognised option '" + a + "'");
         else read_paths.push_back(a);
     }
     (void) debug;   // haplotype annotation / plots are debug output of the reference, not part of the hot path
 
-    if (kmer_path.empty() && !parse_only) throw std::invalid_argument("You need to specify path to kmers");
+    if (kmer_path.empty() && !parse_only && !load_only) throw std::invalid_argument("You need to specify path to kmers");
     if (dump_kmers) {
         const hga_host::KmerSet ks = hga_host::load_text_file_kmers(kmer_path);
         std::cout << "#K " << ks.k << " " << ks.kmers.size() << "\n";
@@ -122,9 +125,20 @@ int main(int argc, char **argv) {
     }
     if (read_paths.empty()) throw std::invalid_argument("You need to specify paths to read files");
 
+    // the CUDA context is created on a second thread while the files are read (seconds on a cold machine)
+    std::thread cuda_start;
+    if (!parse_only && !load_only) cuda_start = std::thread([device] { (void) hga_init(device); });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{cuda_start};
     hga_host::KmerSet ks;
-    if (!parse_only) ks = hga_host::load_text_file_kmers(kmer_path);
-    hga_host::SequenceRecords reads(read_paths);
+    Timer t_load("Loading of k-mers and reads");
+    if (!parse_only && !kmer_path.empty()) ks = hga_host::load_text_file_kmers(kmer_path, config.threads > 1 ? config.threads : 0);
+    hga_host::SequenceRecords reads(read_paths, config.threads > 1 ? config.threads : 0);
+    if (!parse_only) t_load.done();
+    if (load_only) {
+        for (const auto &m : reads.file_meta) std::cout << m.repr();
+        std::cout << ks.kmers.size() << " k-mers, k = " << ks.k << "\n";
+        return 0;
+    }
     if (parse_only) {
         for (const auto &m : reads.file_meta)
             std::cout << "#META " << m.filename << " " << m.records << " " << m.total_bases << " " << m.avg_read_length << " " << m.max_read_length << " "
@@ -133,8 +147,7 @@ int main(int argc, char **argv) {
         std::cout << "#AGG " << m.filename << " " << m.records << " " << m.total_bases << " " << m.avg_read_length << " " << m.max_read_length << " "
                   << m.min_read_length << "\n";
         for (size_t i = 0; i < reads.n_reads(); i++)
-            std::cout << (i + 1) << "\t" << reads.headers[i] << "\t" << reads.bases.substr(reads.seq_off[i], reads.seq_off[i + 1] - reads.seq_off[i]) << "\t"
-                      << reads.qualities[i] << "\n";
+            std::cout << (i + 1) << "\t" << reads.header(i) << "\t" << reads.sequence(i) << "\t" << reads.quality(i) << "\n";
         return 0;
     }
     for (const auto &m : reads.file_meta) std::cout << m.repr();
@@ -152,10 +165,18 @@ int main(int argc, char **argv) {
     hga_handle *h = nullptr;
     {
         Timer t("Index construction");               // table build + scan + inverted index = construct_indices (:234-299)
+        if (cuda_start.joinable()) cuda_start.join();
+        const auto w0 = std::chrono::steady_clock::now();
         check(hga_create(device, ks.k, ks.kmers.data(), ks.kmers.size(), &h), "hga_create");
-        check(hga_scan(h, reads.bases.data(), reads.seq_off.data(), reads.n_reads(), 1), "hga_scan");
+        const auto w1 = std::chrono::steady_clock::now();
+        check(hga_scan(h, reads.bases_data, reads.seq_off.data(), reads.n_reads(), 1), "hga_scan");
+        const auto w2 = std::chrono::steady_clock::now();
         check(hga_build_index(h), "hga_build_index");
+        const auto w3 = std::chrono::steady_clock::now();
         t.done();
+        std::fprintf(stderr, "hga_b200: wall ms: create (CUDA context + table) %.0f, scan (H2D inside) %.0f, index %.0f\n",
+                     std::chrono::duration<double, std::milli>(w1 - w0).count(), std::chrono::duration<double, std::milli>(w2 - w1).count(),
+                     std::chrono::duration<double, std::milli>(w3 - w2).count());
     }
     {
         Timer t("Calculation of connections between reads");
@@ -191,7 +212,7 @@ int main(int argc, char **argv) {
             files[comp.comp_label[c]] = std::ofstream(output_folder_path + "/#" + std::to_string(comp.comp_label[c]) + ".fa", std::ios::binary);
         for (uint64_t r = 0; r < comp.n_reads; r++) {
             auto it = files.find(comp.label[r]);
-            if (it != files.end()) it->second << reads.fastx_string(r) << std::endl;
+            if (it != files.end()) { reads.write_fastx(it->second, r); it->second.put('\n'); }
         }
         for (auto &f : files) f.second.close();
         std::cout << "Exported " << comp.n_components << " components\n";
@@ -213,7 +234,9 @@ int main(int argc, char **argv) {
             files[fin.final_id[c]] = std::ofstream(output_folder_path + "/#" + std::to_string(fin.final_id[c]) + ".fa", std::ios::binary);
         for (uint64_t r = 0; r < fin.n_reads; r++) {
             if (fin.assignment[r] == 0) continue;
-            files[fin.assignment[r]] << reads.fastx_string(r) << std::endl;
+            std::ofstream &f = files[fin.assignment[r]];
+            reads.write_fastx(f, r);
+            f.put('\n');
         }
         for (auto &f : files) f.second.close();
         std::cout << "Exported " << fin.n_final << " components\n";

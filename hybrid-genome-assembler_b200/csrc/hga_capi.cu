@@ -86,6 +86,12 @@ int hga_device_count(int *count) {
     return HGA_OK;
 }
 
+int hga_init(int device) {
+    HGA_CUDA(cudaSetDevice(device));
+    HGA_CUDA(cudaFree(nullptr));
+    return HGA_OK;
+}
+
 int hga_host_alloc(void **ptr, size_t bytes) {
     HGA_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
     return HGA_OK;

@@ -52,6 +52,9 @@ const char *hga_last_error(void);
 /* library + build identification, e.g. "hga_b200 0.1 sm_100a" */
 const char *hga_version(void);
 int hga_device_count(int *count);
+/* Optional: create the CUDA context of `device` ahead of time. The one-off driver / context start-up takes seconds on a cold
+ * machine; a host can run this on a second thread while it reads its input files (the CLI does). */
+int hga_init(int device);
 
 /* Pinned host memory helpers (H2D from pinned buffers runs at PCIe speed). */
 int hga_host_alloc(void **ptr, size_t bytes);
