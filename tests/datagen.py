@@ -119,3 +119,23 @@ def make_diploid_case(outdir, genome_size, divergence, k, read_len, coverage, se
     kp = os.path.join(outdir, f"{k}-mers.txt")
     write_kmers(kp, rng.permutation(sdk), k)
     return paths, kp
+
+
+def make_polyploid_case(outdir, genome_size, divergence, k, read_len, coverage, seed, n_haplotypes=4, error_rate=0.0, length_sigma=0.0):
+    """BASELINE config 5 in small: a base haplotype + independent mutated copies, one read file per haplotype, DENSE discriminative
+    set = canonical k-mers absent from at least one haplotype. Returns (read_paths, kmer_path)."""
+    os.makedirs(outdir, exist_ok=True)
+    base = random_genome(genome_size, 1000 * seed)
+    haps = [base] + [mutate(base, divergence, 1000 * seed + 1 + i) for i in range(n_haplotypes - 1)]
+    paths = []
+    for i, h in enumerate(haps):
+        n_reads = max(1, int(coverage * genome_size / read_len))
+        reads = sample_reads(h, n_reads, read_len, 1000 * seed + 10 + i, error_rate=error_rate, length_sigma=length_sigma, min_len=min(50, genome_size))
+        p = os.path.join(outdir, f"hap{i}.fa")
+        write_fasta(p, reads, prefix=f"h{i}_")
+        paths.append(p)
+    sdk = discriminative_kmers(haps, k, mode="not_all")
+    rng = np.random.default_rng(1000 * seed + 98)
+    kp = os.path.join(outdir, f"{k}-mers.txt")
+    write_kmers(kp, rng.permutation(sdk), k)
+    return paths, kp

@@ -130,6 +130,33 @@ def test_long_reads(oracle, k):
     _run_and_compare(oracle, bases, off, k, kmers, min_size=5, check_sorted_hits=(k == 19))
 
 
+def test_config5_like_tetraploid(oracle):
+    """BASELINE config 5 in small: four haplotypes, dense discriminative set (k-mers absent from at least one haplotype);
+    all stages plus the merge + enrichment stage"""
+    import hga_b200
+    import oracle_lib
+    from test_gpu_golden import _gpu_enrichment
+    base = datagen.random_genome(60000, 7000)
+    haps = [base] + [datagen.mutate(base, 0.01, 7001 + i) for i in range(3)]
+    reads = []
+    for i, h in enumerate(haps):
+        reads += datagen.sample_reads(h, 240, 5000, 7010 + i, error_rate=0.03, length_sigma=0.5, max_len=40000)
+    bases, off = _pack([datagen.to_ascii(r) for r in reads])
+    kmers = datagen.discriminative_kmers(haps, 19, mode="not_all")
+    ref, _ = _run_and_compare(oracle, bases, off, 19, kmers, min_size=5, check_sorted_hits=False)
+    want = oracle_lib.enrich(oracle, ref, len(kmers), min_size=5, enrich_min=20)
+    with hga_b200.Handle(kmers, 19) as h:
+        h.scan(bases, off); h.build_index(); h.pair_count(min_score=1); h.select_edges(fraction=0.15)
+        got = _gpu_enrichment(h, 5, 20)
+    assert np.array_equal(got["core_id"], want["core_id"]) and np.array_equal(got["final_id"], want["final_id"])
+    assert np.array_equal(got["purged_off"], want["purged_off"]) and np.array_equal(got["purged_read"], want["purged_read"])
+    for g, w in zip(got["econn"], want["econn"]):
+        assert np.array_equal(g, w)
+    for g, w in zip(got["final_reads"], want["final_reads"]):
+        assert np.array_equal(g, w)
+    assert len(want["core_id"]) >= 1
+
+
 def test_heavy_rows_overflow_shared_accumulator(oracle):
     """one repeated segment present in > 3072 reads: partner sets overflow the shared-memory table"""
     rng = np.random.default_rng(5)

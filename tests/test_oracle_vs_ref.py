@@ -128,6 +128,14 @@ def test_merge_and_enrichment_long_reads(oracle, ref_driver, tmp_path, enrich, m
     assert ref["cores"] >= 1
 
 
+def test_config5_like_tetraploid(oracle, ref_driver, tmp_path):
+    # BASELINE config 5 in small: four haplotype read files, dense discriminative set (k-mers absent from at least one haplotype)
+    paths, kp = datagen.make_polyploid_case(str(tmp_path), genome_size=12000, divergence=0.02, k=19, read_len=1500, coverage=10, seed=31,
+                                            error_rate=0.02, length_sigma=0.4)
+    ref, _ = _full_compare(oracle, ref_driver, paths, kp, min_size=4, enrich=20)
+    assert ref["n_reads"] == 4 * 80 and ref["scaffold_components"] >= 1
+
+
 def test_non_acgt_and_crlf(oracle, ref_driver, tmp_path):
     a = datagen.random_genome(3000, 11)
     reads = [datagen.to_ascii(r) for r in datagen.sample_reads(a, 120, 100, 12)]
