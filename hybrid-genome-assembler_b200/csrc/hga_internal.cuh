@@ -91,11 +91,10 @@ struct PinBuf {
 //   filter    : blocked Bloom filter; block = 32 B (8 words) selected by B, word + 2 bits inside the block
 //               selected by an independent hash of the k-mer. Sized to stay L2-resident; consulted first so
 //               that a non-member costs one 4 B probe that its neighbours share.
-//   key table : buckets of 16 x u64 keys (one 128 B line) selected by B; inside a bucket the probe sequence starts
-//               in the 4-slot sector (32 B) picked by the k-mer hash, goes round the bucket's sectors, then moves to
-//               the next bucket, for at most HGA_CHAIN_BUCKETS buckets (load factor 1/3: a lookup usually ends
-//               after one 32 B load). Keys that find no room there go to a plain open-addressing overflow
-//               table hashed by k-mer. The internal k-mer id ("slot") is the index of the key in the (main | overflow) key
+//   key table : buckets of 16 x u64 keys (one 128 B line) selected by B, load factor 1/3; a lookup reads the whole home
+//               bucket in one round trip (eight independent 16 B loads). Keys that find no room in their chain of
+//               chain_buckets buckets (default 1: the home bucket only; 3 % of the keys of config 4) go to a plain
+//               open-addressing overflow table hashed by k-mer, which only lookups that meet a FULL bucket consult. The internal k-mer id ("slot") is the index of the key in the (main | overflow) key
 //               array; slot_kid maps it back to the caller's kmer_id.
 // ------------------------------------------------------------------------------------------------
 #define HGA_MIN_W 8
@@ -125,6 +124,7 @@ struct KmerTable {
     uint32_t n_blocks = 0;
     uint32_t n_slots = 0;           // n_main + n_over
     uint32_t slot_bits = 0;         // ceil(log2(n_slots))
+    uint32_t chain_buckets = 1;     // buckets a key may live in (home bucket first, at most HGA_CHAIN_BUCKETS); experiment switch HGA_CHAIN_BUCKETS
     KmerGeom geom;
 };
 

@@ -20,7 +20,8 @@ __global__ void table_insert_main_kernel(const uint64_t *__restrict__ kmers, uin
         atomicOr(&t.filter[(size_t) hga_scale(B, t.n_blocks) * 8 + hga_bits_word(hb)], hga_bits_mask(hb));
         const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS, start = hga_bits_sector(hb);
         bool done = false;
-        for (uint32_t j = 0; j < HGA_CHAIN_SLOTS && !done; j++) {
+        const uint32_t chain_slots = t.chain_buckets * HGA_BUCKET_SLOTS;
+        for (uint32_t j = 0; j < chain_slots && !done; j++) {
             const uint32_t slot = home + hga_chain_slot(start, j);
             unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&keys[slot]);
             if (cur == HGA_EMPTY_KEY) cur = atomicCAS(&keys[slot], (unsigned long long) HGA_EMPTY_KEY, key);
@@ -66,6 +67,7 @@ int hga_table_build(hga_handle *h, const uint64_t *host_kmers) {
 
     KmerTable &t = h->table;
     t.geom = hga_make_geom(h->k, n);
+    if (const char *e = getenv("HGA_CHAIN_BUCKETS")) t.chain_buckets = (uint32_t) std::min(HGA_CHAIN_BUCKETS, std::max(1, atoi(e)));
     t.n_buckets = (uint32_t) ((3 * n + HGA_BUCKET_SLOTS - 1) / HGA_BUCKET_SLOTS + 1);   // load factor <= 1/3
     t.n_main = (t.n_buckets + HGA_CHAIN_BUCKETS) * HGA_BUCKET_SLOTS;                    // slack: chains never wrap
     t.n_over = 0;
