@@ -14,7 +14,7 @@
 // unsupported.
 //
 // Extra switches: --scaffolds-only (stop after union_find and export the scaffold components), --load-only (load the k-mers and
-// the reads, print the meta data and the load time, no GPU), --parse-only (print the
+// the reads, print the meta data and the load time, no GPU), --export-test (writer self-test, no GPU), --parse-only (print the
 // record stream and meta data, no GPU), --dump-kmers (print the canonical k-mer values of the --kmers file, no GPU), --device N.
 #include <chrono>
 #include <cstdio>
@@ -83,7 +83,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> read_paths;
     std::string kmer_path, output_folder_path;
     Config config;
-    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false;
+    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false, export_test = false;
     int device = 0;
 
     auto need = [&](int &i) -> const char * {
@@ -110,13 +110,14 @@ int main(int argc, char **argv) {
         else if (a == "--dump-kmers") dump_kmers = true;
         else if (a == "--scaffolds-only") scaffolds_only = true;
         else if (a == "--load-only") load_only = true;
+        else if (a == "--export-test") export_test = true;
         else if (a == "--device") device = std::atoi(need(i));
         else if (a.size() > 1 && a[0] == '-') throw std::invalid_argument("unrecognised option '" + a + "'");
         else read_paths.push_back(a);
     }
     (void) debug;   // haplotype annotation / plots are debug output of the reference, not part of the hot path
 
-    if (kmer_path.empty() && !parse_only && !load_only) throw std::invalid_argument("You need to specify path to kmers");
+    if (kmer_path.empty() && !parse_only && !load_only && !export_test) throw std::invalid_argument("You need to specify path to kmers");
     if (dump_kmers) {
         const hga_host::KmerSet ks = hga_host::load_text_file_kmers(kmer_path);
         std::cout << "#K " << ks.k << " " << ks.kmers.size() << "\n";
@@ -127,13 +128,21 @@ int main(int argc, char **argv) {
 
     // the CUDA context is created on a second thread while the files are read (seconds on a cold machine)
     std::thread cuda_start;
-    if (!parse_only && !load_only) cuda_start = std::thread([device] { (void) hga_init(device); });
+    if (!parse_only && !load_only && !export_test) cuda_start = std::thread([device] { (void) hga_init(device); });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{cuda_start};
     hga_host::KmerSet ks;
     Timer t_load("Loading of k-mers and reads");
     if (!parse_only && !kmer_path.empty()) ks = hga_host::load_text_file_kmers(kmer_path, config.threads > 1 ? config.threads : 0);
     hga_host::SequenceRecords reads(read_paths, config.threads > 1 ? config.threads : 0);
     if (!parse_only) t_load.done();
+    if (export_test) {   // writer self-test (no GPU): read r (1-based) goes to component 1 + r % 3, every 7th read to none
+        std::vector<uint32_t> of_read(reads.n_reads());
+        for (size_t r = 0; r < reads.n_reads(); r++) of_read[r] = ((r + 1) % 7 == 0) ? 0u : (uint32_t) (1 + (r + 1) % 3);
+        std::filesystem::remove_all(output_folder_path);
+        std::filesystem::create_directories(output_folder_path);
+        hga_host::export_components(reads, {1, 2, 3}, of_read.data(), output_folder_path, config.threads);
+        return 0;
+    }
     if (load_only) {
         for (const auto &m : reads.file_meta) std::cout << m.repr();
         std::cout << ks.kmers.size() << " k-mers, k = " << ks.k << "\n";
@@ -206,15 +215,13 @@ int main(int argc, char **argv) {
     // export_components (:804-826): one file per component, records in input order; reads of no component are dropped
     std::filesystem::remove_all(output_folder_path);
     std::filesystem::create_directories(output_folder_path);
-    std::map<uint32_t, std::ofstream> files;
+    const int io_threads = config.threads > 1 ? config.threads : 0;
     if (scaffolds_only) {
-        for (uint64_t c = 0; c < comp.n_components; c++)
-            files[comp.comp_label[c]] = std::ofstream(output_folder_path + "/#" + std::to_string(comp.comp_label[c]) + ".fa", std::ios::binary);
-        for (uint64_t r = 0; r < comp.n_reads; r++) {
-            auto it = files.find(comp.label[r]);
-            if (it != files.end()) { reads.write_fastx(it->second, r); it->second.put('\n'); }
-        }
-        for (auto &f : files) f.second.close();
+        std::vector<uint32_t> of_read(comp.n_reads, 0), ids(comp.comp_label, comp.comp_label + comp.n_components);
+        std::sort(ids.begin(), ids.end());
+        for (uint64_t r = 0; r < comp.n_reads; r++)
+            if (std::binary_search(ids.begin(), ids.end(), comp.label[r])) of_read[r] = comp.label[r];
+        hga_host::export_components(reads, ids, of_read.data(), output_folder_path, io_threads);
         std::cout << "Exported " << comp.n_components << " components\n";
     } else {
         if (comp.n_components > 2)
@@ -230,15 +237,9 @@ int main(int argc, char **argv) {
             check(hga_get_enrichment(h, &fin), "hga_get_enrichment");
             t.done();
         }
-        for (uint64_t c = 0; c < fin.n_final; c++)
-            files[fin.final_id[c]] = std::ofstream(output_folder_path + "/#" + std::to_string(fin.final_id[c]) + ".fa", std::ios::binary);
-        for (uint64_t r = 0; r < fin.n_reads; r++) {
-            if (fin.assignment[r] == 0) continue;
-            std::ofstream &f = files[fin.assignment[r]];
-            reads.write_fastx(f, r);
-            f.put('\n');
-        }
-        for (auto &f : files) f.second.close();
+        Timer t_exp("Export of components");
+        hga_host::export_components(reads, std::vector<uint32_t>(fin.final_id, fin.final_id + fin.n_final), fin.assignment, output_folder_path, io_threads);
+        t_exp.done();
         std::cout << "Exported " << fin.n_final << " components\n";
     }
 

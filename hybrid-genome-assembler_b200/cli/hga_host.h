@@ -335,4 +335,76 @@ struct SequenceRecords {
     }
 };
 
+// export_components (clustering/ReadClusteringEngine.cpp:804-826): <dir>/#<component id>.fa per component, the records of its
+// reads in input order, each followed by a newline (operator<< std::endl, :820). The bytes are the reference's; the writing is
+// parallel: every record's size is known, so every record has a fixed offset in its file and `threads` workers pwrite
+// disjoint read ranges into the pre-sized files.
+inline void export_components(const SequenceRecords &reads, const std::vector<uint32_t> &component_ids, const uint32_t *component_of_read /* 0 = none */,
+                              const std::string &dir, int threads = 0) {
+    const size_t n = reads.n_reads();
+    std::vector<uint32_t> ids(component_ids);
+    std::sort(ids.begin(), ids.end());
+    auto file_of = [&](uint32_t c) -> int {
+        auto it = std::lower_bound(ids.begin(), ids.end(), c);
+        return (it != ids.end() && *it == c) ? (int) (it - ids.begin()) : -1;
+    };
+    auto rec_size = [&](size_t r) -> uint64_t {
+        const uint64_t q = reads.quality(r).size();
+        return 1 + reads.header(r).size() + 1 + reads.sequence(r).size() + (q ? 3 + q : 0) + 1;
+    };
+    std::vector<uint64_t> file_size(ids.size(), 0), rec_off(n, 0);
+    std::vector<int> rec_file(n, -1);
+    for (size_t r = 0; r < n; r++) {
+        const int f = component_of_read[r] ? file_of(component_of_read[r]) : -1;
+        rec_file[r] = f;
+        if (f >= 0) { rec_off[r] = file_size[f]; file_size[f] += rec_size(r); }
+    }
+    std::vector<int> fds(ids.size(), -1);
+    for (size_t f = 0; f < ids.size(); f++) {
+        const std::string path = dir + "/#" + std::to_string(ids[f]) + ".fa";
+        fds[f] = ::open(path.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+        if (fds[f] < 0) throw std::runtime_error("cannot create " + path);
+        if (file_size[f] && ftruncate(fds[f], (off_t) file_size[f]) != 0) throw std::runtime_error("cannot size " + path);
+    }
+    int T = threads > 0 ? threads : (reads.bases_size < ((uint64_t) 8 << 20) ? 1 : (int) std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+    std::vector<std::string> errors(T);
+    auto work = [&](int t) {
+        const size_t a = n * (size_t) t / T, b = n * (size_t) (t + 1) / T;
+        std::string buf;
+        buf.reserve(1 << 20);
+        int cur = -1;
+        uint64_t cur_off = 0;
+        auto flush = [&]() {
+            size_t done = 0;
+            while (cur >= 0 && done < buf.size()) {
+                const ssize_t w = pwrite(fds[cur], buf.data() + done, buf.size() - done, (off_t) (cur_off + done));
+                if (w <= 0) { errors[t] = "write failed"; break; }
+                done += (size_t) w;
+            }
+            buf.clear();
+        };
+        for (size_t r = a; r < b; r++) {
+            const int f = rec_file[r];
+            if (f < 0) continue;
+            if (f != cur || cur_off + buf.size() != rec_off[r] || buf.size() > (1u << 20)) { flush(); cur = f; cur_off = rec_off[r]; }
+            const std::string_view q = reads.quality(r), hd = reads.header(r), sq = reads.sequence(r);
+            buf.push_back(q.empty() ? '>' : '@');
+            buf.append(hd.data(), hd.size());
+            buf.push_back('\n');
+            buf.append(sq.data(), sq.size());
+            if (!q.empty()) { buf.append("\n+\n", 3); buf.append(q.data(), q.size()); }
+            buf.push_back('\n');
+        }
+        flush();
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; t++) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    for (int fd : fds) if (fd >= 0) ::close(fd);
+    for (const auto &e : errors) if (!e.empty()) throw std::runtime_error("export_components: " + e);
+}
+
 }  // namespace hga_host

@@ -281,13 +281,21 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         ex = h->h_sx.as<uint32_t>(); ey = h->h_sy.as<uint32_t>();
     }
+    // pivot subsets (--sc_score): a pair with ONE pivot endpoint is in the reference's list in one direction only, pivot first
+    std::vector<uint8_t> is_pivot;
+    if (h->pair_subset && M2) {
+        is_pivot.resize(n + 1);
+        HGA_CUDA(cudaMemcpyAsync(is_pivot.data(), h->d_pivot_flag.p, n, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+    }
     pc.mark("selection sort + D2H");
     std::vector<uint32_t> parent(n + 1), size(n + 1, 1);
     std::vector<uint8_t> touched(n + 1, 0);
     std::iota(parent.begin(), parent.end(), 0u);
     for (uint64_t i = 0; i < M2; i++) {
         // the reference's list holds (x, y) and (y, x) back to back; the second is a no-op after the first
-        const uint32_t x = ex[i], y = ey[i];
+        uint32_t x = ex[i], y = ey[i];
+        if (!is_pivot.empty() && !is_pivot[x]) std::swap(x, y);                                // (pivot, non-pivot) as get_connections emits it
         touched[x] = touched[y] = 1;                                                           // :427-431
         const uint32_t px = dsu_find(parent, x), py = dsu_find(parent, y);                     // :453-454
         if (px == py) continue;                                                                // :455

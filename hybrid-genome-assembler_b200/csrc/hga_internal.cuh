@@ -283,6 +283,7 @@ struct hga_handle {
     uint32_t pair_pivot_mul = 1, pair_pivot_add = 0;   // local row t is global row t * mul + add (rank, rank + G, ...)
     bool have_pairs = false;
     uint32_t pair_min_score = 1;
+    bool pair_subset = false;             // the pairs come from a pivot subset (d_pivot_flag marks the pivots)
 
     // selection
     uint64_t sel_n_directed = 0, sel_cut = 0, n_selected = 0;

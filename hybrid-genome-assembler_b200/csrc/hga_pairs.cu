@@ -437,6 +437,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     const bool multi = h->comm && hga_comm_size(h) > 1;
     const uint64_t n_rows = h->pair_rows;         // rows of the by-read incidence (all reads with a communicator)
     h->pair_min_score = min_score;
+    h->pair_subset = pivots != nullptr;
     if (multi && pivots) { hga_set_error("hga_pair_count: pivot subsets are not supported with a communicator"); return HGA_E_ARG; }
 
     HGA_TRY(h->d_pair_scalars.ensure(sizeof(PairScalars)));

@@ -95,7 +95,7 @@ public:
     Probe(SequenceRecordIterator &it, ReadClusteringConfig cfg) : ReadClusteringEngine(it, cfg) {}
 
     int run(std::unordered_set<Kmer> &kmers, int k, const std::string &out, bool do_dump, double fraction, int min_size,
-            ConnectionScore min_score, int stop_after, ConnectionScore enrich_min = 0) {
+            ConnectionScore min_score, int stop_after, ConnectionScore enrich_min = 0, ConnectionScore sc_score = 0) {
         // KmerID assignment order = iteration order of the very same unordered_set object (.cpp:237-241)
         std::vector<Kmer> id2kmer;
         for (auto kmer : kmers) id2kmer.push_back(kmer);
@@ -157,7 +157,15 @@ public:
         if (stop_after == 1) { fclose(meta); return 0; }
 
         t0 = now_ms();
-        auto connections = get_all_connections(min_score);
+        std::vector<ComponentConnection> connections;
+        if (sc_score > 0) {
+            // --sc_score S (run_clustering :749-752): pivots = components with at least S discriminative k-mers, min score S
+            std::vector<ComponentID> ids;
+            for (auto p : component_index) if (p.second->discriminative_kmer_ids.size() >= sc_score) ids.push_back(p.first);
+            connections = get_connections(ids, sc_score);
+        } else {
+            connections = get_all_connections(min_score);
+        }
         double t_conn = now_ms() - t0;
         uint64_t score_sum = 0;
         for (auto &c : connections) score_sum += c.score;
@@ -169,6 +177,12 @@ public:
         // clustering/ReadClusteringEngine.cpp:755
         size_t n = connections.size() * fraction;
         uint64_t cut_score = n > 0 ? connections[n - 1].score : 0;
+        if (sc_score > 0) {
+            // :752 filter_connections(score > S): a prefix of the sorted list
+            n = 0;
+            while (n < connections.size() && connections[n].score > sc_score) n++;
+            cut_score = sc_score;
+        }
         size_t above = 0, tied = 0;
         for (auto &c : connections) { if (c.score > cut_score) above++; else if (c.score == cut_score) tied++; }
         fprintf(meta, "cut_n=%zu\ncut_score=%lu\ndirected_above_cut=%zu\ndirected_tied_at_cut=%zu\ncanonical_sort_ms=%.3f\n", n,
@@ -319,7 +333,7 @@ int usage() {
             "ref_driver canon <kmer file> <out dir>\n"
             "ref_driver records <out dir> <reads...>\n"
             "ref_driver run --kmers F --out DIR [--threads T] [--fraction 0.15] [--min-size 30] [--min-score 1]\n"
-            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] <reads...>\n");
+            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] [--sc-score S] <reads...>\n");
     return 2;
 }
 
@@ -374,7 +388,7 @@ int main(int argc, char **argv) {
     int min_size = config.scaffold_component_min_size;
     ConnectionScore min_score = 1;
     int stop_after = 0;
-    ConnectionScore enrich_min = 0;
+    ConnectionScore enrich_min = 0, sc_score = 0;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) exit(usage()); return argv[++i]; };
@@ -386,6 +400,7 @@ int main(int argc, char **argv) {
         else if (a == "--min-score") min_score = std::stoul(next());
         else if (a == "--stop-after") stop_after = std::stoi(next());
         else if (a == "--enrich") enrich_min = std::stoul(next());
+        else if (a == "--sc-score") sc_score = std::stoul(next());
         else if (a == "--no-dump") do_dump = false;
         else paths.push_back(a);
     }
@@ -399,7 +414,7 @@ int main(int argc, char **argv) {
     reader.show_progress = false;
     double t_meta = now_ms() - t0;
     Probe engine(reader, config);
-    int rc = engine.run(kk.first, kk.second, out, do_dump, fraction, min_size, min_score, stop_after, enrich_min);
+    int rc = engine.run(kk.first, kk.second, out, do_dump, fraction, min_size, min_score, stop_after, enrich_min, sc_score);
     FILE *meta = fopen((out + "/meta.txt").c_str(), "a");
     fprintf(meta, "kmer_load_ms=%.3f\nmeta_pass_ms=%.3f\nthreads=%d\n", t_load, t_meta, config.threads);
     fclose(meta);

@@ -82,7 +82,7 @@ def main():
         res["cli_wall_s"] = time.perf_counter() - t0
         res["cli_rc"] = r.returncode
         res["cli_stdout_stages"] = [l for l in r.stdout.split("\n") if " took " in l or l.startswith("Exported")]
-        res["cli_stderr_tail"] = r.stderr.strip().split("\n")[-3:]
+        res["cli_stderr_tail"] = r.stderr.strip().split("\n")[-12:]
         if r.returncode != 0:
             print(json.dumps(res)); return 1
         got = {}

@@ -132,13 +132,21 @@ class Oracle:
         return out
 
     # -- whole hot path on in-memory reads: returns a dict mirroring the ref_driver dump
-    def run(self, seq: bytes, seq_off, k, kmers_sorted, fraction=0.15, min_size=30, min_score=1):
+    def run(self, seq: bytes, seq_off, k, kmers_sorted, fraction=0.15, min_size=30, min_score=1, sc_score=0):
         row_off, kid, pos = self.scan(seq, seq_off, k, kmers_sorted)
         inv_off, inv_read = self.index(row_off, kid, len(kmers_sorted))
-        cx, cy, cs = self.connections(row_off, kid, inv_off, inv_read, min_score=min_score)
-        sx, sy, ss = self.canonical_sort(cx, cy, cs)
-        n = int(len(sx) * fraction)
-        cut = int(ss[n - 1]) if n > 0 else 0
+        if sc_score > 0:
+            # --sc_score S (run_clustering :749-752): pivots = components with >= S discriminative k-mers, keep score > S
+            pivots = (np.nonzero(np.diff(row_off.astype(np.int64)) >= sc_score)[0] + 1).astype(np.uint32)
+            cx, cy, cs = self.connections(row_off, kid, inv_off, inv_read, min_score=sc_score, pivots=pivots)
+            sx, sy, ss = self.canonical_sort(cx, cy, cs)
+            n = int((ss > sc_score).sum())
+            cut = sc_score
+        else:
+            cx, cy, cs = self.connections(row_off, kid, inv_off, inv_read, min_score=min_score)
+            sx, sy, ss = self.canonical_sort(cx, cy, cs)
+            n = int(len(sx) * fraction)
+            cut = int(ss[n - 1]) if n > 0 else 0
         comp = self.union_find(sx[:n], sy[:n], min_size=min_size)
         return dict(row_off=row_off, hit_kid=kid, hit_pos=pos, inv_off=inv_off, inv_read=inv_read, conn=(sx, sy, ss), cut_n=n, cut_score=cut,
                     comp=comp)

@@ -16,7 +16,7 @@ _FILES = {
 _DT = {"u32": np.uint32, "u64": np.uint64}
 
 
-def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0):
+def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0, sc_score=0):
     tmp = None
     if outdir is None:
         tmp = tempfile.TemporaryDirectory()
@@ -29,6 +29,8 @@ def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score
         cmd += ["--stop-after", str(stop_after)]
     if enrich:
         cmd += ["--enrich", str(enrich)]
+    if sc_score:
+        cmd += ["--sc-score", str(sc_score)]
     cmd += list(read_paths)
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     out = {}

@@ -36,6 +36,27 @@ def test_cli_kmer_loader_matches_reference(exe):
     assert [int(v) for v in out[1:] if v] == [int(v) for v in z["kmers"]]
 
 
+@pytest.mark.parametrize("fmt,threads", [("fasta", 1), ("fastq", 1), ("fastq", 5)])
+def test_cli_parallel_export_writes_the_reference_bytes(exe, tmp_path, fmt, threads):
+    """export_components (ReadClusteringEngine.cpp:804-826): records in input order, '@h\\nseq\\n+\\nqual' or '>h\\nseq', newline after each"""
+    g = datagen.random_genome(5000, 77)
+    reads = [datagen.to_ascii(r) for r in datagen.sample_reads(g, 500, 300, 78, length_sigma=0.6, min_len=1)]
+    p = str(tmp_path / ("r.fq" if fmt == "fastq" else "r.fa"))
+    (datagen.write_fastq if fmt == "fastq" else datagen.write_fasta)(p, reads, prefix="x")
+    out = str(tmp_path / "out")
+    subprocess.run([exe, "--export-test", p, "-o", out, "--threads", str(threads)], check=True)
+    want = {1: b"", 2: b"", 3: b""}
+    for i, s in enumerate(reads):
+        r = i + 1
+        if r % 7 == 0:
+            continue
+        rec = (f"@x{i}\n{s}\n+\n{'I' * len(s)}\n" if fmt == "fastq" else f">x{i}\n{s}\n").encode()
+        want[1 + r % 3] += rec
+    assert sorted(os.listdir(out)) == ["#1.fa", "#2.fa", "#3.fa"]
+    for c, data in want.items():
+        assert open(os.path.join(out, f"#{c}.fa"), "rb").read() == data
+
+
 def test_cli_errors(exe, tmp_path):
     bad = tmp_path / "bad.txt"
     bad.write_text("hello\nworld\n")

@@ -157,6 +157,36 @@ def test_config5_like_tetraploid(oracle):
     assert len(want["core_id"]) >= 1
 
 
+def test_sc_score_mode_with_enrichment(oracle):
+    """--sc_score S: pivot subset + score > S selection, then merge + enrichment on top of it"""
+    import hga_b200
+    import oracle_lib
+    from test_gpu_golden import _gpu_enrichment
+    a = datagen.random_genome(30000, 61); b = datagen.mutate(a, 0.03, 62)
+    reads = datagen.sample_reads(a, 6000, 150, 63, error_rate=0.005) + datagen.sample_reads(b, 6000, 150, 64, error_rate=0.005)
+    bases, off = _pack([datagen.to_ascii(r) for r in reads])
+    kmers = datagen.discriminative_kmers([a, b], 19)
+    S = 60
+    res = oracle.run(bases, off, 19, kmers, min_size=10, sc_score=S)
+    want = oracle_lib.enrich(oracle, res, len(kmers), min_size=10, enrich_min=20)
+    with hga_b200.Handle(kmers, 19) as h:
+        h.scan(bases, off); h.build_index()
+        ro, _, _ = h.get_hits()
+        pivots = (np.nonzero(np.diff(ro.astype(np.int64)) >= S)[0] + 1).astype(np.uint32)
+        h.pair_count(min_score=S, pivots=pivots)
+        h.select_edges(score_threshold=S)
+        sel = h.get_selection()
+        assert sel["n_directed"] == res["cut_n"]
+        got = _gpu_enrichment(h, 10, 20)
+    assert len(want["core_id"]) >= 2
+    assert np.array_equal(got["core_id"], want["core_id"]) and np.array_equal(got["final_id"], want["final_id"])
+    assert np.array_equal(got["purged_off"], want["purged_off"]) and np.array_equal(got["purged_read"], want["purged_read"])
+    for g, w in zip(got["econn"], want["econn"]):
+        assert np.array_equal(g, w)
+    for g, w in zip(got["final_reads"], want["final_reads"]):
+        assert np.array_equal(g, w)
+
+
 def test_heavy_rows_overflow_shared_accumulator(oracle):
     """one repeated segment present in > 3072 reads: partner sets overflow the shared-memory table"""
     rng = np.random.default_rng(5)

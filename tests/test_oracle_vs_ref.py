@@ -54,10 +54,10 @@ def test_load_kmers_matches_ref(oracle, ref_driver, tmp_path):
     assert k == kr == 19 and np.array_equal(a, b)
 
 
-def _full_compare(oracle, ref_driver, paths, kp, fraction=0.15, min_size=30, threads=1, enrich=0):
+def _full_compare(oracle, ref_driver, paths, kp, fraction=0.15, min_size=30, threads=1, enrich=0, sc_score=0):
     reads, kmers, k = _load_case(oracle, paths, kp)
-    ref = refdump.run_ref(ref_driver, paths, kp, fraction=fraction, min_size=min_size, threads=threads, enrich=enrich)
-    res = oracle.run(reads["seq"], reads["seq_off"], k, kmers, fraction=fraction, min_size=min_size)
+    ref = refdump.run_ref(ref_driver, paths, kp, fraction=fraction, min_size=min_size, threads=threads, enrich=enrich, sc_score=sc_score)
+    res = oracle.run(reads["seq"], reads["seq_off"], k, kmers, fraction=fraction, min_size=min_size, sc_score=sc_score)
     assert ref["k"] == k and ref["n_kmers"] == kmers.shape[0] and ref["n_reads"] == reads["n_reads"]
     compare.check_hits(ref, res["row_off"], res["hit_kid"], res["hit_pos"], kmers)
     compare.check_index(ref, res["inv_off"], res["inv_read"], kmers)
@@ -126,6 +126,15 @@ def test_merge_and_enrichment_long_reads(oracle, ref_driver, tmp_path, enrich, m
                                           error_rate=0.05, length_sigma=0.5)
     ref, _ = _full_compare(oracle, ref_driver, paths, kp, min_size=min_size, enrich=enrich)
     assert ref["cores"] >= 1
+
+
+def test_sc_score_mode_with_enrichment(oracle, ref_driver, tmp_path):
+    # --sc_score S: pivot subset, score > S (a connection between a pivot and a non-pivot would exist in ONE direction only, which
+    # decides whose root survives a size tie in union_find, :459-466; with min score = pivot threshold that needs repeated k-mers)
+    paths, kp = datagen.make_diploid_case(str(tmp_path), genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=7,
+                                          error_rate=0.005, fmt="fastq")
+    ref, res = _full_compare(oracle, ref_driver, paths, kp, min_size=10, enrich=20, sc_score=60)
+    assert ref["cut_n"] > 100 and ref["cores"] >= 2
 
 
 def test_config5_like_tetraploid(oracle, ref_driver, tmp_path):
