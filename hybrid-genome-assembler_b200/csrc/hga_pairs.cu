@@ -14,7 +14,10 @@
 //      that can produce a (pivot < partner) pair is read (four entries per aligned 16 B load), and every unordered
 //      pair is produced exactly once. Lists longer than PW_LONG are walked by the whole warp with coalesced loads.
 //      (Merging equal candidates of a step with __match_any_sync so that the update is a plain read-modify-write was
-//      measured 5 % SLOWER than the shared-memory atomics and dropped.)
+//      measured 5 % SLOWER than the shared-memory atomics and dropped. A FLATTENED variant - 32 lists per step, tails found by
+//      binary search, laid end to end and consumed one entry per lane - executed 29 % fewer warp instructions and was 3 %
+//      slower: the kernel is bound by random DRAM traffic, 123 GB read at 1.8 TB/s for 6.4 G increments, not by issue slots;
+//      profiles/r03p_pair_count_memory_bound.md.)
 //   2. pair_count_kernel: rows whose partner set overflowed tier 1; one CTA per row, 4096-entry accumulator.
 //   3. pair_count_heavy_kernel: rows that overflow tier 2; per-CTA accumulator in HBM.
 // Output: (key = min_row << 32 | max_row, score) appended through one atomic cursor bump per row, then one
