@@ -456,7 +456,7 @@ def main():
             "pairs_per_s": pairs_total / (pair_ms * 1e-3) if pair_ms > 0 else None,
             "increments_per_s": incr_total / (pair_ms * 1e-3) if pair_ms > 0 else None,
             "diagnostics": {"filter_candidates_per_base": m["n_candidates"] / max(1, m["n_bases"]), "table_overflow_keys": m["table_overflow_keys"],
-                            "table_bytes": m["table_bytes"], "filter_bytes": m["filter_bytes"], "pair_mid_rows": m["mid_pivots"],
+                            "table_bytes": m["table_bytes"], "filter_bytes": m["filter_bytes"], "pair_redo_rows": m["redo_pivots"], "pair_mid_rows": m["mid_pivots"],
                             "pair_heavy_rows": m["heavy_pivots"], "exchange_ms": m["exchange_ms"]},
             "roofline": {"kernel": "scan_probe_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic_gb, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu capture profiles/r03m, same workload)",

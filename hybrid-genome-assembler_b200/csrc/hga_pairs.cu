@@ -34,7 +34,8 @@
 #define HV_THREADS 256
 #define PW_THREADS 128
 #define PW_WARPS (PW_THREADS / 32)
-#define PW_CMAX 1024
+#define PW_CMAX 1024               // accumulator of the second pass of tier 1
+#define PW_CMAX_FIRST 512          // accumulator of the first pass (more resident warps)
 #define PW_LONG 96
 #define PW_DEFER 32
 
@@ -50,6 +51,8 @@ struct PairScalars {
     unsigned long long increments;
     unsigned long long mid_count;
     unsigned long long mid_ticket;
+    unsigned long long redo_count;    // rows whose partner set overflowed the first-pass accumulator of tier 1
+    unsigned long long redo_ticket;
     unsigned int overflow;
     unsigned int pad;
 };
@@ -71,6 +74,7 @@ struct PairParams {
     uint64_t *out_key;
     uint32_t *out_score;
     uint64_t capacity;
+    uint32_t *redo_list;
     uint32_t *mid_list;
     uint32_t *heavy_list;
     uint32_t *heavy_tab;            // per-CTA tables of heavy_cap (key,val) pairs
@@ -117,15 +121,17 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_red,
 }
 
 // ---- tier 1 ---------------------------------------------------------------------------------------------------
+template<int CMAX>
 struct WarpAcc {
-    uint32_t key[PW_CMAX];
-    uint32_t val[PW_CMAX];
+    uint32_t key[CMAX];
+    uint32_t val[CMAX];
     uint2 defer[PW_DEFER];          // long lists: [lo, hi)
     uint32_t distinct, overflow, n_defer, pad;
 };
 
 // ++count[y] with shared-memory atomics; most calls find y already present: one plain read, one atomic add
-__device__ __forceinline__ void acc_add(WarpAcc &A, uint32_t y, uint32_t c, uint32_t cmask, int cshift, uint32_t limit) {
+template<int CMAX>
+__device__ __forceinline__ void acc_add(WarpAcc<CMAX> &A, uint32_t y, uint32_t c, uint32_t cmask, int cshift, uint32_t limit) {
     uint32_t h = hash_row(y) >> cshift;
     for (;;) {
         uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&A.key[h]);
@@ -139,27 +145,34 @@ __device__ __forceinline__ void acc_add(WarpAcc &A, uint32_t y, uint32_t c, uint
     }
 }
 
-__global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(PairParams p) {
-    __shared__ WarpAcc s_acc[PW_WARPS];
+// CMAX / REDO: the kernel is latency bound and its time is inversely proportional to the number of resident warps (r3s: 1 / 2 / 3 /
+// 4 / 6 CTAs per SM -> 359 / 186 / 130 / 102 / 75 ms), and the accumulator is what limits them. The first pass therefore runs with
+// a 512-entry accumulator (17 KB per CTA: 11 CTAs = 44 warps per SM); the rows whose partner set does not fit it are listed and
+// redone by a second pass with 1024 entries (6 CTAs per SM), and only what overflows that goes on to tier 2.
+template<int CMAX, bool REDO>
+__global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(const __grid_constant__ PairParams p) {
+    __shared__ WarpAcc<CMAX> s_acc[PW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpAcc &A = s_acc[warp];
+    WarpAcc<CMAX> &A = s_acc[warp];
     const bool tail = p.mode == PAIR_MODE_TAIL;
+    const unsigned long long n_items = REDO ? p.sc->redo_count : p.n_pivots;
 
     for (;;) {
         unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(&p.sc->ticket, 1ull);
+        if (lane == 0) t = atomicAdd(REDO ? &p.sc->redo_ticket : &p.sc->ticket, 1ull);
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
-        if (t >= p.n_pivots) break;
+        if (t >= n_items) break;
         // x: global row (what the inverted lists hold); xl: row of the by-read incidence on this GPU
-        const uint32_t x = p.pivot_rows ? p.pivot_rows[t] : (uint32_t) t * p.pivot_mul + p.pivot_add;
-        const uint32_t xl = p.pivot_rows ? x : (uint32_t) t;
+        uint32_t x, xl;
+        if (REDO) { xl = p.redo_list[t]; x = p.pivot_rows ? xl : xl * p.pivot_mul + p.pivot_add; }
+        else { x = p.pivot_rows ? p.pivot_rows[t] : (uint32_t) t * p.pivot_mul + p.pivot_add; xl = p.pivot_rows ? x : (uint32_t) t; }
         const uint64_t a = p.row_off[xl], b = p.row_off[xl + 1];
         if (a == b) continue;
 
         uint32_t C = 64;
-        while (C < PW_CMAX && C < 4 * (b - a)) C <<= 1;
+        while (C < CMAX && C < 4 * (b - a)) C <<= 1;
         for (bool retry = false;; retry = true) {
-            if (retry) C = PW_CMAX;
+            if (retry) C = CMAX;
             const uint32_t cmask = C - 1, limit = (C / 4) * 3;
             const int cshift = 32 - (31 - __clz(C));
             for (uint32_t i = lane; i < C; i += 32) { A.key[i] = PC_EMPTY; A.val[i] = 0; }
@@ -251,8 +264,11 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(PairParams 
                 }
                 break;
             }
-            if (C == PW_CMAX) {      // more partners than a warp accumulator holds: tier 2
-                if (lane == 0) p.mid_list[atomicAdd(&p.sc->mid_count, 1ull)] = xl;
+            if (C == CMAX) {         // more partners than this accumulator holds: second pass, then tier 2
+                if (lane == 0) {
+                    if (REDO) p.mid_list[atomicAdd(&p.sc->mid_count, 1ull)] = xl;
+                    else p.redo_list[atomicAdd(&p.sc->redo_count, 1ull)] = xl;
+                }
                 break;
             }
         }
@@ -428,6 +444,28 @@ __global__ void increments_kernel(const uint32_t *__restrict__ inv_off, uint32_t
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// Pivot order: min-hash of the row's k-mers (table slots). Reads that overlap on the genome share most of their k-mers, so they
+// share their min-hash with a probability equal to their Jaccard similarity: sorting the pivots by it puts groups of overlapping
+// reads next to each other in ticket order, and the inverted lists one of them pulls into L2 are found there by the others.
+__global__ void row_minhash_kernel(const uint64_t *__restrict__ row_off, const uint32_t *__restrict__ row_slot, uint64_t n_rows, uint32_t *__restrict__ key,
+                                   uint32_t *__restrict__ row) {
+    const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+    const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t r = w; r < n_rows; r += warps) {
+        const uint64_t a = row_off[r], b = row_off[r + 1];
+        uint32_t m = 0xFFFFFFFFu;
+        for (uint64_t i = a + lane; i < b; i += 32) {
+            uint32_t h = row_slot[i] * 0x9E3779B1u;
+            h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+            m = min(m, h);
+        }
+        #pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
+        if (lane == 0) { key[r] = m; row[r] = (uint32_t) r; }
+    }
+}
+
 __global__ void mark_pivots_kernel(const uint32_t *__restrict__ pivot_rows, uint64_t n, uint8_t *flag) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) flag[pivot_rows[i]] = 1;
 }
@@ -447,6 +485,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     PairScalars *d_sc = h->d_pair_scalars.as<PairScalars>();
     HGA_TRY(h->d_heavy_list.ensure((n_rows + 1) * 4));
     HGA_TRY(h->d_mid_list.ensure((n_rows + 1) * 4));
+    HGA_TRY(h->d_redo_list.ensure((n_rows + 1) * 4));
 
     PairParams p;
     memset(&p, 0, sizeof(p));
@@ -462,6 +501,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     p.mode = PAIR_MODE_TAIL;
     p.min_score = min_score;
     p.mid_list = h->d_mid_list.as<uint32_t>();
+    p.redo_list = h->d_redo_list.as<uint32_t>();
     p.heavy_list = h->d_heavy_list.as<uint32_t>();
     p.heavy_tab = nullptr; p.heavy_cap = 0;
     p.sc = d_sc;
@@ -492,14 +532,30 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     }
 
     StageTimer timer(h, &h->metrics.pair_ms);
+    bool minhash_order = !multi && !pivots && n_rows > 4096;
+    if (const char *e = getenv("HGA_PAIR_ORDER")) minhash_order = minhash_order && atoi(e) != 0;
+    if (minhash_order) {
+        HGA_TRY(h->d_pivot_order.ensure((n_rows + 1) * 4 * 4));
+        uint32_t *k_in = h->d_pivot_order.as<uint32_t>(), *r_in = k_in + (n_rows + 1), *k_out = r_in + (n_rows + 1), *r_out = k_out + (n_rows + 1);
+        row_minhash_kernel<<<(int) std::min<uint64_t>((n_rows * 32 + 255) / 256, (uint64_t) h->sm_count * 32), 256, 0, h->stream>>>(p.row_off, p.row_slot, n_rows, k_in, r_in);
+        size_t tmp_bytes = 0;
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, r_in, r_out, n_rows, 0, 32, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp_bytes, k_in, k_out, r_in, r_out, n_rows, 0, 32, h->stream));
+        h->metrics.kernel_launches += 6;
+        HGA_CUDA(cudaGetLastError());
+        p.pivot_rows = r_out;        // all rows, TAIL mode, in min-hash order
+    }
     uint64_t capacity = std::max<uint64_t>(h->pair_capacity, std::max<uint64_t>(64 * n_rows, 1ull << 20));
     int occ_w = 0, occ_c = 0;
-    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel, PW_THREADS, 0));
+    int occ_r = 0;
+    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel<PW_CMAX_FIRST, false>, PW_THREADS, 0));
+    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, pair_count_warp_kernel<PW_CMAX, true>, PW_THREADS, 0));
+    if (occ_r < 1) occ_r = 1;
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pair_count_kernel, PC_THREADS, 0));
     if (occ_w < 1) occ_w = 1;
     if (occ_c < 1) occ_c = 1;
     const int grid_w = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) h->sm_count * occ_w, (p.n_pivots + PW_WARPS - 1) / PW_WARPS));
-
     PairScalars sc;
     h->metrics.pair_retries = 0;
     for (int attempt = 0;; attempt++) {
@@ -508,12 +564,21 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
         p.out_key = h->d_pair_key.as<uint64_t>(); p.out_score = h->d_pair_score.as<uint32_t>(); p.capacity = capacity;
         HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(PairScalars), h->stream));
         if (p.n_pivots) {
-            pair_count_warp_kernel<<<grid_w, PW_THREADS, 0, h->stream>>>(p);
+            pair_count_warp_kernel<PW_CMAX_FIRST, false><<<grid_w, PW_THREADS, 0, h->stream>>>(p);
             h->metrics.kernel_launches++;
             HGA_CUDA(cudaGetLastError());
         }
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
+        if (sc.redo_count) {
+            const int grid_r = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) h->sm_count * occ_r, (sc.redo_count + PW_WARPS - 1) / PW_WARPS));
+            pair_count_warp_kernel<PW_CMAX, true><<<grid_r, PW_THREADS, 0, h->stream>>>(p);
+            h->metrics.kernel_launches++;
+            HGA_CUDA(cudaGetLastError());
+            HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        h->metrics.redo_pivots = sc.redo_count;
         if (sc.mid_count) {
             const int grid_c = (int) std::min<uint64_t>(sc.mid_count, (uint64_t) h->sm_count * occ_c);
             pair_count_kernel<<<grid_c, PC_THREADS, 0, h->stream>>>(p);

@@ -176,6 +176,7 @@ typedef struct {
     uint64_t n_candidates;     /* windows that passed the membership filter in the last scan (hits + false positives) */
     double enrich_ms;          /* hga_enrich, host replay of the union_find roots included */
     uint64_t n_cores, n_enrich_connections, n_final_components;
+    uint64_t redo_pivots;      /* pivot rows redone by the second pass of pair-count tier 1 (1024-entry accumulator) */
 } hga_metrics_t;
 int hga_metrics(hga_handle *h, hga_metrics_t *out);
 
