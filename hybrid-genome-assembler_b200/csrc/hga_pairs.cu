@@ -181,8 +181,9 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(const __gri
 
             // every lane: one list at a time, two lists ahead in flight: the bounds of list j + 64 are being loaded while the
             // last 16 B chunk of list j + 32 (bounds known by now) is prefetched into L2 and list j is walked. (Requesting
-            // every chunk one step before it is used - a register double buffer - was measured 14 % SLOWER (r1t); halving the
-            // accumulator to 512 entries for 44 resident warps / SM was 8 % slower (r1x).)
+            // every chunk one step before it is used - a register double buffer - was measured 14 % SLOWER (r1t). Giving every
+            // lane one contiguous block of the row's entries instead of the interleaved lane, lane + 32, ... was 27 % slower (r3v):
+            // neighbouring lanes walking neighbouring lists is what coalesces the list loads.)
             uint64_t j = a + lane;
             uint32_t cur_lo = 0, cur_i = 0, n1_lo = 0, n1_hi = 0, n2_lo = 0, n2_hi = 0;
             bool have1 = j < b, have2 = j + 32 < b;
