@@ -453,15 +453,20 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
     pc.mark("enrichment connections");
 
     // ---- 4. host: canonical order, restricted union_find (:424-489 with restricted = cores, min 2, max -1), final merge -----
-    std::sort(conns.begin(), conns.end(), [](const Conn &a, const Conn &b) {
-        if (a.s != b.s) return a.s > b.s;
-        const uint32_t amin = std::min(a.x, a.y), amax = std::max(a.x, a.y), bmin = std::min(b.x, b.y), bmax = std::max(b.x, b.y);
-        if (amin != bmin) return amin < bmin;
-        if (amax != bmax) return amax < bmax;
-        return a.x < b.x;
-    });
-    res.conn_x.resize(conns.size()); res.conn_y.resize(conns.size()); res.conn_score.resize(conns.size());
-    for (size_t i = 0; i < conns.size(); i++) { res.conn_x[i] = conns[i].x; res.conn_y[i] = conns[i].y; res.conn_score[i] = conns[i].s; }
+    {   // (score desc, min asc, max asc, x asc) as two packed 64-bit keys
+        struct Key { uint64_t hi, lo; uint32_t y; };
+        std::vector<Key> keys(conns.size());
+        for (size_t i = 0; i < conns.size(); i++) {
+            const Conn &c = conns[i];
+            keys[i] = {((uint64_t) ~c.s << 32) | std::min(c.x, c.y), ((uint64_t) std::max(c.x, c.y) << 32) | c.x, c.y};
+        }
+        std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return a.hi != b.hi ? a.hi < b.hi : a.lo < b.lo; });
+        res.conn_x.resize(conns.size()); res.conn_y.resize(conns.size()); res.conn_score.resize(conns.size());
+        for (size_t i = 0; i < keys.size(); i++) {
+            conns[i] = {(uint32_t) keys[i].lo, keys[i].y, ~(uint32_t) (keys[i].hi >> 32)};
+            res.conn_x[i] = conns[i].x; res.conn_y[i] = conns[i].y; res.conn_score[i] = conns[i].s;
+        }
+    }
 
     std::iota(parent.begin(), parent.end(), 0u);
     std::fill(size.begin(), size.end(), 1u);
