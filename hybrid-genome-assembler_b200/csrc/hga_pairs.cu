@@ -196,16 +196,27 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(const __gri
                     const uint32_t q = (cur_i - 1) >> 2, cb = q << 2;
                     const uint4 c = __ldg(reinterpret_cast<const uint4 *>(p.inv_row) + q);
                     const uint32_t ys[4] = {c.x, c.y, c.z, c.w};
+                    // the four accumulator probes are issued together (four independent shared-memory loads), then resolved: the
+                    // common case - partner already present - is one plain read and one atomic add per entry
+                    bool ok[4], stop = false;
+                    uint32_t hh[4], kk[4];
                     #pragma unroll
-                    for (int e = 3; e >= 0; e--) {
+                    for (int e = 0; e < 4; e++) {
                         const uint32_t idx = cb + e;
-                        if (idx < cur_i && idx >= cur_lo) {
-                            const uint32_t yy = ys[e];
-                            if (tail && yy <= x) cur_i = cur_lo;                  // ascending list: nothing further down can be > x
-                            else if (keep_candidate(x, yy, p.mode, p.pivot_flag)) acc_add(A, yy, 1u, cmask, cshift, limit);
-                        }
+                        const bool inr = idx < cur_i && idx >= cur_lo;
+                        stop |= inr && tail && ys[e] <= x;                    // ascending list: nothing further down can be > x
+                        ok[e] = inr && keep_candidate(x, ys[e], p.mode, p.pivot_flag);
+                        hh[e] = hash_row(ys[e]) >> cshift;
                     }
-                    if (cur_i > cur_lo) cur_i = max(cb, cur_lo);
+                    #pragma unroll
+                    for (int e = 0; e < 4; e++) kk[e] = ok[e] ? *reinterpret_cast<volatile uint32_t *>(&A.key[hh[e]]) : 0u;
+                    #pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        if (!ok[e]) continue;
+                        if (kk[e] == ys[e]) atomicAdd(&A.val[hh[e]], 1u);
+                        else acc_add(A, ys[e], 1u, cmask, cshift, limit);
+                    }
+                    cur_i = stop ? cur_lo : max(cb, cur_lo);
                 } else if (have1) {
                     cur_lo = n1_lo; cur_i = n1_hi;
                     if (cur_i - cur_lo > PW_LONG) {                           // long list: leave it to the whole warp
