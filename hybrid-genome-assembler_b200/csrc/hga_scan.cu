@@ -513,7 +513,16 @@ __global__ void scan_fix_rows_kernel(const uint64_t *__restrict__ read_off, uint
 }
 
 int launch_scan(hga_handle *h, const ScanParams &p, int grid) {
-    scan_probe_kernel<<<grid, SCAN_THREADS, 0, h->stream>>>(p);
+    // experiment switch: HGA_SCAN_PAD_KB pads every CTA with unused dynamic shared memory (fewer resident CTAs per SM)
+    size_t pad = 0;
+    if (const char *e = getenv("HGA_SCAN_PAD_KB")) {
+        pad = (size_t) atoi(e) * 1024;
+        cudaFuncSetAttribute(scan_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pad);
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel, SCAN_THREADS, pad);
+        grid = std::min(grid, h->sm_count * std::max(occ, 1));
+    }
+    scan_probe_kernel<<<grid, SCAN_THREADS, pad, h->stream>>>(p);
     HGA_CUDA(cudaGetLastError());
     h->metrics.kernel_launches++;
     return HGA_OK;

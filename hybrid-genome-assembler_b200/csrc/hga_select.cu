@@ -11,6 +11,7 @@
 #include "hga_internal.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 
 #define SEL_CHUNK 2048
@@ -158,11 +159,19 @@ int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold) {
             HGA_TRY(h->d_sort_a.ensure((P + 1) * 4));
             uint32_t *d_sorted = h->d_sort_a.as<uint32_t>();
             if (P > 0) {
-                size_t tmp_bytes = 0;
+                // scores are small (a few thousand at most at config 4): sort only the bits the largest one needs
+                size_t tmp_bytes = 0, red_bytes = 0;
+                uint32_t *d_max = reinterpret_cast<uint32_t *>(d_hist);
+                HGA_CUDA(cub::DeviceReduce::Max(nullptr, red_bytes, h->d_pair_score.as<uint32_t>(), d_max, P, h->stream));
                 HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, h->d_pair_score.as<uint32_t>(), d_sorted, P, 0, 32, h->stream));
-                HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
-                HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, tmp_bytes, h->d_pair_score.as<uint32_t>(), d_sorted, P, 0, 32, h->stream));
-                h->metrics.kernel_launches += 6;
+                HGA_TRY(h->d_sort_tmp.ensure(std::max(tmp_bytes, red_bytes) + 16));
+                HGA_CUDA(cub::DeviceReduce::Max(h->d_sort_tmp.p, red_bytes, h->d_pair_score.as<uint32_t>(), d_max, P, h->stream));
+                uint32_t max_score = 0;
+                HGA_CUDA(cudaMemcpyAsync(&max_score, d_max, 4, cudaMemcpyDeviceToHost, h->stream));
+                HGA_CUDA(cudaStreamSynchronize(h->stream));
+                const int end_bit = (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) max_score + 1), 1);
+                HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, tmp_bytes, h->d_pair_score.as<uint32_t>(), d_sorted, P, 0, end_bit, h->stream));
+                h->metrics.kernel_launches += (uint64_t) (end_bit + 7) / 8 + 4;
             }
             const uint64_t rank = (n_directed + 1) / 2;   // the n-th directed entry belongs to the rank-th pair (descending)
             uint32_t hi_bin = 0;
