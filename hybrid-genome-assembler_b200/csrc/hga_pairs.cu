@@ -146,6 +146,112 @@ __device__ __forceinline__ void acc_add(WarpAcc<CMAX> &A, uint32_t y, uint32_t c
     }
 }
 
+// The walk of one pivot row's incidence entries [a, b) by one warp into its accumulator A.
+template<int CMAX>
+__device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, uint32_t x, uint64_t a, uint64_t b, bool tail, uint32_t cmask, int cshift,
+                                         uint32_t limit, int lane) {
+    // every lane: one list at a time, two lists ahead in flight: the bounds of list j + 64 are being loaded while the
+    // last 16 B chunk of list j + 32 (bounds known by now) is prefetched into L2 and list j is walked. (Requesting
+    // every chunk one step before it is used - a register double buffer - was measured 14 % SLOWER (r1t). Giving every
+    // lane one contiguous block of the row's entries instead of the interleaved lane, lane + 32, ... was 27 % slower (r3v):
+    // neighbouring lanes walking neighbouring lists is what coalesces the list loads.)
+    uint64_t j = a + lane;
+    uint32_t cur_lo = 0, cur_i = 0, n1_lo = 0, n1_hi = 0, n2_lo = 0, n2_hi = 0;
+    bool have1 = j < b, have2 = j + 32 < b;
+    if (have1) { const uint32_t slot = __ldg(&p.row_slot[j]); n1_lo = __ldg(&p.inv_off[slot]); n1_hi = __ldg(&p.inv_off[slot + 1]); }
+    if (have2) { const uint32_t slot = __ldg(&p.row_slot[j + 32]); n2_lo = __ldg(&p.inv_off[slot]); n2_hi = __ldg(&p.inv_off[slot + 1]); }
+    while (__any_sync(0xFFFFFFFFu, have1 || cur_i > cur_lo)) {
+        if (cur_i > cur_lo) {
+            // four list entries per step (one aligned 16 B load), walked from the end of the list
+            const uint32_t q = (cur_i - 1) >> 2, cb = q << 2;
+            const uint4 c = __ldg(reinterpret_cast<const uint4 *>(p.inv_row) + q);
+            const uint32_t ys[4] = {c.x, c.y, c.z, c.w};
+            // the four accumulator probes are issued together (four independent shared-memory loads), then resolved: the
+            // common case - partner already present - is one plain read and one atomic add per entry (r4a: 71.1 -> 64.0 ms;
+            // two chunks = eight probes per step needs 62 registers and was slower, 77.5 ms, r4b)
+            bool ok[4], stop = false;
+            uint32_t hh[4], kk[4];
+            #pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const uint32_t idx = cb + e;
+                const bool inr = idx < cur_i && idx >= cur_lo;
+                stop |= inr && tail && ys[e] <= x;                    // ascending list: nothing further down can be > x
+                ok[e] = inr && keep_candidate(x, ys[e], p.mode, p.pivot_flag);
+                hh[e] = hash_row(ys[e]) >> cshift;
+            }
+            #pragma unroll
+            for (int e = 0; e < 4; e++) kk[e] = ok[e] ? *reinterpret_cast<volatile uint32_t *>(&A.key[hh[e]]) : 0u;
+            #pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (!ok[e]) continue;
+                if (kk[e] == ys[e]) atomicAdd(&A.val[hh[e]], 1u);
+                else acc_add(A, ys[e], 1u, cmask, cshift, limit);
+            }
+            cur_i = stop ? cur_lo : max(cb, cur_lo);
+        } else if (have1) {
+            cur_lo = n1_lo; cur_i = n1_hi;
+            if (cur_i - cur_lo > PW_LONG) {                           // long list: leave it to the whole warp
+                const uint32_t at = atomicAdd(&A.n_defer, 1u);
+                if (at < PW_DEFER) { A.defer[at] = make_uint2(cur_lo, cur_i); cur_i = cur_lo; }
+            }
+            j += 32;
+            have1 = have2; n1_lo = n2_lo; n1_hi = n2_hi;
+            if (have1 && n1_hi > n1_lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.inv_row + (((size_t) n1_hi - 1) & ~(size_t) 3)));
+            have2 = j + 32 < b;
+            if (have2) { const uint32_t slot = __ldg(&p.row_slot[j + 32]); n2_lo = __ldg(&p.inv_off[slot]); n2_hi = __ldg(&p.inv_off[slot + 1]); }
+        }
+        if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) { cur_i = cur_lo; have1 = false; }
+    }
+    __syncwarp();
+    const uint32_t nd = min(*reinterpret_cast<volatile uint32_t *>(&A.n_defer), (uint32_t) PW_DEFER);
+    for (uint32_t d = 0; d < nd && !*reinterpret_cast<volatile uint32_t *>(&A.overflow); d++) {
+        const uint2 r = A.defer[d];
+        for (int64_t i = (int64_t) r.y - 1 - lane;; i -= 32) {
+            bool go = i >= (int64_t) r.x;
+            if (go) {
+                const uint32_t y = __ldg(&p.inv_row[i]);
+                if (tail && y <= x) go = false;
+                else if (keep_candidate(x, y, p.mode, p.pivot_flag)) acc_add(A, y, 1u, cmask, cshift, limit);
+            }
+            if (!__any_sync(0xFFFFFFFFu, go)) break;
+        }
+    }
+    __syncwarp();
+}
+
+// entries of A with score >= min_score -> output (one cursor bump per call)
+template<int CMAX>
+__device__ __forceinline__ void flush_table(WarpAcc<CMAX> &A, const PairParams &p, uint32_t x, uint32_t C, int lane) {
+    // flush: entries with score >= min_score
+    uint32_t total = 0;
+    for (uint32_t i0 = 0; i0 < C; i0 += 32) {
+        const bool ok = A.key[i0 + lane] != PC_EMPTY && A.val[i0 + lane] >= p.min_score;
+        total += __popc(__ballot_sync(0xFFFFFFFFu, ok));
+    }
+    if (total) {
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&p.sc->cursor, (unsigned long long) total);
+            if (base + total > p.capacity) p.sc->overflow = 1;
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base + total <= p.capacity) {
+            uint32_t off = 0;
+            for (uint32_t i0 = 0; i0 < C; i0 += 32) {
+                const uint32_t y = A.key[i0 + lane], v = A.val[i0 + lane];
+                const bool ok = y != PC_EMPTY && v >= p.min_score;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+                if (ok) {
+                    const uint64_t at = base + off + __popc(bal & ((1u << lane) - 1));
+                    p.out_key[at] = ((uint64_t) min(x, y) << 32) | max(x, y);
+                    p.out_score[at] = v;
+                }
+                off += __popc(bal);
+            }
+        }
+    }
+}
+
 // CMAX / REDO: the kernel is latency bound and its time is inversely proportional to the number of resident warps (r3s: 1 / 2 / 3 /
 // 4 / 6 CTAs per SM -> 359 / 186 / 130 / 102 / 75 ms), and the accumulator is what limits them. The first pass therefore runs with
 // a 512-entry accumulator (17 KB per CTA: 11 CTAs = 44 warps per SM); the rows whose partner set does not fit it are listed and
@@ -180,102 +286,9 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(const __gri
             if (lane == 0) { A.distinct = 0; A.overflow = 0; A.n_defer = 0; }
             __syncwarp();
 
-            // every lane: one list at a time, two lists ahead in flight: the bounds of list j + 64 are being loaded while the
-            // last 16 B chunk of list j + 32 (bounds known by now) is prefetched into L2 and list j is walked. (Requesting
-            // every chunk one step before it is used - a register double buffer - was measured 14 % SLOWER (r1t). Giving every
-            // lane one contiguous block of the row's entries instead of the interleaved lane, lane + 32, ... was 27 % slower (r3v):
-            // neighbouring lanes walking neighbouring lists is what coalesces the list loads.)
-            uint64_t j = a + lane;
-            uint32_t cur_lo = 0, cur_i = 0, n1_lo = 0, n1_hi = 0, n2_lo = 0, n2_hi = 0;
-            bool have1 = j < b, have2 = j + 32 < b;
-            if (have1) { const uint32_t slot = __ldg(&p.row_slot[j]); n1_lo = __ldg(&p.inv_off[slot]); n1_hi = __ldg(&p.inv_off[slot + 1]); }
-            if (have2) { const uint32_t slot = __ldg(&p.row_slot[j + 32]); n2_lo = __ldg(&p.inv_off[slot]); n2_hi = __ldg(&p.inv_off[slot + 1]); }
-            while (__any_sync(0xFFFFFFFFu, have1 || cur_i > cur_lo)) {
-                if (cur_i > cur_lo) {
-                    // four list entries per step (one aligned 16 B load), walked from the end of the list
-                    const uint32_t q = (cur_i - 1) >> 2, cb = q << 2;
-                    const uint4 c = __ldg(reinterpret_cast<const uint4 *>(p.inv_row) + q);
-                    const uint32_t ys[4] = {c.x, c.y, c.z, c.w};
-                    // the four accumulator probes are issued together (four independent shared-memory loads), then resolved: the
-                    // common case - partner already present - is one plain read and one atomic add per entry (r4a: 71.1 -> 64.0 ms;
-                    // two chunks = eight probes per step needs 62 registers and was slower, 77.5 ms, r4b)
-                    bool ok[4], stop = false;
-                    uint32_t hh[4], kk[4];
-                    #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const uint32_t idx = cb + e;
-                        const bool inr = idx < cur_i && idx >= cur_lo;
-                        stop |= inr && tail && ys[e] <= x;                    // ascending list: nothing further down can be > x
-                        ok[e] = inr && keep_candidate(x, ys[e], p.mode, p.pivot_flag);
-                        hh[e] = hash_row(ys[e]) >> cshift;
-                    }
-                    #pragma unroll
-                    for (int e = 0; e < 4; e++) kk[e] = ok[e] ? *reinterpret_cast<volatile uint32_t *>(&A.key[hh[e]]) : 0u;
-                    #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        if (!ok[e]) continue;
-                        if (kk[e] == ys[e]) atomicAdd(&A.val[hh[e]], 1u);
-                        else acc_add(A, ys[e], 1u, cmask, cshift, limit);
-                    }
-                    cur_i = stop ? cur_lo : max(cb, cur_lo);
-                } else if (have1) {
-                    cur_lo = n1_lo; cur_i = n1_hi;
-                    if (cur_i - cur_lo > PW_LONG) {                           // long list: leave it to the whole warp
-                        const uint32_t at = atomicAdd(&A.n_defer, 1u);
-                        if (at < PW_DEFER) { A.defer[at] = make_uint2(cur_lo, cur_i); cur_i = cur_lo; }
-                    }
-                    j += 32;
-                    have1 = have2; n1_lo = n2_lo; n1_hi = n2_hi;
-                    if (have1 && n1_hi > n1_lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.inv_row + (((size_t) n1_hi - 1) & ~(size_t) 3)));
-                    have2 = j + 32 < b;
-                    if (have2) { const uint32_t slot = __ldg(&p.row_slot[j + 32]); n2_lo = __ldg(&p.inv_off[slot]); n2_hi = __ldg(&p.inv_off[slot + 1]); }
-                }
-                if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) { cur_i = cur_lo; have1 = false; }
-            }
-            __syncwarp();
-            const uint32_t nd = min(*reinterpret_cast<volatile uint32_t *>(&A.n_defer), (uint32_t) PW_DEFER);
-            for (uint32_t d = 0; d < nd && !*reinterpret_cast<volatile uint32_t *>(&A.overflow); d++) {
-                const uint2 r = A.defer[d];
-                for (int64_t i = (int64_t) r.y - 1 - lane;; i -= 32) {
-                    bool go = i >= (int64_t) r.x;
-                    if (go) {
-                        const uint32_t y = __ldg(&p.inv_row[i]);
-                        if (tail && y <= x) go = false;
-                        else if (keep_candidate(x, y, p.mode, p.pivot_flag)) acc_add(A, y, 1u, cmask, cshift, limit);
-                    }
-                    if (!__any_sync(0xFFFFFFFFu, go)) break;
-                }
-            }
-            __syncwarp();
+            walk_row<CMAX>(A, p, x, a, b, tail, cmask, cshift, limit, lane);
             if (!*reinterpret_cast<volatile uint32_t *>(&A.overflow)) {
-                // flush: entries with score >= min_score
-                uint32_t total = 0;
-                for (uint32_t i0 = 0; i0 < C; i0 += 32) {
-                    const bool ok = A.key[i0 + lane] != PC_EMPTY && A.val[i0 + lane] >= p.min_score;
-                    total += __popc(__ballot_sync(0xFFFFFFFFu, ok));
-                }
-                if (total) {
-                    unsigned long long base = 0;
-                    if (lane == 0) {
-                        base = atomicAdd(&p.sc->cursor, (unsigned long long) total);
-                        if (base + total > p.capacity) p.sc->overflow = 1;
-                    }
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (base + total <= p.capacity) {
-                        uint32_t off = 0;
-                        for (uint32_t i0 = 0; i0 < C; i0 += 32) {
-                            const uint32_t y = A.key[i0 + lane], v = A.val[i0 + lane];
-                            const bool ok = y != PC_EMPTY && v >= p.min_score;
-                            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
-                            if (ok) {
-                                const uint64_t at = base + off + __popc(bal & ((1u << lane) - 1));
-                                p.out_key[at] = ((uint64_t) min(x, y) << 32) | max(x, y);
-                                p.out_score[at] = v;
-                            }
-                            off += __popc(bal);
-                        }
-                    }
-                }
+                flush_table<CMAX>(A, p, x, C, lane);
                 break;
             }
             if (C == CMAX) {         // more partners than this accumulator holds: second pass, then tier 2
@@ -287,6 +300,56 @@ __global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(const __gri
             }
         }
         __syncwarp();
+    }
+}
+
+// Second pass of tier 1, for the rows whose partner set overflowed the 512-entry accumulator. They are few (2 732 of 1 M at
+// config 4) and they are the longest rows, so one warp per row leaves the GPU waiting for the slowest of them (5.6 ms); here a
+// CTA takes a row: every warp walks a quarter of the row's incidence entries into its own 1024-entry accumulator, then warps
+// 1 .. 3 pour theirs into warp 0's, which is flushed. A row whose merged partner set still does not fit goes to tier 2.
+__global__ void __launch_bounds__(PW_THREADS) pair_count_redo_kernel(const __grid_constant__ PairParams p) {
+    __shared__ WarpAcc<PW_CMAX> s_acc[PW_WARPS];
+    __shared__ unsigned long long s_ticket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpAcc<PW_CMAX> &A = s_acc[warp];
+    const bool tail = p.mode == PAIR_MODE_TAIL;
+    const unsigned long long n_items = p.sc->redo_count;
+    const uint32_t C = PW_CMAX, cmask = C - 1, limit = (C / 4) * 3;
+    const int cshift = 32 - (31 - __clz(C));
+
+    for (;;) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&p.sc->redo_ticket, 1ull);
+        __syncthreads();
+        const unsigned long long t = s_ticket;
+        if (t >= n_items) break;
+        const uint32_t xl = p.redo_list[t];
+        const uint32_t x = p.pivot_rows ? xl : xl * p.pivot_mul + p.pivot_add;
+        const uint64_t a0 = p.row_off[xl], b0 = p.row_off[xl + 1];
+        // quarters in multiples of 32 entries: inside a warp, neighbouring lanes still walk neighbouring lists
+        const uint64_t per = (((b0 - a0 + PW_WARPS - 1) / PW_WARPS) + 31) & ~(uint64_t) 31;
+        const uint64_t a = min(b0, a0 + warp * per), b = min(b0, a + per);
+        for (uint32_t i = lane; i < C; i += 32) { A.key[i] = PC_EMPTY; A.val[i] = 0; }
+        if (lane == 0) { A.distinct = 0; A.overflow = 0; A.n_defer = 0; }
+        __syncwarp();
+        if (a < b) walk_row<PW_CMAX>(A, p, x, a, b, tail, cmask, cshift, limit, lane);
+        __syncthreads();
+        bool over = false;
+        #pragma unroll
+        for (int w = 0; w < PW_WARPS; w++) over |= *reinterpret_cast<volatile uint32_t *>(&s_acc[w].overflow) != 0;
+        if (!over && warp > 0) {
+            for (uint32_t i = lane; i < C; i += 32) {
+                const uint32_t y = A.key[i];
+                if (y != PC_EMPTY) acc_add(s_acc[0], y, A.val[i], cmask, cshift, limit);
+            }
+        }
+        __syncthreads();
+        over |= *reinterpret_cast<volatile uint32_t *>(&s_acc[0].overflow) != 0;
+        if (over) {
+            if (threadIdx.x == 0) p.mid_list[atomicAdd(&p.sc->mid_count, 1ull)] = xl;
+        } else if (warp == 0) {
+            flush_table<PW_CMAX>(s_acc[0], p, x, C, lane);
+        }
+        __syncthreads();
     }
 }
 
@@ -564,7 +627,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     int occ_w = 0, occ_c = 0;
     int occ_r = 0;
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel<PW_CMAX_FIRST, false>, PW_THREADS, 0));
-    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, pair_count_warp_kernel<PW_CMAX, true>, PW_THREADS, 0));
+    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, pair_count_redo_kernel, PW_THREADS, 0));
     if (occ_r < 1) occ_r = 1;
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pair_count_kernel, PC_THREADS, 0));
     if (occ_w < 1) occ_w = 1;
@@ -591,8 +654,8 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         if (sc.redo_count) {
-            const int grid_r = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) h->sm_count * occ_r, (sc.redo_count + PW_WARPS - 1) / PW_WARPS));
-            pair_count_warp_kernel<PW_CMAX, true><<<grid_r, PW_THREADS, 0, h->stream>>>(p);
+            const int grid_r = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) h->sm_count * occ_r, sc.redo_count));
+            pair_count_redo_kernel<<<grid_r, PW_THREADS, 0, h->stream>>>(p);
             h->metrics.kernel_launches++;
             HGA_CUDA(cudaGetLastError());
             HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
