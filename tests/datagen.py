@@ -139,3 +139,30 @@ def make_polyploid_case(outdir, genome_size, divergence, k, read_len, coverage, 
     kp = os.path.join(outdir, f"{k}-mers.txt")
     write_kmers(kp, rng.permutation(sdk), k)
     return paths, kp
+
+
+def fuzz_case(seed):
+    """Random small diploid case for the parity fuzz tests: (haplotypes, reads as code arrays, k, fraction, min_size, enrich_min)."""
+    rng = np.random.default_rng(9000 + seed)
+    k = int(rng.choice([11, 13, 15, 17, 19, 21, 25]))
+    gsize = int(rng.integers(3000, 40000))
+    div = float(rng.choice([0.01, 0.02, 0.03, 0.05]))
+    long_reads = bool(rng.integers(0, 2))
+    read_len = int(rng.integers(800, 4000)) if long_reads else int(rng.integers(80, 300))
+    cov = float(rng.integers(8, 35))
+    err = float(rng.choice([0.0, 0.005, 0.02, 0.06])) if long_reads else float(rng.choice([0.0, 0.005, 0.01]))
+    a = random_genome(gsize, 9100 + seed)
+    if rng.integers(0, 3) == 0:           # a repeat: k-mers that occur several times per read
+        rep = a[:min(400, gsize // 4)].copy()
+        pos = int(rng.integers(gsize // 2, gsize - rep.shape[0]))
+        a[pos:pos + rep.shape[0]] = rep
+    b = mutate(a, div, 9200 + seed)
+    n = max(4, int(cov * gsize / read_len))
+    reads = sample_reads(a, n, read_len, 9300 + seed, error_rate=err, length_sigma=0.5 if long_reads else 0.0, min_len=min(40, gsize)) + \
+        sample_reads(b, n, read_len, 9400 + seed, error_rate=err, length_sigma=0.5 if long_reads else 0.0, min_len=min(40, gsize))
+    order = rng.permutation(len(reads))   # haplotypes interleaved: read ids carry no haplotype information
+    reads = [reads[i] for i in order]
+    fraction = float(rng.choice([0.05, 0.15, 0.3, 0.6]))
+    min_size = int(rng.choice([2, 3, 5, 10, 30]))
+    enrich_min = int(rng.choice([1, 2, 5, 20, 40]))
+    return [a, b], reads, k, fraction, min_size, enrich_min

@@ -157,6 +157,29 @@ def test_config5_like_tetraploid(oracle):
     assert len(want["core_id"]) >= 1
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_all_stages(oracle, seed):
+    """the fuzz cases of tests/test_oracle_vs_ref.py (where the oracle is checked against the real reference) through the C-ABI"""
+    import hga_b200
+    import oracle_lib
+    from test_gpu_golden import _gpu_enrichment
+    haps, reads, k, fraction, min_size, enrich_min = datagen.fuzz_case(seed)
+    bases, off = _pack([datagen.to_ascii(r) for r in reads])
+    kmers = datagen.discriminative_kmers(haps, k)
+    ref, _ = _run_and_compare(oracle, bases, off, k, kmers, fraction=fraction, min_size=min_size, check_sorted_hits=False)
+    want = oracle_lib.enrich(oracle, ref, len(kmers), min_size=min_size, enrich_min=enrich_min)
+    with hga_b200.Handle(kmers, k) as h:
+        h.scan(bases, off); h.build_index(); h.pair_count(min_score=1); h.select_edges(fraction=fraction)
+        got = _gpu_enrichment(h, min_size, enrich_min)
+    assert np.array_equal(got["core_id"], want["core_id"]) and np.array_equal(got["final_id"], want["final_id"])
+    assert np.array_equal(got["purged_off"], want["purged_off"]) and np.array_equal(got["purged_read"], want["purged_read"])
+    for g, w in zip(got["econn"], want["econn"]):
+        assert np.array_equal(g, w)
+    assert len(got["final_reads"]) == len(want["final_reads"])
+    for g, w in zip(got["final_reads"], want["final_reads"]):
+        assert np.array_equal(g, w)
+
+
 def test_sc_score_mode_with_enrichment(oracle):
     """--sc_score S: pivot subset + score > S selection, then merge + enrichment on top of it"""
     import hga_b200

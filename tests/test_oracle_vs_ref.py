@@ -137,6 +137,17 @@ def test_sc_score_mode_with_enrichment(oracle, ref_driver, tmp_path):
     assert ref["cut_n"] > 100 and ref["cores"] >= 2
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_all_stages_against_the_reference(oracle, ref_driver, tmp_path, seed):
+    # random k, genome, read length, coverage, error, repeats, fraction, component sizes, enrichment threshold; every stage from
+    # the hit lists to the final components against the real reference
+    haps, reads, k, fraction, min_size, enrich_min = datagen.fuzz_case(seed)
+    rp = str(tmp_path / "r.fa"); kp = str(tmp_path / "k.txt")
+    datagen.write_fasta(rp, reads)
+    datagen.write_kmers(kp, np.random.default_rng(seed).permutation(datagen.discriminative_kmers(haps, k)), k)
+    _full_compare(oracle, ref_driver, [rp], kp, fraction=fraction, min_size=min_size, enrich=enrich_min)
+
+
 def test_config5_like_tetraploid(oracle, ref_driver, tmp_path):
     # BASELINE config 5 in small: four haplotype read files, dense discriminative set (k-mers absent from at least one haplotype)
     paths, kp = datagen.make_polyploid_case(str(tmp_path), genome_size=12000, divergence=0.02, k=19, read_len=1500, coverage=10, seed=31,
