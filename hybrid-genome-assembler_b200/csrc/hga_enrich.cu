@@ -190,6 +190,27 @@ __global__ void enr_filter_kernel(const uint64_t *__restrict__ run_key, const ui
     }
 }
 
+// sort keys of the connection list, read through the current permutation. STAGE 0: x (and perm = identity); 1: min << 32 | max;
+// 2: ~score
+template<int STAGE>
+__global__ void enr_conn_key_kernel(const uint32_t *__restrict__ cx, const uint32_t *__restrict__ cy, const uint32_t *__restrict__ cs, const uint32_t *__restrict__ perm,
+                                    uint64_t n, uint32_t *__restrict__ k32, uint64_t *__restrict__ k64, uint32_t *__restrict__ perm_out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t j = STAGE == 0 ? (uint32_t) i : perm[i];
+        if (STAGE == 0) { k32[i] = cx[j]; perm_out[i] = (uint32_t) i; }
+        else if (STAGE == 1) { const uint32_t x = cx[j], y = cy[j]; k64[i] = ((uint64_t) min(x, y) << 32) | max(x, y); }
+        else k32[i] = ~cs[j];
+    }
+}
+
+__global__ void enr_conn_gather_kernel(const uint32_t *__restrict__ cx, const uint32_t *__restrict__ cy, const uint32_t *__restrict__ cs, const uint32_t *__restrict__ perm,
+                                       uint64_t n, uint32_t *__restrict__ ox, uint32_t *__restrict__ oy, uint32_t *__restrict__ os) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t j = perm[i];
+        ox[i] = cx[j]; oy[i] = cy[j]; os[i] = cs[j];
+    }
+}
+
 __global__ void enr_key_rows_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *x, uint32_t *y) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         x[i] = (uint32_t) (keys[i] >> 32); y[i] = (uint32_t) keys[i];
@@ -271,6 +292,23 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
         unsigned long long kept = 0;
         HGA_CUDA(cudaMemcpyAsync(&kept, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
+        // second level: the survivors of the doubling batches (a large batch admits many edges between the same two components:
+        // 2.56 M of 14.0 M at config 4) once more, in small fixed batches; what the host replays is then close to the N - 1 edges
+        // that actually join components
+        if (kept > (1u << 16)) {
+            enr_iota_kernel<<<grid_for(h, n), 256, 0, h->stream>>>(d_par, n);
+            const uint64_t small = 1 << 14;
+            for (uint64_t lo = 0; lo < kept; lo += small) {
+                const uint64_t hi = std::min<uint64_t>(kept, lo + small);
+                enr_edge_filter_kernel<<<grid_for(h, hi - lo), 256, 0, h->stream>>>(d_kept, lo, hi, d_par, d_flag);
+                enr_edge_hook_kernel<<<grid_for(h, hi - lo), 256, 0, h->stream>>>(d_kept, lo, hi, d_par, d_flag);
+                h->metrics.kernel_launches += 2;
+            }
+            HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, tmp2, d_kept, d_flag, d_key, d_count, kept, h->stream));   // d_key is free by now
+            HGA_CUDA(cudaMemcpyAsync(&kept, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            std::swap(d_key, d_kept);
+        }
         M2 = kept;
         enr_key_rows_kernel<<<grid_for(h, M2), 256, 0, h->stream>>>(d_kept, M2, d_x, d_y);
         h->metrics.kernel_launches += 3;
@@ -303,6 +341,8 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
         parent[smaller] = bigger;                                                              // :468-470
         size[bigger] += size[smaller];                                                         // :471
     }
+    if (pc.on) fprintf(stderr, "hga_enrich: %llu of %llu selected edges replayed\n", (unsigned long long) M2, (unsigned long long) M);
+    pc.mark("  replay loop");
     // cores = components with >= min_size vertices (:482-486), identified by their root = element [0] = the survivor (:366)
     std::vector<int32_t> core_of(n + 1, -1);
     std::vector<uint32_t> surv_row;
@@ -441,9 +481,30 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             std::vector<uint32_t> cx(n_conn), cy(n_conn), cs(n_conn);
             if (n_conn) {
-                HGA_CUDA(cudaMemcpyAsync(cx.data(), d_cx, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
-                HGA_CUDA(cudaMemcpyAsync(cy.data(), d_cy, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
-                HGA_CUDA(cudaMemcpyAsync(cs.data(), d_cs, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
+                // canonical order (score desc, min asc, max asc, x asc) = three stable radix sorts of a permutation, least significant
+                // key first: x, then (min << 32 | max), then ~score
+                HGA_TRY(h->d_enr_keys2.ensure((n_conn + 1) * (8 + 8 + 4 + 4 + 4 + 4 + 4 * 3)));
+                uint64_t *k64_in = h->d_enr_keys2.as<uint64_t>(), *k64_out = k64_in + (n_conn + 1);
+                uint32_t *k32_in = reinterpret_cast<uint32_t *>(k64_out + (n_conn + 1)), *k32_out = k32_in + (n_conn + 1);
+                uint32_t *perm_a = k32_out + (n_conn + 1), *perm_b = perm_a + (n_conn + 1);
+                uint32_t *ox = perm_b + (n_conn + 1), *oy = ox + (n_conn + 1), *os = oy + (n_conn + 1);
+                size_t t32 = 0, t64 = 0;
+                HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t32, k32_in, k32_out, perm_a, perm_b, n_conn, 0, 32, h->stream));
+                HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t64, k64_in, k64_out, perm_a, perm_b, n_conn, 0, 64, h->stream));
+                HGA_TRY(h->d_sort_tmp.ensure(std::max(t32, t64) + 16));
+                const int g = grid_for(h, n_conn);
+                enr_conn_key_kernel<0><<<g, 256, 0, h->stream>>>(d_cx, d_cy, d_cs, nullptr, n_conn, k32_in, k64_in, perm_a);            // x, perm = iota
+                HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t32, k32_in, k32_out, perm_a, perm_b, n_conn, 0, 32, h->stream));
+                enr_conn_key_kernel<1><<<g, 256, 0, h->stream>>>(d_cx, d_cy, d_cs, perm_b, n_conn, k32_in, k64_in, nullptr);            // (min, max) in perm order
+                HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t64, k64_in, k64_out, perm_b, perm_a, n_conn, 0, 64, h->stream));
+                enr_conn_key_kernel<2><<<g, 256, 0, h->stream>>>(d_cx, d_cy, d_cs, perm_a, n_conn, k32_in, k64_in, nullptr);            // ~score in perm order
+                HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t32, k32_in, k32_out, perm_a, perm_b, n_conn, 0, 32, h->stream));
+                enr_conn_gather_kernel<<<g, 256, 0, h->stream>>>(d_cx, d_cy, d_cs, perm_b, n_conn, ox, oy, os);
+                h->metrics.kernel_launches += 20;
+                HGA_CUDA(cudaGetLastError());
+                HGA_CUDA(cudaMemcpyAsync(cx.data(), ox, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
+                HGA_CUDA(cudaMemcpyAsync(cy.data(), oy, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
+                HGA_CUDA(cudaMemcpyAsync(cs.data(), os, n_conn * 4, cudaMemcpyDeviceToHost, h->stream));
                 HGA_CUDA(cudaStreamSynchronize(h->stream));
             }
             conns.resize(n_conn);
@@ -453,21 +514,10 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
     pc.mark("enrichment connections");
 
     // ---- 4. host: canonical order, restricted union_find (:424-489 with restricted = cores, min 2, max -1), final merge -----
-    {   // (score desc, min asc, max asc, x asc) as two packed 64-bit keys
-        struct Key { uint64_t hi, lo; uint32_t y; };
-        std::vector<Key> keys(conns.size());
-        for (size_t i = 0; i < conns.size(); i++) {
-            const Conn &c = conns[i];
-            keys[i] = {((uint64_t) ~c.s << 32) | std::min(c.x, c.y), ((uint64_t) std::max(c.x, c.y) << 32) | c.x, c.y};
-        }
-        std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return a.hi != b.hi ? a.hi < b.hi : a.lo < b.lo; });
-        res.conn_x.resize(conns.size()); res.conn_y.resize(conns.size()); res.conn_score.resize(conns.size());
-        for (size_t i = 0; i < keys.size(); i++) {
-            conns[i] = {(uint32_t) keys[i].lo, keys[i].y, ~(uint32_t) (keys[i].hi >> 32)};
-            res.conn_x[i] = conns[i].x; res.conn_y[i] = conns[i].y; res.conn_score[i] = conns[i].s;
-        }
-    }
-
+    // the connections arrive in canonical order (sorted on the GPU above)
+    res.conn_x.resize(conns.size()); res.conn_y.resize(conns.size()); res.conn_score.resize(conns.size());
+    for (size_t i = 0; i < conns.size(); i++) { res.conn_x[i] = conns[i].x; res.conn_y[i] = conns[i].y; res.conn_score[i] = conns[i].s; }
+    pc.mark("  canonical sort of the connections");
     std::iota(parent.begin(), parent.end(), 0u);
     std::fill(size.begin(), size.end(), 1u);
     std::vector<uint8_t> restricted(n + 1, 0), affected(n + 1, 0);
@@ -483,6 +533,7 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
         size[bigger] += size[smaller];
         restricted[bigger] |= restricted[smaller];                                             // :478
     }
+    pc.mark("  restricted union-find loop");
     // final id of every read: the root of its enrichment component when that has >= 2 vertices (union_find's min_size = 2),
     // otherwise the id it had; a core's members follow their survivor. get_component_ids keeps ids with >= min_size reads.
     std::vector<uint32_t> final_of(n + 1, 0xFFFFFFFFu);    // row -> final survivor row
