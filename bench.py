@@ -440,7 +440,7 @@ def main():
         # algorithmic bytes of the fused pack+scan kernel: 1 B/base ASCII read + 8 B per hit written
         scan_bytes_per_rank = (1.0 + 8.0 * hpb) * (total_bases_all / world)
         achieved = scan_bytes_per_rank / (scan_ms * 1e-3) / 1e9
-        # measured DRAM traffic of the scan kernel for the default workload on one GPU (ncu --set full, profiles/r04z_scan_pair_ncu_full.csv)
+        # measured DRAM traffic of the scan kernel for the default workload on one GPU (ncu --set full, profiles/r05z_scan_pair_ncu_full.csv)
         default_cfg = (args.genome_mbp, args.coverage, args.mean_len, args.divergence, args.error, args.seed) == (100.0, 50.0, 10000.0, 0.01, 0.05, 4000)
         traffic_gb = 120.0 if (default_cfg and world == 1) else None
         ms_per_step = ms_total / args.steps
@@ -459,7 +459,7 @@ def main():
                             "table_bytes": m["table_bytes"], "filter_bytes": m["filter_bytes"], "pair_redo_rows": m["redo_pivots"], "pair_mid_rows": m["mid_pivots"],
                             "pair_heavy_rows": m["heavy_pivots"], "exchange_ms": m["exchange_ms"]},
             "roofline": {"kernel": "scan_probe_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic_gb, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu capture profiles/r04z, same workload)",
+                         "traffic": traffic_gb, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu capture profiles/r05z, same workload)",
                          "algorithmic_gb_per_launch": scan_bytes_per_rank / 1e9, "peak_source": peak_src, "bytes_per_base": 1.0 + 8.0 * hpb,
                          "note": "achieved = (1 + 8*hits/base) B/base x bases per GPU / scan stage time (CUDA events on the launch stream; the stage also "
                                  "holds the 1/64 sampling pre-pass, the segment reorder and the row fix-up, so the kernel alone is slightly faster)"},
