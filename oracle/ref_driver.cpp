@@ -14,6 +14,8 @@
 //   union_find                        clustering/ReadClusteringEngine.cpp:424-489
 //   merge_components (--enrich)       clustering/ReadClusteringEngine.cpp:349-422
 //   get_connections  (--enrich)       clustering/ReadClusteringEngine.cpp:301-333  (pivots = the merged cores)
+//   get_core_component_connections, spectral_clustering (--enrich N --full)   clustering/ReadClusteringEngine.cpp:491-697, lib/clustering/*
+//                                     (compiled against the Eigen2 stand-in of oracle/shim/eigen2: Jacobi eigen-solver)
 // Restated here because read_clustering.cpp cannot be compiled (boost::program_options is absent):
 //   load_text_file_kmers              read_clustering.cpp:18-33   (7 lines, uses the real KmerIterator)
 //   the 15 % cut                      clustering/ReadClusteringEngine.cpp:754-755
@@ -39,15 +41,14 @@
 std::vector<std::pair<Component, SpanningTree>>
 union_find(std::vector<ComponentConnection> &connections, std::set<ComponentID> &restricted, int min_component_size, int max_component_size);
 
-// Spectral stage is outside the hot path and Eigen2 is absent: link-time stubs only (never called).
-#include "lib/clustering/SpectralClustering.h"
-SpectralClustering::SpectralClustering(Eigen::MatrixXd &, int numDims) : mNumDims(numDims), mNumClusters(0) {
-    throw std::logic_error("spectral stage is not part of the hot-path oracle");
-}
-SpectralClustering::~SpectralClustering() {}
-std::vector<std::vector<int>> SpectralClustering::clusterRotate() { return {}; }
-std::vector<std::vector<int>> SpectralClustering::clusterKmeans(int) { return {}; }
-int SpectralClustering::getNumClusters() { return 0; }
+// free functions of the reference with external linkage (clustering/ReadClusteringEngine.cpp:126, :653)
+std::vector<ComponentConnection> filter_connections(std::vector<ComponentConnection> &original, const std::function<bool(ComponentConnection &)> &func);
+std::vector<Component> spectral_clustering(std::vector<ComponentConnection> &connections, int dims);
+
+// lib/clustering/{SpectralClustering,ClusterRotate,Evrot}.cpp are compiled unmodified against the Eigen2 stand-in of
+// oracle/shim/eigen2 (Jacobi eigen-solver). Kmeans.cpp is not compiled: clusterKmeans is never called by categorization.
+#include "lib/clustering/Kmeans.h"
+std::vector<std::vector<int>> Kmeans::cluster(Eigen::MatrixXd &, int) { throw std::logic_error("k-means is not part of the categorization path"); }
 
 namespace {
 
@@ -95,7 +96,7 @@ public:
     Probe(SequenceRecordIterator &it, ReadClusteringConfig cfg) : ReadClusteringEngine(it, cfg) {}
 
     int run(std::unordered_set<Kmer> &kmers, int k, const std::string &out, bool do_dump, double fraction, int min_size,
-            ConnectionScore min_score, int stop_after, ConnectionScore enrich_min = 0, ConnectionScore sc_score = 0) {
+            ConnectionScore min_score, int stop_after, ConnectionScore enrich_min = 0, ConnectionScore sc_score = 0, bool full = false) {
         // KmerID assignment order = iteration order of the very same unordered_set object (.cpp:237-241)
         std::vector<Kmer> id2kmer;
         for (auto kmer : kmers) id2kmer.push_back(kmer);
@@ -240,6 +241,51 @@ public:
         t0 = now_ms();
         auto scaffold_ids = merge_components(scaffold_components);
         double t_merge = now_ms() - t0;
+        if (full && scaffold_ids.size() > 2) {
+            // ---- SURVEY §8f-2, run_clustering :768-777, all real reference code (with the Eigen2 stand-in underneath): tails of the
+            // spanning trees, tail amplification, tail connections, spectral clustering of the scaffold components, merge.
+            // The driver imposes the canonical order on the tail connections before the spectral stage (their order decides the
+            // row order of the affinity matrix, :657-663).
+            t0 = now_ms();
+            auto core_forming = get_core_component_connections(comps);
+            double t_tail = now_ms() - t0;
+            std::sort(core_forming.begin(), core_forming.end(), canonical_less);
+            auto strong = filter_connections(core_forming, [](ComponentConnection &conn) { return conn.score > 5; });
+            fprintf(meta, "tail_connections=%zu\nstrong_tail_connections=%zu\ntail_connections_ms=%.3f\n", core_forming.size(), strong.size(), t_tail);
+            if (do_dump) {
+                std::vector<uint32_t> cx, cy;
+                std::vector<uint64_t> cs;
+                for (auto &c : core_forming) { cx.push_back(c.component_x_id); cy.push_back(c.component_y_id); cs.push_back(c.score); }
+                dump(out, "tconn_x.u32", cx);
+                dump(out, "tconn_y.u32", cy);
+                dump(out, "tconn_score.u64", cs);
+            }
+            if (!strong.empty()) {
+                t0 = now_ms();
+                auto spectral = spectral_clustering(strong, config.spectral_dims);
+                double t_spec = now_ms() - t0;
+                fprintf(meta, "spectral_clusters=%zu\nspectral_ms=%.3f\n", spectral.size(), t_spec);
+                if (do_dump) {
+                    // clusters ordered by their smallest component id; members sorted
+                    std::vector<std::vector<uint32_t>> cl;
+                    for (auto &c : spectral) { if (c.empty()) continue; std::vector<uint32_t> m(c.begin(), c.end()); std::sort(m.begin(), m.end()); cl.push_back(m); }
+                    std::sort(cl.begin(), cl.end());
+                    std::vector<uint64_t> off{0};
+                    std::vector<uint32_t> mem;
+                    for (auto &c : cl) { mem.insert(mem.end(), c.begin(), c.end()); off.push_back(mem.size()); }
+                    dump(out, "spectral_off.u64", off);
+                    dump(out, "spectral_member.u32", mem);
+                }
+                // empty clusters (a rotated dimension that no point prefers) would make merge_components read element [0] of an
+                // empty vector (:362-366); the reference has the same hazard, the driver skips them
+                std::vector<Component> nonempty;
+                for (auto &c : spectral) if (!c.empty()) nonempty.push_back(c);
+                merge_components(nonempty);
+            }
+            for (auto it = component_index.begin(); it != component_index.end();) {       // remove_merged_components (:718-725), without the free()
+                if (it->second->size() == 0) it = component_index.erase(it); else ++it;
+            }
+        }
         std::vector<ComponentID> core_ids;
         for (auto p : component_index) if (p.second->size() >= (uint64_t) min_size) core_ids.push_back(p.first);
         std::sort(core_ids.begin(), core_ids.end());
@@ -333,7 +379,7 @@ int usage() {
             "ref_driver canon <kmer file> <out dir>\n"
             "ref_driver records <out dir> <reads...>\n"
             "ref_driver run --kmers F --out DIR [--threads T] [--fraction 0.15] [--min-size 30] [--min-score 1]\n"
-            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] [--sc-score S] <reads...>\n");
+            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] [--sc-score S] [--full] <reads...>\n");
     return 2;
 }
 
@@ -389,6 +435,7 @@ int main(int argc, char **argv) {
     ConnectionScore min_score = 1;
     int stop_after = 0;
     ConnectionScore enrich_min = 0, sc_score = 0;
+    bool full = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) exit(usage()); return argv[++i]; };
@@ -401,6 +448,7 @@ int main(int argc, char **argv) {
         else if (a == "--stop-after") stop_after = std::stoi(next());
         else if (a == "--enrich") enrich_min = std::stoul(next());
         else if (a == "--sc-score") sc_score = std::stoul(next());
+        else if (a == "--full") full = true;
         else if (a == "--no-dump") do_dump = false;
         else paths.push_back(a);
     }
@@ -414,7 +462,7 @@ int main(int argc, char **argv) {
     reader.show_progress = false;
     double t_meta = now_ms() - t0;
     Probe engine(reader, config);
-    int rc = engine.run(kk.first, kk.second, out, do_dump, fraction, min_size, min_score, stop_after, enrich_min, sc_score);
+    int rc = engine.run(kk.first, kk.second, out, do_dump, fraction, min_size, min_score, stop_after, enrich_min, sc_score, full);
     FILE *meta = fopen((out + "/meta.txt").c_str(), "a");
     fprintf(meta, "kmer_load_ms=%.3f\nmeta_pass_ms=%.3f\nthreads=%d\n", t_load, t_meta, config.threads);
     fclose(meta);

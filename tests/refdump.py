@@ -12,11 +12,12 @@ _FILES = {
     "tree_off": "u64", "tree_x": "u32", "tree_y": "u32",
     "core_id": "u32", "core_kmer_off": "u64", "core_kmer": "u64", "core_read_off": "u64", "core_read": "u32", "purged_off": "u64", "purged_read": "u32",
     "econn_x": "u32", "econn_y": "u32", "econn_score": "u64", "final_id": "u32", "final_off": "u64", "final_read": "u32",
+    "tconn_x": "u32", "tconn_y": "u32", "tconn_score": "u64", "spectral_off": "u64", "spectral_member": "u32",
 }
 _DT = {"u32": np.uint32, "u64": np.uint64}
 
 
-def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0, sc_score=0):
+def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0, sc_score=0, full=False):
     tmp = None
     if outdir is None:
         tmp = tempfile.TemporaryDirectory()
@@ -31,6 +32,8 @@ def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score
         cmd += ["--enrich", str(enrich)]
     if sc_score:
         cmd += ["--sc-score", str(sc_score)]
+    if full:
+        cmd.append("--full")
     cmd += list(read_paths)
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     out = {}

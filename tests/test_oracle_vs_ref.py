@@ -148,6 +148,27 @@ def test_fuzz_all_stages_against_the_reference(oracle, ref_driver, tmp_path, see
     _full_compare(oracle, ref_driver, [rp], kp, fraction=fraction, min_size=min_size, enrich=enrich_min)
 
 
+def test_reference_runs_its_whole_pipeline_in_the_driver(oracle, ref_driver, tmp_path):
+    # SURVEY §8f-2 oracle (round-2 groundwork): ref_driver --full runs the reference's own tails, tail amplification, tail
+    # connections, spectral clustering (lib/clustering compiled against the Eigen2 stand-in), merges and enrichment. No product
+    # counterpart yet; this pins that the real-code oracle exists and is self-consistent.
+    paths, kp = datagen.make_diploid_case(str(tmp_path), genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=7,
+                                          error_rate=0.005, fmt="fastq")
+    ref = refdump.run_ref(ref_driver, paths, kp, enrich=20, full=True)
+    assert ref["scaffold_components"] > 2 and ref["tail_connections"] > 0 and ref["spectral_clusters"] >= 1
+    so = ref["spectral_off"].astype(np.int64)
+    members = ref["spectral_member"]
+    assert so[-1] == members.shape[0] and len(set(members.tolist())) == members.shape[0]            # clusters are disjoint
+    scaffold_roots = set(int(r) for r in ref["comp_root"])
+    assert set(members.tolist()) <= scaffold_roots                                                # ... and made of scaffold components
+    assert set(ref["tconn_x"].tolist()) | set(ref["tconn_y"].tolist()) <= scaffold_roots
+    merged_away = int(sum(max(0, int(so[i + 1] - so[i]) - 1) for i in range(len(so) - 1)))
+    assert ref["cores"] == ref["scaffold_components"] - merged_away
+    fo = ref["final_off"].astype(np.int64)
+    assert ref["final_components"] == len(fo) - 1 == ref["cores"]
+    assert len(set(ref["final_read"].tolist())) == ref["final_read"].shape[0]                      # a read is in at most one final component
+
+
 def test_config5_like_tetraploid(oracle, ref_driver, tmp_path):
     # BASELINE config 5 in small: four haplotype read files, dense discriminative set (k-mers absent from at least one haplotype)
     paths, kp = datagen.make_polyploid_case(str(tmp_path), genome_size=12000, divergence=0.02, k=19, read_len=1500, coverage=10, seed=31,
