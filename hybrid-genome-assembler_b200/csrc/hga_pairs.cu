@@ -5,19 +5,22 @@
 // (duplicates included) and every entry of each k-mer's inverted list (duplicates included) and does
 // ++count[candidate] in a tsl::robin_map. This is a sparse integer A * A^T; here it is row-wise Gustavson in
 // three tiers:
-//   1. pair_count_warp_kernel: one WARP per pivot row, a per-warp shared-memory open-addressing accumulator
-//      (<= 1024 partners). Each LANE owns one incidence entry at a time and walks that k-mer's inverted list
-//      itself, so a warp has 32 independent list walks (and their random offset look-ups) in flight; a lane that
-//      finishes a list picks up the row's next entry without waiting for the others, and the offsets of its next
-//      list are prefetched while it walks the current one. Lists are sorted by row, so with all rows as pivots
-//      the walk runs from the END of the list and stops at the first row <= pivot: only the half of every list
-//      that can produce a (pivot < partner) pair is read (four entries per aligned 16 B load), and every unordered
-//      pair is produced exactly once. Lists longer than PW_LONG are walked by the whole warp with coalesced loads.
-//      (Merging equal candidates of a step with __match_any_sync so that the update is a plain read-modify-write was
-//      measured 5 % SLOWER than the shared-memory atomics and dropped. A FLATTENED variant - 32 lists per step, tails found by
-//      binary search, laid end to end and consumed one entry per lane - executed 29 % fewer warp instructions and was 3 %
-//      slower: the kernel is bound by random DRAM traffic, 123 GB read at 1.8 TB/s for 6.4 G increments, not by issue slots;
-//      profiles/r03p_pair_count_memory_bound.md.)
+//   1. pair_count_warp_kernel<512>: one WARP per pivot row, a per-warp shared-memory open-addressing accumulator. Each LANE
+//      owns one incidence entry at a time and walks that k-mer's inverted list itself, so a warp has 32 independent list walks
+//      (and their random offset look-ups) in flight; a lane that finishes a list picks up the row's next entry without
+//      waiting for the others, and the offsets of its next list are prefetched while it walks the current one. Lists are
+//      sorted by row, so with all rows as pivots the walk runs from the END of the list and stops at the first row <= pivot:
+//      only the half of every list that can produce a (pivot < partner) pair is read (four entries per aligned 16 B load, their
+//      four accumulator probes issued together), and every unordered pair is produced exactly once. Lists longer than PW_LONG
+//      are walked by the whole warp with coalesced loads. The kernel is LATENCY bound (time inversely proportional to the
+//      resident warps up to 24 per SM), so the first pass runs with 512-entry accumulators (44 warps per SM) and the few rows
+//      whose partner set does not fit are redone by pair_count_redo_kernel (a CTA per row, four warps on quarter ranges with
+//      1024-entry accumulators that are merged at the end). On one GPU the pivots take their tickets in min-hash order
+//      (row_minhash_kernel): overlapping reads run close together and find each other's lists in L2. With a communicator
+//      (index keyed by kmer_id: neighbouring hits have unrelated lists) the first pass is skipped: one pass with 1024 entries.
+//      Measured and dropped: __match_any_sync merging of equal candidates (5 % slower), a flattened one-entry-per-lane walk
+//      (29 % fewer instructions, 3 % slower), eight probes per step (62 registers, slower), a blocked lane-to-entry mapping
+//      (27 % slower), longest rows first (no change); profiles/r03p_pair_count_memory_bound.md, DESIGN.md 3.4.
 //   2. pair_count_kernel: rows whose partner set overflowed tier 1; one CTA per row, 4096-entry accumulator.
 //   3. pair_count_heavy_kernel: rows that overflow tier 2; per-CTA accumulator in HBM.
 // Output: (key = min_row << 32 | max_row, score) appended through one atomic cursor bump per row, then one
