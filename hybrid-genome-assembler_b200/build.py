@@ -20,6 +20,7 @@ EXE = os.path.join(HERE, "categorization")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
               "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
+CPP_SOURCES = ["hga_spectral.cpp"]        # host-only translation units (g++)
 CU_SOURCES = ["hga_capi.cu", "hga_table.cu", "hga_scan.cu", "hga_index.cu", "hga_pairs.cu", "hga_select.cu", "hga_cc.cu", "hga_enrich.cu", "hga_comm.cu"]
 
 
@@ -50,6 +51,12 @@ def build(force=False, verbose=False):
         objs.append(o)
         if force or _stale(o, [s] + headers):
             jobs.append([NVCC] + NVCC_FLAGS + ["-c", s, "-o", o])
+    for src in CPP_SOURCES:
+        sfile = os.path.join(CSRC, src)
+        o = os.path.join(BUILD, src.replace(".cpp", ".o"))
+        objs.append(o)
+        if force or _stale(o, [sfile] + headers):
+            jobs.append(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-I", os.path.join(ROOT, "include"), "-c", sfile, "-o", o])
     logs = {}
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:

@@ -62,7 +62,7 @@ class Metrics(C.Structure):
 # every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_init", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
-           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers",
+           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering",
            "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
 
 
@@ -118,6 +118,24 @@ def _arr(ptr, n, dtype):
     if n == 0:
         return np.zeros(0, dtype=dtype)
     return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+
+
+def spectral_clustering(conn_x, conn_y, conn_score, dims=16):
+    """Host-side spectral clustering of scaffold components (hga_spectral_clustering). Returns the clusters as a list of uint32
+    arrays of component ids (element [0] = the member closest to the cluster centre); empty clusters are kept."""
+    lib = load_library()
+    x = np.ascontiguousarray(conn_x, dtype=np.uint32); y = np.ascontiguousarray(conn_y, dtype=np.uint32)
+    s = np.ascontiguousarray(conn_score, dtype=np.uint64)
+    n = x.shape[0]
+    out = np.zeros(2 * n + 1, dtype=np.uint32)
+    off = np.zeros(max(dims, 2) + 2, dtype=np.uint64)
+    n_comp = C.c_uint64(); n_cl = C.c_uint64()
+    lib.hga_spectral_clustering.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
+                                            C.POINTER(C.c_uint64)]
+    _check(lib.hga_spectral_clustering(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), n, int(dims),
+                                       out.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), C.byref(n_comp), C.byref(n_cl)))
+    o = off.astype(np.int64)
+    return [out[o[i]:o[i + 1]].copy() for i in range(n_cl.value)]
 
 
 def device_count():

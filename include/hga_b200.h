@@ -12,6 +12,7 @@
  *   hga_pair_count       <- get_connections / get_all_connections           clustering/ReadClusteringEngine.cpp:301-339
  *   hga_select_edges     <- the 15 % slice / --sc_score filter              clustering/ReadClusteringEngine.cpp:748-756
  *   hga_components       <- union_find(edges, {}, min, -1)                  clustering/ReadClusteringEngine.cpp:424-489, call :763
+ *   hga_spectral_clustering <- spectral_clustering(connections, dims)       clustering/ReadClusteringEngine.cpp:653-697, lib/clustering/*
  *   hga_enrich           <- merge_components(scaffolds), get_connections(cores, min), union_find(conns, cores, 2, -1),
  *                           merge_components, get_component_ids             clustering/ReadClusteringEngine.cpp:349-422, :764, :785-794
  *
@@ -164,6 +165,15 @@ typedef struct {
     const uint32_t *kmer_id;       /* unique inside a core, unordered */
 } hga_core_kmers_t;
 int hga_get_core_kmers(hga_handle *h, hga_core_kmers_t *out);
+
+/* Spectral clustering of scaffold components from their tail connections (HOST arithmetic, no GPU involved; first piece of SURVEY
+ * §8f-2): spectral_clustering(connections, dims) of clustering/ReadClusteringEngine.cpp:653-697 with lib/clustering's
+ * SpectralClustering / ClusterRotate / Evrot. connections in the order the caller wants the affinity matrix built in (the
+ * reference: its sorted tail connections with score > 5, :770). Output: the component ids cluster by cluster (out_component,
+ * capacity 2 * n_conn; element [0] of a cluster is the member closest to the cluster centre = the surviving id in
+ * merge_components) and the cluster boundaries (out_cluster_off, capacity dims + 1; empty clusters are kept). */
+int hga_spectral_clustering(const uint32_t *conn_x, const uint32_t *conn_y, const uint64_t *conn_score, uint64_t n_conn, int dims,
+                            uint32_t *out_component, uint64_t *out_cluster_off, uint64_t *out_n_components, uint64_t *out_n_clusters);
 
 /* Per-stage device time (CUDA events on the handle's stream) and counters of the most recent run. */
 typedef struct {

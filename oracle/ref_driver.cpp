@@ -267,14 +267,15 @@ public:
                 fprintf(meta, "spectral_clusters=%zu\nspectral_ms=%.3f\n", spectral.size(), t_spec);
                 if (do_dump) {
                     // clusters ordered by their smallest component id; members sorted
-                    std::vector<std::vector<uint32_t>> cl;
-                    for (auto &c : spectral) { if (c.empty()) continue; std::vector<uint32_t> m(c.begin(), c.end()); std::sort(m.begin(), m.end()); cl.push_back(m); }
+                    std::vector<std::pair<std::vector<uint32_t>, uint32_t>> cl;      // (sorted members, element [0] = survivor of the merge)
+                    for (auto &c : spectral) { if (c.empty()) continue; std::vector<uint32_t> m(c.begin(), c.end()); std::sort(m.begin(), m.end()); cl.push_back({m, c[0]}); }
                     std::sort(cl.begin(), cl.end());
                     std::vector<uint64_t> off{0};
-                    std::vector<uint32_t> mem;
-                    for (auto &c : cl) { mem.insert(mem.end(), c.begin(), c.end()); off.push_back(mem.size()); }
+                    std::vector<uint32_t> mem, first;
+                    for (auto &c : cl) { mem.insert(mem.end(), c.first.begin(), c.first.end()); off.push_back(mem.size()); first.push_back(c.second); }
                     dump(out, "spectral_off.u64", off);
                     dump(out, "spectral_member.u32", mem);
+                    dump(out, "spectral_first.u32", first);
                 }
                 // empty clusters (a rotated dimension that no point prefers) would make merge_components read element [0] of an
                 // empty vector (:362-366); the reference has the same hazard, the driver skips them

@@ -50,12 +50,30 @@ def main_enrich():
         save_case("enrich_long", paths, kp, 0.15, 5, enrich=20)
 
 
+def main_spectral():
+    """SURVEY §8f-2 fixtures: strong tail connections -> spectral clusters, from ref_driver --full (the reference's own
+    spectral_clustering + lib/clustering, compiled against the Eigen2 stand-in of oracle/shim)."""
+    cases = {"spectral_a": dict(genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=7, error_rate=0.005, fmt="fastq"),
+             "spectral_b": dict(genome_size=100000, divergence=0.03, k=19, read_len=400, coverage=25, seed=10, error_rate=0.01)}
+    for name, kw in cases.items():
+        with tempfile.TemporaryDirectory() as d:
+            paths, kp = datagen.make_diploid_case(d, **kw)
+            ref = refdump.run_ref(DRIVER, paths, kp, enrich=20, full=True)
+        m = ref["tconn_score"] > 5
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), conn_x=ref["tconn_x"][m], conn_y=ref["tconn_y"][m], conn_score=ref["tconn_score"][m],
+                            dims=np.int64(16), cluster_off=ref["spectral_off"], cluster_member=ref["spectral_member"], cluster_first=ref["spectral_first"])
+        print(name, int(m.sum()), "connections,", len(ref["spectral_off"]) - 1, "clusters")
+
+
 def main():
+    if "--spectral-only" in sys.argv:
+        return main_spectral()
     if not os.path.exists(DRIVER):
         subprocess.run(["make", "-C", os.path.dirname(os.path.dirname(DRIVER)), "ref"], check=True)
     if "--enrich-only" in sys.argv:
         return main_enrich()
     main_enrich()
+    main_spectral()
     with tempfile.TemporaryDirectory() as d:
         # KAT 2 of SURVEY §8c: multiplicity
         rng = np.random.default_rng(7)
