@@ -302,7 +302,13 @@ struct SequenceRecords {
         if (meta.records == 0) throw std::logic_error("File is empty");
         meta.avg_read_length /= meta.records;          // aggregate max_read_length stays 0 (never updated, :59-62)
         for (size_t i = 0; i < names.size(); i++) meta.filename += (i ? "__" : "") + names[i];
-        for (auto &fm : file_meta) if (fm.records) fm.avg_read_length /= fm.records;
+        // data.avg_read_length /= data.records for EVERY file (:69-71): a file to which no record was attributed (its lines were
+        // swallowed by a record that began in the previous file and ended in the next one) is a division by zero there, and the
+        // reference dies with SIGFPE; the drop-in refuses the input as well
+        for (auto &fm : file_meta) {
+            if (!fm.records) throw std::runtime_error("Floating point exception: a read file contributed no record (division by zero in load_meta_data)");
+            fm.avg_read_length /= fm.records;
+        }
 
         // phase 2: the sequence bytes, in parallel
         bases_size = seq_off.back();

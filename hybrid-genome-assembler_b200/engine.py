@@ -169,8 +169,10 @@ class SequenceRecords:
         self.meta.avg_read_length //= self.meta.records       # aggregate max_read_length stays 0 (never updated, :59-62)
         self.meta.filename = "__".join(filenames)
         for fm in self.file_meta:
-            if fm.records:
-                fm.avg_read_length //= fm.records
+            if not fm.records:
+                # data.avg_read_length /= data.records for every file (:69-71): SIGFPE in the reference when a file got no record
+                raise ZeroDivisionError("a read file contributed no record (division by zero in load_meta_data)")
+            fm.avg_read_length //= fm.records
         self.headers, self.qualities = hdrs, quals
         self.file_index = np.array(fidx, dtype=np.int32)
         lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))

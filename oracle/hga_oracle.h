@@ -16,6 +16,7 @@ extern "C" {
 #define ORC_E_HEADER 4      /* std::out_of_range from header.substr(1) on an empty header  */
 #define ORC_E_K 5           /* std::invalid_argument  "Kmer size is too big"               */
 #define ORC_E_NOMEM 6
+#define ORC_E_DIVZERO 7     /* SIGFPE: a file (or the whole input) without a record, avg /= records (SequenceRecordIterator.cpp:64,70) */
 
 typedef struct {
     uint64_t n_reads;

@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 import pytest
 
-import datagen
+import datagen  # noqa: E402
 import golden_util
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -113,3 +113,55 @@ def test_cli_end_to_end_final_components(exe, oracle, tmp_path):
         lines = open(os.path.join(outdir, f)).read().split("\n")
         assert [l[1:] for l in lines[0::4] if l] == hdrs           # input order = ascending read id
     assert f"Exported {len(want)} components" in r.stdout
+
+
+def _mangled_files(tmp_path, seed):
+    """A few small FASTA / FASTQ files with the irregularities the reference's reader reacts to: format switches between files, a
+    trailing blank line, CRLF line ends, a file without final newline, an empty header line, too few lines."""
+    rng = np.random.default_rng(seed)
+    g = datagen.random_genome(800, seed)
+    paths = []
+    for i in range(int(rng.integers(1, 4))):
+        reads = [datagen.to_ascii(r) for r in datagen.sample_reads(g, int(rng.integers(1, 5)), int(rng.integers(5, 60)), seed * 10 + i)]
+        fq = bool(rng.integers(0, 2))
+        nl = "\r\n" if rng.integers(0, 4) == 0 else "\n"
+        p = str(tmp_path / f"f{seed}_{i}.{'fq' if fq else 'fa'}")
+        (datagen.write_fastq if fq else datagen.write_fasta)(p, reads, prefix=f"s{seed}_{i}_", newline=nl)
+        tweak = int(rng.integers(0, 7))
+        data = open(p, "rb").read()
+        if tweak == 1:
+            data += b"\n"                                   # one trailing blank line: tolerated at the end of the LAST file only
+        elif tweak == 2:
+            data = data.rstrip(b"\r\n")                      # no final newline
+        elif tweak == 3:
+            data += b"\n\n"                                  # two blank lines: header.substr(1) on an empty header
+        elif tweak == 4 and fq:
+            data = data[:data.rfind(b"+")]                   # truncated last record
+        elif tweak == 5:
+            data = data.replace(b"A", b"n", 3)               # non-ACGT bytes are just bytes to the reader
+        open(p, "wb").write(data)
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_cli_reader_fuzz_against_the_reference(exe, ref_driver, tmp_path, seed):
+    """record stream, per-file and aggregate meta data, and WHETHER the run fails, for mangled multi-file inputs: the C++ loader of
+    the CLI against the reference's SequenceRecordIterator (ref_driver records)"""
+    import refdump
+    paths = _mangled_files(tmp_path, seed)
+    rc, metas, recs = refdump.ref_records(ref_driver, paths)
+    r = subprocess.run([exe, "--parse-only"] + paths, capture_output=True)
+    if rc != 0:
+        assert r.returncode != 0, "the reference aborts on this input, the CLI must fail too"
+        return
+    assert r.returncode == 0, r.stderr.decode()[-300:]
+    got_meta, got_recs = [], []
+    for line in r.stdout.decode().split("\n"):
+        if line.startswith("#META ") or line.startswith("#AGG "):
+            got_meta.append(line.split(" "))
+        elif line:
+            i, h, s, q = line.split("\t")
+            got_recs.append((int(i), h, s, q))
+    assert got_recs == recs
+    assert got_meta == metas

@@ -112,3 +112,25 @@ def test_two_rank_plumbing_over_gloo():
         assert p.exitcode == 0
     assert res[0][1] == res[1][1] == bytes(range(128))
     assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == 1000
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_record_readers_fuzz_against_the_reference(oracle, ref_driver, tmp_path, seed):
+    """mangled multi-file inputs (format switches, blank lines, CRLF, truncation): the Python mirror and the C oracle accept / refuse
+    exactly what the reference's SequenceRecordIterator accepts / dies on, and yield the same records"""
+    import hga_b200
+    import refdump
+    from test_cli import _mangled_files
+    paths = _mangled_files(tmp_path, seed)
+    rc, metas, recs = refdump.ref_records(ref_driver, paths)
+    orc_rc, d = oracle.load_reads(paths)
+    assert (orc_rc != 0) == (rc != 0)
+    if rc != 0:
+        with pytest.raises((ValueError, IndexError, ZeroDivisionError)):
+            hga_b200.SequenceRecords(paths)
+        return
+    r = hga_b200.SequenceRecords(paths)
+    assert r.n_reads == len(recs) == d["n_reads"]
+    for i, (rid, h, s, q) in enumerate(recs):
+        assert r.headers[i].decode() == h and r.sequence(rid).decode() == s and r.qualities[i].decode() == q
+        assert d["seq"][int(d["seq_off"][i]):int(d["seq_off"][i + 1])].decode() == s
