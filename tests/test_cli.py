@@ -165,3 +165,42 @@ def test_cli_reader_fuzz_against_the_reference(exe, ref_driver, tmp_path, seed):
             got_recs.append((int(i), h, s, q))
     assert got_recs == recs
     assert got_meta == metas
+
+
+def _mangled_kmer_file(tmp_path, seed):
+    """k-mer file with lines of different lengths, duplicates, lowercase / N / CRLF bytes, an empty line, no final newline, a line > 32"""
+    rng = np.random.default_rng(500 + seed)
+    k = int(rng.integers(3, 33))
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTNacgt", dtype=np.uint8)
+    lines = []
+    for _ in range(int(rng.integers(1, 40))):
+        L = k if rng.integers(0, 5) else int(rng.integers(1, 33))
+        lines.append(alphabet[rng.integers(0, alphabet.shape[0], size=L)].tobytes())
+    if rng.integers(0, 4) == 0:
+        lines.insert(int(rng.integers(0, len(lines))), b"")
+    if rng.integers(0, 6) == 0:
+        lines.append(b"ACGT" * 9)                                   # 36 > 32: "Kmer size is too big"
+    if lines and rng.integers(0, 3) == 0:
+        lines.append(lines[0])                                      # duplicate
+    nl = b"\r\n" if rng.integers(0, 5) == 0 else b"\n"
+    data = nl.join(lines) + (b"" if rng.integers(0, 3) == 0 else nl)
+    p = str(tmp_path / f"k{seed}.txt")
+    open(p, "wb").write(data)
+    return p
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_cli_kmer_loader_fuzz_against_the_reference(exe, ref_driver, tmp_path, seed):
+    """k is the length of the LAST line, every line is canonicalised with its own length (read_clustering.cpp:18-33)"""
+    import refdump
+    p = _mangled_kmer_file(tmp_path, seed)
+    r = subprocess.run([exe, "--dump-kmers", "--kmers", p], capture_output=True, text=True)
+    try:
+        want, want_k = refdump.ref_canon(ref_driver, p)
+    except subprocess.CalledProcessError:
+        assert r.returncode != 0, "the reference aborts on this k-mer file, the CLI must fail too"
+        return
+    assert r.returncode == 0, r.stderr[-300:]
+    out = r.stdout.split("\n")
+    assert out[0] == f"#K {want_k} {len(want)}"
+    assert [int(v) for v in out[1:] if v] == [int(v) for v in want]

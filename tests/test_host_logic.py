@@ -134,3 +134,25 @@ def test_record_readers_fuzz_against_the_reference(oracle, ref_driver, tmp_path,
     for i, (rid, h, s, q) in enumerate(recs):
         assert r.headers[i].decode() == h and r.sequence(rid).decode() == s and r.qualities[i].decode() == q
         assert d["seq"][int(d["seq_off"][i]):int(d["seq_off"][i + 1])].decode() == s
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_kmer_loaders_fuzz_against_the_reference(oracle, ref_driver, tmp_path, seed):
+    """the Python mirror and the C oracle of load_text_file_kmers against the reference on mangled k-mer files"""
+    import subprocess
+    import hga_b200
+    import refdump
+    from test_cli import _mangled_kmer_file
+    p = _mangled_kmer_file(tmp_path, seed)
+    try:
+        want, want_k = refdump.ref_canon(ref_driver, p)
+    except subprocess.CalledProcessError:
+        with pytest.raises(ValueError):
+            hga_b200.load_text_file_kmers(p)
+        with pytest.raises(RuntimeError):
+            oracle.load_kmers(p)
+        return
+    got, k = hga_b200.load_text_file_kmers(p)
+    assert k == want_k and np.array_equal(got, want)
+    og, ok = oracle.load_kmers(p)
+    assert ok == want_k and np.array_equal(og, want)
