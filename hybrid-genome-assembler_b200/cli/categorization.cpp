@@ -86,12 +86,42 @@ int main(int argc, char **argv) {
     bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false, export_test = false;
     int device = 0;
 
-    auto need = [&](int &i) -> const char * {
-        if (i + 1 >= argc) throw std::invalid_argument(std::string("the required argument for option '") + argv[i] + "' is missing");
-        return argv[++i];
-    };
+    // boost::program_options' default style (read_clustering.cpp:60-66): --name=value and --name value, -k value and -kvalue,
+    // and unambiguous prefixes of long names (--kmer for --kmers)
+    static const char *long_names[] = {"--help", "--read_paths", "--kmers", "--output", "--sc_max_size", "--sc_min_size", "--sc_fraction", "--sc_score",
+                                       "--tail_amplification", "--core_enrichment", "--spectral_dims", "--spectral", "--debug", "--threads",
+                                       "--parse-only", "--dump-kmers", "--scaffolds-only", "--load-only", "--export-test", "--device"};
+    std::vector<std::string> args;
     for (int i = 1; i < argc; i++) {
-        const std::string a = argv[i];
+        std::string a = argv[i];
+        std::string value;
+        bool has_value = false;
+        if (a.rfind("--", 0) == 0 && a.size() > 2) {
+            const size_t eq = a.find('=');
+            if (eq != std::string::npos) { value = a.substr(eq + 1); a = a.substr(0, eq); has_value = true; }
+            std::vector<std::string> matches;
+            bool exact = false;
+            for (const char *n : long_names) {
+                if (a == n) { exact = true; break; }
+                if (std::string(n).rfind(a, 0) == 0) matches.push_back(n);
+            }
+            if (!exact) {
+                if (matches.size() == 1) a = matches[0];
+                else if (matches.size() > 1) throw std::invalid_argument("option '" + a + "' is ambiguous");
+            }
+        } else if (a.size() > 2 && a[0] == '-' && a[1] != '-' && std::string("kot").find(a[1]) != std::string::npos) {
+            value = a.substr(2); a = a.substr(0, 2); has_value = true;      // -kFILE
+        }
+        args.push_back(a);
+        if (has_value) args.push_back(value);
+    }
+    const int nargs = (int) args.size();
+    auto need = [&](int &i) -> const char * {
+        if (i + 1 >= nargs) throw std::invalid_argument("the required argument for option '" + args[i] + "' is missing");
+        return args[++i].c_str();
+    };
+    for (int i = 0; i < nargs; i++) {
+        const std::string a = args[i];
         if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (a == "-k" || a == "--kmers") kmer_path = need(i);
         else if (a == "-o" || a == "--output") output_folder_path = need(i);

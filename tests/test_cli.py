@@ -57,6 +57,20 @@ def test_cli_parallel_export_writes_the_reference_bytes(exe, tmp_path, fmt, thre
         assert open(os.path.join(out, f"#{c}.fa"), "rb").read() == data
 
 
+def test_cli_option_styles(exe):
+    """boost::program_options' default style: --name=value, -kvalue, unambiguous prefixes of long names"""
+    z = np.load(os.path.join(golden_util.GOLDEN, "kmers_fixture.npz"))
+    kf = os.path.join(golden_util.GOLDEN, "kmers_fixture.txt")
+    want = subprocess.run([exe, "--dump-kmers", "--kmers", kf], capture_output=True, text=True, check=True).stdout
+    assert want.startswith(f"#K {int(z['k'])} ")
+    for args in (["--dump-kmers", f"--kmers={kf}"], ["--dump-kmers", f"-k{kf}"], ["--dump-kmers", "-k", kf], ["--dump-k", "--kmer", kf]):
+        assert subprocess.run([exe] + args, capture_output=True, text=True, check=True).stdout == want
+    r = subprocess.run([exe, "--s", "x"], capture_output=True, text=True)          # --sc_..., --spectral..., --scaffolds-only
+    assert r.returncode != 0 and "ambiguous" in r.stderr
+    r = subprocess.run([exe, "--nonsense"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unrecognised option" in r.stderr
+
+
 def test_cli_errors(exe, tmp_path):
     bad = tmp_path / "bad.txt"
     bad.write_text("hello\nworld\n")
