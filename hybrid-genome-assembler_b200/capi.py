@@ -62,7 +62,7 @@ class Metrics(C.Structure):
 # every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_init", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
-           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering",
+           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering",
            "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
 
 
@@ -96,6 +96,7 @@ def load_library():
         lib.hga_components.argtypes = [C.c_void_p, C.c_int]
         lib.hga_get_components.argtypes = [C.c_void_p, C.POINTER(_Components)]
         lib.hga_enrich.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        lib.hga_enrich_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32]
         lib.hga_get_enrichment.argtypes = [C.c_void_p, C.POINTER(_Enrichment)]
         lib.hga_get_purged_index.argtypes = [C.c_void_p, C.POINTER(_Index)]
         lib.hga_get_core_kmers.argtypes = [C.c_void_p, C.POINTER(_CoreKmers)]
@@ -249,8 +250,11 @@ class Handle:
         return dict(read_id_first=int(out.read_id_first), label=_arr(out.label, out.n_reads, np.uint32),
                     comp_label=_arr(out.comp_label, out.n_components, np.uint32), comp_size=_arr(out.comp_size, out.n_components, np.uint32))
 
-    def enrich(self, min_size=30, enrichment_min_score=20):
-        _check(self.lib.hga_enrich(self._h, int(min_size), int(enrichment_min_score)))
+    def enrich(self, min_size=30, enrichment_min_score=20, max_size=-1):
+        if max_size == -1:
+            _check(self.lib.hga_enrich(self._h, int(min_size), int(enrichment_min_score)))
+        else:
+            _check(self.lib.hga_enrich_ex(self._h, int(min_size), int(max_size), int(enrichment_min_score)))
 
     def get_enrichment(self):
         out = _Enrichment()

@@ -196,8 +196,9 @@ int main(int argc, char **argv) {
                      "and is not part of this build\n";
         return 3;
     }
-    if (config.scaffold_component_max_size != -1) {
-        std::cerr << "categorization: --sc_max_size needs the order-dependent sequential union_find and is not supported on the GPU path\n";
+    if (config.scaffold_component_max_size != -1 && scaffolds_only) {
+        std::cerr << "categorization: --sc_max_size makes the scaffold components depend on the edge order (sequential union_find); they are computed "
+                     "inside the merge + enrichment stage, not by the GPU components stage --scaffolds-only exports\n";
         return 3;
     }
 
@@ -254,7 +255,7 @@ int main(int argc, char **argv) {
         hga_host::export_components(reads, ids, of_read.data(), output_folder_path, io_threads);
         std::cout << "Exported " << comp.n_components << " components\n";
     } else {
-        if (comp.n_components > 2)
+        if (comp.n_components > 2 || config.scaffold_component_max_size != -1)
             std::cerr << "categorization: " << comp.n_components << " scaffold components; the tail / spectral merge of scaffold components "
                          "(ReadClusteringEngine.cpp:768-777) is not part of this build: every scaffold component becomes a core, as in the reference "
                          "when it finds no strong tail connection\n";
@@ -263,7 +264,8 @@ int main(int argc, char **argv) {
             // the reference times these separately ("Merging of initial components", "Calculation of enrichment connections",
             // "Merging into core components"); here they are one library call
             Timer t("Merging of initial components, calculation of enrichment connections and merging into core components");
-            check(hga_enrich(h, config.scaffold_component_min_size, (uint32_t) config.enrichment_connections_min_score), "hga_enrich");
+            check(hga_enrich_ex(h, config.scaffold_component_min_size, config.scaffold_component_max_size, (uint32_t) config.enrichment_connections_min_score),
+                  "hga_enrich");
             check(hga_get_enrichment(h, &fin), "hga_get_enrichment");
             t.done();
         }

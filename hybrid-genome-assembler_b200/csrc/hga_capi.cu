@@ -274,7 +274,13 @@ int hga_get_index(hga_handle *h, hga_index *out) {
 int hga_enrich(hga_handle *h, int min_size, uint32_t enrichment_min_score) {
     if (!h) { hga_set_error("NULL handle"); return HGA_E_ARG; }
     HGA_TRY(use_device(h));
-    return hga_enrich_run(h, min_size, enrichment_min_score);
+    return hga_enrich_run(h, min_size, -1, enrichment_min_score);
+}
+
+int hga_enrich_ex(hga_handle *h, int min_size, int max_size, uint32_t enrichment_min_score) {
+    if (!h) { hga_set_error("NULL handle"); return HGA_E_ARG; }
+    HGA_TRY(use_device(h));
+    return hga_enrich_run(h, min_size, max_size, enrichment_min_score);
 }
 
 int hga_get_enrichment(hga_handle *h, hga_enrichment_t *out) {

@@ -243,10 +243,15 @@ struct PhaseClock {
 
 }  // namespace
 
-int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
+int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score) {
     if (!h->have_selection || !h->have_index || !h->have_scan) { hga_set_error("hga_enrich: needs hga_scan, hga_build_index and hga_select_edges"); return HGA_E_STATE; }
     if (h->comm && hga_comm_size(h) > 1) { hga_set_error("hga_enrich: not available with a communicator yet (single GPU only)"); return HGA_E_STATE; }
     if (min_size < 2) { hga_set_error("hga_enrich: min_size must be >= 2 (a core is a merged component)"); return HGA_E_ARG; }
+    if (max_size != -1 && max_size < 1) { hga_set_error("hga_enrich: max_size must be -1 (no limit) or positive"); return HGA_E_ARG; }
+    // --sc_max_size: a union is skipped when the merged component would exceed the limit (:457), so "already connected by earlier
+    // edges" no longer means "no-op" and the GPU pre-filter does not apply: the host replays every selected edge
+    const bool limited = max_size != -1;
+    const uint64_t max_comp = limited ? (uint64_t) max_size : ~0ull;
     h->have_enrichment = false;
     EnrichResult &res = h->enrich;
     res = EnrichResult();
@@ -282,6 +287,10 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
         HGA_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp.p, tmp, h->d_sel_score.as<uint32_t>(), d_score, h->d_sel_key.as<uint64_t>(), d_key, M, 0, 32, h->stream));
         enr_iota_kernel<<<grid_for(h, n), 256, 0, h->stream>>>(d_par, n);
         h->metrics.kernel_launches += 6;
+        unsigned long long kept = M;
+        if (limited) {
+            std::swap(d_key, d_kept);          // every edge, in canonical order
+        } else {
         for (uint64_t lo = 0, batch = 1 << 16; lo < M; lo += batch, batch *= 2) {
             const uint64_t hi = std::min(M, lo + batch);
             enr_edge_filter_kernel<<<grid_for(h, hi - lo), 256, 0, h->stream>>>(d_key, lo, hi, d_par, d_flag);
@@ -289,13 +298,13 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
             h->metrics.kernel_launches += 2;
         }
         HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, tmp2, d_key, d_flag, d_kept, d_count, M, h->stream));
-        unsigned long long kept = 0;
         HGA_CUDA(cudaMemcpyAsync(&kept, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
+        }
         // second level: the survivors of the doubling batches (a large batch admits many edges between the same two components:
         // 2.56 M of 14.0 M at config 4) once more, in small fixed batches; what the host replays is then close to the N - 1 edges
         // that actually join components
-        if (kept > (1u << 16)) {
+        if (!limited && kept > (1u << 16)) {
             enr_iota_kernel<<<grid_for(h, n), 256, 0, h->stream>>>(d_par, n);
             const uint64_t small = 1 << 14;
             for (uint64_t lo = 0; lo < kept; lo += small) {
@@ -337,6 +346,7 @@ int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score) {
         touched[x] = touched[y] = 1;                                                           // :427-431
         const uint32_t px = dsu_find(parent, x), py = dsu_find(parent, y);                     // :453-454
         if (px == py) continue;                                                                // :455
+        if ((uint64_t) size[px] + size[py] > max_comp) continue;                               // :457
         const uint32_t bigger = size[px] > size[py] ? px : py, smaller = bigger == px ? py : px;   // :459-466 (ties: y's root)
         parent[smaller] = bigger;                                                              // :468-470
         size[bigger] += size[smaller];                                                         // :471

@@ -318,7 +318,7 @@ int hga_index_run(hga_handle *h);
 int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
 int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold);
 int hga_cc_run(hga_handle *h, int min_size);
-int hga_enrich_run(hga_handle *h, int min_size, uint32_t min_score);
+int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score);
 
 // multi-GPU hooks (hga_comm.cu); all are no-ops / never called without a communicator
 int hga_comm_build_global_index(hga_handle *h);

@@ -256,7 +256,7 @@ class ReadClusteringEngine:
         return _canonical_sort(np.concatenate([x, y]), np.concatenate([y, x]), np.concatenate([s, s]).astype(np.uint64))
 
     # the hot first third of run_clustering (.cpp:737-765): returns the scaffold components (lists of read ids)
-    def scaffold_components(self):
+    def _select_scaffold_edges(self):
         cfg = self.config
         if cfg.scaffold_forming_score > 0:
             row_off, _, _ = self.handle.get_hits()
@@ -266,8 +266,12 @@ class ReadClusteringEngine:
         else:
             self.handle.pair_count(min_score=1)
             self.handle.select_edges(fraction=cfg.scaffold_forming_fraction)
+
+    def scaffold_components(self):
+        cfg = self.config
+        self._select_scaffold_edges()
         if cfg.scaffold_component_max_size != -1:
-            raise NotImplementedError("--sc_max_size needs the sequential order-dependent union_find (not on the GPU path yet)")
+            raise NotImplementedError("--sc_max_size: the size-limited components come from run_clustering (hga_enrich_ex), not from the GPU components stage")
         self.handle.components(min_size=cfg.scaffold_component_min_size)
         comp = self.handle.get_components()
         label = comp["label"]
@@ -285,8 +289,9 @@ class ReadClusteringEngine:
         if cfg.force_spectral:
             raise NotImplementedError("--spectral (lib/clustering) is not part of this build")
         self.construct_indices(discriminative_kmers, k)
-        self.scaffold_components()
-        self.handle.enrich(min_size=cfg.scaffold_component_min_size, enrichment_min_score=cfg.enrichment_connections_min_score)
+        self._select_scaffold_edges()
+        self.handle.enrich(min_size=cfg.scaffold_component_min_size, enrichment_min_score=cfg.enrichment_connections_min_score,
+                           max_size=cfg.scaffold_component_max_size)
         e = self.handle.get_enrichment()
         off = e["final_off"].astype(np.int64)
         self.final_components = {int(fid): e["final_read"][off[i]:off[i + 1]] for i, fid in enumerate(e["final_id"])}

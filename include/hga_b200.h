@@ -141,6 +141,10 @@ int hga_get_components(hga_handle *h, hga_components_t *out);
  *   connections    : get_connections(cores, enrichment_min_score) on the merged state, directed core -> partner, canonical order
  *   final          : components after union_find(connections, restricted = cores, 2, -1) + merge; id = surviving component id */
 int hga_enrich(hga_handle *h, int min_size, uint32_t enrichment_min_score);
+/* the same with --sc_max_size: a scaffold union is skipped when the merged component would exceed max_size reads (union_find,
+ * :426, :457; -1 = no limit). The limit makes the components depend on the edge order, so they come from the sequential replay
+ * of ALL selected edges on the host, not from hga_components (whose labels ignore the limit). */
+int hga_enrich_ex(hga_handle *h, int min_size, int max_size, uint32_t enrichment_min_score);
 typedef struct {
     uint64_t n_cores;
     const uint32_t *core_id;       /* n_cores, ascending */

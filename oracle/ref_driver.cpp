@@ -380,7 +380,7 @@ int usage() {
             "ref_driver canon <kmer file> <out dir>\n"
             "ref_driver records <out dir> <reads...>\n"
             "ref_driver run --kmers F --out DIR [--threads T] [--fraction 0.15] [--min-size 30] [--min-score 1]\n"
-            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] [--sc-score S] [--full] <reads...>\n");
+            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] [--sc-score S] [--full] [--max-size N] <reads...>\n");
     return 2;
 }
 
@@ -450,6 +450,7 @@ int main(int argc, char **argv) {
         else if (a == "--enrich") enrich_min = std::stoul(next());
         else if (a == "--sc-score") sc_score = std::stoul(next());
         else if (a == "--full") full = true;
+        else if (a == "--max-size") config.scaffold_component_max_size = std::stoi(next());
         else if (a == "--no-dump") do_dump = false;
         else paths.push_back(a);
     }

@@ -132,7 +132,7 @@ class Oracle:
         return out
 
     # -- whole hot path on in-memory reads: returns a dict mirroring the ref_driver dump
-    def run(self, seq: bytes, seq_off, k, kmers_sorted, fraction=0.15, min_size=30, min_score=1, sc_score=0):
+    def run(self, seq: bytes, seq_off, k, kmers_sorted, fraction=0.15, min_size=30, min_score=1, sc_score=0, max_size=-1):
         row_off, kid, pos = self.scan(seq, seq_off, k, kmers_sorted)
         inv_off, inv_read = self.index(row_off, kid, len(kmers_sorted))
         if sc_score > 0:
@@ -147,7 +147,7 @@ class Oracle:
             sx, sy, ss = self.canonical_sort(cx, cy, cs)
             n = int(len(sx) * fraction)
             cut = int(ss[n - 1]) if n > 0 else 0
-        comp = self.union_find(sx[:n], sy[:n], min_size=min_size)
+        comp = self.union_find(sx[:n], sy[:n], min_size=min_size, max_size=max_size)
         return dict(row_off=row_off, hit_kid=kid, hit_pos=pos, inv_off=inv_off, inv_read=inv_read, conn=(sx, sy, ss), cut_n=n, cut_score=cut,
                     comp=comp)
 

@@ -17,7 +17,7 @@ _FILES = {
 _DT = {"u32": np.uint32, "u64": np.uint64}
 
 
-def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0, sc_score=0, full=False):
+def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0, sc_score=0, full=False, max_size=-1):
     tmp = None
     if outdir is None:
         tmp = tempfile.TemporaryDirectory()
@@ -34,6 +34,8 @@ def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score
         cmd += ["--sc-score", str(sc_score)]
     if full:
         cmd.append("--full")
+    if max_size != -1:
+        cmd += ["--max-size", str(max_size)]
     cmd += list(read_paths)
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     out = {}

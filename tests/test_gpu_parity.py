@@ -180,6 +180,30 @@ def test_fuzz_all_stages(oracle, seed):
         assert np.array_equal(g, w)
 
 
+@pytest.mark.parametrize("max_size", [40, 120])
+def test_sc_max_size_with_enrichment(oracle, max_size):
+    """--sc_max_size (hga_enrich_ex): the size-limited sequential union_find replayed on the host over all selected edges"""
+    import hga_b200
+    import oracle_lib
+    from test_gpu_golden import _gpu_enrichment
+    a = datagen.random_genome(30000, 71); b = datagen.mutate(a, 0.03, 72)
+    reads = datagen.sample_reads(a, 6000, 150, 73, error_rate=0.005) + datagen.sample_reads(b, 6000, 150, 74, error_rate=0.005)
+    bases, off = _pack([datagen.to_ascii(r) for r in reads])
+    kmers = datagen.discriminative_kmers([a, b], 19)
+    res = oracle.run(bases, off, 19, kmers, min_size=10, max_size=max_size)
+    want = oracle_lib.enrich(oracle, res, len(kmers), min_size=10, enrich_min=20)
+    with hga_b200.Handle(kmers, 19) as h:
+        h.scan(bases, off); h.build_index(); h.pair_count(min_score=1); h.select_edges(fraction=0.15)
+        h.enrich(min_size=10, enrichment_min_score=20, max_size=max_size)
+        e = h.get_enrichment()
+        po, pr = h.get_purged_index()
+    assert len(want["core_id"]) >= 2 and max(len(r) for r in want["core_reads"]) <= max_size
+    assert np.array_equal(e["core_id"], want["core_id"]) and np.array_equal(e["core_read"], np.concatenate(want["core_reads"]))
+    assert np.array_equal(po, want["purged_off"]) and np.array_equal(pr, want["purged_read"])
+    assert np.array_equal(e["conn_x"], want["econn"][0]) and np.array_equal(e["conn_y"], want["econn"][1]) and np.array_equal(e["conn_score"].astype(np.uint64), want["econn"][2])
+    assert np.array_equal(e["final_id"], want["final_id"]) and np.array_equal(e["final_read"], np.concatenate(want["final_reads"]))
+
+
 def test_sc_score_mode_with_enrichment(oracle):
     """--sc_score S: pivot subset + score > S selection, then merge + enrichment on top of it"""
     import hga_b200

@@ -54,10 +54,10 @@ def test_load_kmers_matches_ref(oracle, ref_driver, tmp_path):
     assert k == kr == 19 and np.array_equal(a, b)
 
 
-def _full_compare(oracle, ref_driver, paths, kp, fraction=0.15, min_size=30, threads=1, enrich=0, sc_score=0):
+def _full_compare(oracle, ref_driver, paths, kp, fraction=0.15, min_size=30, threads=1, enrich=0, sc_score=0, max_size=-1):
     reads, kmers, k = _load_case(oracle, paths, kp)
-    ref = refdump.run_ref(ref_driver, paths, kp, fraction=fraction, min_size=min_size, threads=threads, enrich=enrich, sc_score=sc_score)
-    res = oracle.run(reads["seq"], reads["seq_off"], k, kmers, fraction=fraction, min_size=min_size, sc_score=sc_score)
+    ref = refdump.run_ref(ref_driver, paths, kp, fraction=fraction, min_size=min_size, threads=threads, enrich=enrich, sc_score=sc_score, max_size=max_size)
+    res = oracle.run(reads["seq"], reads["seq_off"], k, kmers, fraction=fraction, min_size=min_size, sc_score=sc_score, max_size=max_size)
     assert ref["k"] == k and ref["n_kmers"] == kmers.shape[0] and ref["n_reads"] == reads["n_reads"]
     compare.check_hits(ref, res["row_off"], res["hit_kid"], res["hit_pos"], kmers)
     compare.check_index(ref, res["inv_off"], res["inv_read"], kmers)
@@ -167,6 +167,16 @@ def test_reference_runs_its_whole_pipeline_in_the_driver(oracle, ref_driver, tmp
     fo = ref["final_off"].astype(np.int64)
     assert ref["final_components"] == len(fo) - 1 == ref["cores"]
     assert len(set(ref["final_read"].tolist())) == ref["final_read"].shape[0]                      # a read is in at most one final component
+
+
+@pytest.mark.parametrize("max_size", [40, 120])
+def test_sc_max_size_with_enrichment(oracle, ref_driver, tmp_path, max_size):
+    # --sc_max_size: unions that would exceed the limit are skipped (:457); the components then depend on the edge order
+    paths, kp = datagen.make_diploid_case(str(tmp_path), genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=7,
+                                          error_rate=0.005, fmt="fastq")
+    ref, res = _full_compare(oracle, ref_driver, paths, kp, min_size=10, enrich=20, max_size=max_size)
+    co = res["comp"][0].astype(np.int64)
+    assert ref["cores"] >= 2 and int(np.diff(co).max()) <= max_size
 
 
 def test_config5_like_tetraploid(oracle, ref_driver, tmp_path):
