@@ -62,7 +62,7 @@ class Metrics(C.Structure):
 # every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_init", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
-           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering",
+           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering", "hga_host_tail_connections",
            "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
 
 
@@ -137,6 +137,28 @@ def spectral_clustering(conn_x, conn_y, conn_score, dims=16):
                                        out.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), C.byref(n_comp), C.byref(n_cl)))
     o = off.astype(np.int64)
     return [out[o[i]:o[i + 1]].copy() for i in range(n_cl.value)]
+
+
+def host_tail_connections(row_off, kmer_id, pos, read_len, avg_read_length, comp_off, comp_member, tree_off, tree_x, tree_y, purged_off, purged_read,
+                          amplification_min_score=40, read_id_first=1):
+    """Host-side tail connections between scaffold components (hga_host_tail_connections). Rows must be sorted by (kmer_id, pos)."""
+    lib = load_library()
+    a = [np.ascontiguousarray(row_off, dtype=np.uint64), np.ascontiguousarray(kmer_id, dtype=np.uint32), np.ascontiguousarray(pos, dtype=np.uint32),
+         np.ascontiguousarray(read_len, dtype=np.uint32), np.ascontiguousarray(comp_off, dtype=np.uint64), np.ascontiguousarray(comp_member, dtype=np.uint32),
+         np.ascontiguousarray(tree_off, dtype=np.uint64), np.ascontiguousarray(tree_x, dtype=np.uint32), np.ascontiguousarray(tree_y, dtype=np.uint32),
+         np.ascontiguousarray(purged_off, dtype=np.uint64), np.ascontiguousarray(purged_read, dtype=np.uint32)]
+    n_reads = a[0].shape[0] - 1
+    n_comp = a[4].shape[0] - 1
+    cap = max(1, n_comp * (n_comp - 1) // 2)
+    ox = np.zeros(cap, dtype=np.uint32); oy = np.zeros(cap, dtype=np.uint32); osc = np.zeros(cap, dtype=np.uint64)
+    n = C.c_uint64()
+    P = C.c_void_p
+    lib.hga_host_tail_connections.argtypes = [C.c_uint64, P, P, P, P, C.c_uint64, C.c_uint32, C.c_uint64, P, P, P, P, P, P, P, C.c_uint32, P, P, P, C.POINTER(C.c_uint64)]
+    ptr = [x.ctypes.data_as(P) for x in a]
+    _check(lib.hga_host_tail_connections(n_reads, ptr[0], ptr[1], ptr[2], ptr[3], int(avg_read_length), int(read_id_first), n_comp, ptr[4], ptr[5], ptr[6], ptr[7],
+                                         ptr[8], ptr[9], ptr[10], int(amplification_min_score), ox.ctypes.data_as(P), oy.ctypes.data_as(P), osc.ctypes.data_as(P),
+                                         C.byref(n)))
+    return ox[:n.value].copy(), oy[:n.value].copy(), osc[:n.value].copy()
 
 
 def device_count():

@@ -1,0 +1,199 @@
+// Tail connections between scaffold components (HOST code; SURVEY.md §8f-2, second piece).
+//
+// Replaces ReadClusteringEngine::get_core_component_connections (clustering/ReadClusteringEngine.cpp:594-651) and what it calls:
+// approximate_read_overlap (:491-508), get_spanning_tree_tails (:510-581), amplify_component (:583-592), accumulate_kmer_ids
+// (:340-346). It runs on the engine state AFTER merge_components(scaffold_components) (:764), which is what the caller hands over:
+//   * hits by read, every row sorted by (kmer_id, pos)   (hga_get_hits(h, 1, ..): discriminative_kmer_ids with duplicates and
+//     kmer_positions = first occurrence per k-mer);
+//   * the scaffold components, element [0] = the surviving id, and their spanning trees (the edges that performed a union);
+//   * the PURGED inverted index (hga_get_purged_index).
+// The k-mer list of a component id is, as in the reference after the merge: the sorted UNIQUE union of all members' lists for a
+// survivor (:379), the read's own sorted list with duplicates for every other id (merged-away members keep theirs).
+//
+// Per component: the two ends of the spanning tree by a double sweep (farthest vertex from an arbitrary start, farthest from
+// that, farthest from that; distance = read lengths minus approximate overlaps along the tree path), the vertices within two
+// average read lengths of each end (the "tails"), every tail amplified by the reads it reaches with at least
+// `amplification_min_score` shared k-mers, the unique k-mer union of every amplified tail; per pair of components the largest of
+// the four tail-to-tail intersections. The reference starts the first sweep at adjacency_map.begin() (whatever its hash map puts
+// first), so WHICH end it calls left and which right is arbitrary; the connection score is a maximum over all four combinations
+// and does not depend on it. Here the first sweep starts at the smallest vertex id and distance ties go to the smallest id.
+//
+// Small host arithmetic (a few hundred tree vertices per component): sequential in the reference, sequential here. The
+// amplification walks purged lists on the host in this first version; its GPU form is hga_enrich's connection kernel with the
+// tails as pivots.
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <queue>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hga_b200.h"
+
+void hga_set_error(const char *fmt, ...);
+
+namespace {
+
+struct TailState {
+    uint64_t n_reads;
+    uint32_t first_id;
+    const uint64_t *row_off;
+    const uint32_t *kid, *pos, *read_len;
+    const uint64_t *purged_off;
+    const uint32_t *purged_read;
+    std::unordered_map<uint32_t, std::vector<uint32_t>> survivor_list;   // survivor id -> unique union
+
+    // discriminative_kmer_ids of a component id in the current engine state
+    void list_of(uint32_t id, const uint32_t *&p, size_t &n) const {
+        auto it = survivor_list.find(id);
+        if (it != survivor_list.end()) { p = it->second.data(); n = it->second.size(); return; }
+        const uint64_t r = id - first_id;
+        p = kid + row_off[r]; n = (size_t) (row_off[r + 1] - row_off[r]);
+    }
+    // read_metas[id].kmer_positions[k]: first occurrence in READ id; operator[] default-inserts 0 for a k-mer the read does not hold
+    uint32_t first_pos(uint32_t id, uint32_t k) const {
+        const uint64_t r = id - first_id, a = row_off[r], b = row_off[r + 1];
+        const uint32_t *lo = std::lower_bound(kid + a, kid + b, k);
+        return (lo != kid + b && *lo == k) ? pos[lo - kid] : 0u;
+    }
+    // :491-508
+    int overlap(uint32_t x, uint32_t y) const {
+        const uint32_t *px, *py;
+        size_t nx, ny;
+        list_of(x, px, nx); list_of(y, py, ny);
+        int max_x = 0, max_y = 0, min_x = 0, min_y = 0;
+        bool any = false;
+        size_t i = 0, j = 0;
+        while (i < nx && j < ny) {                           // get_vectors_intersection (Utils.h:125-141): one for one
+            if (px[i] < py[j]) i++;
+            else if (py[j] < px[i]) j++;
+            else {
+                const int a = (int) first_pos(x, px[i]), b = (int) first_pos(y, px[i]);
+                if (!any) { max_x = min_x = a; max_y = min_y = b; any = true; }
+                else { max_x = std::max(max_x, a); min_x = std::min(min_x, a); max_y = std::max(max_y, b); min_y = std::min(min_y, b); }
+                i++; j++;
+            }
+        }
+        return std::max(max_x - min_x, max_y - min_y);
+    }
+};
+
+}  // namespace
+
+extern "C" int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_off, const uint32_t *kmer_id, const uint32_t *pos, const uint32_t *read_len,
+                                         uint64_t avg_read_length, uint32_t read_id_first, uint64_t n_comp, const uint64_t *comp_off,
+                                         const uint32_t *comp_member, const uint64_t *tree_off, const uint32_t *tree_x, const uint32_t *tree_y,
+                                         const uint64_t *purged_off, const uint32_t *purged_read, uint32_t amplification_min_score, uint32_t *out_x,
+                                         uint32_t *out_y, uint64_t *out_score, uint64_t *out_n) {
+    if (!row_off || !comp_off || !tree_off || !purged_off || !out_n || (n_comp > 1 && (!out_x || !out_y || !out_score))) {
+        hga_set_error("hga_host_tail_connections: NULL argument");
+        return HGA_E_ARG;
+    }
+    *out_n = 0;
+    TailState S{n_reads, read_id_first, row_off, kmer_id, pos, read_len, purged_off, purged_read, {}};
+    // the survivors' lists after merge_components: sorted unique union of the members' lists (:379)
+    for (uint64_t c = 0; c < n_comp; c++) {
+        std::vector<uint32_t> u;
+        for (uint64_t i = comp_off[c]; i < comp_off[c + 1]; i++) {
+            const uint64_t r = comp_member[i] - read_id_first;
+            u.insert(u.end(), kmer_id + row_off[r], kmer_id + row_off[r + 1]);
+        }
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        S.survivor_list.emplace(comp_member[comp_off[c]], std::move(u));
+    }
+    const uint64_t tail_length = avg_read_length * 2;                       // :543
+
+    std::map<uint32_t, std::pair<std::vector<uint32_t>, std::vector<uint32_t>>> tails;   // survivor -> (k-mers of one end, of the other)
+    for (uint64_t c = 0; c < n_comp; c++) {
+        // adjacency with the approximate overlap as edge attribute (:511-516)
+        std::map<uint32_t, std::vector<std::pair<uint32_t, int>>> adj;
+        for (uint64_t e = tree_off[c]; e < tree_off[c + 1]; e++) {
+            const int d = S.overlap(tree_x[e], tree_y[e]);
+            adj[tree_x[e]].push_back({tree_y[e], d});
+            adj[tree_y[e]].push_back({tree_x[e], d});
+        }
+        if (adj.empty()) continue;
+        auto bfs = [&](uint32_t start) {                                    // :518-538 (uint64 arithmetic as in the reference)
+            std::map<uint32_t, uint64_t> dist;
+            std::map<uint32_t, bool> visited;
+            std::queue<uint32_t> q;
+            dist[start] = read_len[start - read_id_first];
+            q.push(start);
+            while (!q.empty()) {
+                const uint32_t v = q.front();
+                visited[v] = true;
+                q.pop();
+                for (const auto &nb : adj[v])
+                    if (!visited.count(nb.first)) {
+                        dist[nb.first] = dist[v] + read_len[nb.first - read_id_first] - (uint64_t) (int64_t) nb.second;
+                        q.push(nb.first);
+                    }
+            }
+            return dist;
+        };
+        auto farthest = [](const std::map<uint32_t, uint64_t> &dist) {      // :540-544; ties: smallest id
+            std::pair<uint32_t, uint64_t> best = *dist.begin();
+            for (const auto &d : dist) if (d.second > best.second) best = d;
+            return best;
+        };
+        const auto d0 = bfs(adj.begin()->first);
+        const auto far0 = farthest(d0);
+        const auto d_right = bfs(far0.first);
+        const auto far_right = farthest(d_right);
+        std::vector<uint32_t> end_a, end_b;
+        for (const auto &d : d_right) if (d.second + tail_length > far_right.second) end_a.push_back(d.first);
+        const auto d_left = bfs(far_right.first);
+        const auto far_left = farthest(d_left);
+        for (const auto &d : d_left) if (d.second + tail_length > far_left.second) end_b.push_back(d.first);
+
+        // amplify_component (:583-592): the tail plus both endpoints of every connection a tail vertex has with score >= min
+        auto amplify = [&](const std::vector<uint32_t> &tail) {
+            std::vector<uint32_t> ids(tail);
+            std::unordered_map<uint32_t, uint64_t> count;
+            for (uint32_t pivot : tail) {
+                count.clear();
+                const uint32_t *pl;
+                size_t nl;
+                S.list_of(pivot, pl, nl);
+                for (size_t i = 0; i < nl; i++)                             // duplicates of the pivot's list count (:311-316)
+                    for (uint64_t j = purged_off[pl[i]]; j < purged_off[pl[i] + 1]; j++) count[purged_read[j]]++;
+                count.erase(pivot);                                          // :317
+                for (const auto &cn : count) if (cn.second >= amplification_min_score) ids.push_back(cn.first);
+            }
+            std::sort(ids.begin(), ids.end());
+            ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+            return ids;
+        };
+        // accumulate_kmer_ids (:340-346): sorted unique union of the components' current lists
+        auto kmers_of = [&](const std::vector<uint32_t> &ids) {
+            std::vector<uint32_t> u;
+            for (uint32_t id : ids) { const uint32_t *pl; size_t nl; S.list_of(id, pl, nl); u.insert(u.end(), pl, pl + nl); }
+            std::sort(u.begin(), u.end());
+            u.erase(std::unique(u.begin(), u.end()), u.end());
+            return u;
+        };
+        tails[comp_member[comp_off[c]]] = {kmers_of(amplify(end_b)), kmers_of(amplify(end_a))};
+    }
+
+    // :621-640: for every pair of components the largest of the four tail intersections; :650 keep score > 0
+    auto common = [](const std::vector<uint32_t> &a, const std::vector<uint32_t> &b) {
+        uint64_t n = 0;
+        size_t i = 0, j = 0;
+        while (i < a.size() && j < b.size()) { if (a[i] < b[j]) i++; else if (b[j] < a[i]) j++; else { n++; i++; j++; } }
+        return n;
+    };
+    struct Conn { uint32_t x, y; uint64_t s; };
+    std::vector<Conn> conns;
+    for (auto a = tails.begin(); a != tails.end(); ++a)
+        for (auto b = std::next(a); b != tails.end(); ++b) {
+            const uint64_t s = std::max(std::max(common(a->second.first, b->second.first), common(a->second.first, b->second.second)),
+                                        std::max(common(a->second.second, b->second.first), common(a->second.second, b->second.second)));
+            if (s > 0) conns.push_back({a->first, b->first, s});
+        }
+    // canonical order (score desc, min asc, max asc); x < y by construction
+    std::sort(conns.begin(), conns.end(), [](const Conn &p, const Conn &q) { return p.s != q.s ? p.s > q.s : (p.x != q.x ? p.x < q.x : p.y < q.y); });
+    for (size_t i = 0; i < conns.size(); i++) { out_x[i] = conns[i].x; out_y[i] = conns[i].y; out_score[i] = conns[i].s; }
+    *out_n = conns.size();
+    return HGA_OK;
+}

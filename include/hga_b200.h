@@ -12,6 +12,7 @@
  *   hga_pair_count       <- get_connections / get_all_connections           clustering/ReadClusteringEngine.cpp:301-339
  *   hga_select_edges     <- the 15 % slice / --sc_score filter              clustering/ReadClusteringEngine.cpp:748-756
  *   hga_components       <- union_find(edges, {}, min, -1)                  clustering/ReadClusteringEngine.cpp:424-489, call :763
+ *   hga_host_tail_connections <- get_core_component_connections             clustering/ReadClusteringEngine.cpp:491-651
  *   hga_spectral_clustering <- spectral_clustering(connections, dims)       clustering/ReadClusteringEngine.cpp:653-697, lib/clustering/*
  *   hga_enrich           <- merge_components(scaffolds), get_connections(cores, min), union_find(conns, cores, 2, -1),
  *                           merge_components, get_component_ids             clustering/ReadClusteringEngine.cpp:349-422, :764, :785-794
@@ -178,6 +179,20 @@ int hga_get_core_kmers(hga_handle *h, hga_core_kmers_t *out);
  * merge_components) and the cluster boundaries (out_cluster_off, capacity dims + 1; empty clusters are kept). */
 int hga_spectral_clustering(const uint32_t *conn_x, const uint32_t *conn_y, const uint64_t *conn_score, uint64_t n_conn, int dims,
                             uint32_t *out_component, uint64_t *out_cluster_off, uint64_t *out_n_components, uint64_t *out_n_clusters);
+
+/* Tail connections between scaffold components (HOST arithmetic, no GPU involved; second piece of SURVEY §8f-2):
+ * get_core_component_connections(components_and_trees) of clustering/ReadClusteringEngine.cpp:594-651 (spanning-tree tails :510-581,
+ * approximate_read_overlap :491-508, amplify_component :583-592, accumulate_kmer_ids :340-346) on the engine state after
+ * merge_components(scaffold components).
+ *   row_off / kmer_id / pos : hits by read, every row sorted by (kmer_id, pos) (hga_get_hits(h, 1, ..)); read_len per read
+ *   comp_off / comp_member  : the scaffold components, element [0] = the surviving id; tree_off / tree_x / tree_y their spanning trees
+ *   purged_off / purged_read: the purged inverted index by kmer_id (hga_get_purged_index)
+ * Output (capacity n_comp * (n_comp - 1) / 2): connections x < y with score > 0 in canonical order (score desc, x asc, y asc). */
+int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_off, const uint32_t *kmer_id, const uint32_t *pos, const uint32_t *read_len,
+                              uint64_t avg_read_length, uint32_t read_id_first, uint64_t n_comp, const uint64_t *comp_off, const uint32_t *comp_member,
+                              const uint64_t *tree_off, const uint32_t *tree_x, const uint32_t *tree_y, const uint64_t *purged_off,
+                              const uint32_t *purged_read, uint32_t amplification_min_score, uint32_t *out_x, uint32_t *out_y, uint64_t *out_score,
+                              uint64_t *out_n);
 
 /* Per-stage device time (CUDA events on the handle's stream) and counters of the most recent run. */
 typedef struct {

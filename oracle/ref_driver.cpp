@@ -246,6 +246,31 @@ public:
             // spanning trees, tail amplification, tail connections, spectral clustering of the scaffold components, merge.
             // The driver imposes the canonical order on the tail connections before the spectral stage (their order decides the
             // row order of the affinity matrix, :657-663).
+            if (do_dump) {
+                // per scaffold component (in the order of comp_off: by smallest member): the tail vertices of its spanning tree
+                // (:505-581), left then right, and the amplified tails (:583-592); all sorted
+                std::vector<std::pair<uint32_t, size_t>> order;
+                for (size_t i = 0; i < comps.size(); i++) order.push_back({*std::min_element(comps[i].first.begin(), comps[i].first.end()), i});
+                std::sort(order.begin(), order.end());
+                std::vector<uint64_t> tail_off{0}, amp_off{0};
+                std::vector<uint32_t> tail_v, amp_v;
+                for (auto &o : order) {
+                    auto tails = get_spanning_tree_tails(comps[o.second].second);
+                    for (auto *side : {&tails.first, &tails.second}) {
+                        std::vector<uint32_t> v(side->begin(), side->end());
+                        std::sort(v.begin(), v.end());
+                        tail_v.insert(tail_v.end(), v.begin(), v.end());
+                        tail_off.push_back(tail_v.size());
+                        auto amp = amplify_component(*side, config.tail_amplification_min_score);
+                        amp_v.insert(amp_v.end(), amp.begin(), amp.end());
+                        amp_off.push_back(amp_v.size());
+                    }
+                }
+                dump(out, "tail_off.u64", tail_off);
+                dump(out, "tail_vertex.u32", tail_v);
+                dump(out, "amp_off.u64", amp_off);
+                dump(out, "amp_vertex.u32", amp_v);
+            }
             t0 = now_ms();
             auto core_forming = get_core_component_connections(comps);
             double t_tail = now_ms() - t0;

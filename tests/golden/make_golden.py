@@ -65,15 +65,31 @@ def main_spectral():
         print(name, int(m.sum()), "connections,", len(ref["spectral_off"]) - 1, "clusters")
 
 
+def main_tails():
+    """SURVEY §8f-2 fixture: reads + k-mers -> tail connections between the scaffold components, from ref_driver --full."""
+    orc = oracle_lib.load()
+    with tempfile.TemporaryDirectory() as d:
+        paths, kp = datagen.make_diploid_case(d, genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=7, error_rate=0.005, fmt="fastq")
+        ref = refdump.run_ref(DRIVER, paths, kp, enrich=20, full=True, min_size=30)
+        rc, reads = orc.load_reads(paths)
+        kmers, k = orc.load_kmers(kp)
+    np.savez_compressed(os.path.join(HERE, "tails_a.npz"), bases=np.frombuffer(reads["seq"], dtype=np.uint8), seq_off=reads["seq_off"], kmers=kmers, k=np.int64(k),
+                        min_size=np.int64(30), amplification_min_score=np.int64(40), tconn_x=ref["tconn_x"], tconn_y=ref["tconn_y"], tconn_score=ref["tconn_score"])
+    print("tails_a", len(ref["tconn_x"]), "tail connections,", ref["scaffold_components"], "scaffold components")
+
+
 def main():
     if "--spectral-only" in sys.argv:
         return main_spectral()
+    if "--tails-only" in sys.argv:
+        return main_tails()
     if not os.path.exists(DRIVER):
         subprocess.run(["make", "-C", os.path.dirname(os.path.dirname(DRIVER)), "ref"], check=True)
     if "--enrich-only" in sys.argv:
         return main_enrich()
     main_enrich()
     main_spectral()
+    main_tails()
     with tempfile.TemporaryDirectory() as d:
         # KAT 2 of SURVEY §8c: multiplicity
         rng = np.random.default_rng(7)

@@ -13,6 +13,7 @@ _FILES = {
     "core_id": "u32", "core_kmer_off": "u64", "core_kmer": "u64", "core_read_off": "u64", "core_read": "u32", "purged_off": "u64", "purged_read": "u32",
     "econn_x": "u32", "econn_y": "u32", "econn_score": "u64", "final_id": "u32", "final_off": "u64", "final_read": "u32",
     "tconn_x": "u32", "tconn_y": "u32", "tconn_score": "u64", "spectral_off": "u64", "spectral_member": "u32", "spectral_first": "u32",
+    "tail_off": "u64", "tail_vertex": "u32", "amp_off": "u64", "amp_vertex": "u32",
 }
 _DT = {"u32": np.uint32, "u64": np.uint64}
 
