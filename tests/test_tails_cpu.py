@@ -66,3 +66,40 @@ def test_tail_connections_golden(oracle):
     a = _inputs(oracle, z["bases"].tobytes(), z["seq_off"], int(z["k"]), z["kmers"], int(z["min_size"]))
     x, y, s = hga_b200.capi.host_tail_connections(amplification_min_score=int(z["amplification_min_score"]), **a)
     assert np.array_equal(x, z["tconn_x"]) and np.array_equal(y, z["tconn_y"]) and np.array_equal(s, z["tconn_score"])
+
+
+@pytest.mark.parametrize("name", ["long_k15", "short_ties"])
+def test_whole_tail_spectral_block_reaches_the_reference_final_components(oracle, ref_driver, tmp_path, name):
+    """run_clustering :764-794 INCLUDING the tail / spectral block: scaffold merge -> hga_host_tail_connections -> hga_spectral_clustering
+    -> merge of the clusters (the oracle's engine state; the product's GPU form of this second merge is round-2 work) -> enrichment:
+    final components and their ids equal to the reference's (ref_driver --full)"""
+    import hga_b200
+    import oracle_lib
+    kw = dict(CASES[name])
+    min_size = kw.pop("_min_size")
+    paths, kp = datagen.make_diploid_case(str(tmp_path), **kw)
+    ref = refdump.run_ref(ref_driver, paths, kp, enrich=20, full=True, min_size=min_size)
+    rc, reads = oracle.load_reads(paths)
+    kmers, k = oracle.load_kmers(kp)
+    a = _inputs(oracle, reads["seq"], reads["seq_off"], k, kmers, min_size)
+    x, y, s = hga_b200.capi.host_tail_connections(amplification_min_score=40, **a)
+    clusters = [c for c in hga_b200.capi.spectral_clustering(x[s > 5], y[s > 5], s[s > 5], 16) if len(c)]
+    res = oracle.run(reads["seq"], reads["seq_off"], k, kmers, min_size=min_size)
+    eng = oracle_lib.Engine(oracle, res["row_off"], res["hit_kid"], len(kmers), res["inv_off"], res["inv_read"])
+    try:
+        eng.merge(res["comp"][0], res["comp"][1])                                    # :764
+        if clusters:                                                                 # :774
+            off = np.cumsum([0] + [len(c) for c in clusters]).astype(np.uint64)
+            eng.merge(off, np.concatenate(clusters))
+        cores = eng.ids(min_size)
+        ex, ey, es = oracle.canonical_sort(*eng.connections(cores, 20))             # :787
+        eo, em, _, _, _ = oracle.union_find(ex, ey, min_size=2, max_size=-1, restricted=cores)
+        eng.merge(eo, em)
+        final = eng.ids(min_size)
+        got = sorted((int(np.sort(eng.component_reads(c))[0]), int(c), np.sort(eng.component_reads(c)).tolist()) for c in final)
+    finally:
+        eng.close()
+    fo = ref["final_off"].astype(np.int64)
+    want = [(int(ref["final_read"][fo[i]]), int(ref["final_id"][i]), ref["final_read"][fo[i]:fo[i + 1]].tolist()) for i in range(len(fo) - 1)]
+    assert len(cores) == ref["cores"]
+    assert got == want
