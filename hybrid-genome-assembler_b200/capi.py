@@ -62,7 +62,7 @@ class Metrics(C.Structure):
 # every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_init", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
-           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering", "hga_host_tail_connections",
+           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering", "hga_host_tail_connections", "hga_host_sym_eigen",
            "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
 
 
@@ -137,6 +137,17 @@ def spectral_clustering(conn_x, conn_y, conn_score, dims=16):
                                        out.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), C.byref(n_comp), C.byref(n_cl)))
     o = off.astype(np.int64)
     return [out[o[i]:o[i + 1]].copy() for i in range(n_cl.value)]
+
+
+def host_sym_eigen(a):
+    """eigenvalues (ascending) and eigenvectors (columns) of a symmetric matrix with the library's own solver"""
+    lib = load_library()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    val = np.zeros(n, dtype=np.float64); vec = np.zeros((n, n), dtype=np.float64)
+    lib.hga_host_sym_eigen.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(lib.hga_host_sym_eigen(n, a.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p)))
+    return val, vec
 
 
 def host_tail_connections(row_off, kmer_id, pos, read_len, avg_read_length, comp_off, comp_member, tree_off, tree_x, tree_y, purged_off, purged_read,

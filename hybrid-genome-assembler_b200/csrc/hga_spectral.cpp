@@ -11,9 +11,10 @@
 // are the reference's: exponent range 0.3 .. 20 for the affinities (:670-674), step 1.0, at most 200 sweeps, stop when the
 // quality gained over two sweeps is below 1e-3 (Evrot.cpp:44,88,105-109), a dimension count is kept when its quality is within
 // 1e-3 of the best so far (ClusterRotate.cpp:38-45), members ordered by their distance to the cluster centre (:62-74; element [0]
-// becomes the surviving component id in merge_components). The eigen-solver is a cyclic Jacobi iteration - the same as the
-// Eigen2 stand-in the oracle build compiles the reference's sources against (oracle/shim/eigen2/Eigen/Core); against a real
-// Eigen2 build eigenvectors agree up to sign and rotation inside degenerate eigenspaces.
+// becomes the surviving component id in merge_components). The eigen-solver is Householder tridiagonalisation + implicit QL -
+// the same routine as in the Eigen2 stand-in the oracle build compiles the reference's sources against
+// (oracle/shim/eigen2/Eigen/Core), checked on its own against numpy.linalg.eigh; against a real Eigen2 build eigenvectors agree up
+// to sign and rotation inside degenerate eigenspaces.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -46,32 +47,117 @@ Mat matmul(const Mat &a, const Mat &b) {
     return o;
 }
 
-// symmetric eigen-decomposition, cyclic Jacobi; eigenvalues ascending, eigenvectors in the columns of vec
-void jacobi_eigen(const Mat &A0, std::vector<double> &val, Mat &vec) {
-    const int n = A0.r;
-    Mat A = A0, V(n, n);
-    for (int i = 0; i < n; i++) V.at(i, i) = 1.0;
-    for (int sweep = 0; sweep < 100; sweep++) {
-        double off = 0;
-        for (int p = 0; p < n; p++) for (int q = p + 1; q < n; q++) off += A.at(p, q) * A.at(p, q);
-        if (off < 1e-26) break;
-        for (int p = 0; p < n; p++)
-            for (int q = p + 1; q < n; q++) {
-                if (std::fabs(A.at(p, q)) < 1e-300) continue;
-                const double theta = (A.at(q, q) - A.at(p, p)) / (2.0 * A.at(p, q));
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-                const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
-                for (int k = 0; k < n; k++) { const double x = A.at(k, p), y = A.at(k, q); A.at(k, p) = cs * x - sn * y; A.at(k, q) = sn * x + cs * y; }
-                for (int k = 0; k < n; k++) { const double x = A.at(p, k), y = A.at(q, k); A.at(p, k) = cs * x - sn * y; A.at(q, k) = sn * x + cs * y; }
-                for (int k = 0; k < n; k++) { const double x = V.at(k, p), y = V.at(k, q); V.at(k, p) = cs * x - sn * y; V.at(k, q) = sn * x + cs * y; }
+// Symmetric eigen-decomposition: Householder reduction to tridiagonal form, then implicit-shift QL (the classical EISPACK
+// tred2 / tql2 pair). a (n x n, row major) holds the matrix on entry and the eigenvectors (columns) on exit; d the eigenvalues,
+// in no particular order. Returns false when an eigenvalue does not converge in 60 iterations.
+static bool sym_eigen_tridiagonal_ql(int n, std::vector<double> &a, std::vector<double> &d) {
+    auto A = [&](int i, int j) -> double & { return a[(size_t) i * n + j]; };
+    std::vector<double> e((size_t) n, 0.0);
+    d.assign((size_t) n, 0.0);
+    for (int i = n - 1; i >= 1; i--) {
+        const int l = i - 1;
+        double h = 0.0, scale = 0.0;
+        if (l > 0) {
+            for (int k = 0; k <= l; k++) scale += std::fabs(A(i, k));
+            if (scale == 0.0) {
+                e[i] = A(i, l);
+            } else {
+                for (int k = 0; k <= l; k++) { A(i, k) /= scale; h += A(i, k) * A(i, k); }
+                double f = A(i, l);
+                double g = f >= 0.0 ? -std::sqrt(h) : std::sqrt(h);
+                e[i] = scale * g;
+                h -= f * g;
+                A(i, l) = f - g;
+                f = 0.0;
+                for (int j = 0; j <= l; j++) {
+                    A(j, i) = A(i, j) / h;
+                    g = 0.0;
+                    for (int k = 0; k <= j; k++) g += A(j, k) * A(i, k);
+                    for (int k = j + 1; k <= l; k++) g += A(k, j) * A(i, k);
+                    e[j] = g / h;
+                    f += e[j] * A(i, j);
+                }
+                const double hh = f / (h + h);
+                for (int j = 0; j <= l; j++) {
+                    f = A(i, j);
+                    e[j] = g = e[j] - hh * f;
+                    for (int k = 0; k <= j; k++) A(j, k) -= f * e[k] + g * A(i, k);
+                }
             }
+        } else {
+            e[i] = A(i, l);
+        }
+        d[i] = h;
     }
-    std::vector<int> order(n);
+    if (n > 0) { d[0] = 0.0; e[0] = 0.0; }
+    for (int i = 0; i < n; i++) {
+        const int l = i - 1;
+        if (d[i] != 0.0) {
+            for (int j = 0; j <= l; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= l; k++) g += A(i, k) * A(k, j);
+                for (int k = 0; k <= l; k++) A(k, j) -= g * A(k, i);
+            }
+        }
+        d[i] = A(i, i);
+        A(i, i) = 1.0;
+        for (int j = 0; j <= l; j++) A(j, i) = A(i, j) = 0.0;
+    }
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];
+    if (n > 0) e[n - 1] = 0.0;
+    for (int l = 0; l < n; l++) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; m++) {
+                const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+                if (std::fabs(e[m]) <= 2.220446049250313e-16 * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 60) return false;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; i--) {
+                    double f = s * e[i];
+                    const double b = c * e[i];
+                    e[i + 1] = r = std::hypot(f, g);
+                    if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    d[i + 1] = g + (p = s * r);
+                    g = c * r - b;
+                    for (int k = 0; k < n; k++) {
+                        f = A(k, i + 1);
+                        A(k, i + 1) = s * A(k, i) + c * f;
+                        A(k, i) = c * A(k, i) - s * f;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[m] = 0.0;
+            }
+        } while (m != l);
+    }
+    return true;
+}
+
+// eigenvalues ascending (stable), eigenvectors in the columns of vec
+bool sym_eigen(const Mat &A0, std::vector<double> &val, Mat &vec) {
+    const int n = A0.r;
+    std::vector<double> a = A0.v, d;
+    const bool converged = sym_eigen_tridiagonal_ql(n, a, d);
+    std::vector<int> order((size_t) n);
     for (int i = 0; i < n; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return A.at(a, a) < A.at(b, b); });
-    val.assign(n, 0.0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return d[x] < d[y]; });
+    val.assign((size_t) n, 0.0);
     vec = Mat(n, n);
-    for (int j = 0; j < n; j++) { val[j] = A.at(order[j], order[j]); for (int i = 0; i < n; i++) vec.at(i, j) = V.at(i, order[j]); }
+    for (int j = 0; j < n; j++) { val[j] = d[order[j]]; for (int i = 0; i < n; i++) vec.at(i, j) = a[(size_t) i * n + order[j]]; }
+    return converged;
 }
 
 // The alignment of one set of eigenvectors X (n x d): angles of the d (d - 1) / 2 Givens rotations that make every row of X R as
@@ -198,7 +284,9 @@ extern "C" int hga_spectral_clustering(const uint32_t *conn_x, const uint32_t *c
     for (int i = 0; i < S; i++) for (int j = 0; j < S; j++) L.at(i, j) = deg[i] * W.at(i, j) * deg[j];
     std::vector<double> val;
     Mat vec;
-    jacobi_eigen(L, val, vec);
+    // A matrix of NaNs (all scores equal: 0 / 0 above) never converges; the reference carries on with what its solver left behind,
+    // every quality comparison below then fails and no cluster is formed. Same here: the return value is not an error.
+    (void) sym_eigen(L, val, vec);
     for (int i = 0; i < S - 1; i++) {                                  // largest eigenvalue first (selection, :38-46)
         int k = 0;
         for (int j = 1; j < S - i; j++) if (val[i + j] > val[i + k]) k = j;
@@ -243,5 +331,19 @@ extern "C" int hga_spectral_clustering(const uint32_t *conn_x, const uint32_t *c
     }
     *out_n_components = (uint64_t) S;
     *out_n_clusters = n_clusters;
+    return HGA_OK;
+}
+
+
+// The eigen-solver on its own (exposed so that it can be checked against an independent implementation): a = symmetric n x n, row
+// major; eigenvalues ascending in val[n], eigenvectors in the columns of vec (n x n, row major).
+extern "C" int hga_host_sym_eigen(int n, const double *a, double *val, double *vec) {
+    if (n < 0 || (n && (!a || !val || !vec))) { hga_set_error("hga_host_sym_eigen: bad argument"); return HGA_E_ARG; }
+    Mat A(n, n), V;
+    std::copy(a, a + (size_t) n * n, A.v.begin());
+    std::vector<double> w;
+    if (!sym_eigen(A, w, V)) { hga_set_error("hga_host_sym_eigen: no convergence"); return HGA_E_STATE; }
+    std::copy(w.begin(), w.end(), val);
+    std::copy(V.v.begin(), V.v.end(), vec);
     return HGA_OK;
 }

@@ -180,6 +180,10 @@ int hga_get_core_kmers(hga_handle *h, hga_core_kmers_t *out);
 int hga_spectral_clustering(const uint32_t *conn_x, const uint32_t *conn_y, const uint64_t *conn_score, uint64_t n_conn, int dims,
                             uint32_t *out_component, uint64_t *out_cluster_off, uint64_t *out_n_components, uint64_t *out_n_clusters);
 
+/* The symmetric eigen-solver hga_spectral_clustering uses (Householder tridiagonalisation + implicit QL), exposed so that it can be
+ * checked against an independent implementation: a = n x n row major; val[n] ascending; vec = eigenvectors in columns, row major. */
+int hga_host_sym_eigen(int n, const double *a, double *val, double *vec);
+
 /* Tail connections between scaffold components (HOST arithmetic, no GPU involved; second piece of SURVEY §8f-2):
  * get_core_component_connections(components_and_trees) of clustering/ReadClusteringEngine.cpp:594-651 (spanning-tree tails :510-581,
  * approximate_read_overlap :491-508, amplify_component :583-592, accumulate_kmer_ids :340-346) on the engine state after
