@@ -176,21 +176,39 @@ extern "C" int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_o
         tails[comp_member[comp_off[c]]] = {kmers_of(amplify(end_b)), kmers_of(amplify(end_a))};
     }
 
-    // :621-640: for every pair of components the largest of the four tail intersections; :650 keep score > 0
-    auto common = [](const std::vector<uint32_t> &a, const std::vector<uint32_t> &b) {
-        uint64_t n = 0;
-        size_t i = 0, j = 0;
-        while (i < a.size() && j < b.size()) { if (a[i] < b[j]) i++; else if (b[j] < a[i]) j++; else { n++; i++; j++; } }
-        return n;
-    };
+    // :621-640: for every pair of components the largest of the four tail-to-tail intersections; :650 keep score > 0. The reference
+    // intersects the sorted unions pair by pair (S^2 / 2 pairs x 4 merges); the unions are sets, so |A n B| is the number of
+    // k-mers that list both tails: one pass over a k-mer -> tails posting list counts all pairs at once.
     struct Conn { uint32_t x, y; uint64_t s; };
     std::vector<Conn> conns;
-    for (auto a = tails.begin(); a != tails.end(); ++a)
-        for (auto b = std::next(a); b != tails.end(); ++b) {
-            const uint64_t s = std::max(std::max(common(a->second.first, b->second.first), common(a->second.first, b->second.second)),
-                                        std::max(common(a->second.second, b->second.first), common(a->second.second, b->second.second)));
-            if (s > 0) conns.push_back({a->first, b->first, s});
+    {
+        std::vector<uint32_t> comp_id;                                     // tail t belongs to component comp_id[t / 2]
+        std::vector<std::pair<uint32_t, uint32_t>> posting;                // (k-mer, tail index)
+        uint32_t t = 0;
+        for (const auto &tc : tails) {
+            comp_id.push_back(tc.first);
+            for (uint32_t k : tc.second.first) posting.push_back({k, t});
+            for (uint32_t k : tc.second.second) posting.push_back({k, t + 1});
+            t += 2;
         }
+        std::sort(posting.begin(), posting.end());
+        std::unordered_map<uint64_t, uint64_t> shared;                     // (tail a << 32 | tail b), a < b, different components
+        for (size_t i = 0; i < posting.size();) {
+            size_t j = i;
+            while (j < posting.size() && posting[j].first == posting[i].first) j++;
+            for (size_t p = i; p < j; p++)
+                for (size_t q = p + 1; q < j; q++)
+                    if (posting[p].second / 2 != posting[q].second / 2) shared[((uint64_t) posting[p].second << 32) | posting[q].second]++;
+            i = j;
+        }
+        std::unordered_map<uint64_t, uint64_t> best;                       // (component index a << 32 | b) -> max over the four combinations
+        for (const auto &e : shared) {
+            const uint64_t key = ((e.first >> 33) << 32) | ((e.first & 0xFFFFFFFFu) >> 1);
+            uint64_t &m = best[key];
+            m = std::max(m, e.second);
+        }
+        for (const auto &e : best) conns.push_back({comp_id[e.first >> 32], comp_id[e.first & 0xFFFFFFFFu], e.second});
+    }
     // canonical order (score desc, min asc, max asc); x < y by construction
     std::sort(conns.begin(), conns.end(), [](const Conn &p, const Conn &q) { return p.s != q.s ? p.s > q.s : (p.x != q.x ? p.x < q.x : p.y < q.y); });
     for (size_t i = 0; i < conns.size(); i++) { out_x[i] = conns[i].x; out_y[i] = conns[i].y; out_score[i] = conns[i].s; }
