@@ -45,6 +45,11 @@ class _Enrichment(C.Structure):
                 ("n_reads", C.c_uint64), ("read_id_first", C.c_uint32), ("assignment", u32p)]
 
 
+class _TailBlock(C.Structure):
+    _fields_ = [("ran", C.c_int), ("n_scaffold_cores", C.c_uint64), ("n_connections", C.c_uint64), ("conn_x", u32p), ("conn_y", u32p), ("conn_score", u64p),
+                ("n_clusters", C.c_uint64), ("cluster_off", u64p), ("cluster_member", u32p)]
+
+
 class _CoreKmers(C.Structure):
     _fields_ = [("n_cores", C.c_uint64), ("off", u64p), ("kmer_id", u32p)]
 
@@ -62,7 +67,7 @@ class Metrics(C.Structure):
 # every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_init", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
-           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering", "hga_host_tail_connections", "hga_host_sym_eigen",
+           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_enrich_full", "hga_get_tail_block", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering", "hga_host_tail_connections", "hga_host_sym_eigen",
            "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
 
 
@@ -97,6 +102,8 @@ def load_library():
         lib.hga_get_components.argtypes = [C.c_void_p, C.POINTER(_Components)]
         lib.hga_enrich.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
         lib.hga_enrich_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+        lib.hga_enrich_full.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+        lib.hga_get_tail_block.argtypes = [C.c_void_p, C.POINTER(_TailBlock)]
         lib.hga_get_enrichment.argtypes = [C.c_void_p, C.POINTER(_Enrichment)]
         lib.hga_get_purged_index.argtypes = [C.c_void_p, C.POINTER(_Index)]
         lib.hga_get_core_kmers.argtypes = [C.c_void_p, C.POINTER(_CoreKmers)]
@@ -288,6 +295,21 @@ class Handle:
             _check(self.lib.hga_enrich(self._h, int(min_size), int(enrichment_min_score)))
         else:
             _check(self.lib.hga_enrich_ex(self._h, int(min_size), int(max_size), int(enrichment_min_score)))
+
+    def enrich_full(self, read_off, min_size=30, enrichment_min_score=20, max_size=-1, tail_amplification_min_score=40, spectral_dims=16):
+        """hga_enrich_full: merge + enrichment INCLUDING the tail / spectral block (run_clustering :764-794). read_off as given to scan()."""
+        ro = np.ascontiguousarray(read_off, dtype=np.uint64)
+        _check(self.lib.hga_enrich_full(self._h, int(min_size), int(max_size), int(enrichment_min_score), int(tail_amplification_min_score), int(spectral_dims),
+                                        ro.ctypes.data_as(C.c_void_p)))
+
+    def get_tail_block(self):
+        out = _TailBlock()
+        _check(self.lib.hga_get_tail_block(self._h, C.byref(out)))
+        off = _arr(out.cluster_off, out.n_clusters + 1, np.uint64) if out.n_clusters else np.zeros(1, dtype=np.uint64)
+        mem = _arr(out.cluster_member, int(off[-1]), np.uint32)
+        return dict(ran=bool(out.ran), n_scaffold_cores=int(out.n_scaffold_cores), conn_x=_arr(out.conn_x, out.n_connections, np.uint32),
+                    conn_y=_arr(out.conn_y, out.n_connections, np.uint32), conn_score=_arr(out.conn_score, out.n_connections, np.uint64),
+                    clusters=[mem[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)])
 
     def get_enrichment(self):
         out = _Enrichment()

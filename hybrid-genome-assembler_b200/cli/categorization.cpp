@@ -83,14 +83,14 @@ int main(int argc, char **argv) {
     std::vector<std::string> read_paths;
     std::string kmer_path, output_folder_path;
     Config config;
-    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false, export_test = false;
+    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false, export_test = false, tail_block = false;
     int device = 0;
 
     // boost::program_options' default style (read_clustering.cpp:60-66): --name=value and --name value, -k value and -kvalue,
     // and unambiguous prefixes of long names (--kmer for --kmers)
     static const char *long_names[] = {"--help", "--read_paths", "--kmers", "--output", "--sc_max_size", "--sc_min_size", "--sc_fraction", "--sc_score",
                                        "--tail_amplification", "--core_enrichment", "--spectral_dims", "--spectral", "--debug", "--threads",
-                                       "--parse-only", "--dump-kmers", "--scaffolds-only", "--load-only", "--export-test", "--device"};
+                                       "--parse-only", "--dump-kmers", "--scaffolds-only", "--load-only", "--export-test", "--device", "--tail-block"};
     std::vector<std::string> args;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -142,6 +142,7 @@ int main(int argc, char **argv) {
         else if (a == "--load-only") load_only = true;
         else if (a == "--export-test") export_test = true;
         else if (a == "--device") device = std::atoi(need(i));
+        else if (a == "--tail-block") tail_block = true;
         else if (a.size() > 1 && a[0] == '-') throw std::invalid_argument("unrecognised option '" + a + "'");
         else read_paths.push_back(a);
     }
@@ -255,17 +256,21 @@ int main(int argc, char **argv) {
         hga_host::export_components(reads, ids, of_read.data(), output_folder_path, io_threads);
         std::cout << "Exported " << comp.n_components << " components\n";
     } else {
-        if (comp.n_components > 2 || config.scaffold_component_max_size != -1)
+        if (!tail_block && (comp.n_components > 2 || config.scaffold_component_max_size != -1))
             std::cerr << "categorization: " << comp.n_components << " scaffold components; the tail / spectral merge of scaffold components "
-                         "(ReadClusteringEngine.cpp:768-777) is not part of this build: every scaffold component becomes a core, as in the reference "
-                         "when it finds no strong tail connection\n";
+                         "(ReadClusteringEngine.cpp:768-777) runs with --tail-block only (hga_enrich_full; opt-in until it has been through the GPU "
+                         "parity run): without it every scaffold component becomes a core, as in the reference when it finds no strong tail connection\n";
         hga_enrichment_t fin;
         {
             // the reference times these separately ("Merging of initial components", "Calculation of enrichment connections",
             // "Merging into core components"); here they are one library call
             Timer t("Merging of initial components, calculation of enrichment connections and merging into core components");
-            check(hga_enrich_ex(h, config.scaffold_component_min_size, config.scaffold_component_max_size, (uint32_t) config.enrichment_connections_min_score),
-                  "hga_enrich");
+            if (tail_block)
+                check(hga_enrich_full(h, config.scaffold_component_min_size, config.scaffold_component_max_size, (uint32_t) config.enrichment_connections_min_score,
+                                      (uint32_t) config.tail_amplification_min_score, config.spectral_dims, reads.seq_off.data()), "hga_enrich_full");
+            else
+                check(hga_enrich_ex(h, config.scaffold_component_min_size, config.scaffold_component_max_size, (uint32_t) config.enrichment_connections_min_score),
+                      "hga_enrich");
             check(hga_get_enrichment(h, &fin), "hga_get_enrichment");
             t.done();
         }

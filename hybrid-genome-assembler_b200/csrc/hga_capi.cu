@@ -142,7 +142,7 @@ void hga_destroy(hga_handle *h) {
                      &h->d_sort_b, &h->d_sort_tmp, &h->d_pair_key, &h->d_pair_score, &h->d_pair_key2, &h->d_pair_score2, &h->d_pair_scalars,
                      &h->d_heavy_list, &h->d_mid_list, &h->d_redo_list, &h->d_heavy_tab, &h->d_pivot_flag, &h->d_pivot_order, &h->d_hist, &h->d_sel_key, &h->d_sel_score, &h->d_sel_scalars, &h->d_parent,
                      &h->d_comp_size, &h->d_comp_label, &h->d_comp_scalars, &h->d_export_a, &h->d_export_b, &h->d_export_c, &h->d_enr_parent, &h->d_enr_core_of,
-                     &h->d_enr_surv, &h->d_enr_R, &h->d_enr_scalars, &h->d_enr_keys, &h->d_enr_keys2, &h->d_enr_core_koff, &h->d_purged_off, &h->d_purged_row};
+                     &h->d_enr_surv, &h->d_enr_R, &h->d_enr_scalars, &h->d_enr_keys, &h->d_enr_keys2, &h->d_enr_core_koff, &h->d_purged_off, &h->d_purged_row, &h->d_purged2_off, &h->d_purged2_row};
     for (DevBuf *b : dev) b->release();
     PinBuf *pin[] = {&h->h_row_off, &h->h_kid, &h->h_pos, &h->h_inv_off, &h->h_inv_read, &h->h_px, &h->h_py, &h->h_ps, &h->h_sx, &h->h_sy, &h->h_ss,
                      &h->h_label, &h->h_clabel, &h->h_csize, &h->h_scalars};
@@ -274,13 +274,33 @@ int hga_get_index(hga_handle *h, hga_index *out) {
 int hga_enrich(hga_handle *h, int min_size, uint32_t enrichment_min_score) {
     if (!h) { hga_set_error("NULL handle"); return HGA_E_ARG; }
     HGA_TRY(use_device(h));
-    return hga_enrich_run(h, min_size, -1, enrichment_min_score);
+    return hga_enrich_run(h, min_size, -1, enrichment_min_score, nullptr);
 }
 
 int hga_enrich_ex(hga_handle *h, int min_size, int max_size, uint32_t enrichment_min_score) {
     if (!h) { hga_set_error("NULL handle"); return HGA_E_ARG; }
     HGA_TRY(use_device(h));
-    return hga_enrich_run(h, min_size, max_size, enrichment_min_score);
+    return hga_enrich_run(h, min_size, max_size, enrichment_min_score, nullptr);
+}
+
+int hga_enrich_full(hga_handle *h, int min_size, int max_size, uint32_t enrichment_min_score, uint32_t tail_amplification_min_score, int spectral_dims,
+                    const uint64_t *read_off) {
+    if (!h || !read_off) { hga_set_error("NULL argument"); return HGA_E_ARG; }
+    if (spectral_dims < 2) { hga_set_error("hga_enrich_full: spectral_dims must be >= 2"); return HGA_E_ARG; }
+    HGA_TRY(use_device(h));
+    const TailParams tail{read_off, tail_amplification_min_score, spectral_dims};
+    return hga_enrich_run(h, min_size, max_size, enrichment_min_score, &tail);
+}
+
+int hga_get_tail_block(hga_handle *h, hga_tail_block_t *out) {
+    if (!h || !out) { hga_set_error("NULL argument"); return HGA_E_ARG; }
+    if (!h->have_enrichment) { hga_set_error("hga_get_tail_block: no enrichment result"); return HGA_E_STATE; }
+    const EnrichResult &r = h->enrich;
+    out->ran = r.tail_block_ran ? 1 : 0;
+    out->n_scaffold_cores = r.n_scaffold_cores;
+    out->n_connections = r.tconn_x.size(); out->conn_x = r.tconn_x.data(); out->conn_y = r.tconn_y.data(); out->conn_score = r.tconn_score.data();
+    out->n_clusters = r.cluster_off.empty() ? 0 : r.cluster_off.size() - 1; out->cluster_off = r.cluster_off.data(); out->cluster_member = r.cluster_member.data();
+    return HGA_OK;
 }
 
 int hga_get_enrichment(hga_handle *h, hga_enrichment_t *out) {
@@ -411,3 +431,5 @@ int hga_metrics(hga_handle *h, hga_metrics_t *out) {
 }
 
 }  // extern "C"
+
+int hga_export_index(hga_handle *h, const uint32_t *d_off, const uint32_t *d_row, uint64_t E, hga_index *out) { return export_index(h, d_off, d_row, E, out); }

@@ -4,8 +4,11 @@
 //   :763-764  union_find(...) roots + merge_components(scaffold_components)      (merge_components: :349-422)
 //   :785-794  get_connections(core_component_ids, enrichment_connections_min_score), union_find(conns, restricted = cores,
 //             2, -1), merge_components, get_component_ids(scaffold_component_min_size)
-// The tail / spectral block in between (:768-777) is SURVEY §8f-2 and not part of this stage: what runs here is the reference's
-// own path when it has at most two scaffold components or finds no strong tail connection.
+// The tail / spectral block in between (:768-777) runs when the caller asks for it (hga_enrich_full -> `tail`): the
+// state after the scaffold merge goes to the host stages hga_host_tail_connections / hga_spectral_clustering and the clusters they
+// return are merged by a SECOND merge_components on the GPU (enr_merge2_keys_kernel, enr_purge2_kernel; rule at the kernels).
+// Without it (hga_enrich, hga_enrich_ex) what runs here is the reference's own path when it has at most two scaffold components
+// or finds no strong tail connection.
 //
 // What the reference's merge does to the engine state, restated as data-parallel rules (oracle: orc_engine_merge):
 //   * the survivor of a component (element [0] = the root the sequential union_find ended with) receives the sorted UNIQUE
@@ -217,6 +220,57 @@ __global__ void enr_key_rows_kernel(const uint64_t *__restrict__ keys, uint64_t 
     }
 }
 
+// ---- second merge: merge_components(spectral clusters) on the state the first merge left (:774) ------------------------------------
+// A cluster is a set of cores (merged scaffold components); element [0] survives. What merge_components (:349-422) does then, as rules:
+//   * the survivor's list becomes the unique union of the members' lists, which after the first merge are the unions U_c: every key
+//     (core, slot) of the sorted unique array moves to the core its cluster merges into (sort + unique afterwards);
+//   * removal list of k-mer k (:385-389): every member c of a multi-member cluster with k in U_c, once (U_c is unique), and the
+//     cluster's survivor for every k of the new union. R2(k) = the largest of them; the two-pointer purge (:405-416) again stops
+//     with the removal list. A purged list holds reads outside every core and stale copies of first-merge survivors (a survivor that
+//     held k m times kept m - 1 entries, and then k is in its U_c), so: new list = { e < R2(k) } minus the FIRST copy of every
+//     entry that is the survivor of a core in a multi-member cluster.
+// map[c] = index of the core that c merges into, in the new (compacted) core numbering, | 1 << 31 when c's cluster has several members.
+__global__ void enr_merge2_keys_kernel(const uint64_t *__restrict__ ukeys, uint64_t n, const uint32_t *__restrict__ map, const uint32_t *__restrict__ surv_old,
+                                       const uint32_t *__restrict__ surv_new, uint32_t *R2, uint64_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t k = ukeys[i];
+        const uint32_t slot = (uint32_t) k, c = (uint32_t) (k >> 32), m = map[c], nc = m & 0x7FFFFFFFu;
+        if (m >> 31) {
+            atomicMax(&R2[slot], surv_old[c] + 1);
+            atomicMax(&R2[slot], surv_new[nc] + 1);
+        }
+        out[i] = ((uint64_t) nc << 32) | slot;
+    }
+}
+
+template<bool FILL>
+__global__ void enr_purge2_kernel(const uint32_t *__restrict__ p_off, const uint32_t *__restrict__ p_row, uint32_t n_slots, const uint32_t *__restrict__ R2,
+                                  const uint8_t *__restrict__ removed_once, uint32_t *__restrict__ cnt, const uint32_t *__restrict__ out_off,
+                                  uint32_t *__restrict__ out_row) {
+    for (uint64_t s = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t lo = p_off[s], hi = p_off[s + 1];
+        uint32_t n = 0;
+        uint32_t w = FILL ? out_off[s] : 0;
+        if (lo != hi) {
+            const uint32_t r1 = R2[s];                // largest removed row + 1; 0: no merged cluster lists this k-mer
+            if (r1 == 0) {
+                n = hi - lo;
+                if (FILL) for (uint32_t i = lo; i < hi; i++) out_row[w++] = p_row[i];
+            } else {
+                uint32_t prev = 0xFFFFFFFFu;
+                for (uint32_t i = lo; i < hi; i++) {
+                    const uint32_t e = p_row[i];
+                    if (e + 1 >= r1) break;
+                    const bool keep = !removed_once[e] || prev == e;
+                    prev = e;
+                    if (keep) { n++; if (FILL) out_row[w++] = e; }
+                }
+            }
+        }
+        if (!FILL) cnt[s] = n;
+    }
+}
+
 uint32_t dsu_find(std::vector<uint32_t> &parent, uint32_t v) {
     uint32_t r = v;
     while (parent[r] != r) r = parent[r];
@@ -243,7 +297,7 @@ struct PhaseClock {
 
 }  // namespace
 
-int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score) {
+int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score, const TailParams *tail) {
     if (!h->have_selection || !h->have_index || !h->have_scan) { hga_set_error("hga_enrich: needs hga_scan, hga_build_index and hga_select_edges"); return HGA_E_STATE; }
     if (h->comm && hga_comm_size(h) > 1) { hga_set_error("hga_enrich: not available with a communicator yet (single GPU only)"); return HGA_E_STATE; }
     if (min_size < 2) { hga_set_error("hga_enrich: min_size must be >= 2 (a core is a merged component)"); return HGA_E_ARG; }
@@ -339,6 +393,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
     std::vector<uint32_t> parent(n + 1), size(n + 1, 1);
     std::vector<uint8_t> touched(n + 1, 0);
     std::iota(parent.begin(), parent.end(), 0u);
+    std::vector<std::pair<uint32_t, uint32_t>> tree_edges;    // the edges that performed a union = the spanning forest (:474-476); tail block only
     for (uint64_t i = 0; i < M2; i++) {
         // the reference's list holds (x, y) and (y, x) back to back; the second is a no-op after the first
         uint32_t x = ex[i], y = ey[i];
@@ -350,6 +405,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
         const uint32_t bigger = size[px] > size[py] ? px : py, smaller = bigger == px ? py : px;   // :459-466 (ties: y's root)
         parent[smaller] = bigger;                                                              // :468-470
         size[bigger] += size[smaller];                                                         // :471
+        if (tail) tree_edges.push_back({x, y});                                                // :474
     }
     if (pc.on) fprintf(stderr, "hga_enrich: %llu of %llu selected edges replayed\n", (unsigned long long) M2, (unsigned long long) M);
     pc.mark("  replay loop");
@@ -358,23 +414,26 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
     std::vector<uint32_t> surv_row;
     for (uint64_t r = 0; r < n; r++)
         if (touched[r] && parent[r] == r && size[r] >= (uint32_t) min_size) { core_of[r] = (int32_t) surv_row.size(); surv_row.push_back((uint32_t) r); }
-    const uint32_t C = (uint32_t) surv_row.size();
+    uint32_t C = (uint32_t) surv_row.size();
     for (uint64_t r = 0; r < n; r++)
         if (touched[r] && parent[r] != r) core_of[r] = core_of[dsu_find(parent, (uint32_t) r)];
-    res.core_id.resize(C);
-    res.core_off.assign(C + 1, 0);
-    for (uint32_t c = 0; c < C; c++) { res.core_id[c] = surv_row[c] + first_id; res.core_off[c + 1] = size[surv_row[c]]; }
-    for (uint32_t c = 0; c < C; c++) res.core_off[c + 1] += res.core_off[c];
-    res.core_read.resize(res.core_off[C]);
-    {
+    // cores of the result: survivor ids ascending, members ascending (again after the tail block, which merges cores)
+    auto fill_cores = [&]() {
+        res.core_id.resize(C);
+        res.core_off.assign(C + 1, 0);
+        for (uint64_t r = 0; r < n; r++) if (core_of[r] >= 0) res.core_off[core_of[r] + 1]++;
+        for (uint32_t c = 0; c < C; c++) { res.core_id[c] = surv_row[c] + first_id; res.core_off[c + 1] += res.core_off[c]; }
+        res.core_read.resize(res.core_off[C]);
         std::vector<uint64_t> cur(res.core_off.begin(), res.core_off.end() - 1);
         for (uint64_t r = 0; r < n; r++) if (core_of[r] >= 0) res.core_read[cur[core_of[r]]++] = (uint32_t) r + first_id;
-    }
+    };
+    fill_cores();
+    res.n_scaffold_cores = C;
 
     pc.mark("host root replay + cores");
     // ---- 2. GPU: unions, removal bounds, purged index ----------------------------------------------------------------------
     HGA_TRY(h->d_enr_core_of.ensure((n + 1) * 4));
-    HGA_TRY(h->d_enr_surv.ensure(((size_t) C + 1) * 4));
+    HGA_TRY(h->d_enr_surv.ensure(((size_t) C + 1) * 4 * 2));        // second half: the survivors after the tail block's merge
     HGA_TRY(h->d_enr_R.ensure(((size_t) n_slots + 1) * 4));
     int32_t *d_core_of = h->d_enr_core_of.as<int32_t>();
     uint32_t *d_surv = h->d_enr_surv.as<uint32_t>(), *d_R = h->d_enr_R.as<uint32_t>();
@@ -449,6 +508,148 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
     h->n_core_kmers = n_u;
 
     pc.mark("purge");
+    // ---- 2b. tail / spectral block (:768-777), on request: host stages on the merged state, second merge on the GPU -------------
+    if (tail && C > 2) {
+        res.tail_block_ran = true;
+        // the engine state the host stages read: hits by read sorted by (kmer_id, pos), purged index by kmer_id, read lengths, the
+        // scaffold components (survivor first) with the spanning trees of the replayed union_find
+        hga_hits hits;
+        HGA_TRY(hga_get_hits(h, 1, &hits));
+        if (hits.n_reads != n) { hga_set_error("hga_enrich_full: the scan covers %llu reads, the index %llu rows", (unsigned long long) hits.n_reads, (unsigned long long) n); return HGA_E_STATE; }
+        hga_index pidx;
+        HGA_TRY(hga_export_index(h, d_poff, d_prow, n_purged, &pidx));
+        std::vector<uint32_t> read_len(n + 1);
+        for (uint64_t r = 0; r < n; r++) read_len[r] = (uint32_t) (tail->read_off[r + 1] - tail->read_off[r]);
+        const uint64_t avg_read_length = n ? (tail->read_off[n] - tail->read_off[0]) / n : 0;      // SequenceRecordIterator.cpp:64
+        std::vector<uint64_t> comp_off(C + 1, 0), tree_off(C + 1, 0);
+        std::vector<uint32_t> comp_member(res.core_read.size());
+        for (uint32_t c = 0; c < C; c++) {
+            comp_off[c] = res.core_off[c];
+            uint64_t w = res.core_off[c];
+            comp_member[w++] = surv_row[c] + first_id;                                              // element [0] = the root (:366)
+            for (uint64_t i = res.core_off[c]; i < res.core_off[c + 1]; i++) if (res.core_read[i] != surv_row[c] + first_id) comp_member[w++] = res.core_read[i];
+        }
+        comp_off[C] = res.core_off[C];
+        for (const auto &e : tree_edges) if (core_of[e.first] >= 0) tree_off[core_of[e.first] + 1]++;
+        for (uint32_t c = 0; c < C; c++) tree_off[c + 1] += tree_off[c];
+        std::vector<uint32_t> tree_x(tree_off[C] + 1), tree_y(tree_off[C] + 1);
+        {
+            std::vector<uint64_t> cur(tree_off.begin(), tree_off.end() - 1);
+            for (const auto &e : tree_edges) if (core_of[e.first] >= 0) { const uint64_t w = cur[core_of[e.first]]++; tree_x[w] = e.first + first_id; tree_y[w] = e.second + first_id; }
+        }
+        const uint64_t cap = (uint64_t) C * (C - 1) / 2;
+        res.tconn_x.resize(cap); res.tconn_y.resize(cap); res.tconn_score.resize(cap);
+        uint64_t n_t = 0;
+        HGA_TRY(hga_host_tail_connections(n, hits.row_off, hits.kmer_id, hits.pos, read_len.data(), avg_read_length, first_id, C, comp_off.data(), comp_member.data(),
+                                          tree_off.data(), tree_x.data(), tree_y.data(), pidx.off, pidx.read_id, tail->amplification_min_score,
+                                          res.tconn_x.data(), res.tconn_y.data(), res.tconn_score.data(), &n_t));
+        res.tconn_x.resize(n_t); res.tconn_y.resize(n_t); res.tconn_score.resize(n_t);
+        pc.mark("  tail connections (host)");
+        uint64_t n_strong = 0;                                                                      // :770 score > 5; the list is score-descending
+        while (n_strong < n_t && res.tconn_score[n_strong] > 5) n_strong++;
+        res.cluster_off.assign(1, 0);
+        if (n_strong) {
+            std::vector<uint32_t> member(2 * n_strong + 1);
+            std::vector<uint64_t> coff((size_t) tail->spectral_dims + 2, 0);
+            uint64_t n_nodes = 0, n_cl = 0;
+            HGA_TRY(hga_spectral_clustering(res.tconn_x.data(), res.tconn_y.data(), res.tconn_score.data(), n_strong, tail->spectral_dims, member.data(), coff.data(),
+                                            &n_nodes, &n_cl));
+            for (uint64_t i = 0; i < n_cl; i++) {
+                if (coff[i + 1] == coff[i]) continue;      // an empty cluster (a rotated dimension no point prefers) would make merge_components read element [0] of an empty vector
+                res.cluster_member.insert(res.cluster_member.end(), member.begin() + (ptrdiff_t) coff[i], member.begin() + (ptrdiff_t) coff[i + 1]);
+                res.cluster_off.push_back(res.cluster_member.size());
+            }
+        }
+        pc.mark("  spectral clustering (host)");
+        // which core every core merges into (itself unless its cluster has several members), new compact numbering of the survivors
+        std::vector<uint32_t> into(C), multi(C, 0);
+        std::iota(into.begin(), into.end(), 0u);
+        bool any_multi = false;
+        for (size_t i = 0; i + 1 < res.cluster_off.size(); i++) {
+            const uint64_t a = res.cluster_off[i], b = res.cluster_off[i + 1];
+            if (b - a < 2) continue;                                                                // :360-365
+            const int32_t s = core_of[res.cluster_member[a] - first_id];
+            for (uint64_t j = a; j < b; j++) {
+                const int32_t c = core_of[res.cluster_member[j] - first_id];
+                if (c < 0 || s < 0 || surv_row[c] + first_id != res.cluster_member[j]) { hga_set_error("hga_enrich_full: a spectral cluster names %u, which is no scaffold survivor", res.cluster_member[j]); return HGA_E_STATE; }
+                into[c] = (uint32_t) s; multi[c] = 1; any_multi = true;
+            }
+        }
+        if (any_multi) {
+            std::vector<uint32_t> new_idx(C, 0), surv_new;
+            for (uint32_t c = 0; c < C; c++) if (into[c] == c) { new_idx[c] = (uint32_t) surv_new.size(); surv_new.push_back(surv_row[c]); }
+            const uint32_t C2 = (uint32_t) surv_new.size();
+            std::vector<uint32_t> map(C);
+            for (uint32_t c = 0; c < C; c++) map[c] = new_idx[into[c]] | (multi[c] << 31);
+            std::vector<uint8_t> removed_once(n + 1, 0);
+            for (uint32_t c = 0; c < C; c++) if (multi[c]) removed_once[surv_row[c]] = 1;
+            // device: map (in the core_koff buffer's place is too small: use d_enr_parent, free since the root replay), flags, survivors
+            HGA_TRY(h->d_enr_parent.ensure((size_t) C * 4 + n + 64));
+            uint32_t *d_map = h->d_enr_parent.as<uint32_t>();
+            uint8_t *d_once = reinterpret_cast<uint8_t *>(d_map + C);
+            uint32_t *d_surv_new = d_surv + (C + 1);
+            HGA_CUDA(cudaMemcpyAsync(d_map, map.data(), (size_t) C * 4, cudaMemcpyHostToDevice, h->stream));
+            HGA_CUDA(cudaMemcpyAsync(d_once, removed_once.data(), n, cudaMemcpyHostToDevice, h->stream));
+            HGA_CUDA(cudaMemcpyAsync(d_surv_new, surv_new.data(), (size_t) C2 * 4, cudaMemcpyHostToDevice, h->stream));
+            HGA_CUDA(cudaMemsetAsync(d_R, 0, ((size_t) n_slots + 1) * 4, h->stream));
+            // unions of the clusters: relabel, sort, unique (back into d_enr_keys)
+            uint64_t n_u2 = 0;
+            if (n_u) {
+                HGA_TRY(h->d_enr_keys2.ensure((n_u + 1) * 8));
+                HGA_TRY(h->d_export_a.ensure((n_u + 1) * 8));
+                uint64_t *d_rel = h->d_enr_keys2.as<uint64_t>(), *d_srt = h->d_export_a.as<uint64_t>(), *d_uniq = h->d_enr_keys.as<uint64_t>();
+                enr_merge2_keys_kernel<<<grid_for(h, n_u), 256, 0, h->stream>>>(d_u, n_u, d_map, d_surv, d_surv_new, d_R, d_rel);
+                const int bits = 32 + (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) C2), 1);
+                size_t t1 = 0, t2 = 0;
+                HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, t1, d_rel, d_srt, n_u, 0, bits, h->stream));
+                HGA_CUDA(cub::DeviceSelect::Unique(nullptr, t2, d_srt, d_uniq, d_count, n_u, h->stream));
+                HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
+                HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, t1, d_rel, d_srt, n_u, 0, bits, h->stream));
+                HGA_CUDA(cub::DeviceSelect::Unique(h->d_sort_tmp.p, t2, d_srt, d_uniq, d_count, n_u, h->stream));
+                h->metrics.kernel_launches += (uint64_t) (bits + 7) / 8 + 4;
+                HGA_CUDA(cudaGetLastError());
+                unsigned long long nu = 0;
+                HGA_CUDA(cudaMemcpyAsync(&nu, d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+                HGA_CUDA(cudaStreamSynchronize(h->stream));
+                n_u2 = nu;
+            }
+            // second purge: purged index -> d_purged2_*, then the buffers change places
+            HGA_TRY(h->d_purged2_off.ensure(((size_t) n_slots + 2) * 4 * 2));
+            uint32_t *d_poff2 = h->d_purged2_off.as<uint32_t>(), *d_cnt2 = d_poff2 + (n_slots + 2);
+            enr_purge2_kernel<false><<<grid_for(h, n_slots), 256, 0, h->stream>>>(d_poff, d_prow, n_slots, d_R, d_once, d_cnt2, nullptr, nullptr);
+            HGA_CUDA(cudaMemsetAsync(d_cnt2 + n_slots, 0, 4, h->stream));
+            {
+                size_t tmp = 0;
+                HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_cnt2, d_poff2, (uint64_t) n_slots + 1, h->stream));
+                HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+                HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, d_cnt2, d_poff2, (uint64_t) n_slots + 1, h->stream));
+            }
+            uint32_t n_purged2 = 0;
+            HGA_CUDA(cudaMemcpyAsync(&n_purged2, d_poff2 + n_slots, 4, cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            HGA_TRY(h->d_purged2_row.ensure(((size_t) n_purged2 + 1) * 4));
+            uint32_t *d_prow2 = h->d_purged2_row.as<uint32_t>();
+            enr_purge2_kernel<true><<<grid_for(h, n_slots), 256, 0, h->stream>>>(d_poff, d_prow, n_slots, d_R, d_once, nullptr, d_poff2, d_prow2);
+            h->metrics.kernel_launches += 4;
+            HGA_CUDA(cudaGetLastError());
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            std::swap(h->d_purged_off, h->d_purged2_off);
+            std::swap(h->d_purged_row, h->d_purged2_row);
+            d_poff = d_poff2; d_prow = d_prow2; n_purged = n_purged2;
+            h->n_purged = n_purged2;
+            // the merged state in the new core numbering
+            for (uint64_t r = 0; r < n; r++) if (core_of[r] >= 0) core_of[r] = (int32_t) new_idx[into[core_of[r]]];
+            surv_row = surv_new;
+            C = C2;
+            d_surv = d_surv_new;
+            n_u = n_u2;
+            h->n_core_kmers = n_u;
+            enr_core_bounds_kernel<<<grid_for(h, (uint64_t) C + 1), 256, 0, h->stream>>>(d_u, n_u, C, d_core_koff);
+            h->metrics.kernel_launches++;
+            fill_cores();
+        }
+        pc.mark("  merge of the spectral clusters");
+    }
     // ---- 3. GPU: enrichment connections = run lengths of the sorted (core, partner) emissions ------------------------------
     std::vector<Conn> conns;
     if (n_u) {

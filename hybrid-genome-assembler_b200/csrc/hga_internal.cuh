@@ -232,6 +232,20 @@ struct EnrichResult {
     std::vector<uint32_t> conn_x, conn_y, conn_score;   // directed (core survivor -> partner), canonical order
     std::vector<uint32_t> final_id, final_read, assignment;
     std::vector<uint64_t> final_off;
+    // tail / spectral block (hga_enrich_full): what it saw and what it merged
+    bool tail_block_ran = false;                        // more than two scaffold components (:768)
+    uint64_t n_scaffold_cores = 0;                      // cores before the merge of the spectral clusters
+    std::vector<uint32_t> tconn_x, tconn_y;             // tail connections, x < y, canonical order (all, not only score > 5)
+    std::vector<uint64_t> tconn_score;
+    std::vector<uint32_t> cluster_member;               // spectral clusters, element [0] of a cluster = the surviving id; empty clusters dropped
+    std::vector<uint64_t> cluster_off;
+};
+
+// hga_enrich_full: the parameters of the tail / spectral block (:768-777)
+struct TailParams {
+    const uint64_t *read_off;       // HOST, n_reads + 1, as given to hga_scan
+    uint32_t amplification_min_score;
+    int spectral_dims;
 };
 
 struct hga_handle {
@@ -297,6 +311,7 @@ struct hga_handle {
 
     // merge + enrichment (hga_enrich.cu)
     DevBuf d_enr_parent, d_enr_core_of, d_enr_surv, d_enr_R, d_enr_scalars, d_enr_keys, d_enr_keys2, d_enr_core_koff, d_purged_off, d_purged_row;
+    DevBuf d_purged2_off, d_purged2_row;  // second purge (merge of the spectral clusters); swapped into d_purged_* when it ran
     uint64_t n_purged = 0, n_core_kmers = 0;
     EnrichResult enrich;
     bool have_enrichment = false;
@@ -318,7 +333,10 @@ int hga_index_run(hga_handle *h);
 int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
 int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold);
 int hga_cc_run(hga_handle *h, int min_size);
-int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score);
+// tail == nullptr: without the tail / spectral block (hga_enrich, hga_enrich_ex)
+int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score, const TailParams *tail);
+// CSR by index key (off u32[keys + 1], rows) -> CSR by the caller's kmer_id with read ids, in the pinned export buffers (hga_capi.cu)
+int hga_export_index(hga_handle *h, const uint32_t *d_off, const uint32_t *d_row, uint64_t E, hga_index *out);
 
 // multi-GPU hooks (hga_comm.cu); all are no-ops / never called without a communicator
 int hga_comm_build_global_index(hga_handle *h);

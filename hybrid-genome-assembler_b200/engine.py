@@ -282,16 +282,22 @@ class ReadClusteringEngine:
 
 
     # run_clustering(discriminative_kmers, k) — .cpp:699-802. Returns the final component ids; their members are in
-    # self.final_components (id -> ascending read ids). The tail / spectral merge of scaffold components (:768-777) is not
-    # built: every scaffold component becomes a core, which is the reference's own path when it finds no strong tail connection.
-    def run_clustering(self, discriminative_kmers, k):
+    # self.final_components (id -> ascending read ids). tail_block=True runs the tail / spectral merge of scaffold components
+    # (:768-777, hga_enrich_full); without it every scaffold component becomes a core, which is the reference's own path when it
+    # finds no strong tail connection.
+    def run_clustering(self, discriminative_kmers, k, tail_block=False):
         cfg = self.config
         if cfg.force_spectral:
             raise NotImplementedError("--spectral (lib/clustering) is not part of this build")
         self.construct_indices(discriminative_kmers, k)
         self._select_scaffold_edges()
-        self.handle.enrich(min_size=cfg.scaffold_component_min_size, enrichment_min_score=cfg.enrichment_connections_min_score,
-                           max_size=cfg.scaffold_component_max_size)
+        if tail_block:
+            self.handle.enrich_full(self.reader.seq_off, min_size=cfg.scaffold_component_min_size, enrichment_min_score=cfg.enrichment_connections_min_score,
+                                    max_size=cfg.scaffold_component_max_size, tail_amplification_min_score=cfg.tail_amplification_min_score,
+                                    spectral_dims=cfg.spectral_dims)
+        else:
+            self.handle.enrich(min_size=cfg.scaffold_component_min_size, enrichment_min_score=cfg.enrichment_connections_min_score,
+                               max_size=cfg.scaffold_component_max_size)
         e = self.handle.get_enrichment()
         off = e["final_off"].astype(np.int64)
         self.final_components = {int(fid): e["final_read"][off[i]:off[i + 1]] for i, fid in enumerate(e["final_id"])}

@@ -16,6 +16,7 @@
  *   hga_spectral_clustering <- spectral_clustering(connections, dims)       clustering/ReadClusteringEngine.cpp:653-697, lib/clustering/*
  *   hga_enrich           <- merge_components(scaffolds), get_connections(cores, min), union_find(conns, cores, 2, -1),
  *                           merge_components, get_component_ids             clustering/ReadClusteringEngine.cpp:349-422, :764, :785-794
+ *   hga_enrich_full      <- the same plus the tail / spectral block in between (second merge_components)     :764-794
  *
  * Conventions
  *   - every function returns 0 on success, non-zero on failure; hga_last_error() gives the message
@@ -170,6 +171,30 @@ typedef struct {
     const uint32_t *kmer_id;       /* unique inside a core, unordered */
 } hga_core_kmers_t;
 int hga_get_core_kmers(hga_handle *h, hga_core_kmers_t *out);
+
+/* The same INCLUDING the tail / spectral block (run_clustering :768-777), i.e. everything run_clustering does after
+ * the scaffold union_find. When the scaffold merge leaves more than two cores: the engine state after the merge (hits, spanning
+ * trees of the replayed union_find, purged index) goes to the host stages hga_host_tail_connections and, for the connections
+ * with score > 5 (:770), hga_spectral_clustering; the clusters are merged by a SECOND merge_components on the GPU (unique unions
+ * of the members' merged k-mer lists, second purge of the already purged index with the same truncation rule: the removal list
+ * of a k-mer holds every member of a multi-member cluster that lists it plus the cluster's survivor); enrichment, restricted
+ * union_find and the final merge then run on that state. With at most two cores, or no strong tail connection, the result is
+ * hga_enrich_ex's. read_off: HOST array of n_reads + 1 offsets as given to hga_scan (read lengths for the spanning-tree
+ * distances; avg_read_length = total bases / reads, SequenceRecordIterator.cpp:64). hga_get_enrichment, hga_get_purged_index and
+ * hga_get_core_kmers then describe the state after the second merge. */
+int hga_enrich_full(hga_handle *h, int min_size, int max_size, uint32_t enrichment_min_score, uint32_t tail_amplification_min_score,
+                    int spectral_dims, const uint64_t *read_off);
+typedef struct {
+    int ran;                       /* 1: more than two scaffold components, the block ran (:768) */
+    uint64_t n_scaffold_cores;     /* cores before the merge of the spectral clusters */
+    uint64_t n_connections;        /* all tail connections (score > 0), x < y, canonical order */
+    const uint32_t *conn_x, *conn_y;
+    const uint64_t *conn_score;
+    uint64_t n_clusters;           /* non-empty spectral clusters; element [0] = the id that survives the merge */
+    const uint64_t *cluster_off;   /* n_clusters + 1 */
+    const uint32_t *cluster_member;
+} hga_tail_block_t;
+int hga_get_tail_block(hga_handle *h, hga_tail_block_t *out);
 
 /* Spectral clustering of scaffold components from their tail connections (HOST arithmetic, no GPU involved; first piece of SURVEY
  * §8f-2): spectral_clustering(connections, dims) of clustering/ReadClusteringEngine.cpp:653-697 with lib/clustering's

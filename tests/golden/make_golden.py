@@ -23,15 +23,15 @@ import refdump  # noqa: E402
 DRIVER = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "ref_driver")
 
 
-def save_case(name, paths, kp, fraction, min_size, enrich=0):
+def save_case(name, paths, kp, fraction, min_size, enrich=0, full=False):
     orc = oracle_lib.load()
     rc, reads = orc.load_reads(paths)
     assert rc == 0
     kmers, k = orc.load_kmers(kp)
-    ref = refdump.run_ref(DRIVER, paths, kp, fraction=fraction, min_size=min_size, enrich=enrich)
+    ref = refdump.run_ref(DRIVER, paths, kp, fraction=fraction, min_size=min_size, enrich=enrich, full=full)
     keep = {k_: v for k_, v in ref.items() if isinstance(v, np.ndarray)}
     if enrich:   # the stages before the merge are pinned by the other fixtures; keep these files small
-        keep = {k_: v for k_, v in keep.items() if k_.split("_")[0] in ("core", "purged", "econn", "final", "comp")}
+        keep = {k_: v for k_, v in keep.items() if k_.split("_")[0] in ("core", "purged", "econn", "final", "comp", "tconn", "spectral")}
     scal = {k_: v for k_, v in ref.items() if not isinstance(v, np.ndarray) and not k_.endswith("_ms")}
     np.savez_compressed(os.path.join(HERE, name + ".npz"), bases=np.frombuffer(reads["seq"], dtype=np.uint8), seq_off=reads["seq_off"],
                         kmers=kmers, k=np.int64(k), fraction=np.float64(fraction), min_size=np.int64(min_size), enrich=np.int64(enrich),
@@ -48,6 +48,19 @@ def main_enrich():
         paths, kp = datagen.make_diploid_case(os.path.join(d, "e2"), genome_size=20000, divergence=0.02, k=15, read_len=2000, coverage=10,
                                               seed=21, error_rate=0.05, length_sigma=0.5)
         save_case("enrich_long", paths, kp, 0.15, 5, enrich=20)
+
+
+def main_full():
+    """SURVEY §8f-2 fixtures: the WHOLE of run_clustering after the scaffold union_find, tail / spectral block included (ref_driver
+    --enrich 20 --full): tail connections, spectral clusters, and the state after the merge of the clusters (cores, merged k-mer lists,
+    purged index), enrichment connections, final components."""
+    with tempfile.TemporaryDirectory() as d:
+        paths, kp = datagen.make_diploid_case(os.path.join(d, "f1"), genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=7,
+                                              error_rate=0.005, fmt="fastq")
+        save_case("full_short", paths, kp, 0.15, 30, enrich=20, full=True)
+        paths, kp = datagen.make_diploid_case(os.path.join(d, "f2"), genome_size=60000, divergence=0.02, k=15, read_len=2000, coverage=12,
+                                              seed=21, error_rate=0.05, length_sigma=0.5)
+        save_case("full_long", paths, kp, 0.15, 5, enrich=20, full=True)
 
 
 def main_spectral():
@@ -87,7 +100,10 @@ def main():
         subprocess.run(["make", "-C", os.path.dirname(os.path.dirname(DRIVER)), "ref"], check=True)
     if "--enrich-only" in sys.argv:
         return main_enrich()
+    if "--full-only" in sys.argv:
+        return main_full()
     main_enrich()
+    main_full()
     main_spectral()
     main_tails()
     with tempfile.TemporaryDirectory() as d:

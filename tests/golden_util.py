@@ -6,6 +6,7 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["kat2", "config1_mini", "longreads_k15", "longreads_k21", "exceptions_crlf"]
 ENRICH_CASES = ["enrich_short", "enrich_long"]     # ref_driver --enrich
+FULL_CASES = ["full_short", "full_long"]           # ref_driver --enrich --full (tail / spectral block included)
 
 
 def load_case(name):

@@ -1,0 +1,123 @@
+"""GPU: hga_enrich_full = everything run_clustering does after the scaffold union_find INCLUDING the tail / spectral block
+(ReadClusteringEngine.cpp:764-794), through the C-ABI, against the dumps of the real reference (ref_driver --enrich 20
+--full, fixtures tests/golden/full_*.npz): tail connections, spectral clusters, the state after the merge of the clusters (cores with
+the reference's survivor ids, merged k-mer lists, twice purged index), enrichment connections, final components. The file sorts last
+on purpose: it is the newest path."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import compare
+import datagen
+import golden_util
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_full(h, c):
+    h.scan(c["bases"], c["seq_off"])
+    h.build_index()
+    h.pair_count(min_score=1)
+    h.select_edges(fraction=c["fraction"])
+    h.enrich_full(c["seq_off"], min_size=c["min_size"], enrichment_min_score=c["enrich"], tail_amplification_min_score=40, spectral_dims=16)
+    e = h.get_enrichment()
+    ko, kk = h.get_core_kmers()
+    po, pr = h.get_purged_index()
+    co = e["core_off"].astype(np.int64); fo = e["final_off"].astype(np.int64); ko = ko.astype(np.int64)
+    return dict(core_id=e["core_id"], core_kmers=[kk[ko[i]:ko[i + 1]] for i in range(len(ko) - 1)],
+                core_reads=[e["core_read"][co[i]:co[i + 1]] for i in range(len(co) - 1)], purged_off=po, purged_read=pr,
+                econn=(e["conn_x"], e["conn_y"], e["conn_score"].astype(np.uint64)), final_id=e["final_id"],
+                final_reads=[e["final_read"][fo[i]:fo[i + 1]] for i in range(len(fo) - 1)], assignment=e["assignment"], read_id_first=e["read_id_first"])
+
+
+@pytest.mark.parametrize("name", golden_util.FULL_CASES)
+def test_cuda_full_run_clustering_vs_reference_golden(name):
+    import hga_b200
+    c = golden_util.load_case(name)
+    ref = c["ref"]
+    with hga_b200.Handle(c["kmers"], c["k"]) as h:
+        e = _run_full(h, c)
+        t = h.get_tail_block()
+        assert t["ran"] and t["n_scaffold_cores"] == ref["merged_scaffolds"]
+        assert np.array_equal(t["conn_x"], ref["tconn_x"]) and np.array_equal(t["conn_y"], ref["tconn_y"]) and np.array_equal(t["conn_score"], ref["tconn_score"])
+        so = ref["spectral_off"].astype(np.int64)
+        want = [(ref["spectral_member"][so[i]:so[i + 1]].tolist(), int(ref["spectral_first"][i])) for i in range(len(so) - 1)]
+        assert sorted((sorted(cl.tolist()), int(cl[0])) for cl in t["clusters"]) == want
+        compare.check_enrichment(ref, e, c["kmers"])
+        a = e["assignment"]
+        for fid, reads in zip(e["final_id"], e["final_reads"]):
+            assert np.all(a[reads - e["read_id_first"]] == fid)
+        m = h.metrics()
+        assert m["n_cores"] == ref["cores"] and m["n_final_components"] == ref["final_components"]
+        # the same handle again without the block: the scaffold cores, more of them
+        h.enrich(min_size=c["min_size"], enrichment_min_score=c["enrich"])
+        assert len(h.get_enrichment()["core_id"]) == ref["merged_scaffolds"] and not h.get_tail_block()["ran"]
+
+
+def test_full_equals_plain_when_the_block_does_not_run():
+    """at most two scaffold components (:768): hga_enrich_full is hga_enrich_ex"""
+    import hga_b200
+    c = golden_util.load_case("full_long")
+    big = 200                                     # only the largest components survive this min_size
+    with hga_b200.Handle(c["kmers"], c["k"]) as h:
+        h.scan(c["bases"], c["seq_off"])
+        h.build_index()
+        h.pair_count(min_score=1)
+        h.select_edges(fraction=c["fraction"])
+        h.enrich(min_size=big, enrichment_min_score=c["enrich"])
+        a = h.get_enrichment()
+        if len(a["core_id"]) > 2:
+            pytest.skip("more than two components of that size")
+        h.enrich_full(c["seq_off"], min_size=big, enrichment_min_score=c["enrich"])
+        b = h.get_enrichment()
+        assert not h.get_tail_block()["ran"]
+        for key in ("core_id", "core_read", "conn_x", "conn_y", "conn_score", "final_id", "final_read", "assignment"):
+            assert np.array_equal(a[key], b[key]), key
+
+
+def test_engine_mirror_run_clustering_with_tail_block():
+    import hga_b200
+    c = golden_util.load_case("full_short")
+    ref = c["ref"]
+
+    class _Reader(hga_b200.SequenceRecords):
+        def __init__(self):
+            self.bases, self.seq_off = c["bases"], c["seq_off"]
+            n = len(c["seq_off"]) - 1
+            self.headers = [b"r%d" % i for i in range(n)]
+            self.qualities = [b""] * n
+
+    eng = hga_b200.ReadClusteringEngine(_Reader(), hga_b200.ReadClusteringConfig(scaffold_component_min_size=c["min_size"],
+                                                                                 enrichment_connections_min_score=c["enrich"]))
+    ids = eng.run_clustering(c["kmers"], c["k"], tail_block=True)
+    assert ids == [int(v) for v in ref["final_id"]]
+    fo = ref["final_off"].astype(np.int64)
+    for i, fid in enumerate(ids):
+        assert np.array_equal(eng.final_components[fid], ref["final_read"][fo[i]:fo[i + 1]])
+    eng.close()
+
+
+def test_cli_tail_block_exports_the_reference_final_components(tmp_path):
+    """categorization --tail-block: files named after the reference's surviving component ids, holding the reference's reads"""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hybrid-genome-assembler_b200", "categorization")
+    c = golden_util.load_case("full_long")
+    ref = c["ref"]
+    so = np.asarray(c["seq_off"]).astype(np.int64)
+    rp, kp, outdir = str(tmp_path / "reads.fa"), str(tmp_path / "kmers.txt"), str(tmp_path / "out")
+    with open(rp, "wb") as f:
+        for i in range(len(so) - 1):
+            f.write(b">r%d\n" % (i + 1) + c["bases"][so[i]:so[i + 1]] + b"\n")
+    with open(kp, "w") as f:
+        for v in c["kmers"]:
+            f.write(datagen.kmer_to_str(v, c["k"]) + "\n")
+    r = subprocess.run([exe, rp, "--kmers", kp, "-o", outdir, "--sc_min_size", str(c["min_size"]), "--tail-block"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    fo = ref["final_off"].astype(np.int64)
+    want = {f"#{int(fid)}.fa": [f"r{int(v)}" for v in ref["final_read"][fo[i]:fo[i + 1]]] for i, fid in enumerate(ref["final_id"])}
+    assert sorted(os.listdir(outdir)) == sorted(want)
+    for name, hdrs in want.items():
+        lines = open(os.path.join(outdir, name)).read().split("\n")
+        assert [l[1:] for l in lines[0::2] if l] == hdrs
+    assert f"Exported {len(want)} components" in r.stdout
