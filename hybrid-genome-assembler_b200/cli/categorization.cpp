@@ -8,12 +8,13 @@
 // behind include/hga_b200.h; there is no CPU path. After the scaffold components (union_find at :763) the run continues
 // with the merge of the scaffold components and the core enrichment (hga_enrich; run_clustering :764, :785-794) and exports
 // the final components under the surviving component ids, like the reference. The tail / spectral block in between
-// (:768-777, SURVEY.md §8f-2: spanning-tree tails, tail amplification, spectral clustering of the scaffold components) is
-// NOT built: with more than two scaffold components the run says so on stderr and goes on the way the reference does when
-// it finds no strong tail connection (:771), i.e. every scaffold component becomes a core. --spectral is reported as
-// unsupported.
+// (:768-777, SURVEY.md §8f-2: spanning-tree tails, tail amplification, spectral clustering of the scaffold components, merge of
+// the clusters) runs with --tail-block (hga_enrich_full; opt-in until it has been through a GPU parity run); without it, with
+// more than two scaffold components, the run says so on stderr and goes on the way the reference does when it finds no strong
+// tail connection (:771), i.e. every scaffold component becomes a core. --spectral (:739-746) takes get_all_connections(5) from
+// the GPU and runs the reference's host-side spectral clustering of the whole data set (hga_spectral_clustering).
 //
-// Extra switches: --scaffolds-only (stop after union_find and export the scaffold components), --load-only (load the k-mers and
+// Extra switches: --tail-block (above), --scaffolds-only (stop after union_find and export the scaffold components), --load-only (load the k-mers and
 // the reads, print the meta data and the load time, no GPU), --export-test (writer self-test, no GPU), --parse-only (print the
 // record stream and meta data, no GPU), --dump-kmers (print the canonical k-mer values of the --kmers file, no GPU), --device N.
 #include <chrono>
@@ -192,11 +193,6 @@ int main(int argc, char **argv) {
     }
     for (const auto &m : reads.file_meta) std::cout << m.repr();
     if (output_folder_path.empty()) output_folder_path = "./" + reads.meta.filename + "_clusters/";
-    if (config.force_spectral) {
-        std::cerr << "categorization: --spectral (spectral clustering of the whole data set, lib/clustering) is a host stage outside the GPU hot path "
-                     "and is not part of this build\n";
-        return 3;
-    }
     if (config.scaffold_component_max_size != -1 && scaffolds_only) {
         std::cerr << "categorization: --sc_max_size makes the scaffold components depend on the edge order (sequential union_find); they are computed "
                      "inside the merge + enrichment stage, not by the GPU components stage --scaffolds-only exports\n";
@@ -218,6 +214,55 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "hga_b200: wall ms: create (CUDA context + table) %.0f, scan (H2D inside) %.0f, index %.0f\n",
                      std::chrono::duration<double, std::milli>(w1 - w0).count(), std::chrono::duration<double, std::milli>(w2 - w1).count(),
                      std::chrono::duration<double, std::milli>(w3 - w2).count());
+    }
+    if (config.force_spectral) {
+        // run_clustering :739-746: get_all_connections(5) on the GPU; spectral clustering of the WHOLE data set on the host (an S x S
+        // eigen-problem over all connected reads, lib/clustering: small inputs only, in the reference as well); merge_components
+        // (element [0] of a cluster survives); components with >= sc_min_size reads are exported. The connection list goes to the
+        // spectral stage in the canonical order (score desc, min id asc, max id asc, x asc), both directions as the reference emits them.
+        hga_pairs pr;
+        {
+            Timer t("Calculation of connections between reads");
+            check(hga_pair_count(h, 5, nullptr, 0), "hga_pair_count");
+            check(hga_get_pairs(h, &pr), "hga_get_pairs");
+            t.done();
+        }
+        std::vector<uint32_t> final_ids, of_read(reads.n_reads(), 0);
+        {
+            Timer t("Forced spectral clustering");
+            std::vector<uint64_t> order(pr.n_pairs);
+            for (uint64_t i = 0; i < pr.n_pairs; i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return pr.score[a] > pr.score[b]; });   // pairs arrive in (x, y) order
+            std::vector<uint32_t> cx(2 * pr.n_pairs + 1), cy(2 * pr.n_pairs + 1), member(4 * pr.n_pairs + 1);
+            std::vector<uint64_t> cs(2 * pr.n_pairs + 1), coff((size_t) config.spectral_dims + 2, 0);
+            for (uint64_t i = 0; i < pr.n_pairs; i++) {
+                const uint64_t j = order[i];
+                cx[2 * i] = pr.x[j]; cy[2 * i] = pr.y[j]; cs[2 * i] = pr.score[j];
+                cx[2 * i + 1] = pr.y[j]; cy[2 * i + 1] = pr.x[j]; cs[2 * i + 1] = pr.score[j];
+            }
+            uint64_t n_nodes = 0, n_clusters = 0;
+            check(hga_spectral_clustering(cx.data(), cy.data(), cs.data(), 2 * pr.n_pairs, config.spectral_dims, member.data(), coff.data(), &n_nodes, &n_clusters),
+                  "hga_spectral_clustering");
+            std::vector<std::pair<uint32_t, uint64_t>> by_first;          // (smallest member, cluster) of the clusters that are large enough
+            for (uint64_t c = 0; c < n_clusters; c++) {
+                const uint64_t a = coff[c], b = coff[c + 1];
+                if (b == a || b - a < (uint64_t) std::max(config.scaffold_component_min_size, 1)) continue;
+                by_first.push_back({*std::min_element(member.begin() + (ptrdiff_t) a, member.begin() + (ptrdiff_t) b), c});
+            }
+            std::sort(by_first.begin(), by_first.end());
+            for (const auto &bc : by_first) {
+                const uint32_t id = member[coff[bc.second]];
+                final_ids.push_back(id);
+                for (uint64_t i = coff[bc.second]; i < coff[bc.second + 1]; i++) of_read[member[i] - 1] = id;
+            }
+            t.done();
+        }
+        std::filesystem::remove_all(output_folder_path);
+        std::filesystem::create_directories(output_folder_path);
+        hga_host::export_components(reads, final_ids, of_read.data(), output_folder_path, config.threads > 1 ? config.threads : 0);
+        std::cout << "Exported " << final_ids.size() << " components\n";
+        hga_destroy(h);
+        return 0;
     }
     {
         Timer t("Calculation of connections between reads");

@@ -287,9 +287,16 @@ class ReadClusteringEngine:
     # finds no strong tail connection.
     def run_clustering(self, discriminative_kmers, k, tail_block=False):
         cfg = self.config
-        if cfg.force_spectral:
-            raise NotImplementedError("--spectral (lib/clustering) is not part of this build")
         self.construct_indices(discriminative_kmers, k)
+        if cfg.force_spectral:
+            # :739-746: get_all_connections(5) on the GPU, spectral clustering of the whole data set on the host (an S x S
+            # eigen-problem over all connected reads, as in the reference: small inputs only), merge_components, ids with >= min size
+            cx, cy, cs = self.get_all_connections(5)
+            self.final_components = forced_spectral_components(cx, cy, cs, cfg.spectral_dims, cfg.scaffold_component_min_size)
+            self.assignment = np.zeros(self.reader.n_reads, dtype=np.uint32)
+            for fid, members in self.final_components.items():
+                self.assignment[members - 1] = fid
+            return list(self.final_components)
         self._select_scaffold_edges()
         if tail_block:
             self.handle.enrich_full(self.reader.seq_off, min_size=cfg.scaffold_component_min_size, enrichment_min_score=cfg.enrichment_connections_min_score,
@@ -318,6 +325,15 @@ class ReadClusteringEngine:
         for f in files.values():
             f.close()
         print(f"Exported {len(wanted)} components")
+
+
+def forced_spectral_components(conn_x, conn_y, conn_score, dims, min_size):
+    """run_clustering with --spectral (.cpp:739-746) after get_all_connections(5): spectral_clustering over the directed connection
+    list in canonical order, merge_components (element [0] of a cluster survives), get_component_ids(min_size). Returns
+    {surviving id: ascending member read ids}, ordered by the smallest member."""
+    clusters = [c for c in capi.spectral_clustering(conn_x, conn_y, conn_score, dims) if len(c) >= max(int(min_size), 1)]
+    clusters.sort(key=lambda c: int(c.min()))
+    return {int(c[0]): np.sort(c).astype(np.uint32) for c in clusters}
 
 
 def _canonical_sort(x, y, s):

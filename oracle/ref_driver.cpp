@@ -96,7 +96,7 @@ public:
     Probe(SequenceRecordIterator &it, ReadClusteringConfig cfg) : ReadClusteringEngine(it, cfg) {}
 
     int run(std::unordered_set<Kmer> &kmers, int k, const std::string &out, bool do_dump, double fraction, int min_size,
-            ConnectionScore min_score, int stop_after, ConnectionScore enrich_min = 0, ConnectionScore sc_score = 0, bool full = false) {
+            ConnectionScore min_score, int stop_after, ConnectionScore enrich_min = 0, ConnectionScore sc_score = 0, bool full = false, bool force_spectral = false) {
         // KmerID assignment order = iteration order of the very same unordered_set object (.cpp:237-241)
         std::vector<Kmer> id2kmer;
         for (auto kmer : kmers) id2kmer.push_back(kmer);
@@ -156,6 +156,47 @@ public:
             dump(out, "inv_read.u32", inv_read);
         }
         if (stop_after == 1) { fclose(meta); return 0; }
+
+        if (force_spectral) {
+            // --spectral (run_clustering :739-746), all real reference code: get_all_connections(5), spectral_clustering of the whole
+            // data set, merge_components, get_component_ids(min size). The driver imposes the canonical order on the connections
+            // (their order decides the row order of the affinity matrix, :657-663) and skips empty clusters (see below).
+            auto conns = get_all_connections(5);
+            std::sort(conns.begin(), conns.end(), canonical_less);
+            t0 = now_ms();
+            auto spectral = spectral_clustering(conns, config.spectral_dims);
+            fprintf(meta, "directed_connections=%zu\nspectral_clusters=%zu\nspectral_ms=%.3f\n", conns.size(), spectral.size(), now_ms() - t0);
+            std::vector<Component> nonempty;
+            for (auto &c : spectral) if (!c.empty()) nonempty.push_back(c);
+            merge_components(nonempty);
+            std::vector<ComponentID> final_ids;
+            for (auto p : component_index) if (p.second->size() >= (uint64_t) min_size) final_ids.push_back(p.first);
+            fprintf(meta, "final_components=%zu\n", final_ids.size());
+            std::vector<std::pair<uint32_t, ComponentID>> forder;
+            for (auto id : final_ids) {
+                auto &r = component_index[id]->contained_read_ids;
+                forder.push_back({*std::min_element(r.begin(), r.end()), id});
+            }
+            std::sort(forder.begin(), forder.end());
+            std::vector<uint32_t> final_id, final_read, cx, cy;
+            std::vector<uint64_t> final_off{0}, cs;
+            for (auto &o : forder) {
+                final_id.push_back(o.second);
+                auto reads = component_index[o.second]->contained_read_ids;
+                std::sort(reads.begin(), reads.end());
+                final_read.insert(final_read.end(), reads.begin(), reads.end());
+                final_off.push_back(final_read.size());
+            }
+            for (auto &c : conns) { cx.push_back(c.component_x_id); cy.push_back(c.component_y_id); cs.push_back(c.score); }
+            dump(out, "conn_x.u32", cx);
+            dump(out, "conn_y.u32", cy);
+            dump(out, "conn_score.u64", cs);
+            dump(out, "final_id.u32", final_id);
+            dump(out, "final_off.u64", final_off);
+            dump(out, "final_read.u32", final_read);
+            fclose(meta);
+            return 0;
+        }
 
         t0 = now_ms();
         std::vector<ComponentConnection> connections;
@@ -405,7 +446,7 @@ int usage() {
             "ref_driver canon <kmer file> <out dir>\n"
             "ref_driver records <out dir> <reads...>\n"
             "ref_driver run --kmers F --out DIR [--threads T] [--fraction 0.15] [--min-size 30] [--min-score 1]\n"
-            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] [--sc-score S] [--full] [--max-size N] <reads...>\n");
+            "               [--no-dump] [--stop-after 1|2] [--enrich MIN_SCORE] [--sc-score S] [--full] [--force-spectral] [--spectral-dims D] [--max-size N] <reads...>\n");
     return 2;
 }
 
@@ -461,7 +502,7 @@ int main(int argc, char **argv) {
     ConnectionScore min_score = 1;
     int stop_after = 0;
     ConnectionScore enrich_min = 0, sc_score = 0;
-    bool full = false;
+    bool full = false, force_spectral = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { if (i + 1 >= argc) exit(usage()); return argv[++i]; };
@@ -475,6 +516,8 @@ int main(int argc, char **argv) {
         else if (a == "--enrich") enrich_min = std::stoul(next());
         else if (a == "--sc-score") sc_score = std::stoul(next());
         else if (a == "--full") full = true;
+        else if (a == "--force-spectral") force_spectral = true;
+        else if (a == "--spectral-dims") config.spectral_dims = std::stoi(next());
         else if (a == "--max-size") config.scaffold_component_max_size = std::stoi(next());
         else if (a == "--no-dump") do_dump = false;
         else paths.push_back(a);
@@ -489,7 +532,7 @@ int main(int argc, char **argv) {
     reader.show_progress = false;
     double t_meta = now_ms() - t0;
     Probe engine(reader, config);
-    int rc = engine.run(kk.first, kk.second, out, do_dump, fraction, min_size, min_score, stop_after, enrich_min, sc_score, full);
+    int rc = engine.run(kk.first, kk.second, out, do_dump, fraction, min_size, min_score, stop_after, enrich_min, sc_score, full, force_spectral);
     FILE *meta = fopen((out + "/meta.txt").c_str(), "a");
     fprintf(meta, "kmer_load_ms=%.3f\nmeta_pass_ms=%.3f\nthreads=%d\n", t_load, t_meta, config.threads);
     fclose(meta);

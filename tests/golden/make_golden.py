@@ -63,6 +63,21 @@ def main_full():
         save_case("full_long", paths, kp, 0.15, 5, enrich=20, full=True)
 
 
+def main_forced_spectral():
+    """--spectral (run_clustering :739-746): get_all_connections(5), spectral clustering of the whole data set, merge, ids >= min size
+    (ref_driver --force-spectral)."""
+    orc = oracle_lib.load()
+    with tempfile.TemporaryDirectory() as d:
+        paths, kp = datagen.make_diploid_case(d, genome_size=20000, divergence=0.02, k=15, read_len=2000, coverage=10, seed=21, error_rate=0.05, length_sigma=0.5)
+        ref = refdump.run_ref(DRIVER, paths, kp, min_size=5, force_spectral=True)
+        rc, reads = orc.load_reads(paths)
+        kmers, k = orc.load_kmers(kp)
+    np.savez_compressed(os.path.join(HERE, "forced_spectral.npz"), bases=np.frombuffer(reads["seq"], dtype=np.uint8), seq_off=reads["seq_off"], kmers=kmers,
+                        k=np.int64(k), min_size=np.int64(5), dims=np.int64(16), conn_x=ref["conn_x"], conn_y=ref["conn_y"], conn_score=ref["conn_score"],
+                        final_id=ref["final_id"], final_off=ref["final_off"], final_read=ref["final_read"])
+    print("forced_spectral", len(ref["conn_x"]), "directed connections,", ref["final_components"], "final components")
+
+
 def main_spectral():
     """SURVEY §8f-2 fixtures: strong tail connections -> spectral clusters, from ref_driver --full (the reference's own
     spectral_clustering + lib/clustering, compiled against the Eigen2 stand-in of oracle/shim)."""
@@ -102,8 +117,11 @@ def main():
         return main_enrich()
     if "--full-only" in sys.argv:
         return main_full()
+    if "--forced-spectral-only" in sys.argv:
+        return main_forced_spectral()
     main_enrich()
     main_full()
+    main_forced_spectral()
     main_spectral()
     main_tails()
     with tempfile.TemporaryDirectory() as d:

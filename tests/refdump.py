@@ -18,7 +18,7 @@ _FILES = {
 _DT = {"u32": np.uint32, "u64": np.uint64}
 
 
-def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0, sc_score=0, full=False, max_size=-1):
+def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score=1, threads=1, dump=True, stop_after=0, outdir=None, enrich=0, sc_score=0, full=False, max_size=-1, force_spectral=False):
     tmp = None
     if outdir is None:
         tmp = tempfile.TemporaryDirectory()
@@ -35,6 +35,8 @@ def run_ref(driver, read_paths, kmer_path, fraction=0.15, min_size=30, min_score
         cmd += ["--sc-score", str(sc_score)]
     if full:
         cmd.append("--full")
+    if force_spectral:
+        cmd.append("--force-spectral")
     if max_size != -1:
         cmd += ["--max-size", str(max_size)]
     cmd += list(read_paths)
