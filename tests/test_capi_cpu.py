@@ -63,6 +63,13 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert e.value.code == 2 and "Kmer size is too big" in str(e.value)      # KmerIterator.cpp:24-26
 
 
+def test_null_arguments_of_the_tail_block_entry_points(lib):
+    lib.hga_enrich_full.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    lib.hga_get_tail_block.argtypes = [C.c_void_p, C.c_void_p]
+    assert lib.hga_enrich_full(None, 30, -1, 20, 40, 16, None) == 2 and b"NULL" in lib.hga_last_error()
+    assert lib.hga_get_tail_block(None, None) == 2
+
+
 def test_product_never_touches_the_oracle():
     """nothing under the package may import, link or execute oracle/"""
     pkg = os.path.join(ROOT, "hybrid-genome-assembler_b200")
