@@ -15,8 +15,11 @@
 // average read lengths of each end (the "tails"), every tail amplified by the reads it reaches with at least
 // `amplification_min_score` shared k-mers, the unique k-mer union of every amplified tail; per pair of components the largest of
 // the four tail-to-tail intersections. The reference starts the first sweep at adjacency_map.begin() (whatever its hash map puts
-// first), so WHICH end it calls left and which right is arbitrary; the connection score is a maximum over all four combinations
-// and does not depend on it. Here the first sweep starts at the smallest vertex id and distance ties go to the smallest id.
+// first). That start matters: the survivor's list is the merged union while its positions are its own read's, so an "overlap" on
+// a tree edge at the survivor can exceed the read lengths, the uint64 distances wrap for some start vertices and not for others,
+// and the tails (even whether they are empty: a wrapped maximum plus the tail length wraps again and nothing is "within" it)
+// differ. Canonical choice, imposed on the reference too (oracle/shim/tsl/robin_map.h orders that one map): the first sweep starts
+// at the SMALLEST vertex id; distance ties go to the smallest id. The arithmetic is the reference's, wrap-around included.
 //
 // Small host arithmetic (a few hundred tree vertices per component): sequential in the reference, sequential here. The
 // amplification walks purged lists on the host in this first version; its GPU form is hga_enrich's connection kernel with the

@@ -4,14 +4,26 @@
 // NON-const key (ConcurrentQueue<IndexRemovalMap::value_type> needs it assignable, .cpp:395).
 // Backed by std::unordered_map, so iteration order is not robin-hood order; the oracle only exposes
 // order-independent results.
+// ONE instantiation is ordered instead: robin_map<ReadID, robin_map<ReadID, int>>, the adjacency map of get_spanning_tree_tails
+// (clustering/ReadClusteringEngine.cpp:510). The reference starts its first distance sweep at adjacency_map.begin() (:545), i.e. at
+// whatever vertex its hash map puts first, and with the survivor's merged k-mer list the "overlaps" along the tree can exceed the
+// read lengths: the uint64 distances then wrap for some start vertices and not for others, and the tails (even whether they are
+// empty) depend on that start. Like the tie order of the edge list, this is pinned to a canonical choice on both sides: the sweep
+// starts at the SMALLEST vertex id (std::map here, hga_tails.cpp in the product).
 #pragma once
+#include <cstdint>
+#include <map>
 #include <unordered_map>
 #include <initializer_list>
 #include <utility>
 namespace tsl {
+template<typename K, typename V> class robin_map;
+template<typename K, typename V> struct robin_map_storage { using type = std::unordered_map<K, V>; };
+template<> struct robin_map_storage<uint32_t, robin_map<uint32_t, int>> { using type = std::map<uint32_t, robin_map<uint32_t, int>>; };
+
 template<typename K, typename V>
 class robin_map {
-    using base_t = std::unordered_map<K, V>;
+    using base_t = typename robin_map_storage<K, V>::type;
     base_t m;
 public:
     using key_type = K;

@@ -37,6 +37,10 @@ CASES = {
     "long_k19": dict(genome_size=120000, divergence=0.02, k=19, read_len=3000, coverage=15, seed=22, error_rate=0.03, length_sigma=0.5, _min_size=5),
     "short_ties": dict(genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=7, error_rate=0.005, fmt="fastq", _min_size=30),
     "mid": dict(genome_size=100000, divergence=0.03, k=19, read_len=400, coverage=25, seed=10, error_rate=0.01, _min_size=30),
+    # the survivors' merged k-mer lists make some tree "overlaps" longer than the reads: the uint64 distances wrap for some start
+    # vertices of the first sweep (the tails then come out EMPTY) and not for others; both sides start at the smallest vertex id
+    "wrapping_k17": dict(genome_size=80000, divergence=0.02, k=17, read_len=2500, coverage=12, seed=61, error_rate=0.04, length_sigma=0.5, _min_size=5),
+    "k21": dict(genome_size=80000, divergence=0.03, k=21, read_len=1500, coverage=14, seed=62, error_rate=0.02, length_sigma=0.4, _min_size=5),
 }
 
 
