@@ -45,4 +45,23 @@ for it in range(int(sys.argv[2])):
             R._check(ref, kmers, R.second_merge_rule(cores, unions, po, pr, R._clusters(ref))); ok_r = True
         except AssertionError:
             ok_r = False
-    print(it, "scaffolds", ref["scaffold_components"], "tconn", len(x), "->cores", ref["cores"], "tails", ok_t, "clusters", ok_c, "rule", ok_r, "" if (ok_t and ok_c is not False and ok_r is not False) else kw)
+    ok_f = None
+    if ok_t and ok_c is not False:
+        # the whole chain to the final components (second merge and enrichment on the oracle's engine state)
+        clusters = [c for c in hga_b200.capi.spectral_clustering(x[s > 5], y[s > 5], s[s > 5], 16) if len(c)] if len(x) and (s > 5).any() else []
+        res = orc.run(reads["seq"], reads["seq_off"], k, kmers, min_size=ms)
+        eng = oracle_lib.Engine(orc, res["row_off"], res["hit_kid"], len(kmers), res["inv_off"], res["inv_read"])
+        try:
+            eng.merge(res["comp"][0], res["comp"][1])
+            if clusters:
+                eng.merge(np.cumsum([0] + [len(c) for c in clusters]).astype(np.uint64), np.concatenate(clusters))
+            cores = eng.ids(ms)
+            ex, ey, es = orc.canonical_sort(*eng.connections(cores, 20))
+            eo, em, _, _, _ = orc.union_find(ex, ey, min_size=2, max_size=-1, restricted=cores)
+            eng.merge(eo, em)
+            got = sorted((int(np.sort(eng.component_reads(c))[0]), int(c), np.sort(eng.component_reads(c)).tolist()) for c in eng.ids(ms))
+        finally:
+            eng.close()
+        fo = ref["final_off"].astype(np.int64)
+        ok_f = got == [(int(ref["final_read"][fo[i]]), int(ref["final_id"][i]), ref["final_read"][fo[i]:fo[i + 1]].tolist()) for i in range(len(fo) - 1)]
+    print(it, "final", ok_f, "scaffolds", ref["scaffold_components"], "tconn", len(x), "->cores", ref["cores"], "tails", ok_t, "clusters", ok_c, "rule", ok_r, "" if (ok_t and ok_c is not False and ok_r is not False and ok_f is not False) else kw)
