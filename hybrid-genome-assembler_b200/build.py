@@ -20,8 +20,8 @@ EXE = os.path.join(HERE, "categorization")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
               "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
-CPP_SOURCES = ["hga_spectral.cpp", "hga_tails.cpp"]        # host-only translation units (g++)
-CU_SOURCES = ["hga_capi.cu", "hga_table.cu", "hga_scan.cu", "hga_index.cu", "hga_pairs.cu", "hga_select.cu", "hga_cc.cu", "hga_enrich.cu", "hga_comm.cu"]
+CPP_SOURCES = ["hga_spectral.cpp", "hga_tails.cpp", "hga_sdk.cpp"]        # host-only translation units (g++)
+CU_SOURCES = ["hga_capi.cu", "hga_table.cu", "hga_scan.cu", "hga_index.cu", "hga_pairs.cu", "hga_select.cu", "hga_cc.cu", "hga_enrich.cu", "hga_comm.cu", "hga_count.cu"]
 
 
 def _stale(target, deps):

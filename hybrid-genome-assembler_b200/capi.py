@@ -67,7 +67,7 @@ class Metrics(C.Structure):
 # every symbol include/hga_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_init", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
-           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_enrich_full", "hga_get_tail_block", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering", "hga_host_tail_connections", "hga_host_sym_eigen",
+           "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_enrich_full", "hga_get_tail_block", "hga_count_kmers", "hga_free_kmer_counts", "hga_host_sdk_merge", "hga_host_sdk_specificity", "hga_host_sdk_select", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering", "hga_host_tail_connections", "hga_host_sym_eigen",
            "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
 
 
@@ -155,6 +155,76 @@ def host_sym_eigen(a):
     lib.hga_host_sym_eigen.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     _check(lib.hga_host_sym_eigen(n, a.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p)))
     return val, vec
+
+
+class _KmerCounts(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("kmer", u64p), ("count", u32p)]
+
+
+def count_kmers(bases, read_off, k, min_count=2, device=0):
+    """hga_count_kmers: exact canonical k-mer counts of a read set on the GPU (the jellyfish step of the SDK selection). Returns
+    (k-mers ascending, counts) of the k-mers that occur at least min_count times."""
+    lib = load_library()
+    lib.hga_count_kmers.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(_KmerCounts)]
+    lib.hga_free_kmer_counts.argtypes = [C.POINTER(_KmerCounts)]
+    lib.hga_free_kmer_counts.restype = None
+    ro = np.ascontiguousarray(read_off, dtype=np.uint64)
+    out = _KmerCounts()
+    _check(lib.hga_count_kmers(int(device), int(k), bytes(bases), ro.ctypes.data_as(C.c_void_p), ro.shape[0] - 1, int(min_count), C.byref(out)))
+    try:
+        return _arr(out.kmer, out.n, np.uint64), _arr(out.count, out.n, np.uint32)
+    finally:
+        lib.hga_free_kmer_counts(C.byref(out))
+
+
+def sdk_merge(per_file):
+    """hga_host_sdk_merge: per_file = [(k-mers ascending, counts), ...] -> (k-mers, total count, largest per-file count, files holding it)"""
+    lib = load_library()
+    P = C.c_void_p
+    lib.hga_host_sdk_merge.argtypes = [C.c_int, P, P, P, P, P, P, P, C.POINTER(C.c_uint64)]
+    off = np.zeros(len(per_file) + 1, dtype=np.uint64)
+    np.cumsum([len(kc[0]) for kc in per_file], out=off[1:])
+    km = np.ascontiguousarray(np.concatenate([np.asarray(kc[0], dtype=np.uint64) for kc in per_file]) if per_file else np.zeros(0, np.uint64))
+    ct = np.ascontiguousarray(np.concatenate([np.asarray(kc[1], dtype=np.uint32) for kc in per_file]) if per_file else np.zeros(0, np.uint32))
+    cap = max(int(off[-1]), 1)
+    ok = np.zeros(cap, dtype=np.uint64); ot = np.zeros(cap, dtype=np.uint32); om = np.zeros(cap, dtype=np.uint32); of = np.zeros(cap, dtype=np.uint32)
+    n = C.c_uint64()
+    _check(lib.hga_host_sdk_merge(len(per_file), off.ctypes.data_as(P), km.ctypes.data_as(P), ct.ctypes.data_as(P), ok.ctypes.data_as(P), ot.ctypes.data_as(P),
+                                  om.ctypes.data_as(P), of.ctypes.data_as(P), C.byref(n)))
+    return ok[:n.value], ot[:n.value], om[:n.value], of[:n.value]
+
+
+SDK_THRESHOLDS = (70, 85, 90, 95, 99, 100, 100.01)      # jellyfish_occurrences.cpp:47
+
+
+def sdk_specificity(total, largest, thresholds=SDK_THRESHOLDS):
+    """hga_host_sdk_specificity: rows (upper specificity, total count, number of distinct k-mers), ordered like the reference's nested map"""
+    lib = load_library()
+    P = C.c_void_p
+    lib.hga_host_sdk_specificity.argtypes = [C.c_uint64, P, P, P, C.c_int, P, P, P, C.c_uint64, C.POINTER(C.c_uint64)]
+    t = np.ascontiguousarray(total, dtype=np.uint32); m = np.ascontiguousarray(largest, dtype=np.uint32)
+    thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+    n = C.c_uint64()
+    _check(lib.hga_host_sdk_specificity(t.shape[0], t.ctypes.data_as(P), m.ctypes.data_as(P), thr.ctypes.data_as(P), thr.shape[0], None, None, None, 0, C.byref(n)))
+    cap = max(n.value, 1)
+    ot = np.zeros(cap, dtype=np.float64); oo = np.zeros(cap, dtype=np.uint32); ou = np.zeros(cap, dtype=np.uint64)
+    _check(lib.hga_host_sdk_specificity(t.shape[0], t.ctypes.data_as(P), m.ctypes.data_as(P), thr.ctypes.data_as(P), thr.shape[0], ot.ctypes.data_as(P),
+                                        oo.ctypes.data_as(P), ou.ctypes.data_as(P), cap, C.byref(n)))
+    return ot[:n.value], oo[:n.value], ou[:n.value]
+
+
+def sdk_select(total, files, lower, upper, percent=1.0, seed=0):
+    """hga_host_sdk_select: mask of the k-mers with lower <= total <= upper (each kept with probability percent), and how many of the
+    selected ones are present in exactly one file"""
+    lib = load_library()
+    P = C.c_void_p
+    lib.hga_host_sdk_select.argtypes = [C.c_uint64, P, P, C.c_uint32, C.c_uint32, C.c_double, C.c_uint64, P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    t = np.ascontiguousarray(total, dtype=np.uint32); f = np.ascontiguousarray(files, dtype=np.uint32)
+    sel = np.zeros(max(t.shape[0], 1), dtype=np.uint8)
+    ns = C.c_uint64(); nd = C.c_uint64()
+    _check(lib.hga_host_sdk_select(t.shape[0], t.ctypes.data_as(P), f.ctypes.data_as(P), int(lower), int(upper), float(percent), int(seed), sel.ctypes.data_as(P),
+                                   C.byref(ns), C.byref(nd)))
+    return sel[:t.shape[0]].astype(bool), int(ns.value), int(nd.value)
 
 
 def host_tail_connections(row_off, kmer_id, pos, read_len, avg_read_length, comp_off, comp_member, tree_off, tree_x, tree_y, purged_off, purged_read,

@@ -16,6 +16,7 @@
  *   hga_spectral_clustering <- spectral_clustering(connections, dims)       clustering/ReadClusteringEngine.cpp:653-697, lib/clustering/*
  *   hga_enrich           <- merge_components(scaffolds), get_connections(cores, min), union_find(conns, cores, 2, -1),
  *                           merge_components, get_component_ids             clustering/ReadClusteringEngine.cpp:349-422, :764, :785-794
+ *   hga_count_kmers / hga_host_sdk_* <- jellyfish + JellyfishOccurrenceReader (the --kmers file)          occurrences/*, jellyfish_occurrences.cpp
  *   hga_enrich_full      <- the same plus the tail / spectral block in between (second merge_components)     :764-794
  *
  * Conventions
@@ -222,6 +223,31 @@ int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_off, const u
                               const uint64_t *tree_off, const uint32_t *tree_x, const uint32_t *tree_y, const uint64_t *purged_off,
                               const uint32_t *purged_read, uint32_t amplification_min_score, uint32_t *out_x, uint32_t *out_y, uint64_t *out_score,
                               uint64_t *out_n);
+
+/* SDK selection: what produces the --kmers file. jellyfish_occurrences.cpp shells out to jellyfish per read file
+ * (occurrences/run_jellyfish.sh, JellyfishOccurrenceReader.cpp:16-38), merges the sorted dumps and exports the k-mers whose total
+ * count lies in a range (:63-134).
+ *   hga_count_kmers  : the counting on the GPU, no handle needed: the canonical k-mers of `bases` (windows with a byte other than
+ *                      A C G T a c g t skipped, as jellyfish does) that occur at least min_count times (2 = the two-pass
+ *                      Bloom-counter filter of run_jellyfish.sh without its false positives), ascending, with exact counts.
+ *                      The arrays are malloc'ed by the library: release them with hga_free_kmer_counts.
+ *   hga_host_sdk_*   : the reader's host arithmetic on those lists (files back to back: file f = [file_off[f], file_off[f + 1])).
+ *                      merge: out arrays need room for file_off[n_files] entries. specificity: rows (threshold, total count,
+ *                      number of k-mers), *out_n = rows needed. select: lower <= total <= upper, kept with probability percent
+ *                      (seeded; percent >= 1 keeps all); n_discriminative = selected k-mers present in exactly one file. */
+typedef struct {
+    uint64_t n;
+    const uint64_t *kmer;
+    const uint32_t *count;
+} hga_kmer_counts_t;
+int hga_count_kmers(int device, int k, const char *bases, const uint64_t *read_off, uint64_t n_reads, uint32_t min_count, hga_kmer_counts_t *out);
+void hga_free_kmer_counts(hga_kmer_counts_t *c);
+int hga_host_sdk_merge(int n_files, const uint64_t *file_off, const uint64_t *kmer, const uint32_t *count, uint64_t *out_kmer, uint32_t *out_total,
+                       uint32_t *out_max, uint32_t *out_files, uint64_t *out_n);
+int hga_host_sdk_specificity(uint64_t n, const uint32_t *total, const uint32_t *max, const double *thresholds, int n_thresholds, double *out_threshold,
+                             uint32_t *out_occurrences, uint64_t *out_unique, uint64_t capacity, uint64_t *out_n);
+int hga_host_sdk_select(uint64_t n, const uint32_t *total, const uint32_t *files, uint32_t lower, uint32_t upper, double percent, uint64_t seed,
+                        uint8_t *out_selected, uint64_t *out_n_selected, uint64_t *out_n_discriminative);
 
 /* Per-stage device time (CUDA events on the handle's stream) and counters of the most recent run. */
 typedef struct {

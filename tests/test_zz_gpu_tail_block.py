@@ -170,3 +170,27 @@ def test_cli_forced_spectral(tmp_path):
     for fid, members in want:
         lines = open(os.path.join(outdir, f"#{fid}.fa")).read().split("\n")
         assert [l[1:] for l in lines[0::2] if l] == [f"r{m}" for m in members]
+
+
+@pytest.mark.parametrize("k", [11, 19, 32])
+def test_cuda_kmer_counts_are_exact(k):
+    """SURVEY §8f-4, the jellyfish step: hga_count_kmers against exact counting in numpy (canonical k-mers, count >= 2, ascending;
+    windows with a non-ACGT byte skipped, lowercase accepted)"""
+    import hga_b200
+    from test_sdk_selection_cpu import exact_counts
+    rng = np.random.default_rng(k)
+    g = datagen.random_genome(4000, 100 + k)
+    reads = [datagen.to_ascii(r) for r in datagen.sample_reads(g, 300, 180, 200 + k, error_rate=0.01)]
+    reads[3] = reads[3][:40] + "N" + reads[3][41:]                 # a window breaker
+    reads[5] = reads[5].lower()                                    # jellyfish counts lowercase bases
+    reads[7] = reads[7][:k - 1]                                    # shorter than k
+    reads[9] = ""
+    seq = "".join(reads).encode()
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    km, ct = hga_b200.capi.count_kmers(seq, off, k, min_count=2)
+    wk, wc = exact_counts(seq, off, k, 2)
+    assert np.array_equal(km, wk) and np.array_equal(ct, wc) and len(km) > 100
+    km1, ct1 = hga_b200.capi.count_kmers(seq, off, k, min_count=1)
+    wk1, wc1 = exact_counts(seq, off, k, 1)
+    assert np.array_equal(km1, wk1) and np.array_equal(ct1, wc1) and int(ct1.sum()) == int(wc1.sum())
