@@ -1,4 +1,4 @@
-"""Builds libhga_b200.so (CUDA kernels + C-ABI, sm_100a only) and the `categorization` host executable, in-tree.
+"""Builds libhga_b200.so (CUDA kernels + C-ABI, sm_100a only) and the `categorization` / `jf_occurrences` host executables, in-tree.
 
     python hybrid-genome-assembler_b200/build.py [--force] [--verbose]
 
@@ -73,6 +73,11 @@ def build(force=False, verbose=False):
         if force or _stale(EXE, cli_deps) or _stale(EXE, [LIB]):
             _run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CLI, "-o", EXE, cli_src,
                   "-L", HERE, "-lhga_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"], verbose)
+    occ_src = os.path.join(CLI, "jf_occurrences.cpp")
+    occ_exe = os.path.join(HERE, "jf_occurrences")
+    if os.path.exists(occ_src) and (force or _stale(occ_exe, [occ_src, os.path.join(CLI, "hga_host.h")] + headers) or _stale(occ_exe, [LIB])):
+        _run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CLI, "-o", occ_exe, occ_src,
+              "-L", HERE, "-lhga_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"], verbose)
     return LIB
 
 

@@ -80,6 +80,18 @@ def test_cli_errors(exe, tmp_path):
     assert r.returncode != 0 and "You need to specify path to kmers" in r.stderr
 
 
+def test_jf_occurrences_without_a_gpu_fails_loudly(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked tests")
+    exe2 = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hybrid-genome-assembler_b200", "jf_occurrences")
+    p = str(tmp_path / "x.fa")
+    open(p, "w").write(">a\nACGTACGTACGTACGTACGT\n")
+    r = subprocess.run([exe2, p, "-k", "5", "-o", str(tmp_path / "o.txt")], input="2 5 1\n", capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU path" in r.stderr and not os.path.exists(str(tmp_path / "o.txt"))
+    assert "Size of kmer to analyze & select" in subprocess.run([exe2, "--help"], capture_output=True, text=True).stdout
+
+
 @pytest.mark.gpu
 def test_cli_end_to_end_components(exe, oracle, tmp_path):
     paths, kp = datagen.make_diploid_case(str(tmp_path / "c"), genome_size=30000, divergence=0.03, k=19, read_len=1200, coverage=12, seed=5,

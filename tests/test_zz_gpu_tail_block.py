@@ -194,3 +194,27 @@ def test_cuda_kmer_counts_are_exact(k):
     km1, ct1 = hga_b200.capi.count_kmers(seq, off, k, min_count=1)
     wk1, wc1 = exact_counts(seq, off, k, 1)
     assert np.array_equal(km1, wk1) and np.array_equal(ct1, wc1) and int(ct1.sum()) == int(wc1.sum())
+
+
+def test_cli_jf_occurrences_exports_the_kmers_file(oracle, tmp_path):
+    """jf_occurrences (the --kmers producer): per-file GPU counts -> merge -> specificity table -> export of a count range, against
+    exact numpy counts pushed through the host functions the reference's reader pins (tests/test_sdk_selection_cpu.py)"""
+    import hga_b200
+    from test_sdk_selection_cpu import exact_counts
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hybrid-genome-assembler_b200", "jf_occurrences")
+    k = 15
+    paths, _ = datagen.make_diploid_case(str(tmp_path), genome_size=6000, divergence=0.03, k=k, read_len=300, coverage=8, seed=6, error_rate=0.01)
+    per_file = []
+    for p in paths:
+        rc, reads = oracle.load_reads([p])
+        per_file.append(exact_counts(reads["seq"], reads["seq_off"], k))
+    km, total, largest, files = hga_b200.capi.sdk_merge(per_file)
+    out = str(tmp_path / "sdk.txt")
+    r = subprocess.run([exe] + paths + ["-k", str(k), "-o", out], input="3 12 1.0\n", capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sel, n_sel, n_disc = hga_b200.capi.sdk_select(total, files, 3, 12)
+    assert [l.strip() for l in open(out) if l.strip()] == [datagen.kmer_to_str(v, k) for v in km[sel]] and n_sel > 0
+    assert f"{n_disc} out of {n_sel} exported kmers are discriminative" in r.stdout
+    t, o, u = hga_b200.capi.sdk_specificity(total, largest)
+    table = [tuple(l.split()) for l in r.stdout.splitlines() if len(l.split()) == 3 and l[0].isdigit()]
+    assert [(float(a), int(b), int(c)) for a, b, c in table] == [(round(float(a), 2), int(b), int(c)) for a, b, c in zip(t, o, u)]
