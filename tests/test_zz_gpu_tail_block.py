@@ -218,3 +218,48 @@ def test_cli_jf_occurrences_exports_the_kmers_file(oracle, tmp_path):
     t, o, u = hga_b200.capi.sdk_specificity(total, largest)
     table = [tuple(l.split()) for l in r.stdout.splitlines() if len(l.split()) == 3 and l[0].isdigit()]
     assert [(float(a), int(b), int(c)) for a, b, c in table] == [(round(float(a), 2), int(b), int(c)) for a, b, c in zip(t, o, u)]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz_full_run_clustering_vs_oracle(oracle, tmp_path, seed):
+    """random cases through hga_enrich_full against the C oracle's engine (scaffold merge, merge of the clusters, enrichment, final
+    merge), with the tail connections and clusters the block itself reports - the chain scripts/fuzz_tail_block.py checks against
+    the real reference on CPU"""
+    import hga_b200
+    import oracle_lib
+    rng = np.random.default_rng(1000 + seed)
+    long_ = seed != 2
+    kw = dict(genome_size=int(rng.integers(30000, 80000)), divergence=float(rng.choice([0.02, 0.03])), k=int(rng.choice([15, 17, 19, 21])),
+              read_len=int(rng.integers(1000, 3000)) if long_ else int(rng.integers(150, 400)), coverage=int(rng.integers(10, 14)) if long_ else int(rng.integers(20, 28)),
+              seed=int(rng.integers(1, 10000)), error_rate=float(rng.choice([0.005, 0.02, 0.05])))
+    if long_:
+        kw["length_sigma"] = 0.5
+    ms = 5 if long_ else 30
+    paths, kp = datagen.make_diploid_case(str(tmp_path), **kw)
+    rc, reads = oracle.load_reads(paths)
+    kmers, k = oracle.load_kmers(kp)
+    with hga_b200.Handle(kmers, k) as h:
+        e = _run_full(h, dict(bases=reads["seq"], seq_off=reads["seq_off"], fraction=0.15, min_size=ms, enrich=20))
+        t = h.get_tail_block()
+    res = oracle.run(reads["seq"], reads["seq_off"], k, kmers, min_size=ms)
+    eng = oracle_lib.Engine(oracle, res["row_off"], res["hit_kid"], len(kmers), res["inv_off"], res["inv_read"])
+    try:
+        ids = eng.merge(res["comp"][0], res["comp"][1])
+        assert t["ran"] == (len(ids) > 2) and t["n_scaffold_cores"] == len(ids)
+        clusters = [c for c in t["clusters"] if len(c)]
+        if clusters:
+            eng.merge(np.cumsum([0] + [len(c) for c in clusters]).astype(np.uint64), np.concatenate(clusters))
+        cores = np.sort(eng.ids(ms))
+        assert np.array_equal(e["core_id"], cores)
+        for c, got_k, got_r in zip(cores, e["core_kmers"], e["core_reads"]):
+            assert np.array_equal(np.sort(got_k), np.sort(eng.component_kmers(c))) and np.array_equal(got_r, np.sort(eng.component_reads(c)))
+        po, pr = eng.index()
+        assert np.array_equal(e["purged_off"], po) and np.array_equal(e["purged_read"], pr)
+        ex, ey, es = oracle.canonical_sort(*eng.connections(cores, 20))
+        assert np.array_equal(e["econn"][0], ex) and np.array_equal(e["econn"][1], ey) and np.array_equal(e["econn"][2], es)
+        eo, em, _, _, _ = oracle.union_find(ex, ey, min_size=2, max_size=-1, restricted=cores)
+        eng.merge(eo, em)
+        want = sorted((int(np.sort(eng.component_reads(c))[0]), int(c), np.sort(eng.component_reads(c)).tolist()) for c in eng.ids(ms))
+    finally:
+        eng.close()
+    assert [(int(r[0]), int(f), r.tolist()) for f, r in zip(e["final_id"], e["final_reads"])] == want
