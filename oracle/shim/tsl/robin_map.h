@@ -20,6 +20,12 @@ namespace tsl {
 template<typename K, typename V> class robin_map;
 template<typename K, typename V> struct robin_map_storage { using type = std::unordered_map<K, V>; };
 template<> struct robin_map_storage<uint32_t, robin_map<uint32_t, int>> { using type = std::map<uint32_t, robin_map<uint32_t, int>>; };
+#ifdef HGA_SHIM_ORDERED_DISTANCES
+// experiment switch (not used by the committed build): also order robin_map<uint32_t, uint64_t>, the type of the distance maps of the
+// tail search (ties of std::max_element then go to the smallest id) - and of the hot counting map of get_connections, which is why
+// it is not the default: it would slow the CPU baseline down
+template<> struct robin_map_storage<uint32_t, uint64_t> { using type = std::map<uint32_t, uint64_t>; };
+#endif
 
 template<typename K, typename V>
 class robin_map {
