@@ -99,7 +99,9 @@ extern "C" int hga_count_kmers(int device, int k, const char *bases, const uint6
     HGA_CUDA(cudaMemcpyAsync(b.bases.p, bases + base0, n_bases, cudaMemcpyHostToDevice, st));
     HGA_CUDA(cudaMemcpyAsync(b.off.p, off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     unsigned long long *d_scal = b.scalars.as<unsigned long long>();
-    const uint64_t CH = 1ull << 28;
+    // positions per chunk; HGA_COUNT_CHUNK overrides it (tests force the multi-chunk merge on small inputs with it)
+    const char *ch_env = getenv("HGA_COUNT_CHUNK");
+    const uint64_t CH = ch_env && std::strtoull(ch_env, nullptr, 10) >= 256 ? std::strtoull(ch_env, nullptr, 10) : (1ull << 28);
     // 2k key bits are enough: no canonical k-mer has all of them set (T...T is not canonical), so the sentinels still sort behind
     // every k-mer and stay together
     const int end_bit = 2 * k;

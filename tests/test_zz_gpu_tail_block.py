@@ -194,6 +194,13 @@ def test_cuda_kmer_counts_are_exact(k):
     km1, ct1 = hga_b200.capi.count_kmers(seq, off, k, min_count=1)
     wk1, wc1 = exact_counts(seq, off, k, 1)
     assert np.array_equal(km1, wk1) and np.array_equal(ct1, wc1) and int(ct1.sum()) == int(wc1.sum())
+    # the multi-chunk path (partial runs of several chunks merged by sort + reduce-by-key), forced with a tiny chunk
+    os.environ["HGA_COUNT_CHUNK"] = "4096"
+    try:
+        km2, ct2 = hga_b200.capi.count_kmers(seq, off, k, min_count=2)
+    finally:
+        del os.environ["HGA_COUNT_CHUNK"]
+    assert np.array_equal(km2, wk) and np.array_equal(ct2, wc)
 
 
 def test_cli_jf_occurrences_exports_the_kmers_file(oracle, tmp_path):
