@@ -171,3 +171,349 @@ def test_second_merge_bodies_match_the_rule(host_kernels):
         assert np.array_equal(out_off.astype(np.uint64), want_off) and np.array_equal(out_row[:out_off[-1]], want_rows)
         got_unions = [np.sort((new_keys[(new_keys >> np.uint64(32)) == np.uint64(c)] & np.uint64(0xFFFFFFFF)).astype(np.int64)) for c in range(len(surv_new))]
         assert all(np.array_equal(a, b) for a, b in zip(got_unions, want_unions))
+
+
+# ---- the whole of hga_count_kmers (kernels + launches + CUB calls + buffers) on the host -----------------------------------------
+# csrc/hga_count.cu is self-contained apart from DevBuf and the error macros: its text is compiled for the host against a few lines
+# that stand in for the CUDA runtime (malloc / memcpy) and for the five CUB entry points it calls (std algorithms honouring the
+# two-phase temp-storage protocol and, for the radix sorts, ONLY the requested bit range), with `<<<...>>>` launches turned into
+# plain calls of the one-thread grid.
+FAKE_CUDA = r"""
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+#include "hga_b200.h"
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline const char *cudaGetErrorString(cudaError_t) { return "fake"; }
+static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 2; return 0; }
+static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void *p) { std::free(p); return 0; }
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static char g_err[512];
+void hga_set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
+extern "C" const char *fake_last_error() { return g_err; }
+namespace cub {
+template<typename K> static inline unsigned long long bits_of(K k, int b0, int b1) { return b1 - b0 >= 64 ? (unsigned long long) k : (((unsigned long long) k >> b0) & ((1ull << (b1 - b0)) - 1)); }
+struct DeviceRadixSort {
+    template<typename K> static cudaError_t SortKeys(void *tmp, size_t &bytes, const K *in, K *out, unsigned long long n, int b0, int b1, cudaStream_t) {
+        if (!tmp) { bytes = 1; return 0; }
+        std::vector<K> v(in, in + n);
+        std::stable_sort(v.begin(), v.end(), [&](K a, K b) { return bits_of(a, b0, b1) < bits_of(b, b0, b1); });
+        std::copy(v.begin(), v.end(), out);
+        return 0;
+    }
+    template<typename K, typename V> static cudaError_t SortPairs(void *tmp, size_t &bytes, const K *kin, K *kout, const V *vin, V *vout, unsigned long long n, int b0, int b1, cudaStream_t) {
+        if (!tmp) { bytes = 1; return 0; }
+        std::vector<size_t> o(n);
+        std::iota(o.begin(), o.end(), (size_t) 0);
+        std::stable_sort(o.begin(), o.end(), [&](size_t a, size_t b) { return bits_of(kin[a], b0, b1) < bits_of(kin[b], b0, b1); });
+        std::vector<K> k2(n); std::vector<V> v2(n);
+        for (size_t i = 0; i < n; i++) { k2[i] = kin[o[i]]; v2[i] = vin[o[i]]; }
+        std::copy(k2.begin(), k2.end(), kout); std::copy(v2.begin(), v2.end(), vout);
+        return 0;
+    }
+    template<typename K, typename V> static cudaError_t SortPairsDescending(void *tmp, size_t &bytes, const K *kin, K *kout, const V *vin, V *vout, unsigned long long n, int b0, int b1, cudaStream_t) {
+        if (!tmp) { bytes = 1; return 0; }
+        std::vector<size_t> o(n);
+        std::iota(o.begin(), o.end(), (size_t) 0);
+        std::stable_sort(o.begin(), o.end(), [&](size_t a, size_t b) { return bits_of(kin[a], b0, b1) > bits_of(kin[b], b0, b1); });
+        std::vector<K> k2(n); std::vector<V> v2(n);
+        for (size_t i = 0; i < n; i++) { k2[i] = kin[o[i]]; v2[i] = vin[o[i]]; }
+        std::copy(k2.begin(), k2.end(), kout); std::copy(v2.begin(), v2.end(), vout);
+        return 0;
+    }
+};
+struct DeviceRunLengthEncode {
+    template<typename K, typename L, typename N> static cudaError_t Encode(void *tmp, size_t &bytes, const K *in, K *uniq, L *len, N *runs, unsigned long long n, cudaStream_t) {
+        if (!tmp) { bytes = 1; return 0; }
+        unsigned long long r = 0;
+        for (unsigned long long i = 0; i < n;) { unsigned long long j = i; while (j < n && in[j] == in[i]) j++; uniq[r] = in[i]; len[r] = (L) (j - i); r++; i = j; }
+        *runs = (N) r;
+        return 0;
+    }
+};
+struct DeviceReduce {
+    template<typename K, typename V, typename N, typename Op> static cudaError_t ReduceByKey(void *tmp, size_t &bytes, const K *kin, K *uniq, const V *vin, V *agg, N *runs, Op op, int n, cudaStream_t) {
+        if (!tmp) { bytes = 1; return 0; }
+        std::vector<K> ku; std::vector<V> va;                    // in and out may alias in the caller: build first, then write
+        for (int i = 0; i < n;) { int j = i + 1; V a = vin[i]; while (j < n && kin[j] == kin[i]) { a = op(a, vin[j]); j++; } ku.push_back(kin[i]); va.push_back(a); i = j; }
+        std::copy(ku.begin(), ku.end(), uniq); std::copy(va.begin(), va.end(), agg);
+        *runs = (N) ku.size();
+        return 0;
+    }
+};
+struct DeviceSelect {
+    template<typename T, typename F, typename N> static cudaError_t Flagged(void *tmp, size_t &bytes, const T *in, const F *flag, T *out, N *nsel, unsigned long long n, cudaStream_t) {
+        if (!tmp) { bytes = 1; return 0; }
+        unsigned long long m = 0;
+        for (unsigned long long i = 0; i < n; i++) if (flag[i]) out[m++] = in[i];
+        *nsel = (N) m;
+        return 0;
+    }
+    template<typename T, typename N> static cudaError_t Unique(void *tmp, size_t &bytes, const T *in, T *out, N *nsel, unsigned long long n, cudaStream_t) {
+        if (!tmp) { bytes = 1; return 0; }
+        unsigned long long m = 0;
+        for (unsigned long long i = 0; i < n; i++) if (i == 0 || in[i] != in[i - 1]) out[m++] = in[i];
+        *nsel = (N) m;
+        return 0;
+    }
+};
+struct DeviceScan {
+    template<typename I, typename O> static cudaError_t ExclusiveSum(void *tmp, size_t &bytes, const I *in, O *out, unsigned long long n, cudaStream_t) {
+        if (!tmp) { bytes = 1; return 0; }
+        O acc = 0;
+        for (unsigned long long i = 0; i < n; i++) { const O v = (O) in[i]; out[i] = acc; acc += v; }
+        return 0;
+    }
+};
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def host_count_kmers(tmp_path_factory):
+    text = open(os.path.join(CSRC, "hga_count.cu")).read()
+    internal = open(os.path.join(CSRC, "hga_internal.cuh")).read()
+    text = re.sub(r'#include\s+"hga_internal.cuh"\n', "", text)
+    text = re.sub(r"#include\s+<cub/[^>]+>\n", "", text)
+    text = re.sub(r"<<<[^;]*?>>>", "", text)                              # kernel<<<grid, block, smem, stream>>>(args) -> kernel(args)
+    macros = _cut_macros(internal)
+    devbuf = internal[internal.index("struct DevBuf {"):internal.index("struct PinBuf {")]
+    d = tmp_path_factory.mktemp("host_count")
+    src, so = str(d / "count_host.cpp"), str(d / "count_host.so")
+    open(src, "w").write(PRELUDE + FAKE_CUDA + macros + devbuf + text)
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("HGA_EMU_ASAN") else []
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared"] + san + ["-I", os.path.join(ROOT, "include"), "-o", so, src], check=True)
+    return C.CDLL(so)
+
+
+def _cut_macros(internal):
+    a = internal.index("#define HGA_CUDA(call)")
+    b = internal.index("while (0)", internal.index("#define HGA_TRY(call)")) + len("while (0)")
+    return internal[a:b] + "\n"
+
+
+class _KC(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("kmer", C.POINTER(C.c_uint64)), ("count", C.POINTER(C.c_uint32))]
+
+
+@pytest.mark.parametrize("k,chunk", [(19, None), (19, "1024"), (11, "256"), (32, "700"), (5, "4096")])
+def test_count_kmers_orchestration_on_host(host_count_kmers, k, chunk):
+    g = datagen.random_genome(3000, 300 + k)
+    reads = [datagen.to_ascii(r) for r in datagen.sample_reads(g, 120, 150, 400 + k, error_rate=0.01)]
+    reads[1] = reads[1][:20] + "N" + reads[1][21:]
+    reads[3] = reads[3].lower()
+    reads[5] = ""
+    seq = ("XXXX" + "".join(reads)).encode()                     # the first read does not start at offset 0
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    off += np.uint64(4)
+    if chunk:
+        os.environ["HGA_COUNT_CHUNK"] = chunk
+    try:
+        for min_count in (1, 2, 3):
+            out = _KC()
+            rc = host_count_kmers.hga_count_kmers(0, k, seq, _p(off), C.c_uint64(len(reads)), C.c_uint32(min_count), C.byref(out))
+            assert rc == 0, C.c_char_p(host_count_kmers.fake_last_error()).value
+            km = np.ctypeslib.as_array(out.kmer, shape=(max(out.n, 1),))[:out.n].copy()
+            ct = np.ctypeslib.as_array(out.count, shape=(max(out.n, 1),))[:out.n].copy()
+            host_count_kmers.hga_free_kmer_counts(C.byref(out))
+            wk, wc = exact_counts(seq[4:], off - np.uint64(4), k, min_count)
+            assert np.array_equal(km, wk) and np.array_equal(ct, wc) and len(km) > 0
+    finally:
+        os.environ.pop("HGA_COUNT_CHUNK", None)
+
+
+# ---- the whole of hga_enrich_run, tail / spectral block included, on the host ----------------------------------------------------
+# csrc/hga_enrich.cu + csrc/hga_internal.cuh compiled for the host like hga_count.cu above, linked with the REAL host stages
+# (csrc/hga_tails.cpp, csrc/hga_spectral.cpp). The handle's "device" state (selected edges, inverted index keyed by slot = kmer_id,
+# hits) is filled from the C oracle; hga_get_hits / hga_export_index (csrc/hga_capi.cu, GPU-verified) are stood in for by a few
+# lines. What runs is the product's own source for: the root replay and its GPU pre-filter, the unions, both purges, the spanning
+# forest, the glue around the host stages, the second merge, the enrichment connections and the final merge.
+FAKE_CUDA_MORE = r"""
+typedef void *cudaEvent_t;
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
+static inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFreeHost(void *p) { std::free(p); return 0; }
+static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
+static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned) (((unsigned long long) a * b) >> 32); }
+static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }
+"""
+
+EMU_HARNESS = r"""
+static struct { std::vector<uint64_t> row_off, idx_off; std::vector<uint32_t> kid, pos, idx_read; } g_emu;
+int hga_comm_size(const hga_handle *) { return 1; }
+extern "C" int hga_get_hits(hga_handle *h, int sorted_by_kmer_id, hga_hits *out) {
+    if (!sorted_by_kmer_id) return HGA_E_ARG;
+    out->n_reads = h->n_reads; out->n_hits = g_emu.kid.size(); out->row_off = g_emu.row_off.data(); out->kmer_id = g_emu.kid.data(); out->pos = g_emu.pos.data();
+    return HGA_OK;
+}
+int hga_export_index(hga_handle *h, const uint32_t *d_off, const uint32_t *d_row, uint64_t E, hga_index *out) {
+    const uint64_t K = h->n_kmers;                             // emulation: slot == kmer_id
+    g_emu.idx_off.assign(K + 1, 0); g_emu.idx_read.assign(E + 1, 0);
+    for (uint64_t k = 0; k <= K; k++) g_emu.idx_off[k] = d_off[k];
+    for (uint64_t i = 0; i < E; i++) g_emu.idx_read[i] = d_row[i] + h->inc_row_first_id;
+    out->n_kmers = K; out->n_entries = E; out->off = g_emu.idx_off.data(); out->read_id = g_emu.idx_read.data();
+    return HGA_OK;
+}
+static hga_handle *g_h = nullptr;
+static std::vector<uint32_t> g_core_kmer;
+static std::vector<uint64_t> g_core_koff;
+static hga_index g_purged;
+extern "C" int emu_enrich(uint64_t n_reads, uint64_t n_kmers, const uint64_t *row_off, const uint32_t *kid, const uint32_t *pos, const uint64_t *inv_off,
+                          const uint32_t *inv_read, uint64_t M, const uint32_t *sel_x, const uint32_t *sel_y, const uint32_t *sel_score, const uint64_t *read_off,
+                          int min_size, uint32_t min_score, uint32_t amp, int dims, int with_tail) {
+    delete g_h;
+    hga_handle *h = g_h = new hga_handle();
+    std::memset(&h->metrics, 0, sizeof h->metrics);
+    h->n_kmers = n_kmers; h->n_reads = n_reads; h->inc_rows = n_reads; h->inc_row_first_id = 1; h->read_id_base = 1; h->sm_count = 2;
+    h->index_keys = (uint32_t) n_kmers; h->n_hits = row_off[n_reads]; h->inc_entries = inv_off[n_kmers];
+    h->have_scan = h->have_index = h->have_selection = true;
+    g_emu.row_off.assign(row_off, row_off + n_reads + 1); g_emu.kid.assign(kid, kid + row_off[n_reads]); g_emu.pos.assign(pos, pos + row_off[n_reads]);
+    if (h->d_inv_off.ensure((n_kmers + 1) * 4) || h->d_inv_row.ensure((inv_off[n_kmers] + 1) * 4) || h->d_sel_key.ensure((M + 1) * 8) || h->d_sel_score.ensure((M + 1) * 4)) return -1;
+    for (uint64_t k = 0; k <= n_kmers; k++) h->d_inv_off.as<uint32_t>()[k] = (uint32_t) inv_off[k];
+    for (uint64_t i = 0; i < inv_off[n_kmers]; i++) h->d_inv_row.as<uint32_t>()[i] = inv_read[i] - 1;
+    for (uint64_t i = 0; i < M; i++) { h->d_sel_key.as<uint64_t>()[i] = ((uint64_t) (sel_x[i] - 1) << 32) | (sel_y[i] - 1); h->d_sel_score.as<uint32_t>()[i] = sel_score[i]; }
+    h->n_selected = M;
+    TailParams tail{read_off, amp, dims};
+    const int rc = hga_enrich_run(h, min_size, -1, min_score, with_tail ? &tail : nullptr);
+    if (rc != HGA_OK) return rc;
+    // what hga_get_core_kmers / hga_get_purged_index return (slot == kmer_id here)
+    const uint64_t C = h->enrich.core_id.size();
+    g_core_kmer.assign(h->n_core_kmers + 1, 0);
+    for (uint64_t i = 0; i < h->n_core_kmers; i++) g_core_kmer[i] = (uint32_t) h->d_enr_keys.as<uint64_t>()[i];
+    g_core_koff.assign(C + 1, 0);
+    for (uint64_t c = 0; c <= C; c++) g_core_koff[c] = h->d_enr_core_koff.as<unsigned long long>()[c];
+    return hga_export_index(h, h->d_purged_off.as<uint32_t>(), h->d_purged_row.as<uint32_t>(), h->n_purged, &g_purged);
+}
+struct EmuOut {
+    uint64_t n_cores; const uint32_t *core_id; const uint64_t *core_off; const uint32_t *core_read; const uint64_t *core_koff; const uint32_t *core_kmer;
+    uint64_t n_conn; const uint32_t *cx, *cy, *cs; uint64_t n_final; const uint32_t *final_id; const uint64_t *final_off; const uint32_t *final_read;
+    uint64_t n_kmers; const uint64_t *purged_off; const uint32_t *purged_read; int ran; uint64_t n_scaffold_cores; uint64_t n_tconn; const uint32_t *tx, *ty; const uint64_t *ts;
+    uint64_t n_clusters; const uint64_t *cl_off; const uint32_t *cl_member;
+};
+extern "C" void emu_out(EmuOut *o) {
+    const EnrichResult &r = g_h->enrich;
+    o->n_cores = r.core_id.size(); o->core_id = r.core_id.data(); o->core_off = r.core_off.data(); o->core_read = r.core_read.data();
+    o->core_koff = g_core_koff.data(); o->core_kmer = g_core_kmer.data();
+    o->n_conn = r.conn_x.size(); o->cx = r.conn_x.data(); o->cy = r.conn_y.data(); o->cs = r.conn_score.data();
+    o->n_final = r.final_id.size(); o->final_id = r.final_id.data(); o->final_off = r.final_off.data(); o->final_read = r.final_read.data();
+    o->n_kmers = g_purged.n_kmers; o->purged_off = g_purged.off; o->purged_read = g_purged.read_id;
+    o->ran = r.tail_block_ran; o->n_scaffold_cores = r.n_scaffold_cores; o->n_tconn = r.tconn_x.size(); o->tx = r.tconn_x.data(); o->ty = r.tconn_y.data(); o->ts = r.tconn_score.data();
+    o->n_clusters = r.cluster_off.empty() ? 0 : r.cluster_off.size() - 1; o->cl_off = r.cluster_off.data(); o->cl_member = r.cluster_member.data();
+}
+"""
+
+
+class _EmuOut(C.Structure):
+    _u32, _u64 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    _fields_ = [("n_cores", C.c_uint64), ("core_id", _u32), ("core_off", _u64), ("core_read", _u32), ("core_koff", _u64), ("core_kmer", _u32),
+                ("n_conn", C.c_uint64), ("cx", _u32), ("cy", _u32), ("cs", _u32), ("n_final", C.c_uint64), ("final_id", _u32), ("final_off", _u64), ("final_read", _u32),
+                ("n_kmers", C.c_uint64), ("purged_off", _u64), ("purged_read", _u32), ("ran", C.c_int), ("n_scaffold_cores", C.c_uint64), ("n_tconn", C.c_uint64),
+                ("tx", _u32), ("ty", _u32), ("ts", _u64), ("n_clusters", C.c_uint64), ("cl_off", _u64), ("cl_member", _u32)]
+
+
+@pytest.fixture(scope="module")
+def host_enrich(tmp_path_factory):
+    internal = open(os.path.join(CSRC, "hga_internal.cuh")).read()
+    internal = internal.replace("#include <cuda_runtime.h>\n", "").replace("#pragma once\n", "").replace('#include "../../include/hga_b200.h"', '#include "hga_b200.h"')
+    text = open(os.path.join(CSRC, "hga_enrich.cu")).read()
+    text = re.sub(r'#include\s+"hga_internal.cuh"\n', "", text)
+    text = re.sub(r"#include\s+<cub/[^>]+>\n", "", text)
+    text = re.sub(r"<<<[^;]*?>>>", "", text)
+    fake = FAKE_CUDA.replace("void hga_set_error(const char *fmt, ...) {", "void hga_set_error_unused(const char *fmt, ...) {")
+    d = tmp_path_factory.mktemp("host_enrich")
+    src, so = str(d / "enrich_host.cpp"), str(d / "enrich_host.so")
+    open(src, "w").write(PRELUDE + "#include <string>\n" + fake + FAKE_CUDA_MORE + internal + text + EMU_HARNESS)
+    err = str(d / "err.cpp")
+    open(err, "w").write('#include <cstdarg>\n#include <cstdio>\nstatic char g[512];\nvoid hga_set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g, sizeof g, fmt, ap); va_end(ap); }\n'
+                         'extern "C" const char *emu_last_error() { return g; }\n')
+    # HGA_EMU_ASAN=1 (with LD_PRELOAD=libasan.so): the emulated "device" buffers are malloc blocks, so AddressSanitizer sees every
+    # out-of-bounds kernel access and every use of a reallocated buffer
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("HGA_EMU_ASAN") else []
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared"] + san + ["-I", os.path.join(ROOT, "include"), "-o", so, src, err,
+                    os.path.join(CSRC, "hga_tails.cpp"), os.path.join(CSRC, "hga_spectral.cpp")], check=True)
+    lib = C.CDLL(so)
+    lib.emu_last_error.restype = C.c_char_p
+    return lib
+
+
+def _emu_run(lib, oracle, c, with_tail):
+    res = oracle.run(c["bases"], c["seq_off"], c["k"], c["kmers"], fraction=c["fraction"], min_size=c["min_size"])
+    n = len(c["seq_off"]) - 1
+    ro = res["row_off"].astype(np.int64)
+    rows = np.repeat(np.arange(n), np.diff(ro))
+    o = np.lexsort((res["hit_pos"], res["hit_kid"], rows))
+    kid, pos = np.ascontiguousarray(res["hit_kid"][o], dtype=np.uint32), np.ascontiguousarray(res["hit_pos"][o], dtype=np.uint32)
+    sx, sy, ss = res["conn"]
+    m = res["cut_n"]
+    lo, hi = np.minimum(sx[:m], sy[:m]).astype(np.uint64), np.maximum(sx[:m], sy[:m]).astype(np.uint64)
+    key, first = np.unique((lo << np.uint64(32)) | hi, return_index=True)                    # unordered selected edges in (x, y) order
+    sel_x, sel_y = (key >> np.uint64(32)).astype(np.uint32), (key & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    sel_s = np.ascontiguousarray(ss[:m][first], dtype=np.uint32)
+    row_off = np.ascontiguousarray(res["row_off"], dtype=np.uint64); inv_off = np.ascontiguousarray(res["inv_off"], dtype=np.uint64)
+    inv_read = np.ascontiguousarray(res["inv_read"], dtype=np.uint32); read_off = np.ascontiguousarray(c["seq_off"], dtype=np.uint64)
+    rc = lib.emu_enrich(C.c_uint64(n), C.c_uint64(len(c["kmers"])), _p(row_off), _p(kid), _p(pos), _p(inv_off), _p(inv_read), C.c_uint64(len(key)), _p(sel_x), _p(sel_y),
+                        _p(sel_s), _p(read_off), c["min_size"], C.c_uint32(c["enrich"]), C.c_uint32(40), 16, int(with_tail))
+    assert rc == 0, lib.emu_last_error()
+    out = _EmuOut()
+    lib.emu_out(C.byref(out))
+
+    def arr(p, k, dt):
+        return np.ctypeslib.as_array(p, shape=(max(int(k), 1),))[:int(k)].astype(dt) if k else np.zeros(0, dt)
+    co = arr(out.core_off, out.n_cores + 1, np.int64); fo = arr(out.final_off, out.n_final + 1, np.int64); ko = arr(out.core_koff, out.n_cores + 1, np.int64)
+    cr = arr(out.core_read, co[-1], np.uint32); fr = arr(out.final_read, fo[-1], np.uint32); ck = arr(out.core_kmer, ko[-1], np.uint32)
+    po = arr(out.purged_off, out.n_kmers + 1, np.uint64)
+    clo = arr(out.cl_off, out.n_clusters + 1, np.int64) if out.n_clusters else np.zeros(1, np.int64)
+    clm = arr(out.cl_member, clo[-1], np.uint32)
+    e = dict(core_id=arr(out.core_id, out.n_cores, np.uint32), core_kmers=[ck[ko[i]:ko[i + 1]] for i in range(len(ko) - 1)],
+             core_reads=[cr[co[i]:co[i + 1]] for i in range(len(co) - 1)], purged_off=po, purged_read=arr(out.purged_read, po[-1], np.uint32),
+             econn=(arr(out.cx, out.n_conn, np.uint32), arr(out.cy, out.n_conn, np.uint32), arr(out.cs, out.n_conn, np.uint64)),
+             final_id=arr(out.final_id, out.n_final, np.uint32), final_reads=[fr[fo[i]:fo[i + 1]] for i in range(len(fo) - 1)])
+    t = dict(ran=bool(out.ran), n_scaffold_cores=int(out.n_scaffold_cores), conn_x=arr(out.tx, out.n_tconn, np.uint32), conn_y=arr(out.ty, out.n_tconn, np.uint32),
+             conn_score=arr(out.ts, out.n_tconn, np.uint64), clusters=[clm[clo[i]:clo[i + 1]] for i in range(len(clo) - 1)])
+    return e, t
+
+
+@pytest.mark.parametrize("name", ["enrich_short", "enrich_long"])
+def test_enrich_run_on_host_without_the_block(host_enrich, oracle, name):
+    """sanity of the emulation itself: the GPU-verified path (hga_enrich) reproduces the reference's golden dump when run this way"""
+    import compare
+    import golden_util
+    c = golden_util.load_case(name)
+    e, t = _emu_run(host_enrich, oracle, c, with_tail=False)
+    compare.check_enrichment(c["ref"], e, c["kmers"])
+    assert not t["ran"]
+
+
+@pytest.mark.parametrize("name", ["full_short", "full_long"])
+def test_enrich_full_on_host_matches_the_reference(host_enrich, oracle, name):
+    """hga_enrich_full's own source, run on the host, against the real reference's --full dump: tail connections, clusters, state after
+    the second merge, enrichment connections, final components"""
+    import compare
+    import golden_util
+    c = golden_util.load_case(name)
+    ref = c["ref"]
+    e, t = _emu_run(host_enrich, oracle, c, with_tail=True)
+    assert t["ran"] and t["n_scaffold_cores"] == ref["merged_scaffolds"]
+    assert np.array_equal(t["conn_x"], ref["tconn_x"]) and np.array_equal(t["conn_y"], ref["tconn_y"]) and np.array_equal(t["conn_score"], ref["tconn_score"])
+    so = ref["spectral_off"].astype(np.int64)
+    want = [(ref["spectral_member"][so[i]:so[i + 1]].tolist(), int(ref["spectral_first"][i])) for i in range(len(so) - 1)]
+    assert sorted((sorted(cl.tolist()), int(cl[0])) for cl in t["clusters"]) == want
+    compare.check_enrichment(ref, e, c["kmers"])
