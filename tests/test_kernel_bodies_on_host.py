@@ -517,3 +517,26 @@ def test_enrich_full_on_host_matches_the_reference(host_enrich, oracle, name):
     want = [(ref["spectral_member"][so[i]:so[i + 1]].tolist(), int(ref["spectral_first"][i])) for i in range(len(so) - 1)]
     assert sorted((sorted(cl.tolist()), int(cl[0])) for cl in t["clusters"]) == want
     compare.check_enrichment(ref, e, c["kmers"])
+
+
+LIVE_CASES = {
+    "wrapping_k17": (dict(genome_size=80000, divergence=0.02, k=17, read_len=2500, coverage=12, seed=61, error_rate=0.04, length_sigma=0.5), 5),
+    "short_k19": (dict(genome_size=40000, divergence=0.03, k=19, read_len=200, coverage=24, seed=77, error_rate=0.005, fmt="fastq"), 30),
+    "long_k21": (dict(genome_size=60000, divergence=0.03, k=21, read_len=1800, coverage=12, seed=78, error_rate=0.02, length_sigma=0.4), 5),
+}
+
+
+@pytest.mark.parametrize("name", list(LIVE_CASES))
+def test_enrich_full_on_host_live_against_the_reference(host_enrich, oracle, ref_driver, tmp_path, name):
+    import compare
+    import refdump
+    kw, ms = LIVE_CASES[name]
+    paths, kp = datagen.make_diploid_case(str(tmp_path), **kw)
+    ref = refdump.run_ref(ref_driver, paths, kp, enrich=20, full=True, min_size=ms)
+    assert ref["scaffold_components"] > 2
+    rc, reads = oracle.load_reads(paths)
+    kmers, k = oracle.load_kmers(kp)
+    c = dict(bases=reads["seq"], seq_off=reads["seq_off"], k=k, kmers=kmers, fraction=0.15, min_size=ms, enrich=20)
+    e, t = _emu_run(host_enrich, oracle, c, with_tail=True)
+    assert np.array_equal(t["conn_x"], ref["tconn_x"]) and np.array_equal(t["conn_y"], ref["tconn_y"]) and np.array_equal(t["conn_score"], ref["tconn_score"])
+    compare.check_enrichment(ref, e, kmers)
