@@ -3,7 +3,7 @@
 TAG=${1:-r2a}
 mkdir -p gpurun_out
 # 1. the blind code: hga_enrich_full (tail / spectral block, second merge), --spectral, hga_count_kmers, jf_occurrences
-timeout 600 python -m pytest tests/test_zz_gpu_tail_block.py -m gpu -q -x > gpurun_out/zz_${TAG}.log 2>&1
+timeout 600 python -m pytest tests/test_zx_gpu_forced_spectral.py tests/test_zy_gpu_tail_block.py tests/test_zz_gpu_sdk_selection.py -m gpu -q > gpurun_out/zz_${TAG}.log 2>&1
 echo "zz tests rc=$?: $(tail -1 gpurun_out/zz_${TAG}.log)"
 # 2. phase times of the block on a case with many scaffold components (HGA_ENRICH_TIMING prints every phase on stderr)
 HGA_ENRICH_TIMING=1 timeout 300 python - > gpurun_out/tail_block_${TAG}.log 2>&1 <<'PY'

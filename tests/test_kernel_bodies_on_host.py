@@ -2,7 +2,7 @@
 enr_merge2_keys / enr_purge2 of csrc/hga_enrich.cu), compiled FOR THE HOST and run as one thread with a one-thread grid: the text of
 each kernel is cut out of the .cu file at test time (nothing is copied into the repo), `__global__`, `blockIdx`, `atomicMax`, ... are
 defined away in a few lines, and the results are compared with numpy. This checks the arithmetic and the indexing of the kernel
-code itself; it says nothing about launches, CUB calls or buffers - the GPU tests (tests/test_zz_gpu_tail_block.py) do that.
+code itself; it says nothing about launches, CUB calls or buffers - the GPU tests (tests/test_zy_gpu_tail_block.py) do that.
 Test infrastructure only: the product never runs this way."""
 import ctypes as C
 import os

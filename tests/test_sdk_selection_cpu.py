@@ -2,7 +2,7 @@
 occurrences/JellyfishOccurrenceReader.cpp compiled unmodified (oracle/_ref/occ_driver). jellyfish is not in the image: the
 per-file dumps the reader merges (`<read file>_<k>-mers_sorted`, which make it skip jellyfish, :19-24) are written here from exact
 numpy counts (canonical k-mers with count >= 2) - the same numbers hga_count_kmers has to produce on the GPU
-(tests/test_zz_gpu_tail_block.py compares it with this counter)."""
+(tests/test_zz_gpu_sdk_selection.py compares it with this counter)."""
 import os
 import subprocess
 

@@ -3,7 +3,7 @@ hga_enrich_full runs on the GPU (enr_merge2_keys_kernel + enr_purge2_kernel, csr
 against the real reference's state after that merge (fixtures full_*.npz from ref_driver --enrich 20 --full; live against the
 driver when it is built). The state BEFORE the second merge comes from the C oracle's engine, which the other tests pin against the
 reference. What this pins is the RULE (removal bounds, truncation, first-copy removal, unions); the kernels that apply it run in
-tests/test_zz_gpu_tail_block.py."""
+tests/test_zy_gpu_tail_block.py."""
 import numpy as np
 import pytest
 

@@ -75,7 +75,7 @@ def test_tail_connections_golden(oracle):
 @pytest.mark.parametrize("name", ["long_k15", "short_ties"])
 def test_whole_tail_spectral_block_reaches_the_reference_final_components(oracle, ref_driver, tmp_path, name):
     """run_clustering :764-794 INCLUDING the tail / spectral block: scaffold merge -> hga_host_tail_connections -> hga_spectral_clustering
-    -> merge of the clusters (here on the oracle's engine state; the product's GPU form is hga_enrich_full, tests/test_zz_gpu_tail_block.py,
+    -> merge of the clusters (here on the oracle's engine state; the product's GPU form is hga_enrich_full, tests/test_zy_gpu_tail_block.py,
     and its rule tests/test_second_merge_rule.py) -> enrichment:
     final components and their ids equal to the reference's (ref_driver --full)"""
     import hga_b200

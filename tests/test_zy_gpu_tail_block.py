@@ -1,8 +1,9 @@
 """GPU: hga_enrich_full = everything run_clustering does after the scaffold union_find INCLUDING the tail / spectral block
 (ReadClusteringEngine.cpp:764-794), through the C-ABI, against the dumps of the real reference (ref_driver --enrich 20
 --full, fixtures tests/golden/full_*.npz): tail connections, spectral clusters, the state after the merge of the clusters (cores with
-the reference's survivor ids, merged k-mer lists, twice purged index), enrichment connections, final components. The file sorts last
-on purpose: it is the newest path."""
+the reference's survivor ids, merged k-mer lists, twice purged index), enrichment connections, final components. The file sorts near the end
+on purpose: it is the newest path (written after round 1's GPU minutes were spent; the same source passes on the host,
+tests/test_kernel_bodies_on_host.py)."""
 import os
 import subprocess
 
@@ -121,110 +122,6 @@ def test_cli_tail_block_exports_the_reference_final_components(tmp_path):
         lines = open(os.path.join(outdir, name)).read().split("\n")
         assert [l[1:] for l in lines[0::2] if l] == hdrs
     assert f"Exported {len(want)} components" in r.stdout
-
-
-def _forced_spectral_case():
-    z = np.load(os.path.join(golden_util.GOLDEN, "forced_spectral.npz"))
-    fo = z["final_off"].astype(np.int64)
-    want = [(int(z["final_id"][i]), z["final_read"][fo[i]:fo[i + 1]].tolist()) for i in range(len(fo) - 1)]
-    return z, want
-
-
-def test_engine_mirror_forced_spectral():
-    """--spectral (run_clustering :739-746): connections with score >= 5 from the GPU, the reference's spectral stage on the host"""
-    import hga_b200
-    z, want = _forced_spectral_case()
-
-    class _Reader(hga_b200.SequenceRecords):
-        def __init__(self):
-            self.bases, self.seq_off = z["bases"].tobytes(), z["seq_off"]
-            n = len(z["seq_off"]) - 1
-            self.headers = [b"r%d" % i for i in range(n)]
-            self.qualities = [b""] * n
-
-    eng = hga_b200.ReadClusteringEngine(_Reader(), hga_b200.ReadClusteringConfig(scaffold_component_min_size=int(z["min_size"]), force_spectral=True,
-                                                                                 spectral_dims=int(z["dims"])))
-    ids = eng.run_clustering(z["kmers"], int(z["k"]))
-    assert [(i, eng.final_components[i].tolist()) for i in ids] == want
-    cx, cy, cs = eng.get_all_connections(5)
-    assert np.array_equal(cx, z["conn_x"]) and np.array_equal(cy, z["conn_y"]) and np.array_equal(cs, z["conn_score"])
-    eng.close()
-
-
-def test_cli_forced_spectral(tmp_path):
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hybrid-genome-assembler_b200", "categorization")
-    z, want = _forced_spectral_case()
-    so = z["seq_off"].astype(np.int64)
-    bases = z["bases"].tobytes()
-    rp, kp, outdir = str(tmp_path / "reads.fa"), str(tmp_path / "kmers.txt"), str(tmp_path / "out")
-    with open(rp, "wb") as f:
-        for i in range(len(so) - 1):
-            f.write(b">r%d\n" % (i + 1) + bases[so[i]:so[i + 1]] + b"\n")
-    with open(kp, "w") as f:
-        for v in z["kmers"]:
-            f.write(datagen.kmer_to_str(v, int(z["k"])) + "\n")
-    r = subprocess.run([exe, rp, "--kmers", kp, "-o", outdir, "--sc_min_size", str(int(z["min_size"])), "--spectral"], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    assert "Forced spectral clustering took" in r.stdout
-    assert sorted(os.listdir(outdir)) == sorted(f"#{fid}.fa" for fid, _ in want)
-    for fid, members in want:
-        lines = open(os.path.join(outdir, f"#{fid}.fa")).read().split("\n")
-        assert [l[1:] for l in lines[0::2] if l] == [f"r{m}" for m in members]
-
-
-@pytest.mark.parametrize("k", [11, 19, 32])
-def test_cuda_kmer_counts_are_exact(k):
-    """SURVEY §8f-4, the jellyfish step: hga_count_kmers against exact counting in numpy (canonical k-mers, count >= 2, ascending;
-    windows with a non-ACGT byte skipped, lowercase accepted)"""
-    import hga_b200
-    from test_sdk_selection_cpu import exact_counts
-    rng = np.random.default_rng(k)
-    g = datagen.random_genome(4000, 100 + k)
-    reads = [datagen.to_ascii(r) for r in datagen.sample_reads(g, 300, 180, 200 + k, error_rate=0.01)]
-    reads[3] = reads[3][:40] + "N" + reads[3][41:]                 # a window breaker
-    reads[5] = reads[5].lower()                                    # jellyfish counts lowercase bases
-    reads[7] = reads[7][:k - 1]                                    # shorter than k
-    reads[9] = ""
-    seq = "".join(reads).encode()
-    off = np.zeros(len(reads) + 1, dtype=np.uint64)
-    np.cumsum([len(r) for r in reads], out=off[1:])
-    km, ct = hga_b200.capi.count_kmers(seq, off, k, min_count=2)
-    wk, wc = exact_counts(seq, off, k, 2)
-    assert np.array_equal(km, wk) and np.array_equal(ct, wc) and len(km) > 100
-    km1, ct1 = hga_b200.capi.count_kmers(seq, off, k, min_count=1)
-    wk1, wc1 = exact_counts(seq, off, k, 1)
-    assert np.array_equal(km1, wk1) and np.array_equal(ct1, wc1) and int(ct1.sum()) == int(wc1.sum())
-    # the multi-chunk path (partial runs of several chunks merged by sort + reduce-by-key), forced with a tiny chunk
-    os.environ["HGA_COUNT_CHUNK"] = "4096"
-    try:
-        km2, ct2 = hga_b200.capi.count_kmers(seq, off, k, min_count=2)
-    finally:
-        del os.environ["HGA_COUNT_CHUNK"]
-    assert np.array_equal(km2, wk) and np.array_equal(ct2, wc)
-
-
-def test_cli_jf_occurrences_exports_the_kmers_file(oracle, tmp_path):
-    """jf_occurrences (the --kmers producer): per-file GPU counts -> merge -> specificity table -> export of a count range, against
-    exact numpy counts pushed through the host functions the reference's reader pins (tests/test_sdk_selection_cpu.py)"""
-    import hga_b200
-    from test_sdk_selection_cpu import exact_counts
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hybrid-genome-assembler_b200", "jf_occurrences")
-    k = 15
-    paths, _ = datagen.make_diploid_case(str(tmp_path), genome_size=6000, divergence=0.03, k=k, read_len=300, coverage=8, seed=6, error_rate=0.01)
-    per_file = []
-    for p in paths:
-        rc, reads = oracle.load_reads([p])
-        per_file.append(exact_counts(reads["seq"], reads["seq_off"], k))
-    km, total, largest, files = hga_b200.capi.sdk_merge(per_file)
-    out = str(tmp_path / "sdk.txt")
-    r = subprocess.run([exe] + paths + ["-k", str(k), "-o", out], input="3 12 1.0\n", capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    sel, n_sel, n_disc = hga_b200.capi.sdk_select(total, files, 3, 12)
-    assert [l.strip() for l in open(out) if l.strip()] == [datagen.kmer_to_str(v, k) for v in km[sel]] and n_sel > 0
-    assert f"{n_disc} out of {n_sel} exported kmers are discriminative" in r.stdout
-    t, o, u = hga_b200.capi.sdk_specificity(total, largest)
-    table = [tuple(l.split()) for l in r.stdout.splitlines() if len(l.split()) == 3 and l[0].isdigit()]
-    assert [(float(a), int(b), int(c)) for a, b, c in table] == [(round(float(a), 2), int(b), int(c)) for a, b, c in zip(t, o, u)]
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
