@@ -378,7 +378,7 @@ static std::vector<uint64_t> g_core_koff;
 static hga_index g_purged;
 extern "C" int emu_enrich(uint64_t n_reads, uint64_t n_kmers, const uint64_t *row_off, const uint32_t *kid, const uint32_t *pos, const uint64_t *inv_off,
                           const uint32_t *inv_read, uint64_t M, const uint32_t *sel_x, const uint32_t *sel_y, const uint32_t *sel_score, const uint64_t *read_off,
-                          int min_size, uint32_t min_score, uint32_t amp, int dims, int with_tail) {
+                          int min_size, uint32_t min_score, uint32_t amp, int dims, int with_tail, int max_size) {
     delete g_h;
     hga_handle *h = g_h = new hga_handle();
     std::memset(&h->metrics, 0, sizeof h->metrics);
@@ -392,7 +392,7 @@ extern "C" int emu_enrich(uint64_t n_reads, uint64_t n_kmers, const uint64_t *ro
     for (uint64_t i = 0; i < M; i++) { h->d_sel_key.as<uint64_t>()[i] = ((uint64_t) (sel_x[i] - 1) << 32) | (sel_y[i] - 1); h->d_sel_score.as<uint32_t>()[i] = sel_score[i]; }
     h->n_selected = M;
     TailParams tail{read_off, amp, dims};
-    const int rc = hga_enrich_run(h, min_size, -1, min_score, with_tail ? &tail : nullptr);
+    const int rc = hga_enrich_run(h, min_size, max_size, min_score, with_tail ? &tail : nullptr);
     if (rc != HGA_OK) return rc;
     // what hga_get_core_kmers / hga_get_purged_index return (slot == kmer_id here)
     const uint64_t C = h->enrich.core_id.size();
@@ -454,7 +454,7 @@ def host_enrich(tmp_path_factory):
     return lib
 
 
-def _emu_run(lib, oracle, c, with_tail):
+def _emu_run(lib, oracle, c, with_tail, max_size=-1):
     res = oracle.run(c["bases"], c["seq_off"], c["k"], c["kmers"], fraction=c["fraction"], min_size=c["min_size"])
     n = len(c["seq_off"]) - 1
     ro = res["row_off"].astype(np.int64)
@@ -470,7 +470,7 @@ def _emu_run(lib, oracle, c, with_tail):
     row_off = np.ascontiguousarray(res["row_off"], dtype=np.uint64); inv_off = np.ascontiguousarray(res["inv_off"], dtype=np.uint64)
     inv_read = np.ascontiguousarray(res["inv_read"], dtype=np.uint32); read_off = np.ascontiguousarray(c["seq_off"], dtype=np.uint64)
     rc = lib.emu_enrich(C.c_uint64(n), C.c_uint64(len(c["kmers"])), _p(row_off), _p(kid), _p(pos), _p(inv_off), _p(inv_read), C.c_uint64(len(key)), _p(sel_x), _p(sel_y),
-                        _p(sel_s), _p(read_off), c["min_size"], C.c_uint32(c["enrich"]), C.c_uint32(40), 16, int(with_tail))
+                        _p(sel_s), _p(read_off), c["min_size"], C.c_uint32(c["enrich"]), C.c_uint32(40), 16, int(with_tail), int(max_size))
     assert rc == 0, lib.emu_last_error()
     out = _EmuOut()
     lib.emu_out(C.byref(out))
@@ -538,5 +538,24 @@ def test_enrich_full_on_host_live_against_the_reference(host_enrich, oracle, ref
     kmers, k = oracle.load_kmers(kp)
     c = dict(bases=reads["seq"], seq_off=reads["seq_off"], k=k, kmers=kmers, fraction=0.15, min_size=ms, enrich=20)
     e, t = _emu_run(host_enrich, oracle, c, with_tail=True)
+    assert np.array_equal(t["conn_x"], ref["tconn_x"]) and np.array_equal(t["conn_y"], ref["tconn_y"]) and np.array_equal(t["conn_score"], ref["tconn_score"])
+    compare.check_enrichment(ref, e, kmers)
+
+
+def test_enrich_full_on_host_with_a_size_limit(host_enrich, oracle, ref_driver, tmp_path):
+    """--sc_max_size together with the tail / spectral block: the scaffold components and their spanning forest come from the sequential
+    replay of ALL selected edges under the size limit (:457), more and smaller components reach the block"""
+    import compare
+    import refdump
+    kw, ms = LIVE_CASES["long_k21"]
+    paths, kp = datagen.make_diploid_case(str(tmp_path), **kw)
+    ref = refdump.run_ref(ref_driver, paths, kp, enrich=20, full=True, min_size=ms, max_size=40)
+    free = refdump.run_ref(ref_driver, paths, kp, enrich=20, full=True, min_size=ms, dump=False)
+    assert ref["scaffold_components"] > free["scaffold_components"] > 2
+    rc, reads = oracle.load_reads(paths)
+    kmers, k = oracle.load_kmers(kp)
+    c = dict(bases=reads["seq"], seq_off=reads["seq_off"], k=k, kmers=kmers, fraction=0.15, min_size=ms, enrich=20)
+    e, t = _emu_run(host_enrich, oracle, c, with_tail=True, max_size=40)
+    assert t["ran"] and t["n_scaffold_cores"] == ref["merged_scaffolds"]
     assert np.array_equal(t["conn_x"], ref["tconn_x"]) and np.array_equal(t["conn_y"], ref["tconn_y"]) and np.array_equal(t["conn_score"], ref["tconn_score"])
     compare.check_enrichment(ref, e, kmers)
