@@ -378,7 +378,7 @@ static std::vector<uint64_t> g_core_koff;
 static hga_index g_purged;
 extern "C" int emu_enrich(uint64_t n_reads, uint64_t n_kmers, const uint64_t *row_off, const uint32_t *kid, const uint32_t *pos, const uint64_t *inv_off,
                           const uint32_t *inv_read, uint64_t M, const uint32_t *sel_x, const uint32_t *sel_y, const uint32_t *sel_score, const uint64_t *read_off,
-                          int min_size, uint32_t min_score, uint32_t amp, int dims, int with_tail, int max_size) {
+                          int min_size, uint32_t min_score, uint32_t amp, int dims, int with_tail, int max_size, const uint8_t *pivot_flag) {
     delete g_h;
     hga_handle *h = g_h = new hga_handle();
     std::memset(&h->metrics, 0, sizeof h->metrics);
@@ -391,6 +391,11 @@ extern "C" int emu_enrich(uint64_t n_reads, uint64_t n_kmers, const uint64_t *ro
     for (uint64_t i = 0; i < inv_off[n_kmers]; i++) h->d_inv_row.as<uint32_t>()[i] = inv_read[i] - 1;
     for (uint64_t i = 0; i < M; i++) { h->d_sel_key.as<uint64_t>()[i] = ((uint64_t) (sel_x[i] - 1) << 32) | (sel_y[i] - 1); h->d_sel_score.as<uint32_t>()[i] = sel_score[i]; }
     h->n_selected = M;
+    if (pivot_flag) {                                            // --sc_score: the pairs come from a pivot subset
+        if (h->d_pivot_flag.ensure(n_reads + 1)) return -1;
+        std::memcpy(h->d_pivot_flag.p, pivot_flag, n_reads);
+        h->pair_subset = true;
+    }
     TailParams tail{read_off, amp, dims};
     const int rc = hga_enrich_run(h, min_size, max_size, min_score, with_tail ? &tail : nullptr);
     if (rc != HGA_OK) return rc;
@@ -454,8 +459,8 @@ def host_enrich(tmp_path_factory):
     return lib
 
 
-def _emu_run(lib, oracle, c, with_tail, max_size=-1):
-    res = oracle.run(c["bases"], c["seq_off"], c["k"], c["kmers"], fraction=c["fraction"], min_size=c["min_size"])
+def _emu_run(lib, oracle, c, with_tail, max_size=-1, sc_score=0):
+    res = oracle.run(c["bases"], c["seq_off"], c["k"], c["kmers"], fraction=c["fraction"], min_size=c["min_size"], sc_score=sc_score)
     n = len(c["seq_off"]) - 1
     ro = res["row_off"].astype(np.int64)
     rows = np.repeat(np.arange(n), np.diff(ro))
@@ -469,8 +474,11 @@ def _emu_run(lib, oracle, c, with_tail, max_size=-1):
     sel_s = np.ascontiguousarray(ss[:m][first], dtype=np.uint32)
     row_off = np.ascontiguousarray(res["row_off"], dtype=np.uint64); inv_off = np.ascontiguousarray(res["inv_off"], dtype=np.uint64)
     inv_read = np.ascontiguousarray(res["inv_read"], dtype=np.uint32); read_off = np.ascontiguousarray(c["seq_off"], dtype=np.uint64)
+    pivot = None
+    if sc_score:
+        pivot = np.ascontiguousarray(np.diff(res["row_off"].astype(np.int64)) >= sc_score, dtype=np.uint8)
     rc = lib.emu_enrich(C.c_uint64(n), C.c_uint64(len(c["kmers"])), _p(row_off), _p(kid), _p(pos), _p(inv_off), _p(inv_read), C.c_uint64(len(key)), _p(sel_x), _p(sel_y),
-                        _p(sel_s), _p(read_off), c["min_size"], C.c_uint32(c["enrich"]), C.c_uint32(40), 16, int(with_tail), int(max_size))
+                        _p(sel_s), _p(read_off), c["min_size"], C.c_uint32(c["enrich"]), C.c_uint32(40), 16, int(with_tail), int(max_size), _p(pivot) if pivot is not None else None)
     assert rc == 0, lib.emu_last_error()
     out = _EmuOut()
     lib.emu_out(C.byref(out))
@@ -556,6 +564,23 @@ def test_enrich_full_on_host_with_a_size_limit(host_enrich, oracle, ref_driver, 
     kmers, k = oracle.load_kmers(kp)
     c = dict(bases=reads["seq"], seq_off=reads["seq_off"], k=k, kmers=kmers, fraction=0.15, min_size=ms, enrich=20)
     e, t = _emu_run(host_enrich, oracle, c, with_tail=True, max_size=40)
+    assert t["ran"] and t["n_scaffold_cores"] == ref["merged_scaffolds"]
+    assert np.array_equal(t["conn_x"], ref["tconn_x"]) and np.array_equal(t["conn_y"], ref["tconn_y"]) and np.array_equal(t["conn_score"], ref["tconn_score"])
+    compare.check_enrichment(ref, e, kmers)
+
+
+def test_enrich_full_on_host_with_sc_score(host_enrich, oracle, ref_driver, tmp_path):
+    """--sc_score S together with the block: connections from a pivot subset, kept when score > S (:749-752)"""
+    import compare
+    import refdump
+    kw, ms = LIVE_CASES["long_k21"]
+    paths, kp = datagen.make_diploid_case(str(tmp_path), **kw)
+    ref = refdump.run_ref(ref_driver, paths, kp, enrich=20, full=True, min_size=ms, sc_score=350)
+    assert ref["scaffold_components"] > 2
+    rc, reads = oracle.load_reads(paths)
+    kmers, k = oracle.load_kmers(kp)
+    c = dict(bases=reads["seq"], seq_off=reads["seq_off"], k=k, kmers=kmers, fraction=0.15, min_size=ms, enrich=20)
+    e, t = _emu_run(host_enrich, oracle, c, with_tail=True, sc_score=350)
     assert t["ran"] and t["n_scaffold_cores"] == ref["merged_scaffolds"]
     assert np.array_equal(t["conn_x"], ref["tconn_x"]) and np.array_equal(t["conn_y"], ref["tconn_y"]) and np.array_equal(t["conn_score"], ref["tconn_score"])
     compare.check_enrichment(ref, e, kmers)
