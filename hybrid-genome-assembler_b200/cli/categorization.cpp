@@ -9,12 +9,12 @@
 // with the merge of the scaffold components and the core enrichment (hga_enrich; run_clustering :764, :785-794) and exports
 // the final components under the surviving component ids, like the reference. The tail / spectral block in between
 // (:768-777, SURVEY.md §8f-2: spanning-tree tails, tail amplification, spectral clustering of the scaffold components, merge of
-// the clusters) runs with --tail-block (hga_enrich_full; opt-in until it has been through a GPU parity run); without it, with
-// more than two scaffold components, the run says so on stderr and goes on the way the reference does when it finds no strong
-// tail connection (:771), i.e. every scaffold component becomes a core. --spectral (:739-746) takes get_all_connections(5) from
+// the clusters) is part of the run, as in the reference (hga_enrich_full); --no-tail-block leaves it out: with more than two
+// scaffold components the run then says so on stderr and goes on the way the reference does when it finds no strong tail
+// connection (:771), i.e. every scaffold component becomes a core. --spectral (:739-746) takes get_all_connections(5) from
 // the GPU and runs the reference's host-side spectral clustering of the whole data set (hga_spectral_clustering).
 //
-// Extra switches: --tail-block (above), --scaffolds-only (stop after union_find and export the scaffold components), --load-only (load the k-mers and
+// Extra switches: --no-tail-block (above; --tail-block is accepted and is the default), --scaffolds-only (stop after union_find and export the scaffold components), --load-only (load the k-mers and
 // the reads, print the meta data and the load time, no GPU), --export-test (writer self-test, no GPU), --parse-only (print the
 // record stream and meta data, no GPU), --dump-kmers (print the canonical k-mer values of the --kmers file, no GPU), --device N.
 #include <chrono>
@@ -84,14 +84,14 @@ int main(int argc, char **argv) {
     std::vector<std::string> read_paths;
     std::string kmer_path, output_folder_path;
     Config config;
-    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false, export_test = false, tail_block = false;
+    bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false, export_test = false, tail_block = true;
     int device = 0;
 
     // boost::program_options' default style (read_clustering.cpp:60-66): --name=value and --name value, -k value and -kvalue,
     // and unambiguous prefixes of long names (--kmer for --kmers)
     static const char *long_names[] = {"--help", "--read_paths", "--kmers", "--output", "--sc_max_size", "--sc_min_size", "--sc_fraction", "--sc_score",
                                        "--tail_amplification", "--core_enrichment", "--spectral_dims", "--spectral", "--debug", "--threads",
-                                       "--parse-only", "--dump-kmers", "--scaffolds-only", "--load-only", "--export-test", "--device", "--tail-block"};
+                                       "--parse-only", "--dump-kmers", "--scaffolds-only", "--load-only", "--export-test", "--device", "--tail-block", "--no-tail-block"};
     std::vector<std::string> args;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -144,6 +144,7 @@ int main(int argc, char **argv) {
         else if (a == "--export-test") export_test = true;
         else if (a == "--device") device = std::atoi(need(i));
         else if (a == "--tail-block") tail_block = true;
+        else if (a == "--no-tail-block") tail_block = false;
         else if (a.size() > 1 && a[0] == '-') throw std::invalid_argument("unrecognised option '" + a + "'");
         else read_paths.push_back(a);
     }
@@ -303,8 +304,8 @@ int main(int argc, char **argv) {
     } else {
         if (!tail_block && (comp.n_components > 2 || config.scaffold_component_max_size != -1))
             std::cerr << "categorization: " << comp.n_components << " scaffold components; the tail / spectral merge of scaffold components "
-                         "(ReadClusteringEngine.cpp:768-777) runs with --tail-block only (hga_enrich_full; opt-in until it has been through the GPU "
-                         "parity run): without it every scaffold component becomes a core, as in the reference when it finds no strong tail connection\n";
+                         "(ReadClusteringEngine.cpp:768-777) is left out (--no-tail-block): every scaffold component becomes a core, as in the reference "
+                         "when it finds no strong tail connection\n";
         hga_enrichment_t fin;
         {
             // the reference times these separately ("Merging of initial components", "Calculation of enrichment connections",

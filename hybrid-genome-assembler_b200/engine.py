@@ -282,10 +282,10 @@ class ReadClusteringEngine:
 
 
     # run_clustering(discriminative_kmers, k) — .cpp:699-802. Returns the final component ids; their members are in
-    # self.final_components (id -> ascending read ids). tail_block=True runs the tail / spectral merge of scaffold components
-    # (:768-777, hga_enrich_full); without it every scaffold component becomes a core, which is the reference's own path when it
+    # self.final_components (id -> ascending read ids). The tail / spectral merge of scaffold components (:768-777) is part of the
+    # run (hga_enrich_full); with tail_block=False every scaffold component becomes a core, which is the reference's own path when it
     # finds no strong tail connection.
-    def run_clustering(self, discriminative_kmers, k, tail_block=False):
+    def run_clustering(self, discriminative_kmers, k, tail_block=True):
         cfg = self.config
         self.construct_indices(discriminative_kmers, k)
         if cfg.force_spectral:

@@ -96,7 +96,7 @@ def main():
             rout = os.path.join(d, "ref")
             os.makedirs(rout)
             t0 = time.perf_counter()
-            subprocess.run([DRIVER, "run", "--kmers", kp, "--out", rout, "--threads", str(os.cpu_count() or 1), "--enrich", "20"] + paths, check=True,
+            subprocess.run([DRIVER, "run", "--kmers", kp, "--out", rout, "--threads", str(os.cpu_count() or 1), "--enrich", "20", "--full"] + paths, check=True,
                            stdout=subprocess.DEVNULL)
             res["reference_wall_s"] = time.perf_counter() - t0
             res["reference_threads"] = os.cpu_count() or 1

@@ -119,12 +119,13 @@ def test_cli_end_to_end_components(exe, oracle, tmp_path):
 
 @pytest.mark.gpu
 def test_cli_end_to_end_final_components(exe, oracle, tmp_path):
-    """default run: scaffold components -> merge -> enrichment -> export under the surviving component ids"""
+    """run without the tail / spectral block (--no-tail-block): scaffold components -> merge -> enrichment -> export under the surviving
+    component ids; the default run, block included, is tests/test_zy_gpu_tail_block.py"""
     import oracle_lib
     paths, kp = datagen.make_diploid_case(str(tmp_path / "c"), genome_size=20000, divergence=0.03, k=19, read_len=150, coverage=30, seed=9,
                                           error_rate=0.005, fmt="fastq")
     outdir = str(tmp_path / "out")
-    r = subprocess.run([exe] + paths + ["--kmers", kp, "-o", outdir], capture_output=True, text=True)
+    r = subprocess.run([exe] + paths + ["--kmers", kp, "-o", outdir, "--no-tail-block"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "Merging of initial components" in r.stdout and "Union-find took" in r.stdout
     rc, reads = oracle.load_reads(paths)

@@ -113,7 +113,7 @@ def test_engine_mirror_run_clustering(tmp_path):
 
     eng = hga_b200.ReadClusteringEngine(_Reader(), hga_b200.ReadClusteringConfig(scaffold_component_min_size=c["min_size"],
                                                                                  enrichment_connections_min_score=c["enrich"]))
-    ids = eng.run_clustering(c["kmers"], c["k"])
+    ids = eng.run_clustering(c["kmers"], c["k"], tail_block=False)          # the fixture is a ref_driver --enrich dump (no tail / spectral block)
     assert ids == [int(v) for v in ref["final_id"]]
     fo = ref["final_off"].astype(np.int64)
     for i, fid in enumerate(ids):

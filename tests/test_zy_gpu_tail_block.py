@@ -92,7 +92,7 @@ def test_engine_mirror_run_clustering_with_tail_block():
 
     eng = hga_b200.ReadClusteringEngine(_Reader(), hga_b200.ReadClusteringConfig(scaffold_component_min_size=c["min_size"],
                                                                                  enrichment_connections_min_score=c["enrich"]))
-    ids = eng.run_clustering(c["kmers"], c["k"], tail_block=True)
+    ids = eng.run_clustering(c["kmers"], c["k"])
     assert ids == [int(v) for v in ref["final_id"]]
     fo = ref["final_off"].astype(np.int64)
     for i, fid in enumerate(ids):
@@ -101,7 +101,7 @@ def test_engine_mirror_run_clustering_with_tail_block():
 
 
 def test_cli_tail_block_exports_the_reference_final_components(tmp_path):
-    """categorization --tail-block: files named after the reference's surviving component ids, holding the reference's reads"""
+    """categorization, default run (tail / spectral block included): files named after the reference's surviving component ids, holding the reference's reads"""
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hybrid-genome-assembler_b200", "categorization")
     c = golden_util.load_case("full_long")
     ref = c["ref"]
@@ -113,7 +113,7 @@ def test_cli_tail_block_exports_the_reference_final_components(tmp_path):
     with open(kp, "w") as f:
         for v in c["kmers"]:
             f.write(datagen.kmer_to_str(v, c["k"]) + "\n")
-    r = subprocess.run([exe, rp, "--kmers", kp, "-o", outdir, "--sc_min_size", str(c["min_size"]), "--tail-block"], capture_output=True, text=True)
+    r = subprocess.run([exe, rp, "--kmers", kp, "-o", outdir, "--sc_min_size", str(c["min_size"])], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     fo = ref["final_off"].astype(np.int64)
     want = {f"#{int(fid)}.fa": [f"r{int(v)}" for v in ref["final_read"][fo[i]:fo[i + 1]]] for i, fid in enumerate(ref["final_id"])}
