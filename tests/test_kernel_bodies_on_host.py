@@ -407,6 +407,18 @@ extern "C" int emu_enrich(uint64_t n_reads, uint64_t n_kmers, const uint64_t *ro
     for (uint64_t c = 0; c <= C; c++) g_core_koff[c] = h->d_enr_core_koff.as<unsigned long long>()[c];
     return hga_export_index(h, h->d_purged_off.as<uint32_t>(), h->d_purged_row.as<uint32_t>(), h->n_purged, &g_purged);
 }
+extern "C" int emu_rerun(const uint64_t *read_off, int min_size, uint32_t min_score, uint32_t amp, int dims, int with_tail) {
+    hga_handle *h = g_h;                                         // the SAME handle again (buffers, swapped purged arrays and all)
+    TailParams tail{read_off, amp, dims};
+    const int rc = hga_enrich_run(h, min_size, -1, min_score, with_tail ? &tail : nullptr);
+    if (rc != HGA_OK) return rc;
+    const uint64_t C = h->enrich.core_id.size();
+    g_core_kmer.assign(h->n_core_kmers + 1, 0);
+    for (uint64_t i = 0; i < h->n_core_kmers; i++) g_core_kmer[i] = (uint32_t) h->d_enr_keys.as<uint64_t>()[i];
+    g_core_koff.assign(C + 1, 0);
+    for (uint64_t c = 0; c <= C; c++) g_core_koff[c] = h->d_enr_core_koff.as<unsigned long long>()[c];
+    return hga_export_index(h, h->d_purged_off.as<uint32_t>(), h->d_purged_row.as<uint32_t>(), h->n_purged, &g_purged);
+}
 struct EmuOut {
     uint64_t n_cores; const uint32_t *core_id; const uint64_t *core_off; const uint32_t *core_read; const uint64_t *core_koff; const uint32_t *core_kmer;
     uint64_t n_conn; const uint32_t *cx, *cy, *cs; uint64_t n_final; const uint32_t *final_id; const uint64_t *final_off; const uint32_t *final_read;
@@ -480,6 +492,10 @@ def _emu_run(lib, oracle, c, with_tail, max_size=-1, sc_score=0):
     rc = lib.emu_enrich(C.c_uint64(n), C.c_uint64(len(c["kmers"])), _p(row_off), _p(kid), _p(pos), _p(inv_off), _p(inv_read), C.c_uint64(len(key)), _p(sel_x), _p(sel_y),
                         _p(sel_s), _p(read_off), c["min_size"], C.c_uint32(c["enrich"]), C.c_uint32(40), 16, int(with_tail), int(max_size), _p(pivot) if pivot is not None else None)
     assert rc == 0, lib.emu_last_error()
+    return _emu_collect(lib)
+
+
+def _emu_collect(lib):
     out = _EmuOut()
     lib.emu_out(C.byref(out))
 
@@ -584,3 +600,20 @@ def test_enrich_full_on_host_with_sc_score(host_enrich, oracle, ref_driver, tmp_
     assert t["ran"] and t["n_scaffold_cores"] == ref["merged_scaffolds"]
     assert np.array_equal(t["conn_x"], ref["tconn_x"]) and np.array_equal(t["conn_y"], ref["tconn_y"]) and np.array_equal(t["conn_score"], ref["tconn_score"])
     compare.check_enrichment(ref, e, kmers)
+
+
+def test_enrich_on_host_same_handle_again(host_enrich, oracle):
+    """full -> plain -> full on ONE handle: the buffers a run leaves behind (the swapped purged arrays, the survivor table with its
+    second half, the relabelled unions) do not leak into the next run"""
+    import compare
+    import golden_util
+    c = golden_util.load_case("full_long")
+    e1, t1 = _emu_run(host_enrich, oracle, c, with_tail=True)
+    read_off = np.ascontiguousarray(c["seq_off"], dtype=np.uint64)
+    assert host_enrich.emu_rerun(_p(read_off), c["min_size"], C.c_uint32(c["enrich"]), C.c_uint32(40), 16, 0) == 0, host_enrich.emu_last_error()
+    e2, t2 = _emu_collect(host_enrich)
+    assert not t2["ran"] and len(e2["core_id"]) == c["ref"]["merged_scaffolds"] > len(e1["core_id"])
+    assert host_enrich.emu_rerun(_p(read_off), c["min_size"], C.c_uint32(c["enrich"]), C.c_uint32(40), 16, 1) == 0, host_enrich.emu_last_error()
+    e3, t3 = _emu_collect(host_enrich)
+    compare.check_enrichment(c["ref"], e3, c["kmers"])
+    assert t3["ran"] and all(np.array_equal(a, b) for a, b in zip(t1["clusters"], t3["clusters"]))
