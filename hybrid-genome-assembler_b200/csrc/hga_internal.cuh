@@ -80,37 +80,39 @@ struct PinBuf {
 // ------------------------------------------------------------------------------------------------
 // k-mer membership structures (device)
 //
-// Every canonical k-mer gets a 32-bit LOCALITY hash B that is shared by most consecutive windows of a read:
-// B = rehash of the minimum, over the W central m-mers of the k-mer, of the hashed canonical m-mer (a strand-
-// symmetric minimizer). Runs of ~(W + 1) / 2 consecutive windows share B, so their probes fall into the same
-// 32 B sector / 128 B bucket and coalesce inside a warp. m is chosen from the size of the set: the number of
-// distinct m-mers (4^m / 2) must be well above the number of keys, otherwise unrelated loci share a minimizer
-// VALUE and pile into the same block (4^m / 2 >= 3 n), and W = k - m + 1 <= HGA_MIN_W. m <= 16 so that m-mers
-// fit 32 bits. For k < HGA_MIN_K_FOR_MIN there is no room for minimizers and B is a plain hash of the k-mer.
+// Everything the scan computes per window is STRAND SYMMETRIC and needs neither the canonical k-mer value nor a 64-bit
+// compare: with F the forward k-mer and R its reverse complement,
+//   bit hash   hb(x) = g(F) + g(R),  g(v) = (hi(v) * ca + lo(v)) * cb   (ca / cb shift the bits above the k-mer out, so the scan
+//              feeds raw 32-bit pieces of its packed streams)
+//   minimizer  Mc(x) = min over ALL m-mers of the k-mer of min(h(m-mer), h(revcomp m-mer)),  h(y) = y * cm + C4
+// Runs of ~(W + 1) / 2 consecutive windows of a read share Mc (W = k - m + 1 m-mers per window), so their filter probes fall into
+// the same 32 B block and coalesce inside a warp, and their keys share a 128 B bucket. m is chosen from the size of the set
+// (4^m / 2 >= 3 n: unrelated loci must not share a minimizer VALUE) with W <= HGA_MIN_W; when k leaves no room for that
+// (k < HGA_MIN_K_FOR_MIN, or k - 16 + 1 > HGA_MIN_W) a mix of hb takes Mc's place (no locality, still correct).
 //
-//   filter    : blocked Bloom filter; block = 32 B (8 words) selected by B, word + 2 bits inside the block
-//               selected by an independent hash of the k-mer. Sized to stay L2-resident; consulted first so
-//               that a non-member costs one 4 B probe that its neighbours share.
-//   key table : buckets of 16 x u64 keys (one 128 B line) selected by B, load factor 1/3; a lookup reads the whole home
-//               bucket in one round trip (eight independent 16 B loads). Keys that find no room in their chain of
-//               chain_buckets buckets (default 1: the home bucket only; 3 % of the keys of config 4) go to a plain
-//               open-addressing overflow table hashed by k-mer, which only lookups that meet a FULL bucket consult. The internal k-mer id ("slot") is the index of the key in the (main | overflow) key
-//               array; slot_kid maps it back to the caller's kmer_id.
+//   filter    : blocked Bloom filter over the canonical keys; block = 32 B (8 words) selected by Mc, word + 2 bits inside the
+//               block selected by hb. Sized to stay L2 resident: measured on B200 (profiles/r2c), a filter of <= 48 MB is served
+//               from L2 while 10 Gbases stream through, 64 MB is not (26.9 -> 37.6 -> 59.2 ms at 48 / 64 / 96 MB).
+//   key table : canonical keys, u64, buckets of 32 (256 B) selected by Mc. Inside the bucket a key starts at the 32 B SECTOR
+//               picked by hb and goes round the bucket's eight sectors; a lookup reads one sector per step (one 256-bit load)
+//               and stops at a match or at a sector with an empty slot: 95 % of the lookups end in the first step (load 1/3).
+//               Keys that find their bucket full (0.3 %) go to a plain open-addressing overflow region hashed by k-mer,
+//               consulted only after eight full sectors. The internal k-mer id ("slot") is the index of the key in the
+//               (main | overflow) array; slot_kid maps it to the caller's id.
 // ------------------------------------------------------------------------------------------------
 #define HGA_MIN_W 8
 #define HGA_MIN_K_FOR_MIN 12
-#define HGA_BUCKET_SLOTS 16      // one 128 B line of u64 keys
-#define HGA_CHAIN_BUCKETS 4      // a key lives within this many buckets of its home bucket, else in the overflow region
-#define HGA_CHAIN_SLOTS (HGA_BUCKET_SLOTS * HGA_CHAIN_BUCKETS)
+#define HGA_BUCKET_SLOTS 32      // two 128 B lines of u64 keys
+#define HGA_SECTOR_SLOTS 4       // one 32 B sector
 
 struct KmerGeom {
     int k = 0;
-    int use_min = 0;      // 1: B from the minimizer, 0: B from the k-mer hash
+    int use_min = 0;      // 1: locality from the minimizer, 0: from the bit hash
     int m = 0;            // m-mer length (<= 16)
-    int W = 0;            // m-mers the minimum is taken over (2 .. HGA_MIN_W)
-    int skip = 0;         // m-mers skipped at each end of the window (> 0 only when k - m + 1 > HGA_MIN_W)
-    uint32_t mmask = 0;   // 2m low bits
-    int rc_shift = 0;     // 2 (k - m): the reverse-complement k-mer's first m-mer
+    int W = 0;            // m-mers per window = k - m + 1 (2 .. HGA_MIN_W)
+    uint32_t cm = 0;      // HGA_C1 << (32 - 2m)
+    uint32_t mtop = 0;    // the top 2m bits of a word
+    uint32_t ca = 0, cb = 0;   // g(v) = (hi * ca + lo) * cb
 };
 
 struct KmerTable {
@@ -118,13 +120,13 @@ struct KmerTable {
     uint32_t *slot_kid = nullptr;   // n_slots
     uint32_t *kid_slot = nullptr;   // n_kmers
     uint32_t *filter = nullptr;     // n_blocks * 8 words
-    uint32_t n_buckets = 0;         // main region: (n_buckets + HGA_CHAIN_BUCKETS) * HGA_BUCKET_SLOTS slots
+    uint32_t n_buckets = 0;         // main region: n_buckets * HGA_BUCKET_SLOTS slots
     uint32_t n_main = 0;            // slots in the main region
     uint32_t n_over = 0;            // slots in the overflow region (0: none; else a power of two)
     uint32_t n_blocks = 0;
     uint32_t n_slots = 0;           // n_main + n_over
     uint32_t slot_bits = 0;         // ceil(log2(n_slots))
-    uint32_t chain_buckets = 1;     // buckets a key may live in (home bucket first, at most HGA_CHAIN_BUCKETS); experiment switch HGA_CHAIN_BUCKETS
+    int sector_by_min = 0;          // hga_start_sector
     KmerGeom geom;
 };
 
@@ -137,44 +139,19 @@ struct KmerTable {
 static inline KmerGeom hga_make_geom(int k, uint64_t n_kmers) {
     KmerGeom g;
     g.k = k;
-    if (k < HGA_MIN_K_FOR_MIN) return g;
+    if (k > 16) { g.ca = HGA_C3 << (64 - 2 * k); g.cb = HGA_C1; }
+    else { g.ca = 0; g.cb = HGA_C1 << (32 - 2 * k); }
+    if (k < HGA_MIN_K_FOR_MIN || k - 16 + 1 > HGA_MIN_W) return g;
     g.use_min = 1;
     int m = 4;
     while (m < 16 && (1ull << (2 * m - 1)) < 3 * n_kmers) m++;      // 4^m / 2 >= 3 n
-    if (m < k - HGA_MIN_W + 1) m = k - HGA_MIN_W + 1;                // W <= HGA_MIN_W where k leaves room
+    if (m < k - HGA_MIN_W + 1) m = k - HGA_MIN_W + 1;                // W <= HGA_MIN_W
     if (m > 16) m = 16;
     if (m > k - 1) m = k - 1;                                         // W >= 2
-    int W = k - m + 1;
-    if (W > HGA_MIN_W) W = ((k - m + 1 - HGA_MIN_W) % 2 == 0) ? HGA_MIN_W : HGA_MIN_W - 1;   // centred: strand symmetric
-    g.m = m; g.W = W;
-    g.skip = (k - m + 1 - W) / 2;
-    g.mmask = (m == 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1);
-    g.rc_shift = 2 * (k - m);
+    g.m = m; g.W = k - m + 1;
+    g.cm = HGA_C1 << (32 - 2 * m);
+    g.mtop = m == 16 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (2 * m));
     return g;
-}
-
-// hash of the k-mer that picks the word and the two bits inside a filter block (independent of B)
-__host__ __device__ __forceinline__ uint32_t hga_bits_hash(uint64_t kmer) {
-    return ((uint32_t) kmer ^ ((uint32_t) (kmer >> 32) * HGA_C3)) * HGA_C1;
-}
-__host__ __device__ __forceinline__ uint32_t hga_bits_word(uint32_t h) { return h >> 29; }
-__host__ __device__ __forceinline__ uint32_t hga_bits_mask(uint32_t h) { return (1u << ((h >> 24) & 31)) | (1u << ((h >> 19) & 31)); }
-// Probe order of a key: the 4-slot SECTOR (32 B) of its home bucket picked by the k-mer hash, then the bucket's other three
-// sectors in cyclic order, then the next bucket the same way. A lookup therefore usually ends after ONE 32 B load.
-#define HGA_SECTOR_SLOTS 4
-__host__ __device__ __forceinline__ uint32_t hga_bits_sector(uint32_t h) { return (h >> 15) & (HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1); }
-// slot (relative to the home bucket) of the j-th probe, j = 0 .. HGA_CHAIN_SLOTS - 1
-__host__ __device__ __forceinline__ uint32_t hga_chain_slot(uint32_t sector, uint32_t j) {
-    const uint32_t in_bucket = j & (HGA_BUCKET_SLOTS - 1);
-    const uint32_t sec = (sector + in_bucket / HGA_SECTOR_SLOTS) & (HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1);
-    return (j & ~(uint32_t) (HGA_BUCKET_SLOTS - 1)) | (sec * HGA_SECTOR_SLOTS) | (in_bucket & (HGA_SECTOR_SLOTS - 1));
-}
-
-// plain k-mer hash: B for small k, and the overflow table's home position
-__host__ __device__ __forceinline__ uint32_t hga_plain_hash(uint64_t kmer) {
-    uint32_t h = (uint32_t) kmer * HGA_C2 + (uint32_t) (kmer >> 32) * HGA_C1;
-    h ^= h >> 16;
-    return h * HGA_C3;
 }
 
 __host__ __device__ __forceinline__ uint32_t hga_scale(uint32_t h, uint32_t n) {
@@ -185,40 +162,74 @@ __host__ __device__ __forceinline__ uint32_t hga_scale(uint32_t h, uint32_t n) {
 #endif
 }
 
-// reverse complement of an m-mer held in the low 2m bits (codes A0 C1 G2 T3)
-__host__ __device__ __forceinline__ uint32_t hga_revcomp32(uint32_t x, int m) {
+// reverse complement of a k-mer held in the low 2k bits (codes A0 C1 G2 T3)
+__host__ __device__ __forceinline__ uint64_t hga_revcomp64(uint64_t x, int k) {
 #ifdef __CUDA_ARCH__
-    x = __brev(x);
+    x = __brevll(x);
 #else
-    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
-    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
-    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
-    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
-    x = (x >> 16) | (x << 16);
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    x = (x >> 32) | (x << 32);
 #endif
-    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);   // bits reversed -> 2-bit groups reversed
-    return (~x) >> (32 - 2 * m);
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);   // bits reversed -> 2-bit groups reversed
+    return (~x) >> (64 - 2 * k);
 }
 
-__host__ __device__ __forceinline__ uint32_t hga_mmer_hash(uint32_t fwd_m, uint32_t rc_m) {
-    return (fwd_m < rc_m ? fwd_m : rc_m) * HGA_C1;
+// one strand's share of the bit hash: v = an oriented k-mer value
+__host__ __device__ __forceinline__ uint32_t hga_strand_hash(uint32_t hi, uint32_t lo, const KmerGeom &g) { return (hi * g.ca + lo) * g.cb; }
+// strand-symmetric hash of the k-mer x (either orientation): picks the word and the two bits inside a filter block and the
+// start sector inside a key bucket
+__host__ __device__ __forceinline__ uint32_t hga_bits_hash(uint64_t x, const KmerGeom &g) {
+    const uint64_t r = hga_revcomp64(x, g.k);
+    return hga_strand_hash((uint32_t) (x >> 32), (uint32_t) x, g) + hga_strand_hash((uint32_t) (r >> 32), (uint32_t) r, g);
 }
-// the minimum of 8 hashes is biased towards small values; the multiply carries its low bits up into the bits hga_scale uses
-__host__ __device__ __forceinline__ uint32_t hga_locality_from_min(uint32_t gmin) { return gmin * HGA_C2; }
+__host__ __device__ __forceinline__ uint32_t hga_bits_word(uint32_t h) { return h >> 29; }
+// the two bit positions inside the filter word come from the HIGH half of hb * C2: its low bits are well mixed, so a wrapping
+// shift takes a bit position straight from the register (three shifts and one 3-input AND, no mask is ever built)
+__host__ __device__ __forceinline__ uint32_t hga_bits_pos(uint32_t hb) { return hga_scale(hb, HGA_C2); }
+__host__ __device__ __forceinline__ uint32_t hga_bits_mask(uint32_t hb) { const uint32_t v = hga_bits_pos(hb); return (1u << (v & 31)) | (1u << ((v >> 5) & 31)); }
+#ifdef __CUDACC__
+__device__ __forceinline__ bool hga_bits_test(uint32_t word, uint32_t hb) {
+    const uint32_t v = hga_bits_pos(hb);
+    return (__funnelshift_r(word, 0u, v) & __funnelshift_r(word, 0u, v >> 5) & 1u) != 0;
+}
+#endif
+// start sector of a key inside its bucket: from the bit hash (keys spread evenly: 95 % of the lookups end in their first sector), or -
+// sector_by_min - from the minimizer (the keys of a run share a sector: fewer DRAM bursts per run of hits, more second steps)
+__host__ __device__ __forceinline__ uint32_t hga_start_sector(uint32_t B, uint32_t hb, int sector_by_min) {
+    return ((sector_by_min ? B >> 7 : hb >> 16)) & (HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1);
+}
+// when there is no minimizer: the locality value is a mix of the bit hash
+__host__ __device__ __forceinline__ uint32_t hga_mix_bits(uint32_t hb) { return (hb ^ (hb >> 15)) * HGA_C3; }
 
-// B computed from the k-mer VALUE alone (table build; scan windows that contain a non-ACGT byte, whose two
-// strands are not reverse complements of each other)
-__host__ __device__ __forceinline__ uint32_t hga_locality_hash(uint64_t kmer, const KmerGeom &g) {
-    if (!g.use_min) return hga_plain_hash(kmer);
-    uint32_t gmin = 0xFFFFFFFFu;
+// plain k-mer hash: the overflow region's home position
+__host__ __device__ __forceinline__ uint32_t hga_plain_hash(uint64_t kmer) {
+    uint32_t h = (uint32_t) kmer * HGA_C2 + (uint32_t) (kmer >> 32) * HGA_C1;
+    h ^= h >> 16;
+    return h * HGA_C3;
+}
+
+// hashed m-mer: x = any word whose LOW 2m bits are the m-mer (cm shifts the rest out)
+__host__ __device__ __forceinline__ uint32_t hga_mmer_hash(uint32_t x, uint32_t cm) { return x * cm + HGA_C4; }
+
+// Mc from the k-mer VALUE (table build; scan windows that contain a non-ACGT byte, whose two strands are not reverse
+// complements of each other). x and its reverse complement give the same result.
+__host__ __device__ __forceinline__ uint32_t hga_minimizer(uint64_t x, uint32_t hb, const KmerGeom &g) {
+    if (!g.use_min) return hga_mix_bits(hb);
+    const uint64_t r = hga_revcomp64(x, g.k);
+    uint32_t mn = 0xFFFFFFFFu;
     for (int o = 0; o < g.W; o++) {
-        const int sh = 2 * (g.k - g.m - g.skip - o);
-        const uint32_t fm = (uint32_t) (kmer >> sh) & g.mmask;
-        const uint32_t h = hga_mmer_hash(fm, hga_revcomp32(fm, g.m));
-        gmin = h < gmin ? h : gmin;
+        const uint32_t hf = hga_mmer_hash((uint32_t) (x >> (2 * o)), g.cm), hr = hga_mmer_hash((uint32_t) (r >> (2 * o)), g.cm);
+        const uint32_t h = hf < hr ? hf : hr;
+        mn = h < mn ? h : mn;
     }
-    return hga_locality_from_min(gmin);
+    return mn;
 }
+// the minimum of W hashes is biased towards small values; the multiply carries its low bits up into the bits hga_scale uses
+__host__ __device__ __forceinline__ uint32_t hga_locality_from_min(uint32_t mn) { return mn * HGA_C2; }
 
 // ------------------------------------------------------------------------------------------------
 // the handle

@@ -3,43 +3,43 @@
 // Replaces the per-read half of ReadClusteringEngine::construct_indices
 // (clustering/ReadClusteringEngine.cpp:246-277) and KmerIterator (common/KmerIterator.cpp:23-76).
 //
-// Work decomposition (B200: 148 SMs x 24 resident warps, every WARP is an independent worker):
-//   * the concatenated base stream is cut into tiles of SCAN_TILE (960) window-end positions; a warp takes a tile
-//     ticket, and nothing in the kernel synchronises two warps: no __syncthreads, no inter-tile waiting (a CTA-wide
-//     tile with barriers and an in-order look-back were both tried; barrier stalls were a third of all samples);
-//   * the warp loads the tile's ASCII bytes (+64 bases of halo = 1024 B) with two coalesced 16 B streaming loads per
-//     lane and packs them into TWO shared-memory streams: forward codes MSB-first and complement codes LSB-first.
-//     Bytes outside {A,C,G,T} are stored as code 0 in BOTH streams, which is exactly the reference's rule
-//     (KmerIterator.cpp:56,62: unordered_map::operator[] default-inserts 0 in both tables);
-//   * every window is EXTRACTED from the two streams with funnel shifts (no rolling dependency): the 32 lanes own
-//     32 consecutive windows per step, the bit offset inside the word is loop invariant, consecutive steps share a word;
-//   * membership probes are made LOCAL: the filter block / key bucket of a window is chosen by the window's
-//     minimizer (sliding minimum of hashed canonical m-mers, computed across lanes with shuffles), which several
-//     consecutive windows share, so a warp's 32 filter probes fall into a few sectors (hga_internal.cuh);
-//   * the per-window loop does nothing but extract, hash and test the filter. Windows that pass are queued (window
-//     index + locality hash) and their key bucket is prefetched into L2; everything else - validity against the read
-//     boundaries, the position inside the read, the key-bucket probe (the whole 128 B bucket in one round trip) -
-//     happens when the queue is drained, DENSE, 32 candidates per warp instruction, re-extracting the k-mer;
-//   * hits are staged in position order; a tile's hits are appended with ONE atomicAdd on a global cursor and a copy
-//     kernel moves the tile segments into stream order (exclusive scan over the tile counts). CSR row offsets are
-//     produced per tile and fixed up with the tile's final offset: no per-hit atomics anywhere;
-//   * windows that contain a non-ACGT byte (their two strands are not reverse complements, so the shared minimizer
-//     would not be the one the table was built with) skip the filter and recompute the locality hash from the k-mer
-//     value; tiles without such bytes never pay for the check.
+// Work decomposition (B200: 148 SMs x 24 resident warps, every WARP is an independent worker, nothing synchronises two warps):
+//   * the concatenated base stream is cut into tiles of SCAN_TILE (992) window-end positions; a warp takes a tile ticket (the
+//     next ticket is requested while the current tile is processed);
+//   * phase A: every lane loads ONE 32 B sector of ASCII bases with a single 256-bit load (LDG.256, sm_100) - 31 lanes hold
+//     the tile, lane 0 the 32 bases before it - and packs them into two words of forward codes (first base most significant)
+//     and two words of complement codes (first base least significant). Bytes outside {A,C,G,T} get code 0 in BOTH streams -
+//     the reference's rule (KmerIterator.cpp:56,62: unordered_map::operator[] default-inserts 0 in both tables) - and a bit in
+//     an exception bitmap (validity = one PRMT lookup of the expected byte per 4 bases); the previous lane's words come over
+//     with four shuffles;
+//   * phase B, lane-sequential: a lane owns 32 CONSECUTIVE window ends. With its 64 bases in registers every piece is a funnel
+//     shift with a compile-time register index: the forward and reverse strand's last 16 bases and the 16 before, the two
+//     hashed m-mers (one IMAD each: the multiplier shifts out everything above the m-mer), the sliding minimum over the last
+//     W symmetric hashes (VIMNMX3, two instructions, no shuffles) and the strand-symmetric bit hash g(F) + g(R). No canonical
+//     VALUE and no 64-bit compare is needed (hga_internal.cuh). (minimizer, bit hash) go to shared memory;
+//   * phase C, lane-parallel: the 32 lanes take 32 ADJACENT windows from shared memory (a transposition through an 8-byte-
+//     entry buffer with an odd row stride, conflict free both ways), so that the ~3.5 consecutive windows that share a
+//     minimizer hit the same 32 B filter block and a warp's 32 probes coalesce into ~9 sectors. Windows that pass are queued;
+//   * drain, dense, 32 candidates per warp instruction: validity against the read boundaries, the forward k-mer re-extracted
+//     from the packed words, its reverse complement, the canonical minimum (KmerIterator.cpp:69), and ONE 256-bit load of the
+//     key sector the bit hash points at (a warp-uniform loop goes round the bucket for the few that need more);
+//   * hits are staged in position order (in the already consumed part of the transposition buffer); a tile's hits are
+//     appended with ONE atomicAdd on a global cursor and a copy kernel moves the tile segments into stream order (exclusive
+//     scan over the tile counts). CSR row offsets are produced per tile and fixed up with the tile's final offset;
+//   * windows that contain a non-ACGT byte skip the filter; the drain rebuilds their reverse strand by the reference's rule and
+//     takes minimizer and bit hash from the k-mer value; tiles without such bytes never pay for the check.
 #include "hga_internal.cuh"
 
 #include <cub/device/device_scan.cuh>
 
-#define SCAN_WARPS 4
+#define SCAN_WARPS 8                             // 9.3 KB of shared memory per warp: 3 CTAs of 8 warps per SM
 #define SCAN_THREADS (SCAN_WARPS * 32)
-#define SCAN_TILE 960                            // window-end positions per warp tile
-#define SCAN_STEPS (SCAN_TILE / 32)              // 30
-#define SCAN_HALO 64
-#define SCAN_CHUNKS ((SCAN_TILE + SCAN_HALO) / 16)   // 64 chunks of 16 bases = 2 per lane
-#define SCAN_UNROLL 3
-#define SCAN_Q 128                               // candidate ring (power of two, >= 31 + 32 * SCAN_UNROLL)
-#define SCAN_EXC_WORDS ((SCAN_TILE + SCAN_HALO) / 32 + 2)
-#define SCAN_BND 64                              // read boundaries of a tile staged in shared memory (more: global search)
+#define SCAN_TILE 992                            // window-end positions per warp tile (31 lanes x 32)
+#define SCAN_SPAN 1024                           // staged bases per tile: 32 of halo + the tile
+#define SCAN_UNROLL 4
+#define SCAN_Q 256                               // candidate ring (power of two, >= 31 + 32 * SCAN_UNROLL)
+#define SCAN_BND 32                              // read boundaries of a tile staged in shared memory (more: global search)
+#define SCAN_TR_STRIDE 33                        // row stride of the transposition buffer in entries (odd: conflict free)
 
 struct ScanScalars {
     unsigned long long ticket;
@@ -52,7 +52,8 @@ struct ScanScalars {
 namespace {
 
 struct ScanParams {
-    const char *bases;
+    const char *frame;                // bases - lead: 32 B aligned
+    uint32_t lead;                    // bytes between the aligned frame and the first base
     uint64_t n_bases;
     const uint64_t *read_off;
     uint64_t n_reads;
@@ -67,26 +68,29 @@ struct ScanParams {
     uint64_t n_tiles;                 // tickets of this launch
     uint64_t tile_begin;              // first tile of this launch (chunked launches while the bases are still arriving)
     uint64_t tile_stride;             // > 0: sampling mode (count only, tile = tile_begin + ticket * stride)
-    int diag;                         // HGA_SCAN_DIAG timing experiments (results are WRONG when set): 1 = no key probes, 2 = no filter probes, 4 = no key-sector prefetch
+    int diag;                         // HGA_SCAN_DIAG experiments: 1 = no key probes (results are WRONG), 4 = L2 prefetch of the key sector when a window is queued
 };
 
-// 4 ASCII bytes (little-endian in w, lowest address = first base) -> forward codes (8 bits, first base most
-// significant) and complement codes (8 bits, first base LEAST significant). Codes follow KmerIterator.cpp:7-19
-// (A0 C1 G2 T3 / complement A3 C2 G1 T0); any other byte gives 0 in both. valid: 0xFF per ACGT byte.
-__device__ __forceinline__ void pack4(uint32_t w, uint32_t &fwd8, uint32_t &rc8, uint32_t &valid) {
-    valid = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) | __vcmpeq4(w, 0x54545454u);
+// shared memory of one warp
+struct WarpTile {
+    uint2 tr[SCAN_TR_STRIDE * 32];   // phase B -> C: x = locality hash, y = bit hash; afterwards: staged hits (x = slot, y = window index)
+    uint32_t pk[SCAN_SPAN / 16 + 4]; // packed forward codes, 16 bases per word, first base most significant
+    uint32_t exc[SCAN_SPAN / 32 + 2];// bit p: staged base p is not one of ACGT
+    uint16_t q[SCAN_Q];              // candidate windows: staged index | 0x8000 when the window holds a non-ACGT byte
+    int32_t bnd[SCAN_BND];           // staged index of the first base of reads r_lo, r_lo + 1, ... (n_bnd of them)
+};
+
+// 4 ASCII bytes (little-endian in w, lowest address = first base) -> forward codes (8 bits, first base most significant) and
+// complement codes (8 bits, first base LEAST significant). Codes follow KmerIterator.cpp:7-19 (A0 C1 G2 T3 / complement A3 C2 G1
+// T0). diff accumulates w ^ (the byte each code stands for): non-zero exactly when a byte is not one of ACGT (its code bits are
+// then garbage; the caller's rare path clears them in both streams).
+__device__ __forceinline__ void pack4(uint32_t w, uint32_t &fwd8, uint32_t &rc8, uint32_t &diff) {
     uint32_t x = (w >> 1) & 0x03030303u;          // A0 C1 G3 T2
     x ^= (x >> 1) & 0x01010101u;                  // A0 C1 G2 T3
-    const uint32_t xc = (x ^ 0x03030303u) & valid;
-    x &= valid;
+    const uint32_t sel = __byte_perm(x | (x >> 4), 0u, 0x4420u);      // the four codes as selector nibbles
+    diff |= w ^ __byte_perm(0x54474341u, 0u, sel);                    // "ACGT"[code]
     fwd8 = (x * 0x40100401u) >> 24;               // b0<<6 | b1<<4 | b2<<2 | b3
-    rc8 = (xc * 0x01041040u) >> 24;               // c0 | c1<<2 | c2<<4 | c3<<6
-}
-
-// byte mask (0xFF / 0x00 per byte) -> 4 bits, bit j = byte j is NOT valid
-__device__ __forceinline__ uint32_t invalid_nibble(uint32_t valid) {
-    const uint32_t x = ~valid & 0x08040201u;
-    return (x | (x >> 8) | (x >> 16) | (x >> 24)) & 0xFu;
+    rc8 = ((x ^ 0x03030303u) * 0x01041040u) >> 24;// c0 | c1<<2 | c2<<4 | c3<<6
 }
 
 // last r in [lo, hi] with read_off[r] <= pos (read_off[lo] <= pos is guaranteed by the caller)
@@ -98,13 +102,13 @@ __device__ __forceinline__ uint64_t find_read(const uint64_t *__restrict__ read_
     return lo;
 }
 
-__device__ __forceinline__ int clamp_local(uint64_t glob, uint64_t tile_start) {
-    const int64_t d = (int64_t) glob - (int64_t) tile_start;
+__device__ __forceinline__ int clamp_local(uint64_t glob, int64_t gbase) {
+    const int64_t d = (int64_t) glob - gbase;
     return (int) max((int64_t) -(1 << 30), min((int64_t) (1 << 30), d));
 }
 
-// L2 eviction policies: the filter is the one structure every window touches (keep it: evict_last); key-table sectors are
-// touched once per candidate and must not push it out (evict_first). The base stream uses ld.global.cs, the hits st.global.cs.
+// L2 eviction policies: the filter is the one structure every window touches (keep it: evict_last); key sectors are touched
+// once per candidate and must not push it out (evict_first); the base stream does not allocate in L1 and leaves L2 first.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t pol;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -120,320 +124,342 @@ __device__ __forceinline__ uint32_t ldg_u32_policy(const uint32_t *a, uint64_t p
     asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
     return v;
 }
-__device__ __forceinline__ ulonglong2 ldg_u64x2_policy(const ulonglong2 *a, uint64_t pol) {
-    ulonglong2 v;
-    asm("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
-    return v;
-}
 
-// Key-table lookup: slot of `key` or 0xFFFFFFFF. The home bucket (one 128 B line, prefetched into L2 when the candidate was
-// queued) is read whole; a bucket with an empty slot and no match closes the search, a full one sends it to the next bucket of
-// the chain (chain_buckets, default 1) and then to the overflow region.
-__device__ __forceinline__ uint32_t probe_key(const KmerTable &t, unsigned long long key, uint32_t B) {
-    uint32_t slot = 0xFFFFFFFFu;
-    const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS;
-    const uint64_t pol_first = l2_policy_evict_first();
-    bool open = true;             // chain not yet closed by an empty slot or a match
-    // whole bucket (one 128 B line, eight independent 16 B loads) per round trip instead of a dependent sector-by-sector chain:
-    // r3h, 10 Gbases: 72.5 ms against 76.9 ms for the sector loop (same table, one-bucket chains)
-    #pragma unroll 1
-    for (uint32_t b = 0; b < t.chain_buckets && open; b++) {
-        const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(t.keys + home + b * HGA_BUCKET_SLOTS);
-        ulonglong2 v[HGA_BUCKET_SLOTS / 2];
-        #pragma unroll
-        for (int i = 0; i < HGA_BUCKET_SLOTS / 2; i++) v[i] = ldg_u64x2_policy(bp + i, pol_first);
-        bool empty = false;
-        #pragma unroll
-        for (int i = 0; i < HGA_BUCKET_SLOTS / 2; i++) {
-            if (v[i].x == key) slot = home + b * HGA_BUCKET_SLOTS + 2 * i;
-            if (v[i].y == key) slot = home + b * HGA_BUCKET_SLOTS + 2 * i + 1;
-            empty |= (v[i].x == HGA_EMPTY_KEY) | (v[i].y == HGA_EMPTY_KEY);
-        }
-        if (slot != 0xFFFFFFFFu || empty) open = false;
-    }
-    if (open && t.n_over) {       // chain full: the key, if present, lives in the overflow region
-        const uint32_t mask = t.n_over - 1;
-        uint32_t q = hga_plain_hash(key) & mask;
-        for (;;) {
-            const unsigned long long a = __ldg(t.keys + t.n_main + q);
-            if (a == key) { slot = t.n_main + q; break; }
-            if (a == HGA_EMPTY_KEY) break;
-            q = (q + 1) & mask;
-        }
-    }
-    return slot;
+// one 32 B sector of the key table
+__device__ __forceinline__ void load_sector(const uint64_t *sp, uint64_t pol, unsigned long long &a, unsigned long long &b, unsigned long long &d, unsigned long long &e) {
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(d), "=l"(e) : "l"(sp), "l"(pol));
 }
-
-// shared memory of one warp
-struct WarpTile {
-    uint32_t fwd[SCAN_CHUNKS + 4];
-    uint32_t rc[SCAN_CHUNKS + 4];
-    uint32_t exc[SCAN_EXC_WORDS];    // bit p: staged base p is not one of ACGT (written as u16 halves by the packers)
-    uint2 q[SCAN_Q];                 // x = locality hash B, y = window index in the tile | 0x8000 when the window holds a non-ACGT byte
-    uint32_t st_slot[SCAN_TILE];     // hits of the tile in position order
-    uint16_t st_w[SCAN_TILE];        // their window index
-    int32_t bnd[SCAN_BND];           // tile-local first base of reads r_lo, r_lo + 1, ... (n_bnd of them)
-};
 
 struct TileCtx {
     const ScanParams *p;
     WarpTile *T;
-    uint64_t tile_start, r_lo, r_hi;
+    int64_t gbase;                   // stream position of staged index 0 (may be negative in the first tile)
+    uint64_t r_lo, r_hi;
     uint32_t n_bnd;                  // 0: too many reads in this tile, search read_off in global memory
-    int n_loc;
-    unsigned long long kmask;
+    int i_end;                       // staged indices >= i_end lie past the end of the stream
 };
 
-// one level of the cross-lane sliding minimum: value of `cur` d positions back (previous step's register for
-// the first d lanes). __shfl_sync takes the source lane modulo 32.
-__device__ __forceinline__ uint32_t back(uint32_t cur, uint32_t prev, int d, int lane) {
-    return __shfl_sync(0xFFFFFFFFu, lane >= 32 - d ? prev : cur, lane - d);
-}
-
-struct MinState { uint32_t g, a1, a2, r; };
-
-// minimum of the hashed m-mers ending at positions e-skip-W+1 .. e-skip (e = this lane's position in this step):
-// log-step doubling (a1 = 2 positions, a2 = 4), then one overlapping combine for the W that are not powers of two
-template<int W>
-__device__ __forceinline__ uint32_t window_min(uint32_t g, MinState &ms, int skip, int lane) {
-    const uint32_t a1 = min(g, back(g, ms.g, 1, lane));
-    uint32_t a2 = 0, r;
-    if (W >= 4) a2 = min(a1, back(a1, ms.a1, 2, lane));
-    if (W == 2) r = a1;
-    else if (W == 3) r = min(a1, back(g, ms.g, 2, lane));
-    else if (W == 4) r = a2;
-    else if (W == 5) r = min(a2, back(g, ms.g, 4, lane));
-    else if (W == 6) r = min(a2, back(a1, ms.a1, 4, lane));
-    else if (W == 7) r = min(a2, back(a2, ms.a2, 3, lane));
-    else r = min(a2, back(a2, ms.a2, 4, lane));
-    uint32_t gm = r;
-    if (skip) gm = back(r, ms.r, skip, lane);
-    ms.g = g; ms.a1 = a1; ms.a2 = a2; ms.r = r;
-    return gm;
-}
-
-// canonical-k-mer pieces of the window ending at tile-local position e
-__device__ __forceinline__ void extract_window(const uint32_t *s_fwd, const uint32_t *s_rc, int e, int k, unsigned long long kmask,
-                                               unsigned long long &fwd, unsigned long long &rc) {
-    const int je = e + SCAN_HALO, js = je - k + 1;     // staged coordinates (0 = tile_start - SCAN_HALO)
-    const int w0 = js >> 4, o = (js & 15) * 2;
-    const uint32_t F0 = s_fwd[w0], F1 = s_fwd[w0 + 1], F2 = s_fwd[w0 + 2];
-    const uint32_t R0 = s_rc[w0], R1 = s_rc[w0 + 1], R2 = s_rc[w0 + 2];
-    fwd = ((((unsigned long long) __funnelshift_l(F1, F0, o)) << 32) | __funnelshift_l(F2, F1, o)) >> (64 - 2 * k);
-    rc = ((((unsigned long long) __funnelshift_r(R1, R2, o)) << 32) | __funnelshift_r(R0, R1, o)) & kmask;
-}
-
-// tile-local first base of the read that holds tile-local base e
-__device__ __forceinline__ int read_start_of(const TileCtx &c, int e) {
+// staged index of the first base of the read that holds staged base i
+__device__ __forceinline__ int read_start_of(const TileCtx &c, int i) {
     if (c.n_bnd) {
         uint32_t lo = 0, hi = c.n_bnd - 1;
-        while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (c.T->bnd[mid] <= e) lo = mid; else hi = mid - 1; }
+        while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (c.T->bnd[mid] <= i) lo = mid; else hi = mid - 1; }
         return c.T->bnd[lo];
     }
-    const uint64_t r = find_read(c.p->read_off, c.r_lo, c.r_hi, c.tile_start + (uint64_t) e);
-    return clamp_local(__ldg(&c.p->read_off[r]), c.tile_start);
+    const int64_t g = c.gbase + i;
+    if (g < 0) return 1 << 30;
+    const uint64_t r = find_read(c.p->read_off, c.r_lo, c.r_hi, (uint64_t) g);
+    return clamp_local(__ldg(&c.p->read_off[r]), c.gbase);
 }
 
-// n (<= 32) queued candidates starting at ring position head: re-extract the k-mer, check the window against the
-// read boundaries, probe the key table; hits are appended to the staging area in position order
-__device__ __forceinline__ uint32_t drain_queue(uint32_t head, uint32_t n, uint32_t st_count, int lane, WarpTile *Tp, const ScanParams *pp,
-                                             uint64_t tile_start, uint64_t r_lo, uint64_t r_hi, uint32_t n_bnd, int n_loc) {
-    TileCtx c;
-    c.p = pp; c.T = Tp; c.tile_start = tile_start; c.r_lo = r_lo; c.r_hi = r_hi; c.n_bnd = n_bnd; c.n_loc = n_loc;
-    const KmerTable &t = pp->t;
-    WarpTile &T = *Tp;
-    const int k = t.geom.k;
-    c.kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-    uint32_t slot = 0xFFFFFFFFu, widx = 0;
-    if ((uint32_t) lane < n) {
-        const uint2 qe = T.q[(head + lane) & (SCAN_Q - 1)];
-        uint32_t B = qe.x;
-        widx = qe.y & 0x7FFFu;
-        const int e = (int) widx;
-        const int start = read_start_of(c, e);
-        if (e < c.n_loc && e - start + 1 >= k && !(pp->diag & 1)) {
-            unsigned long long fwd, rc;
-            extract_window(T.fwd, T.rc, e, k, c.kmask, fwd, rc);
-            const unsigned long long key = fwd < rc ? fwd : rc;                       // KmerIterator.cpp:69
-            if (qe.y & 0x8000u) B = hga_locality_hash(key, t.geom);
-            slot = probe_key(t, key, B);
-        }
-    }
-    const bool hit = slot != 0xFFFFFFFFu;
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
-    if (hit) {
-        const uint32_t idx = st_count + __popc(bal & ((1u << lane) - 1));
-        T.st_slot[idx] = slot; T.st_w[idx] = (uint16_t) widx;
-    }
-    return st_count + __popc(bal);
+// the 2 x 32 bits of forward codes ending at staged index i (i >= 32): lo = the last 16 bases, hi = the 16 before
+__device__ __forceinline__ void extract_window(const uint32_t *pk, int i, uint32_t &lo, uint32_t &hi) {
+    const int q = (i - 15) >> 4, sh = ((i + 1) & 15) * 2;
+    const uint32_t w0 = pk[q - 1], w1 = pk[q], w2 = pk[q + 1];
+    lo = __funnelshift_l(w2, w1, sh);
+    hi = __funnelshift_l(w1, w0, sh);
 }
 
-// W = 0: locality hash = plain k-mer hash (small k); W = 2..8: minimizer over W m-mers
-template<bool EXC, int W>
-__device__ __forceinline__ uint32_t scan_tile_windows(const TileCtx &c, int lane, uint32_t &n_cand) {
+// bit b of x -> bits 2b, 2b + 1 (32 -> 64 bits)
+__device__ __forceinline__ unsigned long long spread_pairs(uint32_t x) {
+    unsigned long long v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v * 3ull;
+}
+
+// non-ACGT flags of the k bases ending at staged index i, bit 31 = base i (i >= 32)
+__device__ __forceinline__ uint32_t window_exc(const uint32_t *exc, int i, int k) {
+    const uint32_t y = __funnelshift_l(exc[(i >> 5) - 1], exc[i >> 5], 31 - (i & 31));
+    return k == 32 ? y : (y >> (32 - k)) << (32 - k);
+}
+
+#define SCAN_NONE 0xFFFFFFFFu
+
+// one probe step of a lookup: sector `sec` of the bucket at base_slot. Returns true when the lookup is over (slot = the key's slot
+// or SCAN_NONE), false when the sector is full of other keys.
+__device__ __forceinline__ bool probe_sector(const uint64_t *keys, uint32_t base_slot, uint32_t sec, unsigned long long key, uint64_t pol, uint32_t &slot) {
+    const uint32_t s0 = base_slot + (sec & (HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1)) * HGA_SECTOR_SLOTS;
+    unsigned long long a, b, d, e;
+    load_sector(keys + s0, pol, a, b, d, e);
+    slot = SCAN_NONE;
+    if (a == key) slot = s0;
+    if (b == key) slot = s0 + 1;
+    if (d == key) slot = s0 + 2;
+    if (e == key) slot = s0 + 3;
+    return slot != SCAN_NONE || a == HGA_EMPTY_KEY || b == HGA_EMPTY_KEY || d == HGA_EMPTY_KEY || e == HGA_EMPTY_KEY;
+}
+
+struct QueueState { uint32_t head, tail, st_count; };     // warp uniform
+
+// n (<= 32) queued candidates starting at ring position head: check the window against the read boundaries, rebuild the canonical
+// k-mer, probe the key table; hits are appended to the staging area in position order
+__device__ __forceinline__ void drain_queue(QueueState &qs, uint32_t n, int lane, const TileCtx &c) {
     const ScanParams &p = *c.p;
+    const KmerTable &t = p.t;
     WarpTile &T = *c.T;
-    const KmerGeom &geo = p.t.geom;
-    const int k = geo.k;
-    const unsigned long long kmask = c.kmask;
-    const uint32_t kbits = (k == 32) ? 0xFFFFFFFFu : ((1u << k) - 1);
-    const uint32_t lane_lt = (1u << lane) - 1;
-    const uint32_t *filter = p.t.filter;
-    const uint32_t n_blocks = p.t.n_blocks, n_buckets = p.t.n_buckets;
-    const uint64_t *keys = p.t.keys;
-    const bool diag2 = (p.diag & 2) != 0, diag4 = (p.diag & 4) != 0;
-    const int skip = W ? geo.skip : 0;
-    // staged coordinates (0 = tile_start - SCAN_HALO) of this lane's first window; every step moves 32 bases = 2 words,
-    // so the bit offset inside the word is loop invariant and consecutive steps share a word
-    const int js0 = lane + SCAN_HALO - k + 1;
-    const uint32_t *pf = T.fwd + (js0 >> 4), *pr = T.rc + (js0 >> 4), *pe = T.exc + (js0 >> 5);
-    const int o = (js0 & 15) * 2, oe = js0 & 31, fsh = 64 - 2 * k;
-    uint32_t q_head = 0, q_tail = 0, st_count = 0;   // warp uniform
-
-    MinState ms = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    if (W) {   // warm-up: the 32 positions before the tile feed the first sliding minima
-        const unsigned long long fwd = ((((unsigned long long) __funnelshift_l(pf[-1], pf[-2], o)) << 32) | __funnelshift_l(pf[0], pf[-1], o)) >> fsh;
-        const unsigned long long rc = ((((unsigned long long) __funnelshift_r(pr[-1], pr[0], o)) << 32) | __funnelshift_r(pr[-2], pr[-1], o)) & kmask;
-        (void) window_min<W ? W : 2>(hga_mmer_hash((uint32_t) fwd & geo.mmask, (uint32_t) (rc >> geo.rc_shift)), ms, skip, lane);
-    }
-    uint32_t F0 = pf[0], R0 = pr[0];
-    const uint64_t pol_last = l2_policy_evict_last();
-
-    // (Fetching the next tile's bytes one tile ahead with cp.async was tried: slower, -5 % at 2 Gbases and -14 % at 10 Gbases:
-    // cp.async has no evict-first path, so the base stream displaced the filter from L2.)
-    // (Splitting the drain into "request the key sector now, compare when the queue has filled again" was tried as well: no gain,
-    // r2c: 13.7 vs 13.2 ms at 2 Gbases, 76.4 vs 75.7 ms at 10 Gbases.)
-    // (Requesting the filter words one group ahead of testing them was tried: no gain - the probes are bound by L1 wavefront
-    // throughput, ~10 distinct lines per warp load, not by their latency - and the extra live registers spilled around the
-    // drain call.)
-    #pragma unroll 1
-    for (int s0 = 0; s0 < SCAN_STEPS; s0 += SCAN_UNROLL, pf += 2 * SCAN_UNROLL, pr += 2 * SCAN_UNROLL, pe += SCAN_UNROLL) {
-        uint32_t msk[SCAN_UNROLL], fw[SCAN_UNROLL], Bv[SCAN_UNROLL];
-        bool exc[SCAN_UNROLL];
-        #pragma unroll
-        for (int u = 0; u < SCAN_UNROLL; u++) {
-            const uint32_t F1 = pf[2 * u + 1], F2 = pf[2 * u + 2], R1 = pr[2 * u + 1], R2 = pr[2 * u + 2];
-            const unsigned long long fwd = ((((unsigned long long) __funnelshift_l(F1, F0, o)) << 32) | __funnelshift_l(F2, F1, o)) >> fsh;
-            const unsigned long long rc = ((((unsigned long long) __funnelshift_r(R1, R2, o)) << 32) | __funnelshift_r(R0, R1, o)) & kmask;
-            F0 = F2; R0 = R2;
-            const unsigned long long canon = fwd < rc ? fwd : rc;                     // KmerIterator.cpp:69
-            if (W) Bv[u] = hga_locality_from_min(window_min<W ? W : 2>(hga_mmer_hash((uint32_t) fwd & geo.mmask, (uint32_t) (rc >> geo.rc_shift)), ms, skip, lane));
-            else Bv[u] = hga_plain_hash(canon);
-            exc[u] = false;
-            if (EXC && W) exc[u] = (__funnelshift_r(pe[u], pe[u + 1], oe) & kbits) != 0;
-            const uint32_t hb = hga_bits_hash(canon);
-            msk[u] = hga_bits_mask(hb);
-            fw[u] = diag2 ? 0u : ldg_u32_policy(filter + ((hga_scale(Bv[u], n_blocks) << 3) | hga_bits_word(hb)), pol_last);
+    const int k = t.geom.k;
+    uint32_t slot = SCAN_NONE, widx = 0, base_slot = 0, sec = 0;
+    unsigned long long key = 0;
+    bool open = false;
+    if ((uint32_t) lane < n) {
+        const uint32_t qe = T.q[(qs.head + lane) & (SCAN_Q - 1)];
+        widx = qe & 0x7FFFu;
+        const int i = (int) widx;
+        uint2 en = T.tr[SCAN_TR_STRIDE * (i >> 5) + (i & 31)];     // x = locality hash, y = bit hash (still there: hits are staged below index i - 32)
+        const int start = read_start_of(c, i);
+        if (i < c.i_end && i - start + 1 >= k && !(p.diag & 1)) {
+            uint32_t lo, hi;
+            extract_window(T.pk, i, lo, hi);
+            const unsigned long long kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+            const unsigned long long F = ((((unsigned long long) hi) << 32) | lo) & kmask;
+            unsigned long long Ft = F;                              // the reverse strand reads a non-ACGT byte as code 0 too, i.e. as a T here
+            if (qe & 0x8000u) Ft |= spread_pairs(__brev(window_exc(T.exc, i, k)));
+            const unsigned long long R = hga_revcomp64(Ft, k);
+            key = F < R ? F : R;                                    // KmerIterator.cpp:69
+            if (qe & 0x8000u) {                                     // the two strands are not reverse complements: hashes from the VALUE
+                en.y = hga_bits_hash(key, t.geom);
+                en.x = hga_locality_from_min(hga_minimizer(key, en.y, t.geom));
+            }
+            base_slot = hga_scale(en.x, t.n_buckets) * HGA_BUCKET_SLOTS;
+            sec = hga_start_sector(en.x, en.y, t.sector_by_min);
+            open = true;
         }
-        #pragma unroll
-        for (int u = 0; u < SCAN_UNROLL; u++) {
-            const bool pass = exc[u] || (fw[u] & msk[u]) == msk[u];
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
-            if (pass) {
-                T.q[(q_tail + __popc(bal & lane_lt)) & (SCAN_Q - 1)] = make_uint2(Bv[u], (uint32_t) (lane + 32 * (s0 + u)) | (exc[u] ? 0x8000u : 0u));
-                // start the key sector's trip from HBM now; the drain that reads it runs a few steps later
-                if (!diag4) {
-                    const uint64_t *kb = keys + (size_t) hga_scale(Bv[u], n_buckets) * HGA_BUCKET_SLOTS;
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(kb));
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(kb + HGA_BUCKET_SLOTS / 2));
+    }
+    __syncwarp();
+    // go round the bucket, one sector per step, all lanes together: 95 % of the lookups end in the first step
+    const uint64_t pol_first = l2_policy_evict_first();
+    for (int step = 0; __any_sync(0xFFFFFFFFu, open); step++) {
+        if (open) {
+            if (probe_sector(t.keys, base_slot, sec + step, key, pol_first, slot)) open = false;
+            else if (step == HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1) {
+                open = false;
+                if (t.n_over) {           // bucket full: the key, if present, lives in the overflow region
+                    const uint32_t mask = t.n_over - 1;
+                    uint32_t q = hga_plain_hash(key) & mask;
+                    for (;;) {
+                        const unsigned long long v = __ldg(t.keys + t.n_main + q);
+                        if (v == key) { slot = t.n_main + q; break; }
+                        if (v == HGA_EMPTY_KEY) break;
+                        q = (q + 1) & mask;
+                    }
                 }
             }
-            q_tail += __popc(bal);
         }
-        __syncwarp();
-        while (q_tail - q_head >= 32) {
-            st_count = drain_queue(q_head, 32, st_count, lane, c.T, c.p, c.tile_start, c.r_lo, c.r_hi, c.n_bnd, c.n_loc);
-            q_head += 32;
-        }
-        __syncwarp();
     }
-    if (q_tail != q_head) st_count = drain_queue(q_head, q_tail - q_head, st_count, lane, c.T, c.p, c.tile_start, c.r_lo, c.r_hi, c.n_bnd, c.n_loc);
-    n_cand += q_tail;
-    return st_count;
+    const bool hit = slot != SCAN_NONE;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
+    if (hit) T.tr[qs.st_count + __popc(bal & ((1u << lane) - 1))] = make_uint2(slot, widx);
+    qs.st_count += __popc(bal);
+    qs.head += n;
 }
 
-template<bool EXC>
-__device__ __forceinline__ uint32_t scan_tile_dispatch(const TileCtx &c, int lane, uint32_t &n_cand) {
-    const KmerGeom &geo = c.p->t.geom;
+// phase B for one lane: P0..P3 / Q0..Q3 = forward / complement codes of the 64 bases ending with the lane's own 32 (P2, P3);
+// row = the lane's row of the transposition buffer
+template<int W, bool KHI>
+__device__ __forceinline__ void phase_b(const uint32_t (&P)[4], const uint32_t (&Q)[4], const KmerGeom &geo, uint2 *row) {
+    constexpr int WU = W > 0 ? W - 1 : 0;          // positions before the lane's own that feed its first sliding minima
+    uint32_t h[32 + 7], t3[32 + 7];
+    const uint32_t cm = geo.cm, mtop = geo.mtop, ca = geo.ca, cb = geo.cb;
+    const int k = geo.k;
+    const int rsh = KHI ? 64 - 2 * k : 32 - 2 * k; // the reverse strand's pieces are top aligned
+    #pragma unroll
+    for (int j = -WU; j < 32; j++) {
+        const int s0 = j + 17;                     // index (in the 64 bases) of the first of the 16 bases ending at the lane's base j
+        const int q = s0 >> 4, off = s0 & 15;
+        const uint32_t lo = off ? __funnelshift_l(P[(q + 1) & 3], P[q], 2 * off) : P[q];                 // forward, last 16 bases
+        const uint32_t rhi = off ? __funnelshift_r(Q[q], Q[(q + 1) & 3], 2 * off) : Q[q];                // complement of the same, base j on top
+        uint32_t mn = 0;
+        if (W > 0) {
+            h[j + 7] = min(hga_mmer_hash(lo, cm), (rhi & mtop) * HGA_C1 + HGA_C4);
+            if (W >= 3 && j >= -WU + 2) t3[j + 7] = __vimin3_u32(h[j + 7], h[j + 6], h[j + 5]);
+            if (j >= 0) {
+                if (W == 2) mn = min(h[j + 7], h[j + 6]);
+                else if (W == 3) mn = t3[j + 7];
+                else if (W == 4) mn = min(t3[j + 7], h[j + 4]);
+                else if (W == 5) mn = __vimin3_u32(t3[j + 7], h[j + 4], h[j + 3]);
+                else if (W == 6) mn = min(t3[j + 7], t3[j + 4]);
+                else if (W == 7) mn = __vimin3_u32(t3[j + 7], t3[j + 4], h[j + 1]);
+                else mn = __vimin3_u32(t3[j + 7], t3[j + 4], t3[j + 2]);
+            }
+        }
+        if (j >= 0) {
+            uint32_t hb;
+            if (KHI) {
+                const uint32_t hi = off ? __funnelshift_l(P[q], P[(q + 3) & 3], 2 * off) : P[(q + 3) & 3];   // ca discards what lies above the k-mer
+                const uint32_t rlo = off ? __funnelshift_r(Q[(q + 3) & 3], Q[q], 2 * off) : Q[(q + 3) & 3];
+                const uint32_t Rlo = __funnelshift_r(rlo, rhi, rsh), Rhi = rhi >> rsh;
+                hb = (hi * ca + lo) * cb + (Rhi * ca + Rlo) * cb;
+            } else {
+                hb = lo * cb + (rhi >> rsh) * cb;                                                           // cb discards what lies above the k-mer
+            }
+            if (W == 0) mn = hga_mix_bits(hb);
+            row[j] = make_uint2(hga_locality_from_min(mn), hb);
+        }
+    }
+}
+
+template<bool KHI>
+__device__ __forceinline__ void phase_b_dispatch(const uint32_t (&P)[4], const uint32_t (&Q)[4], const KmerGeom &geo, uint2 *row) {
     switch (geo.use_min ? geo.W : 0) {
-        case 2: return scan_tile_windows<EXC, 2>(c, lane, n_cand);
-        case 3: return scan_tile_windows<EXC, 3>(c, lane, n_cand);
-        case 4: return scan_tile_windows<EXC, 4>(c, lane, n_cand);
-        case 5: return scan_tile_windows<EXC, 5>(c, lane, n_cand);
-        case 6: return scan_tile_windows<EXC, 6>(c, lane, n_cand);
-        case 7: return scan_tile_windows<EXC, 7>(c, lane, n_cand);
-        case 8: return scan_tile_windows<EXC, 8>(c, lane, n_cand);
-        default: return scan_tile_windows<EXC, 0>(c, lane, n_cand);
+        case 2: phase_b<2, KHI>(P, Q, geo, row); break;
+        case 3: phase_b<3, KHI>(P, Q, geo, row); break;
+        case 4: phase_b<4, KHI>(P, Q, geo, row); break;
+        case 5: phase_b<5, KHI>(P, Q, geo, row); break;
+        case 6: phase_b<6, KHI>(P, Q, geo, row); break;
+        case 7: phase_b<7, KHI>(P, Q, geo, row); break;
+        case 8: phase_b<8, KHI>(P, Q, geo, row); break;
+        default: phase_b<0, KHI>(P, Q, geo, row); break;
     }
 }
 
-// 63 registers, 30.9 KB of shared memory per CTA: 7 CTAs = 28 independent warps per SM. The parameters are __grid_constant__ and
-// every helper is inlined so that NOTHING lives in local memory: a by-value parameter struct whose address is taken, and a
-// tile context handed to a non-inlined drain function, cost 26 % of the scan time when they did (r1y / r1z / r2a).
-__global__ void __launch_bounds__(SCAN_THREADS, 7) scan_probe_kernel(const __grid_constant__ ScanParams p) {
-    __shared__ WarpTile s_tiles[SCAN_WARPS];
+// N steps of phase C starting at row s0: filter probes of 32 adjacent windows per step, passing windows queued
+template<int N, bool EXC>
+__device__ __forceinline__ void phase_c_group(const TileCtx &c, int s0, int lane, QueueState &qs, uint64_t pol_last) {
+    const ScanParams &p = *c.p;
+    WarpTile &T = *c.T;
+    const uint32_t n_blocks = p.t.n_blocks;
+    const uint32_t *filter = p.t.filter;
+    const bool prefetch = (p.diag & 4) != 0;
+    uint2 en[N];
+    uint32_t fw[N];
+    #pragma unroll
+    for (int u = 0; u < N; u++) {
+        en[u] = T.tr[SCAN_TR_STRIDE * (s0 + u) + lane];              // x = locality hash, y = bit hash
+        fw[u] = ldg_u32_policy(filter + (__umulhi(en[u].x, n_blocks) * 8 + hga_bits_word(en[u].y)), pol_last);
+    }
+    #pragma unroll
+    for (int u = 0; u < N; u++) {
+        const int i = 32 * (s0 + u) + lane;
+        bool pass = hga_bits_test(fw[u], en[u].y);
+        bool exc = false;
+        if (EXC) { exc = window_exc(T.exc, i, p.t.geom.k) != 0; pass |= exc; }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
+        if (bal) {                                                   // warp uniform
+            if (pass) {
+                T.q[(qs.tail + __popc(bal & ((1u << lane) - 1))) & (SCAN_Q - 1)] = (uint16_t) ((uint32_t) i | (exc ? 0x8000u : 0u));
+                if (prefetch && (!EXC || !exc)) {                    // experiment: start the key sector's trip from HBM now
+                    const uint64_t *sp = p.t.keys + (size_t) __umulhi(en[u].x, p.t.n_buckets) * HGA_BUCKET_SLOTS +
+                                         hga_start_sector(en[u].x, en[u].y, p.t.sector_by_min) * HGA_SECTOR_SLOTS;
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(sp));
+                }
+            }
+            qs.tail += __popc(bal);
+        }
+    }
+    if (qs.tail - qs.head >= 32) {
+        __syncwarp();
+        do drain_queue(qs, 32, lane, c); while (qs.tail - qs.head >= 32);
+        __syncwarp();
+    }
+}
+
+// phase C + drains: returns the number of staged hits (rows 1 .. 31 of the transposition buffer; row 0 is the halo)
+template<bool EXC>
+__device__ __forceinline__ uint32_t phase_c(const TileCtx &c, int lane, uint32_t &n_cand) {
+    const uint64_t pol_last = l2_policy_evict_last();
+    QueueState qs = {0, 0, 0};
+    phase_c_group<3, EXC>(c, 1, lane, qs, pol_last);
+    #pragma unroll 1
+    for (int s0 = 4; s0 < 32; s0 += SCAN_UNROLL) phase_c_group<SCAN_UNROLL, EXC>(c, s0, lane, qs, pol_last);
+    __syncwarp();
+    if (qs.tail != qs.head) drain_queue(qs, qs.tail - qs.head, lane, c);
+    __syncwarp();
+    n_cand += qs.tail;
+    return qs.st_count;
+}
+
+// 24 independent warps per SM (3 CTAs of 8; 9.3 KB of shared memory per warp). The parameters are __grid_constant__ and every helper
+// is inlined so that nothing lives in local memory.
+// MINB = resident CTAs per SM the register allocation aims at (3: 80 registers, 2: up to 128; experiment switch HGA_SCAN_OCC)
+template<int MINB>
+__global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpTile &T = s_tiles[warp];
-    uint16_t *s_exc16 = reinterpret_cast<uint16_t *>(T.exc);
+    WarpTile &T = reinterpret_cast<WarpTile *>(s_raw)[warp];
     uint32_t n_cand = 0;
     const int kk = p.t.geom.k;
 
-    for (uint32_t i = lane; i < SCAN_EXC_WORDS; i += 32) T.exc[i] = 0;
-    if (lane < 4) { T.fwd[SCAN_CHUNKS + lane] = 0; T.rc[SCAN_CHUNKS + lane] = 0; }
+    if (lane < 4) T.pk[SCAN_SPAN / 16 + lane] = 0;
+    if (lane < 2) T.exc[SCAN_SPAN / 32 + lane] = 0;
 
+    unsigned long long next_ticket = 0;
+    if (lane == 0) next_ticket = atomicAdd(&p.scalars->ticket, 1ull);
     for (;;) {
-        unsigned long long ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&p.scalars->ticket, 1ull);
-        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+        const unsigned long long ticket = __shfl_sync(0xFFFFFFFFu, next_ticket, 0);
         if (ticket >= p.n_tiles) break;
+        if (lane == 0) next_ticket = atomicAdd(&p.scalars->ticket, 1ull);               // in flight while this tile is processed
         const uint64_t tile = p.tile_begin + (p.tile_stride ? ticket * p.tile_stride : ticket);
-        const uint64_t tile_start = tile * SCAN_TILE;
-        const int n_loc = (int) min((uint64_t) SCAN_TILE, p.n_bases - tile_start);      // window ends in this tile
+        // frame coordinate u = stream position + lead; the tile's window ends are u in [992 tile, 992 tile + 992); staged index 0 is u = 992 tile - 32
+        const int64_t ubase = (int64_t) (tile * SCAN_TILE) - 32;
+        const int64_t gbase = ubase - (int64_t) p.lead;
+        const int64_t u_end = (int64_t) p.lead + (int64_t) p.n_bases;                 // first frame position past the stream
 
-        // ---- load + pack (chunk c covers global bases [tile_start - HALO + 16c, +16)) --------------------------
-        bool any_bad = false;
-        #pragma unroll
-        for (int it = 0; it < SCAN_CHUNKS / 32; it++) {
-            const int c = lane + 32 * it;
-            const int64_t g = (int64_t) tile_start - SCAN_HALO + 16 * (int64_t) c;
-            uint4 v = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);   // outside the stream: 'A' (never inside a valid window)
-            if (g >= 0 && (uint64_t) g + 16 <= p.n_bases) {
-                v = __ldcs(reinterpret_cast<const uint4 *>(p.bases + g));
-            } else if (g >= 0 && (uint64_t) g < p.n_bases) {
-                uint32_t t[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
-                for (int i = 0; i < 16 && (uint64_t) g + i < p.n_bases; i++) {
-                    const int sh = 8 * (i & 3);
-                    t[i >> 2] = (t[i >> 2] & ~(0xFFu << sh)) | ((uint32_t) (unsigned char) p.bases[g + i] << sh);
+        // ---- phase A: one 32 B sector per lane, packed to two words per strand ---------------------------------------
+        uint32_t P[4], Q[4], bad = 0;
+        {
+            const int64_t u = ubase + 32 * lane;
+            uint32_t v[8];
+            if (u >= 0 && u < u_end) {
+                asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p.frame + u));
+            } else {
+                #pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = 0x41414141u;                        // outside the stream: 'A' (never inside a valid window)
+            }
+            uint32_t diff = 0, f[8], r[8];
+            #pragma unroll
+            for (int i = 0; i < 8; i++) pack4(v[i], f[i], r[i], diff);
+            P[2] = (f[0] << 24) | (f[1] << 16) | (f[2] << 8) | f[3];
+            P[3] = (f[4] << 24) | (f[5] << 16) | (f[6] << 8) | f[7];
+            Q[2] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+            Q[3] = r[4] | (r[5] << 8) | (r[6] << 16) | (r[7] << 24);
+            if (diff) {                                                                // rare: clear the codes of the non-ACGT bytes, note them
+                #pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    uint32_t d = 0, f0, r0;
+                    pack4(v[i], f0, r0, d);
+                    #pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        if ((d >> (8 * b)) & 0xFFu) {
+                            const int pos = 4 * i + b;
+                            bad |= 1u << pos;
+                            if (pos < 16) { P[2] &= ~(3u << (30 - 2 * pos)); Q[2] &= ~(3u << (2 * pos)); }
+                            else { P[3] &= ~(3u << (30 - 2 * (pos - 16))); Q[3] &= ~(3u << (2 * (pos - 16))); }
+                        }
+                    }
                 }
-                v = make_uint4(t[0], t[1], t[2], t[3]);
             }
-            uint32_t f0, f1, f2, f3, r0, r1, r2, r3, v0, v1, v2, v3;
-            pack4(v.x, f0, r0, v0); pack4(v.y, f1, r1, v1); pack4(v.z, f2, r2, v2); pack4(v.w, f3, r3, v3);
-            T.fwd[c] = (f0 << 24) | (f1 << 16) | (f2 << 8) | f3;
-            T.rc[c] = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
-            uint32_t bad = 0;
-            if ((v0 & v1 & v2 & v3) != 0xFFFFFFFFu) {
-                bad = invalid_nibble(v0) | (invalid_nibble(v1) << 4) | (invalid_nibble(v2) << 8) | (invalid_nibble(v3) << 12);
-                any_bad = true;
-            }
-            s_exc16[c] = (uint16_t) bad;
         }
+        T.pk[2 * lane] = P[2]; T.pk[2 * lane + 1] = P[3];
+        T.exc[lane] = bad;
+        P[0] = __shfl_up_sync(0xFFFFFFFFu, P[2], 1); P[1] = __shfl_up_sync(0xFFFFFFFFu, P[3], 1);
+        Q[0] = __shfl_up_sync(0xFFFFFFFFu, Q[2], 1); Q[1] = __shfl_up_sync(0xFFFFFFFFu, Q[3], 1);
+        if (lane == 0) { P[0] = 0; P[1] = 0; Q[0] = 0; Q[1] = 0; }
+        const bool exc_any = __any_sync(0xFFFFFFFFu, bad != 0);
+
         // read boundaries of the tile (reads r_lo .. r_hi start at or before the tile's last base)
         const uint2 d0 = __ldg(&p.tile_dir[tile]), d1 = __ldg(&p.tile_dir[tile + 1]);
         TileCtx ctx;
-        ctx.p = &p; ctx.T = &T; ctx.tile_start = tile_start; ctx.n_loc = n_loc;
+        ctx.p = &p; ctx.T = &T; ctx.gbase = gbase;
+        ctx.i_end = (int) min((int64_t) SCAN_SPAN, u_end - ubase);
         ctx.r_lo = d0.y; ctx.r_hi = min((uint64_t) d1.y, p.n_reads - 1);
-        ctx.kmask = (kk == 32) ? ~0ull : ((1ull << (2 * kk)) - 1);
         const uint64_t nb = ctx.r_hi - ctx.r_lo + 1;
         ctx.n_bnd = nb <= SCAN_BND ? (uint32_t) nb : 0u;
-        if (nb <= SCAN_BND) for (uint32_t i = lane; i < nb; i += 32) T.bnd[i] = clamp_local(__ldg(&p.read_off[ctx.r_lo + i]), tile_start);
-        const bool exc_any = __any_sync(0xFFFFFFFFu, any_bad);
+        if (nb <= SCAN_BND) for (uint32_t i = lane; i < nb; i += 32) T.bnd[i] = clamp_local(__ldg(&p.read_off[ctx.r_lo + i]), gbase);
+
+        // ---- phase B: lane-sequential hashing of the lane's 32 windows -------------------------------------------------
+        if (kk > 16) phase_b_dispatch<true>(P, Q, p.t.geom, T.tr + SCAN_TR_STRIDE * lane);
+        else phase_b_dispatch<false>(P, Q, p.t.geom, T.tr + SCAN_TR_STRIDE * lane);
         __syncwarp();
 
-        // ---- windows: lane owns window end e_loc = step * 32 + lane --------------------------------------------
+        // ---- phase C: lane-parallel filter probes, drains ------------------------------------------------------------
         uint32_t total;
-        if (exc_any) total = scan_tile_dispatch<true>(ctx, lane, n_cand);
-        else total = scan_tile_dispatch<false>(ctx, lane, n_cand);
+        if (exc_any) total = phase_c<true>(ctx, lane, n_cand);
+        else total = phase_c<false>(ctx, lane, n_cand);
         __syncwarp();
 
         // ---- append the tile's hits (one atomic), tile directory, tile-local CSR row offsets ---------------------
@@ -451,17 +477,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 7) scan_probe_kernel(const __gri
         // rows starting in this tile: number of tile hits whose window ends before the read's first base
         for (uint64_t rr = (uint64_t) d0.x + lane; rr <= ctx.r_hi; rr += 32) {
             const uint64_t ro = __ldg(&p.read_off[rr]);
-            if (ro >= tile_start && ro < tile_start + (uint64_t) n_loc) {
-                const uint32_t q = (uint32_t) (ro - tile_start);
+            if (ro < p.n_bases && (ro + p.lead) / SCAN_TILE == tile) {
+                const uint32_t q = (uint32_t) ((int64_t) ro - gbase);
                 uint32_t lo = 0, hi = total;
-                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (T.st_w[mid] < q) lo = mid + 1; else hi = mid; }
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (T.tr[mid].y < q) lo = mid + 1; else hi = mid; }
                 p.row_off[rr] = lo;       // tile-local; scan_fix_rows_kernel adds the tile's final offset
             }
         }
         if (tile_off + total <= p.capacity) {
             for (uint32_t i = lane; i < total; i += 32) {
-                const int e = T.st_w[i];
-                __stcs(&p.out_slot[tile_off + i], T.st_slot[i]);
+                const uint2 hit = T.tr[i];
+                const int e = (int) hit.y;
+                __stcs(&p.out_slot[tile_off + i], hit.x);
                 __stcs(&p.out_pos[tile_off + i], (uint32_t) (e - read_start_of(ctx, e) + 1));   // KmerIterator::position_in_sequence
             }
         }
@@ -471,9 +498,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 7) scan_probe_kernel(const __gri
 }
 
 // per tile: x = first r in [0, n_reads] with read_off[r] >= tile start, y = last r in [0, n_reads) with read_off[r] <= tile start
-__global__ void scan_tile_dir_kernel(const uint64_t *__restrict__ read_off, uint64_t n_reads, uint64_t n_tiles, uint2 *dir) {
+// (tile start = stream position of the tile's first window end, 992 t - lead, clamped at 0)
+__global__ void scan_tile_dir_kernel(const uint64_t *__restrict__ read_off, uint64_t n_reads, uint64_t n_tiles, uint32_t lead, uint2 *dir) {
     for (uint64_t t = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; t <= n_tiles; t += (uint64_t) gridDim.x * blockDim.x) {
-        const uint64_t pos = t * SCAN_TILE;
+        const uint64_t pos = t * SCAN_TILE > lead ? t * SCAN_TILE - lead : 0;
         uint64_t lo = 0, hi = n_reads;        // lower bound over read_off[0 .. n_reads]
         while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (read_off[mid] < pos) lo = mid + 1; else hi = mid; }
         const uint64_t first = lo;
@@ -501,28 +529,28 @@ __global__ void scan_reorder_kernel(const uint32_t *__restrict__ tmp_slot, const
 
 // row_off[r] (tile-local count) += final offset of the tile holding the read's first base; rows at or past the end
 // of the stream (trailing empty reads, terminal entry) get E
-__global__ void scan_fix_rows_kernel(const uint64_t *__restrict__ read_off, uint64_t n_reads, uint64_t n_bases,
+__global__ void scan_fix_rows_kernel(const uint64_t *__restrict__ read_off, uint64_t n_reads, uint64_t n_bases, uint32_t lead,
                                      const unsigned long long *__restrict__ tile_off, uint64_t n_tiles, uint64_t *row_off) {
     const unsigned long long E = tile_off[n_tiles];
     uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
     for (; i <= n_reads; i += stride) {
         const uint64_t ro = (i == n_reads) ? n_bases : read_off[i];
-        row_off[i] = (ro >= n_bases) ? E : row_off[i] + tile_off[ro / SCAN_TILE];
+        row_off[i] = (ro >= n_bases) ? E : row_off[i] + tile_off[(ro + lead) / SCAN_TILE];
     }
 }
 
+const size_t kScanSmem = SCAN_WARPS * sizeof(WarpTile);
+
+int scan_occ_variant() {
+    static int v = 0;
+    if (!v) { const char *e = getenv("HGA_SCAN_OCC"); v = (e && atoi(e) == 2) ? 2 : 3; }
+    return v;
+}
+
 int launch_scan(hga_handle *h, const ScanParams &p, int grid) {
-    // experiment switch: HGA_SCAN_PAD_KB pads every CTA with unused dynamic shared memory (fewer resident CTAs per SM)
-    size_t pad = 0;
-    if (const char *e = getenv("HGA_SCAN_PAD_KB")) {
-        pad = (size_t) atoi(e) * 1024;
-        cudaFuncSetAttribute(scan_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pad);
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel, SCAN_THREADS, pad);
-        grid = std::min(grid, h->sm_count * std::max(occ, 1));
-    }
-    scan_probe_kernel<<<grid, SCAN_THREADS, pad, h->stream>>>(p);
+    if (scan_occ_variant() == 2) scan_probe_kernel<2><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
+    else scan_probe_kernel<3><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
     HGA_CUDA(cudaGetLastError());
     h->metrics.kernel_launches++;
     return HGA_OK;
@@ -537,7 +565,8 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     HGA_TRY(h->d_row_off.ensure((n_reads + 1) * 8));
     HGA_TRY(h->d_scan_scalars.ensure(sizeof(ScanScalars)));
     ScanScalars *d_sc = h->d_scan_scalars.as<ScanScalars>();
-    const uint64_t n_tiles = (n_reads == 0) ? 0 : (n_bases + SCAN_TILE - 1) / SCAN_TILE;
+    const uint32_t lead = (uint32_t) (reinterpret_cast<uintptr_t>(d_bases) & 31);   // the kernel loads whole 32 B sectors: frame = the bases aligned down
+    const uint64_t n_tiles = (n_reads == 0 || n_bases == 0) ? 0 : (lead + n_bases + SCAN_TILE - 1) / SCAN_TILE;
     HGA_TRY(h->d_tile_state.ensure((n_tiles + 2) * (8 + 8 + 4)));   // tile directory: tmp offset | final offset | count
     unsigned long long *tile_tmp_off = h->d_tile_state.as<unsigned long long>();
     unsigned long long *tile_off = tile_tmp_off + (n_tiles + 2);
@@ -546,7 +575,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
 
     ScanParams p;
     memset(&p, 0, sizeof(p));
-    p.bases = d_bases; p.n_bases = n_bases; p.read_off = d_read_off; p.n_reads = n_reads;
+    p.frame = d_bases - lead; p.lead = lead; p.n_bases = n_bases; p.read_off = d_read_off; p.n_reads = n_reads;
     p.t = h->table;
     p.row_off = h->d_row_off.as<uint64_t>();
     p.tile_dir = h->d_tile_dir.as<uint2>();
@@ -555,7 +584,13 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     if (const char *e = getenv("HGA_SCAN_DIAG")) p.diag = atoi(e);
 
     int occ = 0;
-    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel, SCAN_THREADS, 0));
+    if (scan_occ_variant() == 2) {
+        HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
+        HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<2>, SCAN_THREADS, kScanSmem));
+    } else {
+        HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
+        HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<3>, SCAN_THREADS, kScanSmem));
+    }
     if (occ < 1) occ = 1;
     const int grid_full = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, std::max<uint64_t>((n_tiles + SCAN_WARPS - 1) / SCAN_WARPS, 1));
 
@@ -575,7 +610,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         t.stop();
     }
     if (n_tiles > 0) {
-        scan_tile_dir_kernel<<<(int) std::min<uint64_t>((n_tiles + 256) / 256, (uint64_t) h->sm_count * 8), 256, 0, h->stream>>>(d_read_off, n_reads, n_tiles,
+        scan_tile_dir_kernel<<<(int) std::min<uint64_t>((n_tiles + 256) / 256, (uint64_t) h->sm_count * 8), 256, 0, h->stream>>>(d_read_off, n_reads, n_tiles, lead,
                                                                                                                                h->d_tile_dir.as<uint2>());
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaGetLastError());
@@ -681,7 +716,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         scan_reorder_kernel<<<blocks, 256, 0, h->stream>>>(h->d_sort_a.as<uint32_t>(), h->d_sort_b.as<uint32_t>(), tile_tmp_off, tile_cnt, tile_off, n_tiles,
                                                          h->d_hit_slot.as<uint32_t>(), h->d_hit_pos.as<uint32_t>());
         const int rblocks = (int) std::min<uint64_t>((n_reads + 256) / 256, 2048);
-        scan_fix_rows_kernel<<<rblocks, 256, 0, h->stream>>>(d_read_off, n_reads, n_bases, tile_off, n_tiles, p.row_off);
+        scan_fix_rows_kernel<<<rblocks, 256, 0, h->stream>>>(d_read_off, n_reads, n_bases, lead, tile_off, n_tiles, p.row_off);
         h->metrics.kernel_launches += 4;
         HGA_CUDA(cudaGetLastError());
     } else {

@@ -7,7 +7,7 @@
 
 namespace {
 
-// pass 1: filter bits + main (locality-bucketed) key table; keys whose chain is full are listed for pass 2
+// pass 1: filter bits + main (locality-bucketed) key table; keys whose bucket is full are listed for pass 2
 __global__ void table_insert_main_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KmerTable t, uint32_t *over_list, unsigned int *over_count, int *flags) {
     uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
@@ -15,14 +15,13 @@ __global__ void table_insert_main_kernel(const uint64_t *__restrict__ kmers, uin
     for (; i < n; i += stride) {
         const unsigned long long key = kmers[i];
         if (key == HGA_EMPTY_KEY) { atomicOr(flags, 2); continue; }   // never a canonical k-mer
-        const uint32_t B = hga_locality_hash(key, t.geom);
-        const uint32_t hb = hga_bits_hash(key);
+        const uint32_t hb = hga_bits_hash(key, t.geom);
+        const uint32_t B = hga_locality_from_min(hga_minimizer(key, hb, t.geom));
         atomicOr(&t.filter[(size_t) hga_scale(B, t.n_blocks) * 8 + hga_bits_word(hb)], hga_bits_mask(hb));
-        const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS, start = hga_bits_sector(hb);
+        const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS, start = hga_start_sector(B, hb, t.sector_by_min) * HGA_SECTOR_SLOTS;
         bool done = false;
-        const uint32_t chain_slots = t.chain_buckets * HGA_BUCKET_SLOTS;
-        for (uint32_t j = 0; j < chain_slots && !done; j++) {
-            const uint32_t slot = home + hga_chain_slot(start, j);
+        for (uint32_t j = 0; j < HGA_BUCKET_SLOTS && !done; j++) {
+            const uint32_t slot = home + ((start + j) & (HGA_BUCKET_SLOTS - 1));
             unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&keys[slot]);
             if (cur == HGA_EMPTY_KEY) cur = atomicCAS(&keys[slot], (unsigned long long) HGA_EMPTY_KEY, key);
             if (cur == HGA_EMPTY_KEY) { t.kid_slot[i] = slot; done = true; }
@@ -58,20 +57,22 @@ __global__ void table_slot_kid_kernel(const uint32_t *__restrict__ kid_slot, uin
 int hga_table_build(hga_handle *h, const uint64_t *host_kmers) {
     const uint64_t n = h->n_kmers;
     if (n >= (1ull << 29)) { hga_set_error("too many k-mers (%llu): the slot id space is 32 bit", (unsigned long long) n); return HGA_E_ARG; }
-    double bits_per_key = 16.0, max_mb = 72.0;
+    // filter: sized to stay L2 resident (<= 48 MB, see hga_internal.cuh); HGA_FILTER_* / HGA_TABLE_LOAD are experiment switches
+    double bits_per_key = 16.0, max_mb = 48.0, load = 0.33;
     if (const char *e = getenv("HGA_FILTER_BITS_PER_KEY")) bits_per_key = atof(e);
     if (const char *e = getenv("HGA_FILTER_MAX_MB")) max_mb = atof(e);
+    if (const char *e = getenv("HGA_TABLE_LOAD")) load = std::min(0.9, std::max(0.05, atof(e)));
     uint64_t n_blocks = (uint64_t) (n * bits_per_key / 256.0) + 64;
     const uint64_t max_blocks = (uint64_t) (max_mb * 1024 * 1024 / 32);
     if (n_blocks > max_blocks) n_blocks = max_blocks;
 
     KmerTable &t = h->table;
     t.geom = hga_make_geom(h->k, n);
-    if (const char *e = getenv("HGA_CHAIN_BUCKETS")) t.chain_buckets = (uint32_t) std::min(HGA_CHAIN_BUCKETS, std::max(1, atoi(e)));
-    t.n_buckets = (uint32_t) ((3 * n + HGA_BUCKET_SLOTS - 1) / HGA_BUCKET_SLOTS + 1);   // load factor <= 1/3
-    t.n_main = (t.n_buckets + HGA_CHAIN_BUCKETS) * HGA_BUCKET_SLOTS;                    // slack: chains never wrap
+    t.n_buckets = (uint32_t) ((uint64_t) (n / load) / HGA_BUCKET_SLOTS + 1);
+    t.n_main = t.n_buckets * HGA_BUCKET_SLOTS;
     t.n_over = 0;
     t.n_blocks = (uint32_t) n_blocks;
+    if (const char *e = getenv("HGA_SECTOR_BY_MIN")) t.sector_by_min = atoi(e) != 0;
     HGA_TRY(h->d_keys.ensure((size_t) t.n_main * 8));
     HGA_TRY(h->d_kid_slot.ensure((size_t) (n + 1) * 4));
     HGA_TRY(h->d_filter.ensure((size_t) n_blocks * 32));
