@@ -40,9 +40,9 @@ int hga_index_run(hga_handle *h) {
     const uint32_t n_slots = h->table.n_slots;
 
     if (h->comm && hga_comm_size(h) > 1) {
-        // sharded reads: all-to-all by slot owner + all-gather into a replicated global index (hga_comm.cu)
+        // sharded reads: all-to-all by k-mer owner into a PARTITIONED index (hga_comm.cu)
         StageTimer timer(h, &h->metrics.index_ms);
-        HGA_TRY(hga_comm_build_global_index(h));
+        HGA_TRY(hga_comm_build_owner_index(h));
         timer.stop();
         h->have_index = true;
         return HGA_OK;

@@ -95,8 +95,8 @@ struct PinBuf {
 //               from L2 while 10 Gbases stream through, 64 MB is not (26.9 -> 37.6 -> 59.2 ms at 48 / 64 / 96 MB).
 //   key table : canonical keys, u64, buckets of 32 (256 B) selected by Mc. Inside the bucket a key starts at the 32 B SECTOR
 //               picked by hb and goes round the bucket's eight sectors; a lookup reads one sector per step (one 256-bit load)
-//               and stops at a match or at a sector with an empty slot: 95 % of the lookups end in the first step (load 1/3).
-//               Keys that find their bucket full (0.3 %) go to a plain open-addressing overflow region hashed by k-mer,
+//               and stops at a match or at a sector with an empty slot: 96 % of the lookups end in the first step (load 1/4).
+//               Keys that find their bucket full (0.1 %) go to a plain open-addressing overflow region hashed by k-mer,
 //               consulted only after eight full sectors. The internal k-mer id ("slot") is the index of the key in the
 //               (main | overflow) array; slot_kid maps it to the caller's id.
 // ------------------------------------------------------------------------------------------------
@@ -287,14 +287,14 @@ struct hga_handle {
     uint32_t inc_row_first_id = 1;        // read id of row 0
     uint64_t inc_entries = 0;             // entries of the inverted index
     DevBuf d_x_slot, d_x_row;             // exchange staging (multi-GPU)
-    DevBuf d_hit_kid;                     // multi-GPU: hits keyed by the caller's kmer_id (slots differ between ranks: the table is built with atomics)
-    DevBuf d_g_kid, d_g_row_off;          // multi-GPU: by-read incidence of this rank's pivot rows (index key per hit, u64 row offsets)
-    bool index_by_kid = false;            // the inverted index is keyed by kmer_id (multi-GPU) instead of table slot
-    uint32_t index_keys = 0;              // number of lists in the inverted index: n_slots, or the index-key space when keyed by kmer_id
-    uint32_t index_key_div = 0;           // multi-GPU: index key of kmer_id = kmer_id + kmer_id / index_key_div (one unused key closes every owner's range)
+    DevBuf d_hit_kid;                     // (unused)
+    DevBuf d_g_kid, d_g_row_off;          // multi-GPU: by-row incidence of ALL rows restricted to this rank's k-mers (list number per hit, u64 row offsets)
+    bool index_by_kid = false;            // multi-GPU: the inverted index holds the lists of this rank's k-mers, list number = kmer_id / G (owner = kmer_id mod G)
+    uint32_t index_keys = 0;              // number of lists in the inverted index: n_slots, or ceil(K / G) + 1 with a communicator
+    uint32_t index_key_div = 0;           // (unused)
 
     // inverted index
-    DevBuf d_inv_off;                     // u32[n_slots+1] (the incidence of one GPU has < 2^32 entries)
+    DevBuf d_inv_off;                     // u32[index_keys + 1] (the incidence held by one GPU has < 2^32 entries)
     DevBuf d_inv_row;                     // u32[inc_entries]: ROW numbers (0-based), ascending inside a list
     DevBuf d_sort_a, d_sort_b, d_sort_tmp;
     bool have_index = false;
@@ -350,7 +350,8 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
 int hga_export_index(hga_handle *h, const uint32_t *d_off, const uint32_t *d_row, uint64_t E, hga_index *out);
 
 // multi-GPU hooks (hga_comm.cu); all are no-ops / never called without a communicator
-int hga_comm_build_global_index(hga_handle *h);
+int hga_comm_build_owner_index(hga_handle *h);
+int hga_comm_exchange_partials(hga_handle *h, uint64_t n, uint64_t *out_n);
 int hga_comm_allgather_u64(hga_handle *h, uint64_t mine, std::vector<uint64_t> &all);
 int hga_comm_allgatherv(hga_handle *h, const void *d_mine, void *d_all, const std::vector<uint64_t> &counts, int elem_bytes);
 int hga_comm_allreduce_u64_sum(hga_handle *h, uint64_t *d_buf, size_t n);

@@ -29,6 +29,8 @@
 #include "hga_internal.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_select.cuh>
 
 #define PC_THREADS 128
 #define PC_WARPS (PC_THREADS / 32)
@@ -510,12 +512,10 @@ __global__ void __launch_bounds__(HV_THREADS) pair_count_heavy_kernel(PairParams
     }
 }
 
-// work measure: sum over lists of occ*(occ-1)/2. key_div > 0: keys with key % (key_div + 1) == key_div are the unused
-// closing keys of the multi-GPU key space (their "list" is the padding of an owner's row segment)
-__global__ void increments_kernel(const uint32_t *__restrict__ inv_off, uint32_t n_slots, uint32_t key_div, unsigned long long *out) {
+// work measure: sum over this GPU's lists of occ*(occ-1)/2
+__global__ void increments_kernel(const uint32_t *__restrict__ inv_off, uint32_t n_slots, unsigned long long *out) {
     unsigned long long acc = 0;
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t) gridDim.x * blockDim.x) {
-        if (key_div && i % (key_div + 1) == key_div) continue;
         const unsigned long long len = inv_off[i + 1] - inv_off[i];
         acc += len * (len - (len ? 1 : 0)) / 2;
     }
@@ -546,6 +546,10 @@ __global__ void row_minhash_kernel(const uint64_t *__restrict__ row_off, const u
     }
 }
 
+__global__ void flag_min_score_kernel(const uint32_t *__restrict__ score, uint64_t n, uint32_t min_score, uint8_t *flag) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) flag[i] = score[i] >= min_score;
+}
+
 __global__ void mark_pivots_kernel(const uint32_t *__restrict__ pivot_rows, uint64_t n, uint8_t *flag) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) flag[pivot_rows[i]] = 1;
 }
@@ -570,8 +574,8 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     PairParams p;
     memset(&p, 0, sizeof(p));
     p.n_rows = n_rows;
-    // multi-GPU: the replicated incidence of all reads, keyed by kmer_id like the exchanged index; this GPU's pivots are
-    // the rows rank, rank + G, ... (interleaved: every GPU sees the same mix of early and late rows, and y > x halves the walks)
+    // multi-GPU: ALL rows are pivots on every GPU, each row restricted to its hits on this GPU's k-mers (hga_comm.cu): the scores
+    // that come out are PARTIAL and are reduced at the owner of x further down
     p.row_off = multi ? h->d_g_row_off.as<uint64_t>() : h->d_row_off.as<uint64_t>();
     p.row_slot = multi ? h->d_g_kid.as<uint32_t>() : h->d_hit_slot.as<uint32_t>();
     p.pivot_mul = h->pair_pivot_mul; p.pivot_add = h->pair_pivot_add;
@@ -579,7 +583,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     p.pivot_rows = nullptr; p.pivot_flag = nullptr;
     p.n_pivots = n_rows;
     p.mode = PAIR_MODE_TAIL;
-    p.min_score = min_score;
+    p.min_score = multi ? 1u : min_score;       // partial scores are filtered after the reduction
     p.mid_list = h->d_mid_list.as<uint32_t>();
     p.redo_list = h->d_redo_list.as<uint32_t>();
     p.heavy_list = h->d_heavy_list.as<uint32_t>();
@@ -696,6 +700,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     }
     h->pair_capacity = capacity;
     uint64_t P = sc.cursor;
+    if (multi) HGA_TRY(hga_comm_exchange_partials(h, P, &P));     // partial (x, y, score) -> owner(x); received into d_pair_key / d_pair_score
 
     // canonical physical order: sort by (x_row, y_row)
     HGA_TRY(h->d_pair_key2.ensure((P + 1) * 8));
@@ -710,13 +715,47 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
                                                  h->d_pair_score.as<uint32_t>(), h->d_pair_score2.as<uint32_t>(), P, 0, 32 + row_bits, h->stream));
         h->metrics.kernel_launches += (uint64_t) (32 + row_bits + 7) / 8 + 2;
     }
+    if (multi && P > 0) {
+        // one record per contributing rank and pair, now adjacent: segmented sum -> final scores (back in d_pair_key / d_pair_score), then
+        // the min_score filter the single-GPU kernels apply when they flush a row
+        unsigned long long *d_runs = &d_sc->heavy_ticket;      // a free scalar
+        size_t tmp_bytes = 0;
+        HGA_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp_bytes, h->d_pair_key2.as<uint64_t>(), h->d_pair_key.as<uint64_t>(), h->d_pair_score2.as<uint32_t>(),
+                                                h->d_pair_score.as<uint32_t>(), d_runs, cub::Sum(), P, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
+        HGA_CUDA(cub::DeviceReduce::ReduceByKey(h->d_sort_tmp.p, tmp_bytes, h->d_pair_key2.as<uint64_t>(), h->d_pair_key.as<uint64_t>(), h->d_pair_score2.as<uint32_t>(),
+                                                h->d_pair_score.as<uint32_t>(), d_runs, cub::Sum(), P, h->stream));
+        unsigned long long runs = 0;
+        HGA_CUDA(cudaMemcpyAsync(&runs, d_runs, 8, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+        P = runs;
+        h->metrics.kernel_launches += 3;
+        if (min_score > 1 && P > 0) {
+            HGA_TRY(h->d_pivot_flag.ensure(P + 1));
+            uint8_t *flag = h->d_pivot_flag.as<uint8_t>();
+            flag_min_score_kernel<<<(int) std::min<uint64_t>((P + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(h->d_pair_score.as<uint32_t>(), P, min_score, flag);
+            size_t t1 = 0, t2 = 0;
+            HGA_CUDA(cub::DeviceSelect::Flagged(nullptr, t1, h->d_pair_key.as<uint64_t>(), flag, h->d_pair_key2.as<uint64_t>(), d_runs, P, h->stream));
+            HGA_CUDA(cub::DeviceSelect::Flagged(nullptr, t2, h->d_pair_score.as<uint32_t>(), flag, h->d_pair_score2.as<uint32_t>(), d_runs, P, h->stream));
+            HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
+            HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, t1, h->d_pair_key.as<uint64_t>(), flag, h->d_pair_key2.as<uint64_t>(), d_runs, P, h->stream));
+            HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, t2, h->d_pair_score.as<uint32_t>(), flag, h->d_pair_score2.as<uint32_t>(), d_runs, P, h->stream));
+            HGA_CUDA(cudaMemcpyAsync(&runs, d_runs, 8, cudaMemcpyDeviceToHost, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            P = runs;
+            h->metrics.kernel_launches += 5;
+        } else {
+            std::swap(h->d_pair_key, h->d_pair_key2);      // the swap below puts the reduced arrays back in place
+            std::swap(h->d_pair_score, h->d_pair_score2);
+        }
+    }
     std::swap(h->d_pair_key, h->d_pair_key2);
     std::swap(h->d_pair_score, h->d_pair_score2);
     h->n_pairs = P;
 
     {   // work measure
         HGA_CUDA(cudaMemsetAsync(&d_sc->increments, 0, 8, h->stream));
-        increments_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_inv_off.as<uint32_t>(), h->index_keys, h->index_by_kid ? h->index_key_div : 0u, &d_sc->increments);
+        increments_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_inv_off.as<uint32_t>(), h->index_keys, &d_sc->increments);
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));

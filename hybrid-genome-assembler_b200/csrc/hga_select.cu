@@ -197,12 +197,14 @@ int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold) {
     }
 
     uint64_t n_sel = 0;
-    if (P > 0 && (score_threshold > 0 || n_directed > 0)) {
+    // with a communicator every rank goes through this block, whatever its own pair count: the tie gather below is collective
+    // (a rank that holds no pair contributes no tie; skipping it would leave the others waiting in NCCL)
+    if ((P > 0 || multi) && (score_threshold > 0 || n_directed > 0)) {
         const uint64_t nb = (P + SEL_CHUNK - 1) / SEL_CHUNK;
         HGA_TRY(h->d_sel_scalars.ensure((nb + 1) * 8 * 5 + 64));
         unsigned long long *blk_ties = h->d_sel_scalars.as<unsigned long long>();
         unsigned long long *blk_above = blk_ties + (nb + 1), *tie_base = blk_above + (nb + 1), *blk_sel = tie_base + (nb + 1), *sel_base = blk_sel + (nb + 1);
-        count_chunks_kernel<<<(unsigned) nb, SEL_THREADS, 0, h->stream>>>(h->d_pair_score.as<uint32_t>(), P, (uint32_t) cut, blk_ties, blk_above);
+        if (nb) count_chunks_kernel<<<(unsigned) nb, SEL_THREADS, 0, h->stream>>>(h->d_pair_score.as<uint32_t>(), P, (uint32_t) cut, blk_ties, blk_above);
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaGetLastError());
         size_t tmp_bytes = 0;
@@ -225,7 +227,7 @@ int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold) {
             HGA_TRY(h->d_sel_key.ensure((my_ties + 1) * 8));
             HGA_TRY(h->d_export_a.ensure((T + 1) * 8 * 2 + 64));
             uint64_t *d_mine = h->d_sel_key.as<uint64_t>(), *d_all = h->d_export_a.as<uint64_t>(), *d_all_sorted = d_all + (T + 1);
-            write_ties_kernel<<<(unsigned) nb, SEL_THREADS, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), h->d_pair_score.as<uint32_t>(), P, (uint32_t) cut, tie_base, d_mine);
+            if (nb) write_ties_kernel<<<(unsigned) nb, SEL_THREADS, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), h->d_pair_score.as<uint32_t>(), P, (uint32_t) cut, tie_base, d_mine);
             HGA_CUDA(cudaGetLastError());
             HGA_TRY(hga_comm_allgatherv(h, d_mine, d_all, counts, 8));
             size_t tb2 = 0;
@@ -239,7 +241,7 @@ int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold) {
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             quota = local_quota;
         }
-        chunk_selected_kernel<<<(unsigned) ((nb + 255) / 256), 256, 0, h->stream>>>(blk_ties, tie_base, blk_above, nb, tie_offset, quota, blk_sel);
+        if (nb) chunk_selected_kernel<<<(unsigned) ((nb + 255) / 256), 256, 0, h->stream>>>(blk_ties, tie_base, blk_above, nb, tie_offset, quota, blk_sel);
         HGA_CUDA(cudaMemsetAsync(blk_sel + nb, 0, 8, h->stream));
         HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp_bytes, blk_sel, sel_base, nb + 1, h->stream));
         h->metrics.kernel_launches += 3;
@@ -249,7 +251,7 @@ int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold) {
         n_sel = total_sel;
         HGA_TRY(h->d_sel_key.ensure((n_sel + 1) * 8));
         HGA_TRY(h->d_sel_score.ensure((n_sel + 1) * 4));
-        write_selected_kernel<<<(unsigned) nb, SEL_THREADS, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), h->d_pair_score.as<uint32_t>(), P, (uint32_t) cut,
+        if (nb) write_selected_kernel<<<(unsigned) nb, SEL_THREADS, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), h->d_pair_score.as<uint32_t>(), P, (uint32_t) cut,
                                                                           tie_base, sel_base, tie_offset, quota, h->d_sel_key.as<uint64_t>(),
                                                                           h->d_sel_score.as<uint32_t>());
         h->metrics.kernel_launches++;

@@ -58,7 +58,7 @@ int hga_table_build(hga_handle *h, const uint64_t *host_kmers) {
     const uint64_t n = h->n_kmers;
     if (n >= (1ull << 29)) { hga_set_error("too many k-mers (%llu): the slot id space is 32 bit", (unsigned long long) n); return HGA_E_ARG; }
     // filter: sized to stay L2 resident (<= 48 MB, see hga_internal.cuh); HGA_FILTER_* / HGA_TABLE_LOAD are experiment switches
-    double bits_per_key = 16.0, max_mb = 48.0, load = 0.33;
+    double bits_per_key = 16.0, max_mb = 48.0, load = 0.25;
     if (const char *e = getenv("HGA_FILTER_BITS_PER_KEY")) bits_per_key = atof(e);
     if (const char *e = getenv("HGA_FILTER_MAX_MB")) max_mb = atof(e);
     if (const char *e = getenv("HGA_TABLE_LOAD")) load = std::min(0.9, std::max(0.05, atof(e)));
