@@ -32,14 +32,15 @@
 
 #include <cub/device/device_scan.cuh>
 
-#define SCAN_WARPS 8                             // 9.3 KB of shared memory per warp: 3 CTAs of 8 warps per SM
+#define SCAN_WARPS 8                             // 5.1 KB of shared memory per warp: 4 CTAs of 8 warps per SM at 64 registers
 #define SCAN_THREADS (SCAN_WARPS * 32)
-#define SCAN_TILE 992                            // window-end positions per warp tile (31 lanes x 32)
-#define SCAN_SPAN 1024                           // staged bases per tile: 32 of halo + the tile
+#define SCAN_LANE 16                             // consecutive window ends a lane owns
+#define SCAN_TILE (30 * SCAN_LANE)               // window-end positions per warp tile (30 lanes; lanes 0 and 1 hold the 32 bases before it)
+#define SCAN_SPAN (32 * SCAN_LANE)               // staged bases per tile: 32 of halo + the tile
 #define SCAN_UNROLL 4
 #define SCAN_Q 256                               // candidate ring (power of two, >= 31 + 32 * SCAN_UNROLL)
 #define SCAN_BND 32                              // read boundaries of a tile staged in shared memory (more: global search)
-#define SCAN_TR_STRIDE 33                        // row stride of the transposition buffer in entries (odd: conflict free)
+#define SCAN_TR_STRIDE (SCAN_LANE + 1)            // row stride of the transposition buffer in entries (odd: conflict free)
 
 struct ScanScalars {
     unsigned long long ticket;
@@ -52,7 +53,7 @@ struct ScanScalars {
 namespace {
 
 struct ScanParams {
-    const char *frame;                // bases - lead: 32 B aligned
+    const char *frame;                // bases - lead: 16 B aligned
     uint32_t lead;                    // bytes between the aligned frame and the first base
     uint64_t n_bases;
     const uint64_t *read_off;
@@ -68,17 +69,20 @@ struct ScanParams {
     uint64_t n_tiles;                 // tickets of this launch
     uint64_t tile_begin;              // first tile of this launch (chunked launches while the bases are still arriving)
     uint64_t tile_stride;             // > 0: sampling mode (count only, tile = tile_begin + ticket * stride)
-    int diag;                         // HGA_SCAN_DIAG experiments: 1 = no key probes (results are WRONG), 4 = L2 prefetch of the key sector when a window is queued
+    int diag;                         // HGA_SCAN_DIAG experiment: 1 = no key probes (results are WRONG)
 };
 
 // shared memory of one warp
 struct WarpTile {
     uint2 tr[SCAN_TR_STRIDE * 32];   // phase B -> C: x = locality hash, y = bit hash; afterwards: staged hits (x = slot, y = window index)
     uint32_t pk[SCAN_SPAN / 16 + 4]; // packed forward codes, 16 bases per word, first base most significant
-    uint32_t exc[SCAN_SPAN / 32 + 2];// bit p: staged base p is not one of ACGT
+    uint32_t exc[SCAN_SPAN / 32 + 2];// bit p: staged base p is not one of ACGT (written as u16 halves, one per lane)
     uint16_t q[SCAN_Q];              // candidate windows: staged index | 0x8000 when the window holds a non-ACGT byte
     int32_t bnd[SCAN_BND];           // staged index of the first base of reads r_lo, r_lo + 1, ... (n_bnd of them)
 };
+
+// entry of staged window index i in the transposition buffer
+__device__ __forceinline__ int tr_index(int i) { return SCAN_TR_STRIDE * (i / SCAN_LANE) + (i % SCAN_LANE); }
 
 // 4 ASCII bytes (little-endian in w, lowest address = first base) -> forward codes (8 bits, first base most significant) and
 // complement codes (8 bits, first base LEAST significant). Codes follow KmerIterator.cpp:7-19 (A0 C1 G2 T3 / complement A3 C2 G1
@@ -209,7 +213,7 @@ __device__ __forceinline__ void drain_queue(QueueState &qs, uint32_t n, int lane
         const uint32_t qe = T.q[(qs.head + lane) & (SCAN_Q - 1)];
         widx = qe & 0x7FFFu;
         const int i = (int) widx;
-        uint2 en = T.tr[SCAN_TR_STRIDE * (i >> 5) + (i & 31)];     // x = locality hash, y = bit hash (still there: hits are staged below index i - 32)
+        uint2 en = T.tr[tr_index(i)];     // x = locality hash, y = bit hash (still there: hits are staged below index i - 32)
         const int start = read_start_of(c, i);
         if (i < c.i_end && i - start + 1 >= k && !(p.diag & 1)) {
             uint32_t lo, hi;
@@ -257,21 +261,21 @@ __device__ __forceinline__ void drain_queue(QueueState &qs, uint32_t n, int lane
     qs.head += n;
 }
 
-// phase B for one lane: P0..P3 / Q0..Q3 = forward / complement codes of the 64 bases ending with the lane's own 32 (P2, P3);
+// phase B for one lane: P0..P2 / Q0..Q2 = forward / complement codes of the 48 bases ending with the lane's own 16 (P2);
 // row = the lane's row of the transposition buffer
 template<int W, bool KHI>
-__device__ __forceinline__ void phase_b(const uint32_t (&P)[4], const uint32_t (&Q)[4], const KmerGeom &geo, uint2 *row) {
+__device__ __forceinline__ void phase_b(const uint32_t (&P)[3], const uint32_t (&Q)[3], const KmerGeom &geo, uint2 *row) {
     constexpr int WU = W > 0 ? W - 1 : 0;          // positions before the lane's own that feed its first sliding minima
-    uint32_t h[32 + 7], t3[32 + 7];
+    uint32_t h[SCAN_LANE + 7], t3[SCAN_LANE + 7];
     const uint32_t cm = geo.cm, mtop = geo.mtop, ca = geo.ca, cb = geo.cb;
     const int k = geo.k;
     const int rsh = KHI ? 64 - 2 * k : 32 - 2 * k; // the reverse strand's pieces are top aligned
     #pragma unroll
-    for (int j = -WU; j < 32; j++) {
-        const int s0 = j + 17;                     // index (in the 64 bases) of the first of the 16 bases ending at the lane's base j
+    for (int j = -WU; j < SCAN_LANE; j++) {
+        const int s0 = j + 17;                     // index (in the 48 bases) of the first of the 16 bases ending at the lane's base j
         const int q = s0 >> 4, off = s0 & 15;
-        const uint32_t lo = off ? __funnelshift_l(P[(q + 1) & 3], P[q], 2 * off) : P[q];                 // forward, last 16 bases
-        const uint32_t rhi = off ? __funnelshift_r(Q[q], Q[(q + 1) & 3], 2 * off) : Q[q];                // complement of the same, base j on top
+        const uint32_t lo = off ? __funnelshift_l(P[(q + 1) % 3], P[q], 2 * off) : P[q];                 // forward, last 16 bases
+        const uint32_t rhi = off ? __funnelshift_r(Q[q], Q[(q + 1) % 3], 2 * off) : Q[q];                // complement of the same, base j on top
         uint32_t mn = 0;
         if (W > 0) {
             h[j + 7] = min(hga_mmer_hash(lo, cm), (rhi & mtop) * HGA_C1 + HGA_C4);
@@ -289,8 +293,8 @@ __device__ __forceinline__ void phase_b(const uint32_t (&P)[4], const uint32_t (
         if (j >= 0) {
             uint32_t hb;
             if (KHI) {
-                const uint32_t hi = off ? __funnelshift_l(P[q], P[(q + 3) & 3], 2 * off) : P[(q + 3) & 3];   // ca discards what lies above the k-mer
-                const uint32_t rlo = off ? __funnelshift_r(Q[(q + 3) & 3], Q[q], 2 * off) : Q[(q + 3) & 3];
+                const uint32_t hi = off ? __funnelshift_l(P[q], P[(q + 2) % 3], 2 * off) : P[(q + 2) % 3];   // ca discards what lies above the k-mer
+                const uint32_t rlo = off ? __funnelshift_r(Q[(q + 2) % 3], Q[q], 2 * off) : Q[(q + 2) % 3];
                 const uint32_t Rlo = __funnelshift_r(rlo, rhi, rsh), Rhi = rhi >> rsh;
                 hb = (hi * ca + lo) * cb + (Rhi * ca + Rlo) * cb;
             } else {
@@ -303,7 +307,7 @@ __device__ __forceinline__ void phase_b(const uint32_t (&P)[4], const uint32_t (
 }
 
 template<bool KHI>
-__device__ __forceinline__ void phase_b_dispatch(const uint32_t (&P)[4], const uint32_t (&Q)[4], const KmerGeom &geo, uint2 *row) {
+__device__ __forceinline__ void phase_b_dispatch(const uint32_t (&P)[3], const uint32_t (&Q)[3], const KmerGeom &geo, uint2 *row) {
     switch (geo.use_min ? geo.W : 0) {
         case 2: phase_b<2, KHI>(P, Q, geo, row); break;
         case 3: phase_b<3, KHI>(P, Q, geo, row); break;
@@ -316,65 +320,57 @@ __device__ __forceinline__ void phase_b_dispatch(const uint32_t (&P)[4], const u
     }
 }
 
-// N steps of phase C starting at row s0: filter probes of 32 adjacent windows per step, passing windows queued
-template<int N, bool EXC>
-__device__ __forceinline__ void phase_c_group(const TileCtx &c, int s0, int lane, QueueState &qs, uint64_t pol_last) {
-    const ScanParams &p = *c.p;
-    WarpTile &T = *c.T;
-    const uint32_t n_blocks = p.t.n_blocks;
-    const uint32_t *filter = p.t.filter;
-    const bool prefetch = (p.diag & 4) != 0;
-    uint2 en[N];
-    uint32_t fw[N];
-    #pragma unroll
-    for (int u = 0; u < N; u++) {
-        en[u] = T.tr[SCAN_TR_STRIDE * (s0 + u) + lane];              // x = locality hash, y = bit hash
-        fw[u] = ldg_u32_policy(filter + (__umulhi(en[u].x, n_blocks) * 8 + hga_bits_word(en[u].y)), pol_last);
-    }
-    #pragma unroll
-    for (int u = 0; u < N; u++) {
-        const int i = 32 * (s0 + u) + lane;
-        bool pass = hga_bits_test(fw[u], en[u].y);
-        bool exc = false;
-        if (EXC) { exc = window_exc(T.exc, i, p.t.geom.k) != 0; pass |= exc; }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
-        if (bal) {                                                   // warp uniform
-            if (pass) {
-                T.q[(qs.tail + __popc(bal & ((1u << lane) - 1))) & (SCAN_Q - 1)] = (uint16_t) ((uint32_t) i | (exc ? 0x8000u : 0u));
-                if (prefetch && (!EXC || !exc)) {                    // experiment: start the key sector's trip from HBM now
-                    const uint64_t *sp = p.t.keys + (size_t) __umulhi(en[u].x, p.t.n_buckets) * HGA_BUCKET_SLOTS +
-                                         hga_start_sector(en[u].x, en[u].y, p.t.sector_by_min) * HGA_SECTOR_SLOTS;
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(sp));
-                }
-            }
-            qs.tail += __popc(bal);
-        }
-    }
-    if (qs.tail - qs.head >= 32) {
-        __syncwarp();
-        do drain_queue(qs, 32, lane, c); while (qs.tail - qs.head >= 32);
-        __syncwarp();
-    }
-}
-
-// phase C + drains: returns the number of staged hits (rows 1 .. 31 of the transposition buffer; row 0 is the halo)
+// phase C + drains: returns the number of staged hits. Step s = the 32 adjacent staged windows 32 s .. 32 s + 31 (two lanes' rows); step 0
+// is the halo. One loop, one drain call site (the unrolled code of phases B and C already fills the instruction cache).
 template<bool EXC>
 __device__ __forceinline__ uint32_t phase_c(const TileCtx &c, int lane, uint32_t &n_cand) {
+    const ScanParams &p = *c.p;
+    WarpTile &T = *c.T;
     const uint64_t pol_last = l2_policy_evict_last();
+    const uint32_t n_blocks = p.t.n_blocks, lane_lt = (1u << lane) - 1;
+    const uint32_t *filter = p.t.filter;
+    const int filter_k = p.t.filter_k;
     QueueState qs = {0, 0, 0};
-    phase_c_group<3, EXC>(c, 1, lane, qs, pol_last);
     #pragma unroll 1
-    for (int s0 = 4; s0 < 32; s0 += SCAN_UNROLL) phase_c_group<SCAN_UNROLL, EXC>(c, s0, lane, qs, pol_last);
-    __syncwarp();
-    if (qs.tail != qs.head) drain_queue(qs, qs.tail - qs.head, lane, c);
-    __syncwarp();
+    for (int s0 = 0; s0 <= SCAN_SPAN / 32; s0 += SCAN_UNROLL) {
+        const bool last = s0 >= SCAN_SPAN / 32;                     // one more round that only empties the queue
+        if (!last) {
+            uint2 en[SCAN_UNROLL];
+            uint32_t fw[SCAN_UNROLL];
+            #pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; u++) {
+                en[u] = T.tr[tr_index(32 * (s0 + u) + lane)];       // x = locality hash, y = bit hash
+                fw[u] = ldg_u32_policy(filter + (__umulhi(en[u].x, n_blocks) * 8 + hga_bits_word(en[u].y)), pol_last);
+            }
+            #pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; u++) {
+                if (u == 0 && s0 == 0) continue;                    // the halo's windows belong to the previous tile
+                const int i = 32 * (s0 + u) + lane;
+                bool pass = hga_bits_test(fw[u], en[u].y, filter_k);
+                bool exc = false;
+                if (EXC) { exc = window_exc(T.exc, i, p.t.geom.k) != 0; pass |= exc; }
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
+                if (bal) {                                           // warp uniform
+                    if (pass) T.q[(qs.tail + __popc(bal & lane_lt)) & (SCAN_Q - 1)] = (uint16_t) ((uint32_t) i | (exc ? 0x8000u : 0u));
+                    qs.tail += __popc(bal);
+                }
+            }
+        }
+        const uint32_t need = last ? 1u : 32u;
+        if (qs.tail - qs.head >= need) {
+            __syncwarp();
+            do drain_queue(qs, min(32u, qs.tail - qs.head), lane, c); while (qs.tail - qs.head >= need);
+            __syncwarp();
+        }
+    }
     n_cand += qs.tail;
     return qs.st_count;
 }
 
 // 24 independent warps per SM (3 CTAs of 8; 9.3 KB of shared memory per warp). The parameters are __grid_constant__ and every helper
 // is inlined so that nothing lives in local memory.
-// MINB = resident CTAs per SM the register allocation aims at (3: 80 registers, 2: up to 128; experiment switch HGA_SCAN_OCC)
+// MINB = resident CTAs per SM the register allocation aims at (4: 64 registers = 32 warps, 5: 48 registers = 40 warps, 3: 80
+// registers = 24 warps; experiment switch HGA_SCAN_OCC)
 template<int MINB>
 __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -385,7 +381,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
 
     if (lane < 4) T.pk[SCAN_SPAN / 16 + lane] = 0;
     if (lane < 2) T.exc[SCAN_SPAN / 32 + lane] = 0;
+    __syncwarp();
 
+    const uint64_t pol_stream = l2_policy_evict_first();               // the base stream passes through L2 once
     unsigned long long next_ticket = 0;
     if (lane == 0) next_ticket = atomicAdd(&p.scalars->ticket, 1ull);
     for (;;) {
@@ -393,33 +391,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
         if (ticket >= p.n_tiles) break;
         if (lane == 0) next_ticket = atomicAdd(&p.scalars->ticket, 1ull);               // in flight while this tile is processed
         const uint64_t tile = p.tile_begin + (p.tile_stride ? ticket * p.tile_stride : ticket);
-        // frame coordinate u = stream position + lead; the tile's window ends are u in [992 tile, 992 tile + 992); staged index 0 is u = 992 tile - 32
+        // frame coordinate u = stream position + lead; the tile's window ends are u in [480 tile, 480 tile + 480); staged index 0 is u = 480 tile - 32
         const int64_t ubase = (int64_t) (tile * SCAN_TILE) - 32;
         const int64_t gbase = ubase - (int64_t) p.lead;
         const int64_t u_end = (int64_t) p.lead + (int64_t) p.n_bases;                 // first frame position past the stream
 
-        // ---- phase A: one 32 B sector per lane, packed to two words per strand ---------------------------------------
-        uint32_t P[4], Q[4], bad = 0;
+        // ---- phase A: 16 bases per lane, packed to one word per strand -----------------------------------------------
+        uint32_t P[3], Q[3], bad = 0;
         {
-            const int64_t u = ubase + 32 * lane;
-            uint32_t v[8];
+            const int64_t u = ubase + SCAN_LANE * lane;
+            uint32_t v[4];
             if (u >= 0 && u < u_end) {
-                asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p.frame + u));
+                asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p.frame + u), "l"(pol_stream));
             } else {
                 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = 0x41414141u;                        // outside the stream: 'A' (never inside a valid window)
+                for (int i = 0; i < 4; i++) v[i] = 0x41414141u;                        // outside the stream: 'A' (never inside a valid window)
             }
-            uint32_t diff = 0, f[8], r[8];
+            uint32_t diff = 0, f[4], r[4];
             #pragma unroll
-            for (int i = 0; i < 8; i++) pack4(v[i], f[i], r[i], diff);
+            for (int i = 0; i < 4; i++) pack4(v[i], f[i], r[i], diff);
             P[2] = (f[0] << 24) | (f[1] << 16) | (f[2] << 8) | f[3];
-            P[3] = (f[4] << 24) | (f[5] << 16) | (f[6] << 8) | f[7];
             Q[2] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
-            Q[3] = r[4] | (r[5] << 8) | (r[6] << 16) | (r[7] << 24);
             if (diff) {                                                                // rare: clear the codes of the non-ACGT bytes, note them
                 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < 4; i++) {
                     uint32_t d = 0, f0, r0;
                     pack4(v[i], f0, r0, d);
                     #pragma unroll
@@ -427,18 +423,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
                         if ((d >> (8 * b)) & 0xFFu) {
                             const int pos = 4 * i + b;
                             bad |= 1u << pos;
-                            if (pos < 16) { P[2] &= ~(3u << (30 - 2 * pos)); Q[2] &= ~(3u << (2 * pos)); }
-                            else { P[3] &= ~(3u << (30 - 2 * (pos - 16))); Q[3] &= ~(3u << (2 * (pos - 16))); }
+                            P[2] &= ~(3u << (30 - 2 * pos)); Q[2] &= ~(3u << (2 * pos));
                         }
                     }
                 }
             }
         }
-        T.pk[2 * lane] = P[2]; T.pk[2 * lane + 1] = P[3];
-        T.exc[lane] = bad;
-        P[0] = __shfl_up_sync(0xFFFFFFFFu, P[2], 1); P[1] = __shfl_up_sync(0xFFFFFFFFu, P[3], 1);
-        Q[0] = __shfl_up_sync(0xFFFFFFFFu, Q[2], 1); Q[1] = __shfl_up_sync(0xFFFFFFFFu, Q[3], 1);
-        if (lane == 0) { P[0] = 0; P[1] = 0; Q[0] = 0; Q[1] = 0; }
+        T.pk[lane] = P[2];
+        reinterpret_cast<uint16_t *>(T.exc)[lane] = (uint16_t) bad;
+        P[0] = __shfl_up_sync(0xFFFFFFFFu, P[2], 2); P[1] = __shfl_up_sync(0xFFFFFFFFu, P[2], 1);   // lanes 0 and 1 are the halo: their own windows are never used
+        Q[0] = __shfl_up_sync(0xFFFFFFFFu, Q[2], 2); Q[1] = __shfl_up_sync(0xFFFFFFFFu, Q[2], 1);
         const bool exc_any = __any_sync(0xFFFFFFFFu, bad != 0);
 
         // read boundaries of the tile (reads r_lo .. r_hi start at or before the tile's last base)
@@ -544,13 +538,14 @@ const size_t kScanSmem = SCAN_WARPS * sizeof(WarpTile);
 
 int scan_occ_variant() {
     static int v = 0;
-    if (!v) { const char *e = getenv("HGA_SCAN_OCC"); v = (e && atoi(e) == 2) ? 2 : 3; }
+    if (!v) { const char *e = getenv("HGA_SCAN_OCC"); v = e ? atoi(e) : 4; if (v != 3 && v != 5) v = 4; }
     return v;
 }
 
 int launch_scan(hga_handle *h, const ScanParams &p, int grid) {
-    if (scan_occ_variant() == 2) scan_probe_kernel<2><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
-    else scan_probe_kernel<3><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
+    if (scan_occ_variant() == 3) scan_probe_kernel<3><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
+    else if (scan_occ_variant() == 5) scan_probe_kernel<5><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
+    else scan_probe_kernel<4><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
     HGA_CUDA(cudaGetLastError());
     h->metrics.kernel_launches++;
     return HGA_OK;
@@ -565,7 +560,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     HGA_TRY(h->d_row_off.ensure((n_reads + 1) * 8));
     HGA_TRY(h->d_scan_scalars.ensure(sizeof(ScanScalars)));
     ScanScalars *d_sc = h->d_scan_scalars.as<ScanScalars>();
-    const uint32_t lead = (uint32_t) (reinterpret_cast<uintptr_t>(d_bases) & 31);   // the kernel loads whole 32 B sectors: frame = the bases aligned down
+    const uint32_t lead = (uint32_t) (reinterpret_cast<uintptr_t>(d_bases) & 15);   // the kernel loads aligned 16 B pieces: frame = the bases aligned down
     const uint64_t n_tiles = (n_reads == 0 || n_bases == 0) ? 0 : (lead + n_bases + SCAN_TILE - 1) / SCAN_TILE;
     HGA_TRY(h->d_tile_state.ensure((n_tiles + 2) * (8 + 8 + 4)));   // tile directory: tmp offset | final offset | count
     unsigned long long *tile_tmp_off = h->d_tile_state.as<unsigned long long>();
@@ -584,12 +579,15 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     if (const char *e = getenv("HGA_SCAN_DIAG")) p.diag = atoi(e);
 
     int occ = 0;
-    if (scan_occ_variant() == 2) {
-        HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
-        HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<2>, SCAN_THREADS, kScanSmem));
-    } else {
+    if (scan_occ_variant() == 3) {
         HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
         HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<3>, SCAN_THREADS, kScanSmem));
+    } else if (scan_occ_variant() == 5) {
+        HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
+        HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<5>, SCAN_THREADS, kScanSmem));
+    } else {
+        HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
+        HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<4>, SCAN_THREADS, kScanSmem));
     }
     if (occ < 1) occ = 1;
     const int grid_full = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, std::max<uint64_t>((n_tiles + SCAN_WARPS - 1) / SCAN_WARPS, 1));

@@ -17,7 +17,7 @@ __global__ void table_insert_main_kernel(const uint64_t *__restrict__ kmers, uin
         if (key == HGA_EMPTY_KEY) { atomicOr(flags, 2); continue; }   // never a canonical k-mer
         const uint32_t hb = hga_bits_hash(key, t.geom);
         const uint32_t B = hga_locality_from_min(hga_minimizer(key, hb, t.geom));
-        atomicOr(&t.filter[(size_t) hga_scale(B, t.n_blocks) * 8 + hga_bits_word(hb)], hga_bits_mask(hb));
+        atomicOr(&t.filter[(size_t) hga_scale(B, t.n_blocks) * 8 + hga_bits_word(hb)], hga_bits_mask(hb, t.filter_k));
         const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS, start = hga_start_sector(B, hb, t.sector_by_min) * HGA_SECTOR_SLOTS;
         bool done = false;
         for (uint32_t j = 0; j < HGA_BUCKET_SLOTS && !done; j++) {
@@ -73,6 +73,7 @@ int hga_table_build(hga_handle *h, const uint64_t *host_kmers) {
     t.n_over = 0;
     t.n_blocks = (uint32_t) n_blocks;
     if (const char *e = getenv("HGA_SECTOR_BY_MIN")) t.sector_by_min = atoi(e) != 0;
+    if (const char *e = getenv("HGA_FILTER_K")) t.filter_k = atoi(e) == 2 ? 2 : 3;
     HGA_TRY(h->d_keys.ensure((size_t) t.n_main * 8));
     HGA_TRY(h->d_kid_slot.ensure((size_t) (n + 1) * 4));
     HGA_TRY(h->d_filter.ensure((size_t) n_blocks * 32));
