@@ -308,9 +308,6 @@ int main(int argc, char **argv) {
                          "when it finds no strong tail connection\n";
         hga_enrichment_t fin;
         {
-            // the reference times these separately ("Merging of initial components", "Calculation of enrichment connections",
-            // "Merging into core components"); here they are one library call
-            Timer t("Merging of initial components, calculation of enrichment connections and merging into core components");
             if (tail_block)
                 check(hga_enrich_full(h, config.scaffold_component_min_size, config.scaffold_component_max_size, (uint32_t) config.enrichment_connections_min_score,
                                       (uint32_t) config.tail_amplification_min_score, config.spectral_dims, reads.seq_off.data()), "hga_enrich_full");
@@ -318,7 +315,17 @@ int main(int argc, char **argv) {
                 check(hga_enrich_ex(h, config.scaffold_component_min_size, config.scaffold_component_max_size, (uint32_t) config.enrichment_connections_min_score),
                       "hga_enrich");
             check(hga_get_enrichment(h, &fin), "hga_get_enrichment");
-            t.done();
+            // one library call, reported under the reference's own timer labels (ReadClusteringEngine.cpp:765-791)
+            hga_metrics_t pm;
+            hga_tail_block_t tb;
+            check(hga_metrics(h, &pm), "hga_metrics");
+            const bool block_ran = tail_block && hga_get_tail_block(h, &tb) == HGA_OK && tb.ran;
+            const char *labels[6] = {"Merging of initial components", "Calculation of tail connections", "Spectral clustering", "Merging of scaffold components",
+                                     "Calculation of enrichment connections", "Merging into core components"};
+            for (int i = 0; i < 6; i++) {
+                if (i >= 1 && i <= 3 && !(block_ran && (i == 1 || pm.enrich_phase_ms[i] > 0))) continue;   // :768-775: only with more than two scaffold components / strong tail connections
+                std::cout << labels[i] << " took " << (long long) pm.enrich_phase_ms[i] << "ms\n";
+            }
         }
         Timer t_exp("Export of components");
         hga_host::export_components(reads, std::vector<uint32_t>(fin.final_id, fin.final_id + fin.n_final), fin.assignment, output_folder_path, io_threads);

@@ -280,17 +280,22 @@ uint32_t dsu_find(std::vector<uint32_t> &parent, uint32_t v) {
 
 struct Conn { uint32_t x, y, s; };
 
-// HGA_ENRICH_TIMING=1: wall time of every phase on stderr (synchronises the stream at each mark)
+// Wall time of the phases (the stream is synchronised at each mark), summed into the stage the reference's timers attribute them to
+// (hga_metrics_t::enrich_phase_ms); HGA_ENRICH_TIMING=1 also prints every phase on stderr.
 struct PhaseClock {
     bool on;
     cudaStream_t st;
+    double *stage_ms;
     std::chrono::steady_clock::time_point t0;
-    PhaseClock(cudaStream_t s) : on(getenv("HGA_ENRICH_TIMING") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
-    void mark(const char *what) {
-        if (!on) return;
+    PhaseClock(cudaStream_t s, double *stages) : on(getenv("HGA_ENRICH_TIMING") != nullptr), st(s), stage_ms(stages), t0(std::chrono::steady_clock::now()) {
+        for (int i = 0; i < 6; i++) stage_ms[i] = 0;
+    }
+    void mark(const char *what, int stage) {
         cudaStreamSynchronize(st);
         const auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "hga_enrich: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        stage_ms[stage] += ms;
+        if (on) fprintf(stderr, "hga_enrich: %-28s %8.2f ms\n", what, ms);
         t0 = t1;
     }
 };
@@ -313,7 +318,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
     const uint32_t first_id = h->inc_row_first_id;
     const uint32_t n_slots = h->index_keys;
     StageTimer timer(h, &h->metrics.enrich_ms);
-    PhaseClock pc(h->stream);
+    PhaseClock pc(h->stream, h->metrics.enrich_phase_ms);
     HGA_TRY(h->d_enr_scalars.ensure(64));
     unsigned long long *d_count = h->d_enr_scalars.as<unsigned long long>();
 
@@ -389,7 +394,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
         HGA_CUDA(cudaMemcpyAsync(is_pivot.data(), h->d_pivot_flag.p, n, cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
     }
-    pc.mark("selection sort + D2H");
+    pc.mark("selection sort + D2H", 0);
     std::vector<uint32_t> parent(n + 1), size(n + 1, 1);
     std::vector<uint8_t> touched(n + 1, 0);
     std::iota(parent.begin(), parent.end(), 0u);
@@ -408,7 +413,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
         if (tail) tree_edges.push_back({x, y});                                                // :474
     }
     if (pc.on) fprintf(stderr, "hga_enrich: %llu of %llu selected edges replayed\n", (unsigned long long) M2, (unsigned long long) M);
-    pc.mark("  replay loop");
+    pc.mark("  replay loop", 0);
     // cores = components with >= min_size vertices (:482-486), identified by their root = element [0] = the survivor (:366)
     std::vector<int32_t> core_of(n + 1, -1);
     std::vector<uint32_t> surv_row;
@@ -430,7 +435,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
     fill_cores();
     res.n_scaffold_cores = C;
 
-    pc.mark("host root replay + cores");
+    pc.mark("host root replay + cores", 0);
     // ---- 2. GPU: unions, removal bounds, purged index ----------------------------------------------------------------------
     HGA_TRY(h->d_enr_core_of.ensure((n + 1) * 4));
     HGA_TRY(h->d_enr_surv.ensure(((size_t) C + 1) * 4 * 2));        // second half: the survivors after the tail block's merge
@@ -480,7 +485,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
         }
     }
     const uint64_t *d_keys = h->d_enr_keys.as<uint64_t>();
-    pc.mark("core k-mer unions");
+    pc.mark("core k-mer unions", 0);
     const uint64_t *d_u = d_keys;      // sorted unique (core, slot)
     HGA_TRY(h->d_enr_core_koff.ensure(((size_t) C + 2) * 8));
     unsigned long long *d_core_koff = h->d_enr_core_koff.as<unsigned long long>();
@@ -507,7 +512,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
     h->n_purged = n_purged;
     h->n_core_kmers = n_u;
 
-    pc.mark("purge");
+    pc.mark("purge", 0);
     // ---- 2b. tail / spectral block (:768-777), on request: host stages on the merged state, second merge on the GPU -------------
     if (tail && C > 2) {
         res.tail_block_ran = true;
@@ -544,7 +549,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
                                           tree_off.data(), tree_x.data(), tree_y.data(), pidx.off, pidx.read_id, tail->amplification_min_score,
                                           res.tconn_x.data(), res.tconn_y.data(), res.tconn_score.data(), &n_t));
         res.tconn_x.resize(n_t); res.tconn_y.resize(n_t); res.tconn_score.resize(n_t);
-        pc.mark("  tail connections (host)");
+        pc.mark("  tail connections (host)", 1);
         uint64_t n_strong = 0;                                                                      // :770 score > 5; the list is score-descending
         while (n_strong < n_t && res.tconn_score[n_strong] > 5) n_strong++;
         res.cluster_off.assign(1, 0);
@@ -560,7 +565,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
                 res.cluster_off.push_back(res.cluster_member.size());
             }
         }
-        pc.mark("  spectral clustering (host)");
+        pc.mark("  spectral clustering (host)", 2);
         // which core every core merges into (itself unless its cluster has several members), new compact numbering of the survivors
         std::vector<uint32_t> into(C), multi(C, 0);
         std::iota(into.begin(), into.end(), 0u);
@@ -648,7 +653,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
             h->metrics.kernel_launches++;
             fill_cores();
         }
-        pc.mark("  merge of the spectral clusters");
+        pc.mark("  merge of the spectral clusters", 3);
     }
     // ---- 3. GPU: enrichment connections = run lengths of the sorted (core, partner) emissions ------------------------------
     std::vector<Conn> conns;
@@ -722,13 +727,13 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
             for (uint64_t i = 0; i < n_conn; i++) conns[i] = {cx[i], cy[i], cs[i]};
         }
     }
-    pc.mark("enrichment connections");
+    pc.mark("enrichment connections", 4);
 
     // ---- 4. host: canonical order, restricted union_find (:424-489 with restricted = cores, min 2, max -1), final merge -----
     // the connections arrive in canonical order (sorted on the GPU above)
     res.conn_x.resize(conns.size()); res.conn_y.resize(conns.size()); res.conn_score.resize(conns.size());
     for (size_t i = 0; i < conns.size(); i++) { res.conn_x[i] = conns[i].x; res.conn_y[i] = conns[i].y; res.conn_score[i] = conns[i].s; }
-    pc.mark("  canonical sort of the connections");
+    pc.mark("  canonical sort of the connections", 4);
     std::iota(parent.begin(), parent.end(), 0u);
     std::fill(size.begin(), size.end(), 1u);
     std::vector<uint8_t> restricted(n + 1, 0), affected(n + 1, 0);
@@ -744,7 +749,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
         size[bigger] += size[smaller];
         restricted[bigger] |= restricted[smaller];                                             // :478
     }
-    pc.mark("  restricted union-find loop");
+    pc.mark("  restricted union-find loop", 5);
     // final id of every read: the root of its enrichment component when that has >= 2 vertices (union_find's min_size = 2),
     // otherwise the id it had; a core's members follow their survivor. get_component_ids keeps ids with >= min_size reads.
     std::vector<uint32_t> final_of(n + 1, 0xFFFFFFFFu);    // row -> final survivor row
@@ -780,7 +785,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
             res.assignment[r] = f + first_id;
         }
     }
-    pc.mark("host restricted union-find");
+    pc.mark("host restricted union-find", 5);
     timer.stop();
     h->metrics.n_cores = C; h->metrics.n_enrich_connections = conns.size(); h->metrics.n_final_components = n_final;
     h->have_enrichment = true;

@@ -261,13 +261,19 @@ typedef struct {
     double enrich_ms;          /* hga_enrich, host replay of the union_find roots included */
     uint64_t n_cores, n_enrich_connections, n_final_components;
     uint64_t redo_pivots;      /* pivot rows redone by the second pass of pair-count tier 1 (1024-entry accumulator) */
+    /* wall time of the stages of hga_enrich* under the reference's own timer labels (ReadClusteringEngine.cpp:765-791):
+     * [0] Merging of initial components, [1] Calculation of tail connections, [2] Spectral clustering, [3] Merging of scaffold
+     * components, [4] Calculation of enrichment connections, [5] Merging into core components ([1]..[3]: 0 when the block did not run) */
+    double enrich_phase_ms[6];
 } hga_metrics_t;
 int hga_metrics(hga_handle *h, hga_metrics_t *out);
 
 /* Multi-GPU (one handle per rank/GPU). The 128-byte id comes from hga_comm_unique_id on rank 0 and is
  * distributed by the caller (torch.distributed broadcast, a file, ...). After hga_comm_init:
- *   hga_build_index   routes (kmer, read) incidences to the k-mer's owner rank (all-to-all),
- *   hga_pair_count    reduces partial scores at the owner of x (all-to-all),
+ *   hga_build_index   routes (kmer, read) incidences to the k-mer's owner rank, kmer_id mod nranks (all-to-all); nothing is replicated:
+ *                     hga_get_index on a rank returns the lists of ITS k-mers (every other list empty),
+ *   hga_pair_count    counts partial scores over the owned lists and reduces them at the owner of x, x mod nranks (all-to-all):
+ *                     every unordered pair ends up on exactly one rank,
  *   hga_select_edges  all-reduces the score histogram,
  *   hga_components    iterates union-find with all-reduce(min) on the label array.
  * n_reads_total = number of reads over all ranks (rows are global: rank shards are contiguous id ranges). */

@@ -9,6 +9,12 @@
 //
 //   occ_driver specificity <k> <read paths...>                        -> "<upper specificity> <occurrences> <unique k-mers>" lines
 //   occ_driver export <k> <lower> <upper> <percent> <out> <read paths...>
+//   occ_driver count <k> <min_count> <read paths...>                  -> "<k-mer value> <count>" lines, ascending
+//
+// `count` pins the COUNTING (what jellyfish does upstream of the reader) with reference code: the reference's own record stream
+// (common/SequenceRecordIterator.cpp) and rolling canonical k-mer (common/KmerIterator.cpp) feeding a std::map. On inputs made of
+// A C G T only the jellyfish rule (windows with another byte are skipped) and KmerIterator's rule (another byte reads as code 0)
+// cannot differ, so on such inputs this IS what `jellyfish count -C` + `dump` give, computed by the reference's code.
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -16,12 +22,29 @@
 #include <string>
 #include <vector>
 
+#include <map>
+
+#include "common/KmerIterator.h"
+#include "common/SequenceRecordIterator.h"
 #include "occurrences/JellyfishOccurrenceReader.h"
 
 int main(int argc, char **argv) {
     if (argc < 4) { fprintf(stderr, "usage: occ_driver specificity <k> <paths...> | export <k> <lower> <upper> <percent> <out> <paths...>\n"); return 2; }
     const std::string mode = argv[1];
     const int k = std::atoi(argv[2]);
+    if (mode == "count" && argc >= 5) {
+        const unsigned long min_count = std::strtoul(argv[3], nullptr, 10);
+        std::vector<std::string> paths(argv + 4, argv + argc);
+        SequenceRecordIterator reader(paths, false);
+        std::map<Kmer, unsigned long> counts;
+        std::optional<GenomeReadData> rec;
+        while ((rec = reader.get_next_record()) != std::nullopt) {
+            KmerIterator it(rec->sequence, k);
+            while (it.next_kmer()) counts[it.current_kmer]++;
+        }
+        for (auto &kv : counts) if (kv.second >= min_count) printf("%llu %lu\n", (unsigned long long) kv.first, kv.second);
+        return 0;
+    }
     if (mode == "specificity") {
         std::vector<std::string> paths(argv + 3, argv + argc);
         JellyfishOccurrenceReader reader(paths, k);

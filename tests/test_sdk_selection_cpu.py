@@ -103,3 +103,26 @@ def test_merge_rejects_unsorted_lists():
     import hga_b200
     with pytest.raises(hga_b200.HgaError):
         hga_b200.capi.sdk_merge([(np.array([5, 3], dtype=np.uint64), np.array([2, 2], dtype=np.uint32))])
+
+
+def reference_counts(occ_driver, paths, k, min_count):
+    """canonical k-mer counts by the reference's OWN code: SequenceRecordIterator + KmerIterator + std::map (occ_driver count)"""
+    r = subprocess.run([occ_driver, "count", str(k), str(min_count)] + list(paths), capture_output=True, text=True, check=True)
+    rows = [l.split() for l in r.stdout.replace("\r", "\n").splitlines() if len(l.split()) == 2 and l.split()[0].isdigit() and l.split()[1].isdigit()]
+    return np.array([int(a) for a, _ in rows], dtype=np.uint64), np.array([int(b) for _, b in rows], dtype=np.uint32)
+
+
+@pytest.mark.parametrize("k", [11, 19, 31, 32])
+def test_exact_counts_match_the_reference_kmer_iterator(oracle, occ_driver, tmp_path, k):
+    """the counting step pinned with reference code: on reads made of A C G T only, jellyfish's rule (skip windows with another byte) and
+    KmerIterator's rule (another byte reads as code 0) coincide, so the reference's own iterator + std::map give jellyfish's counts. The
+    numpy checker the GPU counting is compared with must agree with them, for every k-mer and every count."""
+    g = datagen.random_genome(5000, 300 + k)
+    reads = datagen.sample_reads(g, 250, 200, 400 + k, error_rate=0.01)
+    p = str(tmp_path / "reads.fa")
+    datagen.write_fasta(p, reads)
+    rc, rd = oracle.load_reads([p])
+    for mc in (1, 2):
+        wk, wc = exact_counts(rd["seq"], rd["seq_off"], k, mc)
+        rk, rcnt = reference_counts(occ_driver, [p], k, mc)
+        assert np.array_equal(wk, rk) and np.array_equal(wc, rcnt) and len(rk) > 100

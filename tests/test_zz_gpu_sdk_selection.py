@@ -1,6 +1,5 @@
-"""GPU: SDK selection: hga_count_kmers against exact counting in numpy, and the jf_occurrences program end to end.
-Written after round 1's GPU minutes were spent: not yet run on a GPU (the same source passes on the host,
-tests/test_kernel_bodies_on_host.py)."""
+"""GPU: SDK selection: hga_count_kmers against exact counting in numpy and against the reference's own KmerIterator
+(oracle/_ref/occ_driver count), and the jf_occurrences program end to end."""
 import os
 import subprocess
 
@@ -66,3 +65,23 @@ def test_cli_jf_occurrences_exports_the_kmers_file(oracle, tmp_path):
     t, o, u = hga_b200.capi.sdk_specificity(total, largest)
     table = [tuple(l.split()) for l in r.stdout.splitlines() if len(l.split()) == 3 and l[0].isdigit()]
     assert [(float(a), int(b), int(c)) for a, b, c in table] == [(round(float(a), 2), int(b), int(c)) for a, b, c in zip(t, o, u)]
+
+
+@pytest.mark.parametrize("k", [15, 19, 32])
+def test_cuda_kmer_counts_match_the_reference_kmer_iterator(oracle, tmp_path, k):
+    """hga_count_kmers against reference CODE: the reference's record stream + rolling canonical k-mer + std::map (occ_driver count) on
+    ACGT-only reads, where its rule for other bytes cannot differ from jellyfish's (tests/test_sdk_selection_cpu.py pins the same)"""
+    import hga_b200
+    from test_sdk_selection_cpu import reference_counts
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "occ_driver")
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/occ_driver not built")
+    g = datagen.random_genome(20000, 500 + k)
+    reads = datagen.sample_reads(g, 600, 400, 600 + k, error_rate=0.02, length_sigma=0.4)
+    p = str(tmp_path / "reads.fa")
+    datagen.write_fasta(p, reads)
+    rc, rd = oracle.load_reads([p])
+    for mc in (1, 2):
+        km, ct = hga_b200.capi.count_kmers(rd["seq"], rd["seq_off"], k, min_count=mc)
+        rk, rcnt = reference_counts(drv, [p], k, mc)
+        assert np.array_equal(km, rk) and np.array_equal(ct, rcnt) and len(rk) > 1000
