@@ -140,7 +140,7 @@ void hga_destroy(hga_handle *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     hga_comm_destroy(h);
-    DevBuf *dev[] = {&h->d_keys, &h->d_slot_kid, &h->d_kid_slot, &h->d_filter, &h->d_bases, &h->d_read_off, &h->d_row_off, &h->d_hit_slot, &h->d_hit_pos,
+    DevBuf *dev[] = {&h->d_keys, &h->d_slot_kid, &h->d_kid_slot, &h->d_filter, &h->d_bases, &h->d_read_off, &h->d_row_off, &h->d_hit_slot, &h->d_hit_pos, &h->d_pos_tmp,
                      &h->d_tile_state, &h->d_tile_dir, &h->d_scan_scalars, &h->d_x_slot, &h->d_x_row, &h->d_hit_kid, &h->d_g_kid, &h->d_g_row_off, &h->d_inv_off, &h->d_inv_row, &h->d_sort_a,
                      &h->d_sort_b, &h->d_sort_tmp, &h->d_pair_key, &h->d_pair_score, &h->d_pair_key2, &h->d_pair_score2, &h->d_pair_scalars,
                      &h->d_heavy_list, &h->d_mid_list, &h->d_redo_list, &h->d_heavy_tab, &h->d_pivot_flag, &h->d_pivot_order, &h->d_hist, &h->d_sel_key, &h->d_sel_score, &h->d_sel_scalars, &h->d_parent,
@@ -200,6 +200,7 @@ int hga_get_hits(hga_handle *h, int sorted_by_kmer_id, hga_hits *out) {
     const uint64_t E = h->n_hits, R = h->n_reads;
     HGA_TRY(h->d_export_a.ensure((E + 1) * 4));
     uint32_t *d_kid = h->d_export_a.as<uint32_t>();
+    HGA_TRY(hga_scan_finish_positions(h));
     const uint32_t *d_pos = h->d_hit_pos.as<uint32_t>();
     if (E) {
         slots_to_kids_kernel<<<grid_for(h, E), 256, 0, h->stream>>>(h->d_hit_slot.as<uint32_t>(), h->table.slot_kid, E, d_kid);

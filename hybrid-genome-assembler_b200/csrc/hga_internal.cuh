@@ -283,6 +283,10 @@ struct hga_handle {
     DevBuf d_bases, d_read_off;           // staging for hga_scan (host entry)
     DevBuf d_row_off;                     // u64[n_reads+1]
     DevBuf d_hit_slot, d_hit_pos;         // u32[E]
+    DevBuf d_pos_tmp;                     // positions in tile-completion order until hga_get_hits moves them (hga_scan_finish_positions)
+    uint64_t scan_tiles = 0;
+    double scan_density = 0;              // hits per base of the previous scan on this handle (sizes the next one's hit buffers)
+    bool pos_pending = false;
     DevBuf d_tile_state, d_tile_dir, d_scan_scalars;
     bool have_scan = false;
 
@@ -344,6 +348,7 @@ struct hga_handle {
 int hga_table_build(hga_handle *h, const uint64_t *host_kmers);
 // h_bases != nullptr: the bases are still on the host; the run copies them (in chunks, overlapped with the scan when large)
 int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, const char *h_bases);
+int hga_scan_finish_positions(hga_handle *h);
 int hga_index_run(hga_handle *h);
 int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
 int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold);

@@ -506,18 +506,15 @@ __global__ void scan_tile_dir_kernel(const uint64_t *__restrict__ read_off, uint
 }
 
 // tile segments (completion order) -> stream order; one warp per tile
-__global__ void scan_reorder_kernel(const uint32_t *__restrict__ tmp_slot, const uint32_t *__restrict__ tmp_pos,
-                                    const unsigned long long *__restrict__ tile_tmp_off, const uint32_t *__restrict__ tile_cnt,
-                                    const unsigned long long *__restrict__ tile_off, uint64_t n_tiles, uint32_t *out_slot, uint32_t *out_pos) {
+// (one array per launch: the slots are needed by the very next stage, the positions only by hga_get_hits, which moves them on demand)
+__global__ void scan_reorder_kernel(const uint32_t *__restrict__ tmp, const unsigned long long *__restrict__ tile_tmp_off, const uint32_t *__restrict__ tile_cnt,
+                                    const unsigned long long *__restrict__ tile_off, uint64_t n_tiles, uint32_t *out) {
     const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
     const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint64_t t = w; t < n_tiles; t += warps) {
         const unsigned long long src = tile_tmp_off[t], dst = tile_off[t], n = tile_cnt[t];
-        for (unsigned long long i = lane; i < n; i += 32) {
-            __stcs(&out_slot[dst + i], __ldcs(&tmp_slot[src + i]));
-            __stcs(&out_pos[dst + i], __ldcs(&tmp_pos[src + i]));
-        }
+        for (unsigned long long i = lane; i < n; i += 32) __stcs(&out[dst + i], __ldcs(&tmp[src + i]));
     }
 }
 
@@ -644,8 +641,8 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             capacity = std::min<uint64_t>(n_bases, (uint64_t) (est * 1.15) + (1ull << 20));
         }
         HGA_TRY(h->d_sort_a.ensure((capacity + 1) * 4));
-        HGA_TRY(h->d_sort_b.ensure((capacity + 1) * 4));
-        p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_sort_b.as<uint32_t>();
+        HGA_TRY(h->d_pos_tmp.ensure((capacity + 1) * 4));
+        p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_pos_tmp.as<uint32_t>();
         p.capacity = capacity; p.tile_stride = 0;
         HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
         for (uint64_t c = 0; c < n_chunks; c++) {
@@ -671,6 +668,9 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         const uint64_t small_limit = 32ull << 20;
         if (n_bases <= small_limit) {
             capacity = n_bases;
+        } else if (h->scan_density > 0) {
+            // this handle has scanned before: size from the hit density it saw (a denser input overflows and reruns with the exact size below)
+            capacity = std::min<uint64_t>(n_bases, (uint64_t) ((double) n_bases * h->scan_density * 1.25) + (1ull << 20));
         } else {
             const uint64_t stride = 64;
             const uint64_t n_sample = (n_tiles + stride - 1) / stride;
@@ -688,9 +688,9 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     }
 
     for (int attempt = 0; attempt < 2 && n_tiles > 0 && !done; attempt++) {
-        HGA_TRY(h->d_sort_a.ensure((capacity + 1) * 4));      // temporaries (reused by the index sort later)
-        HGA_TRY(h->d_sort_b.ensure((capacity + 1) * 4));
-        p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_sort_b.as<uint32_t>();
+        HGA_TRY(h->d_sort_a.ensure((capacity + 1) * 4));      // temporary slots (reused by the index sort later)
+        HGA_TRY(h->d_pos_tmp.ensure((capacity + 1) * 4));     // temporary positions (kept until hga_get_hits asks for them)
+        p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_pos_tmp.as<uint32_t>();
         p.capacity = capacity; p.n_tiles = n_tiles; p.tile_begin = 0; p.tile_stride = 0;
         HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
         HGA_TRY(launch_scan(h, p, grid_full));
@@ -703,7 +703,6 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     }
 
     HGA_TRY(h->d_hit_slot.ensure((E + 1) * 4));
-    HGA_TRY(h->d_hit_pos.ensure((E + 1) * 4));
     if (n_tiles > 0) {
         size_t tmp_bytes = 0;
         HGA_CUDA(cudaMemsetAsync(tile_cnt + n_tiles, 0, 4, h->stream));
@@ -711,8 +710,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
         HGA_CUDA(cub::DeviceScan::ExclusiveScan(h->d_sort_tmp.p, tmp_bytes, tile_cnt, tile_off, cub::Sum(), 0ull, n_tiles + 1, h->stream));
         const int blocks = (int) std::min<uint64_t>((n_tiles * 32 + 255) / 256, (uint64_t) h->sm_count * 16);
-        scan_reorder_kernel<<<blocks, 256, 0, h->stream>>>(h->d_sort_a.as<uint32_t>(), h->d_sort_b.as<uint32_t>(), tile_tmp_off, tile_cnt, tile_off, n_tiles,
-                                                         h->d_hit_slot.as<uint32_t>(), h->d_hit_pos.as<uint32_t>());
+        scan_reorder_kernel<<<blocks, 256, 0, h->stream>>>(h->d_sort_a.as<uint32_t>(), tile_tmp_off, tile_cnt, tile_off, n_tiles, h->d_hit_slot.as<uint32_t>());
         const int rblocks = (int) std::min<uint64_t>((n_reads + 256) / 256, 2048);
         scan_fix_rows_kernel<<<rblocks, 256, 0, h->stream>>>(d_read_off, n_reads, n_bases, lead, tile_off, n_tiles, p.row_off);
         h->metrics.kernel_launches += 4;
@@ -722,7 +720,25 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     }
     timer.stop();
     h->n_hits = E;
+    h->scan_tiles = n_tiles; h->pos_pending = n_tiles > 0;
+    if (n_bases) h->scan_density = (double) E / (double) n_bases;
     h->metrics.n_bases = n_bases; h->metrics.n_reads = n_reads; h->metrics.n_hits = E; h->metrics.n_candidates = sc.candidates;
     h->have_scan = true;
+    return HGA_OK;
+}
+
+// the hit positions, still in tile-completion order after the scan, into stream order (hga_get_hits is their only reader)
+int hga_scan_finish_positions(hga_handle *h) {
+    if (!h->pos_pending) return HGA_OK;
+    const uint64_t n_tiles = h->scan_tiles;
+    HGA_TRY(h->d_hit_pos.ensure((h->n_hits + 1) * 4));
+    unsigned long long *tile_tmp_off = h->d_tile_state.as<unsigned long long>();
+    unsigned long long *tile_off = tile_tmp_off + (n_tiles + 2);
+    uint32_t *tile_cnt = reinterpret_cast<uint32_t *>(tile_off + (n_tiles + 2));
+    const int blocks = (int) std::min<uint64_t>((n_tiles * 32 + 255) / 256, (uint64_t) h->sm_count * 16);
+    scan_reorder_kernel<<<blocks, 256, 0, h->stream>>>(h->d_pos_tmp.as<uint32_t>(), tile_tmp_off, tile_cnt, tile_off, n_tiles, h->d_hit_pos.as<uint32_t>());
+    HGA_CUDA(cudaGetLastError());
+    h->metrics.kernel_launches++;
+    h->pos_pending = false;
     return HGA_OK;
 }
