@@ -341,6 +341,12 @@ def run_config(args, k, env):
     del sdk
     lens, starts, flip, hap = read_plan(torch, dev, gsize, n_per_hap, args.mean_len, args.seed, args.len_sigma, args.haplotypes)
     n_reads_total = int(lens.shape[0])
+    if os.environ.get("HGA_BENCH_TRUE_ORDER") and world == 1:
+        # experiment (profiles/r2s): the pair count's pivots in TRUE genome order (known to the generator only), the upper bound for any pivot order
+        order = torch.argsort(hap * gsize + starts).to(torch.int32).cpu().numpy().astype(np.uint32)
+        order.tofile("/tmp/hga_true_order.u32")
+        os.environ["HGA_PAIR_ORDER"] = "3"
+        os.environ["HGA_PAIR_ORDER_FILE"] = "/tmp/hga_true_order.u32"
     # contiguous shards balanced by bases
     csum = torch.cumsum(lens, 0).cpu()
     total_bases_all = int(csum[-1])

@@ -33,13 +33,13 @@ __global__ void low32_kernel(const uint64_t *__restrict__ key, uint64_t n, uint3
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) out[i] = (uint32_t) key[i];
 }
 
-// kid_slot == nullptr: the index is keyed by the multi-GPU index key kmer_id + kmer_id / key_div
-// kid_slot != nullptr: the index is keyed by table slot; else (multi-GPU) this rank holds the lists of the k-mers with kmer_id mod G == me
-// under list number kmer_id / G, and every other k-mer's list is empty here
+// G == 0: the index is keyed by table slot. G > 0 (multi-GPU): this rank holds the lists of the slots it owns (hga_owner_of_slot) under
+// their list numbers (hga_list_of_slot), and every other k-mer's list is empty here
 __global__ void kid_list_len_kernel(const uint32_t *__restrict__ kid_slot, uint32_t G, uint32_t me, const uint32_t *__restrict__ inv_off, uint64_t n_kmers, unsigned long long *len) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i <= n_kmers; i += (uint64_t) gridDim.x * blockDim.x) {
-        if (i == n_kmers || (!kid_slot && (uint32_t) i % G != me)) { len[i] = 0; continue; }
-        const uint32_t s = kid_slot ? kid_slot[i] : (uint32_t) i / G;
+        if (i == n_kmers) { len[i] = 0; continue; }
+        uint32_t s = kid_slot[i];
+        if (G) { if (hga_owner_of_slot(s, G) != me) { len[i] = 0; continue; } s = hga_list_of_slot(s, G); }
         len[i] = inv_off[s + 1] - inv_off[s];
     }
 }
@@ -50,8 +50,8 @@ __global__ void kid_list_copy_kernel(const uint32_t *__restrict__ kid_slot, uint
     const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint64_t kid = w; kid < n_kmers; kid += warps) {
-        if (!kid_slot && (uint32_t) kid % G != me) continue;
-        const uint32_t s = kid_slot ? kid_slot[kid] : (uint32_t) kid / G;
+        uint32_t s = kid_slot[kid];
+        if (G) { if (hga_owner_of_slot(s, G) != me) continue; s = hga_list_of_slot(s, G); }
         const uint64_t a = inv_off[s], b = inv_off[s + 1], o = out_off[kid];
         for (uint64_t i = lane; i < b - a; i += 32) out[o + i] = inv_row[a + i] + first_id;
     }
@@ -248,8 +248,8 @@ static int export_index(hga_handle *h, const uint32_t *d_off, const uint32_t *d_
     HGA_TRY(h->d_export_a.ensure((K + 2) * 8 * 2));
     HGA_TRY(h->d_export_b.ensure((E + 1) * 4));
     unsigned long long *len = h->d_export_a.as<unsigned long long>(), *off = len + (K + 2);
-    const uint32_t *kid_slot = h->index_by_kid ? nullptr : h->table.kid_slot;
-    const uint32_t G = (uint32_t) std::max(1, hga_comm_size(h)), me = (uint32_t) hga_comm_rank(h);
+    const uint32_t *kid_slot = h->table.kid_slot;
+    const uint32_t G = h->index_by_kid ? (uint32_t) hga_comm_size(h) : 0u, me = (uint32_t) hga_comm_rank(h);
     kid_list_len_kernel<<<grid_for(h, K + 1), 256, 0, h->stream>>>(kid_slot, G, me, d_off, K, len);
     size_t tmp = 0;
     HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, off, K + 1, h->stream));

@@ -3,8 +3,9 @@
 // The reference has no distributed path; SURVEY.md §8(e) defines this one. Reads shard by contiguous read-id ranges (each rank
 // scans its own shard against a replicated k-mer table); the inverted index is PARTITIONED by k-mer owner and the pair scores
 // are reduced at the owner of x:
-//   1. every rank translates its hits from table slots (which differ between ranks: every rank builds its own table with
-//      atomics) to the caller's kmer_id; owner(kmer_id) = kmer_id mod G, the owner's list number is kmer_id / G;
+//   1. the table layout is a function of the k-mer array (hga_table.cu), so a slot number means the same k-mer on every rank: whole
+//      32-slot buckets are dealt round robin, owner(slot) = (slot / 32) mod G, list number at the owner = (slot / 32) / G * 32 + slot mod 32
+//      (the hits of a minimizer run keep neighbouring list numbers: the pair counter's locality survives the partition);
 //   2. ALL-TO-ALL 1 (grouped ncclSend / ncclRecv): (list number, global row) records go to their owner. Every source sends in
 //      row order and the sources arrive in rank order = global row order, so the received stream IS the owner's by-row
 //      incidence (row offsets from run boundaries, no sort), and one stable sort by list number gives its inverted lists with
@@ -85,18 +86,18 @@ int load_nccl() {
         }                                                                                                               \
     } while (0)
 
-// record = list number at the owner (kmer_id / G) << 32 | global row, owner = kmer_id mod G; one warp per row
+// record = list number at the owner << 32 | global row; one warp per row
 __global__ void pack_records_kernel(const uint64_t *__restrict__ row_off, uint64_t n_rows, uint32_t row_base, const uint32_t *__restrict__ slot,
-                                    const uint32_t *__restrict__ slot_kid, uint32_t G, uint64_t *__restrict__ rec, uint8_t *__restrict__ owner) {
+                                    uint32_t G, uint64_t *__restrict__ rec, uint8_t *__restrict__ owner) {
     const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
     const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint64_t r = w; r < n_rows; r += warps) {
         const uint64_t a = row_off[r], b = row_off[r + 1];
         for (uint64_t i = a + lane; i < b; i += 32) {
-            const uint32_t kid = slot_kid[slot[i]];
-            rec[i] = ((uint64_t) (kid / G) << 32) | ((uint32_t) r + row_base);
-            owner[i] = (uint8_t) (kid % G);
+            const uint32_t s = slot[i];
+            rec[i] = ((uint64_t) hga_list_of_slot(s, G) << 32) | ((uint32_t) r + row_base);
+            owner[i] = (uint8_t) hga_owner_of_slot(s, G);
         }
     }
 }
@@ -210,12 +211,13 @@ int hga_comm_allgatherv(hga_handle *h, const void *d_mine, void *d_all, const st
     return HGA_OK;
 }
 
-// counts all-to-all: every rank's G send counts (device array) -> the G x G matrix on the host (cnt_all[src * G + dst])
+// counts all-to-all: every rank's G send counts + one extra value (device array of G + 1) -> the G x (G + 1) matrix on the host
+// (cnt_all[src * (G + 1) + dst], extra at [src * (G + 1) + G])
 static int exchange_counts(hga_handle *h, const unsigned long long *d_send_cnt, unsigned long long *d_all, std::vector<unsigned long long> &cnt_all) {
     const int G = h->comm->size;
-    cnt_all.assign((size_t) G * G, 0);
-    HGA_NCCL(g_nccl.AllGather(d_send_cnt, d_all, G, ncclUint64, h->comm->comm, h->stream));
-    HGA_CUDA(cudaMemcpyAsync(cnt_all.data(), d_all, (size_t) G * G * 8, cudaMemcpyDeviceToHost, h->stream));
+    cnt_all.assign((size_t) G * (G + 1), 0);
+    HGA_NCCL(g_nccl.AllGather(d_send_cnt, d_all, G + 1, ncclUint64, h->comm->comm, h->stream));
+    HGA_CUDA(cudaMemcpyAsync(cnt_all.data(), d_all, (size_t) G * (G + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
     HGA_CUDA(cudaStreamSynchronize(h->stream));
     return HGA_OK;
 }
@@ -225,15 +227,15 @@ static int exchange_counts(hga_handle *h, const unsigned long long *d_send_cnt, 
 // restricted to those k-mers.
 int hga_comm_build_owner_index(hga_handle *h) {
     const int G = h->comm->size, me = h->comm->rank;
-    const uint64_t K = h->n_kmers;
     const uint64_t E_loc = h->n_hits, R_all = h->n_reads_total;
-    const uint64_t n_lists = (K + G - 1) / G + 1;
+    const uint32_t n_buckets_all = h->table.n_slots / HGA_BUCKET_SLOTS;                         // n_slots is a multiple of 32
+    const uint32_t n_lists = (n_buckets_all + G - 1) / G * HGA_BUCKET_SLOTS;                    // of the fullest owner; a multiple of 32
     const uint32_t row_base = h->read_id_base - 1;
     if (E_loc >= (1ull << 32)) { hga_set_error("local incidence of %llu entries exceeds the 32-bit per-GPU limit", (unsigned long long) E_loc); return HGA_E_OVERFLOW; }
     double comm_ms = 0, part_ms = 0;
+    Trace tr(h);
 
     // 1. packed records partitioned by owner (ONE stable radix pass: every owner segment keeps global row order)
-    const int key_bits = (int) std::max<uint32_t>(hga_ceil_log2(n_lists + 1), 1);
     const int owner_bits = (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) G), 1);
     HGA_TRY(h->d_sort_a.ensure((E_loc + 1) * 8));      // packed records, partitioned
     HGA_TRY(h->d_sort_b.ensure((E_loc + 1) * 8));      // packed records, stream order
@@ -242,8 +244,7 @@ int hga_comm_build_owner_index(hga_handle *h) {
     uint64_t *rec_in = h->d_sort_b.as<uint64_t>(), *rec_out = h->d_sort_a.as<uint64_t>();
     if (E_loc) {
         const int blocks = (int) std::min<uint64_t>((h->n_reads * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
-        pack_records_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->n_reads, row_base, h->d_hit_slot.as<uint32_t>(), h->table.slot_kid, (uint32_t) G,
-                                                        rec_in, own_in);
+        pack_records_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->n_reads, row_base, h->d_hit_slot.as<uint32_t>(), (uint32_t) G, rec_in, own_in);
         size_t tmp = 0;
         HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, own_in, own_out, rec_in, rec_out, E_loc, 0, owner_bits, h->stream));
         HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
@@ -254,25 +255,35 @@ int hga_comm_build_owner_index(hga_handle *h) {
     HGA_TRY(h->comm->d_small.ensure((size_t) (G + 2) * 8 * (G + 2)));
     unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + (G + 2);
     dest_counts_kernel<<<1, 64, 0, h->stream>>>(own_out, E_loc, G, d_cnt);
+    const unsigned long long my_rows = h->n_reads;                                  // rides along: the shard layout check below needs every rank's row count
+    HGA_CUDA(cudaMemcpyAsync(d_cnt + G, &my_rows, 8, cudaMemcpyHostToDevice, h->stream));
     h->metrics.kernel_launches++;
     HGA_CUDA(cudaGetLastError());
+    tr.mark("pack+partition");
     std::vector<unsigned long long> cnt_all;
     HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, cnt_all));                         // the only host synchronisation of the stage
+    tr.mark("counts");
+    const size_t CS = (size_t) G + 1;
+    {   // shards must be contiguous read-id ranges in rank order: the row stream of source s must lie in s's range
+        uint64_t rows_before = 0, tot = 0;
+        for (int g = 0; g < G; g++) { if (g < me) rows_before += cnt_all[g * CS + G]; tot += cnt_all[g * CS + G]; }
+        if (rows_before != row_base) { hga_set_error("hga_build_index: shards must be contiguous read-id ranges in rank order (rank %d starts at row %u, expected %llu)", me, row_base, (unsigned long long) rows_before); return HGA_E_ARG; }
+        if (tot != R_all) { hga_set_error("hga_build_index: the ranks scanned %llu reads, hga_comm_init said %llu", (unsigned long long) tot, (unsigned long long) R_all); return HGA_E_ARG; }
+    }
 
-    // 2. all-to-all: the records of my k-mers from every rank, in rank order = global row order
-    uint64_t E_own = 0, rows_seen = 0;
+    // 2. all-to-all: the records of my lists from every rank, in rank order = global row order
+    uint64_t E_own = 0;
     std::vector<uint64_t> recv_off(G + 1, 0), send_off(G + 1, 0);
-    for (int src = 0; src < G; src++) { recv_off[src] = E_own; E_own += cnt_all[(size_t) src * G + me]; }
-    for (int g = 0; g < G; g++) send_off[g + 1] = send_off[g] + cnt_all[(size_t) me * G + g];
-    (void) rows_seen;
+    for (int src = 0; src < G; src++) { recv_off[src] = E_own; E_own += cnt_all[src * CS + me]; }
+    for (int g = 0; g < G; g++) send_off[g + 1] = send_off[g] + cnt_all[me * CS + g];
     if (E_own >= (1ull << 32)) { hga_set_error("this rank's share of the incidence (%llu entries) exceeds the 32-bit per-GPU limit", (unsigned long long) E_own); return HGA_E_OVERFLOW; }
-    HGA_TRY(h->d_x_slot.ensure((E_own + 1) * 8 * 2));   // received records | sorted records
-    uint64_t *rx = h->d_x_slot.as<uint64_t>(), *rx_sorted = rx + (E_own + 1);
+    HGA_TRY(h->d_x_slot.ensure((E_own + 1) * 8));       // received records
+    uint64_t *rx = h->d_x_slot.as<uint64_t>();
     {
         StageTimer xt(h, &part_ms, true);
         HGA_NCCL(g_nccl.GroupStart());
         for (int g = 0; g < G; g++) {
-            const uint64_t sc = cnt_all[(size_t) me * G + g], rc = cnt_all[(size_t) g * G + me];
+            const uint64_t sc = cnt_all[me * CS + g], rc = cnt_all[g * CS + me];
             if (sc) HGA_NCCL(g_nccl.Send(rec_out + send_off[g], sc, ncclUint64, g, h->comm->comm, h->stream));
             if (rc) HGA_NCCL(g_nccl.Recv(rx + recv_off[g], rc, ncclUint64, g, h->comm->comm, h->stream));
         }
@@ -280,47 +291,33 @@ int hga_comm_build_owner_index(hga_handle *h) {
         xt.stop();
         comm_ms += part_ms;
     }
+    tr.mark("alltoall");
 
-    // by-row incidence = the received stream; inverted lists = one stable sort by list number
+    // by-row incidence = the received stream (list numbers in row order + row offsets from the run boundaries); inverted lists = the
+    // single-GPU list builder over (list number, row)
     HGA_TRY(h->d_g_row_off.ensure((R_all + 2) * 8));
     HGA_TRY(h->d_g_kid.ensure((E_own + 1) * 4));
-    HGA_TRY(h->d_inv_off.ensure((n_lists + 2) * 4));
-    HGA_TRY(h->d_inv_row.ensure((E_own + 4) * 4));
+    HGA_TRY(h->d_sort_b.ensure((E_own + 1) * 4));       // rows in stream order (scratch of the list builder)
     {
         const int blocks = (int) std::min<uint64_t>((E_own + 256) / 256, (uint64_t) h->sm_count * 16);
         field_offsets_kernel<uint64_t, 0><<<blocks, 256, 0, h->stream>>>(rx, E_own, R_all, h->d_g_row_off.as<uint64_t>());
-        if (E_own) {
-            unpack_records_kernel<<<blocks, 256, 0, h->stream>>>(rx, E_own, h->d_g_kid.as<uint32_t>(), nullptr);
-            size_t tmp = 0;
-            HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, rx, rx_sorted, E_own, 32, 32 + key_bits, h->stream));
-            HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
-            HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, tmp, rx, rx_sorted, E_own, 32, 32 + key_bits, h->stream));
-            unpack_records_kernel<<<blocks, 256, 0, h->stream>>>(rx_sorted, E_own, nullptr, h->d_inv_row.as<uint32_t>());
-            h->metrics.kernel_launches += (uint64_t) (key_bits + 7) / 8 + 3;
-        }
-        field_offsets_kernel<uint32_t, 32><<<blocks, 256, 0, h->stream>>>(E_own ? rx_sorted : rx, E_own, n_lists, h->d_inv_off.as<uint32_t>());
+        if (E_own) unpack_records_kernel<<<blocks, 256, 0, h->stream>>>(rx, E_own, h->d_g_kid.as<uint32_t>(), h->d_sort_b.as<uint32_t>());
         h->metrics.kernel_launches += 2;
         HGA_CUDA(cudaGetLastError());
     }
-    // shards must be contiguous read-id ranges in rank order: the row stream of source s must lie in s's range
-    uint64_t rows_before = 0;
-    {   // every rank contributes its row count; cheap check through the count matrix is not possible (it holds entries), so use the ids
-        std::vector<uint64_t> all;
-        HGA_TRY(hga_comm_allgather_u64(h, h->n_reads, all));
-        uint64_t tot = 0;
-        for (int g = 0; g < G; g++) { if (g < me) rows_before += all[g]; tot += all[g]; }
-        if (rows_before != row_base) { hga_set_error("hga_build_index: shards must be contiguous read-id ranges in rank order (rank %d starts at row %u, expected %llu)", me, row_base, (unsigned long long) rows_before); return HGA_E_ARG; }
-        if (tot != R_all) { hga_set_error("hga_build_index: the ranks scanned %llu reads, hga_comm_init said %llu", (unsigned long long) tot, (unsigned long long) R_all); return HGA_E_ARG; }
-    }
+    tr.mark("unpack");
+    HGA_TRY(hga_build_lists(h, h->d_g_kid.as<uint32_t>(), h->d_sort_b.as<uint32_t>(), E_own, n_lists));
+    tr.mark("lists");
     h->inc_rows = R_all;
     h->inc_row_first_id = 1;
     h->inc_entries = E_own;
     h->pair_rows = R_all;
     h->pair_pivot_mul = 1; h->pair_pivot_add = 0;
     h->index_by_kid = true;
-    h->index_keys = (uint32_t) n_lists;
+    h->index_keys = n_lists;
     h->index_key_div = 0;
     h->metrics.exchange_ms = comm_ms;       // NCCL payload calls only (the sorts between them belong to index_ms)
+    tr.dump("index", me);
     return HGA_OK;
 }
 
@@ -330,6 +327,7 @@ int hga_comm_exchange_partials(hga_handle *h, uint64_t n, uint64_t *out_n) {
     const int G = h->comm->size, me = h->comm->rank;
     const int owner_bits = (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) G), 1);
     double part_ms = 0;
+    Trace tr(h);
     HGA_TRY(h->d_x_row.ensure((n + 1) * 2));
     HGA_TRY(h->d_pair_key2.ensure((n + 1) * 8));
     HGA_TRY(h->d_pair_score2.ensure((n + 1) * 4));
@@ -353,12 +351,15 @@ int hga_comm_exchange_partials(hga_handle *h, uint64_t n, uint64_t *out_n) {
     dest_counts_kernel<<<1, 64, 0, h->stream>>>(d_out, n, G, d_cnt);
     h->metrics.kernel_launches++;
     HGA_CUDA(cudaGetLastError());
+    tr.mark("partition");
     std::vector<unsigned long long> cnt_all;
     HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, cnt_all));
+    tr.mark("counts");
     uint64_t n_recv = 0;
     std::vector<uint64_t> recv_off(G + 1, 0), send_off(G + 1, 0);
-    for (int src = 0; src < G; src++) { recv_off[src] = n_recv; n_recv += cnt_all[(size_t) src * G + me]; }
-    for (int g = 0; g < G; g++) send_off[g + 1] = send_off[g] + cnt_all[(size_t) me * G + g];
+    const size_t CS = (size_t) G + 1;
+    for (int src = 0; src < G; src++) { recv_off[src] = n_recv; n_recv += cnt_all[src * CS + me]; }
+    for (int g = 0; g < G; g++) send_off[g + 1] = send_off[g] + cnt_all[me * CS + g];
     // the receive buffers: the (now free) primary pair arrays
     HGA_TRY(h->d_pair_key.ensure((n_recv + 1) * 8));
     HGA_TRY(h->d_pair_score.ensure((n_recv + 1) * 4));
@@ -366,7 +367,7 @@ int hga_comm_exchange_partials(hga_handle *h, uint64_t n, uint64_t *out_n) {
         StageTimer xt(h, &part_ms, true);
         HGA_NCCL(g_nccl.GroupStart());
         for (int g = 0; g < G; g++) {
-            const uint64_t sc = cnt_all[(size_t) me * G + g], rc = cnt_all[(size_t) g * G + me];
+            const uint64_t sc = cnt_all[me * CS + g], rc = cnt_all[g * CS + me];
             if (sc) {
                 HGA_NCCL(g_nccl.Send(key_part + send_off[g], sc, ncclUint64, g, h->comm->comm, h->stream));
                 HGA_NCCL(g_nccl.Send(score_part + send_off[g], sc, ncclUint32, g, h->comm->comm, h->stream));
@@ -381,6 +382,9 @@ int hga_comm_exchange_partials(hga_handle *h, uint64_t n, uint64_t *out_n) {
         h->metrics.exchange_ms += part_ms;
     }
     *out_n = n_recv;
+    tr.mark("alltoall");
+    if (tr.on) fprintf(stderr, "[hga trace r%d partials] sent=%llu received=%llu\n", me, (unsigned long long) n, (unsigned long long) n_recv);
+    tr.dump("partials", me);
     return HGA_OK;
 }
 

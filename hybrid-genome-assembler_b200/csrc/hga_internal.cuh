@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -96,8 +97,8 @@ struct PinBuf {
 //   key table : canonical keys, u64, buckets of 32 (256 B) selected by Mc. Inside the bucket a key starts at the 32 B SECTOR
 //               picked by hb and goes round the bucket's eight sectors; a lookup reads one sector per step (one 256-bit load)
 //               and stops at a match or at a sector with an empty slot: 96 % of the lookups end in the first step (load 1/4).
-//               Keys that find their bucket full (0.1 %) go to a plain open-addressing overflow region hashed by k-mer,
-//               consulted only after eight full sectors. The internal k-mer id ("slot") is the index of the key in the
+//               Keys that find their bucket full (0.1 %) go to the overflow region, a sorted array searched by bisection,
+//               consulted only after eight full sectors. The layout is a function of the k-mer array (hga_table.cu): no insertion races. The internal k-mer id ("slot") is the index of the key in the
 //               (main | overflow) array; slot_kid maps it to the caller's id.
 // ------------------------------------------------------------------------------------------------
 #define HGA_MIN_W 8
@@ -122,7 +123,8 @@ struct KmerTable {
     uint32_t *filter = nullptr;     // n_blocks * 8 words
     uint32_t n_buckets = 0;         // main region: n_buckets * HGA_BUCKET_SLOTS slots
     uint32_t n_main = 0;            // slots in the main region
-    uint32_t n_over = 0;            // slots in the overflow region (0: none; else a power of two)
+    uint32_t n_over = 0;            // slots in the overflow region (0: none; else a multiple of HGA_BUCKET_SLOTS)
+    uint32_t n_over_keys = 0;       // keys in the overflow region: a SORTED array (binary search), HGA_EMPTY_KEY padding behind it
     uint32_t n_blocks = 0;
     uint32_t n_slots = 0;           // n_main + n_over
     uint32_t slot_bits = 0;         // ceil(log2(n_slots))
@@ -209,7 +211,12 @@ __host__ __device__ __forceinline__ uint32_t hga_start_sector(uint32_t B, uint32
 // when there is no minimizer: the locality value is a mix of the bit hash
 __host__ __device__ __forceinline__ uint32_t hga_mix_bits(uint32_t hb) { return (hb ^ (hb >> 15)) * HGA_C3; }
 
-// plain k-mer hash: the overflow region's home position
+// multi-GPU partition of the table slots (and with them of the inverted lists): whole 32-slot buckets round robin, so that the hits of
+// a minimizer run keep neighbouring list numbers at their owner (the locality the pair counter's list walks live on)
+__host__ __device__ __forceinline__ uint32_t hga_owner_of_slot(uint32_t slot, uint32_t G) { return (slot / HGA_BUCKET_SLOTS) % G; }
+__host__ __device__ __forceinline__ uint32_t hga_list_of_slot(uint32_t slot, uint32_t G) { return (slot / HGA_BUCKET_SLOTS) / G * HGA_BUCKET_SLOTS + slot % HGA_BUCKET_SLOTS; }
+
+// plain k-mer hash (unused by the table since the overflow region became a sorted array; kept for experiments)
 __host__ __device__ __forceinline__ uint32_t hga_plain_hash(uint64_t kmer) {
     uint32_t h = (uint32_t) kmer * HGA_C2 + (uint32_t) (kmer >> 32) * HGA_C1;
     h ^= h >> 16;
@@ -297,14 +304,16 @@ struct hga_handle {
     DevBuf d_x_slot, d_x_row;             // exchange staging (multi-GPU)
     DevBuf d_hit_kid;                     // (unused)
     DevBuf d_g_kid, d_g_row_off;          // multi-GPU: by-row incidence of ALL rows restricted to this rank's k-mers (list number per hit, u64 row offsets)
-    bool index_by_kid = false;            // multi-GPU: the inverted index holds the lists of this rank's k-mers, list number = kmer_id / G (owner = kmer_id mod G)
-    uint32_t index_keys = 0;              // number of lists in the inverted index: n_slots, or ceil(K / G) + 1 with a communicator
+    bool index_by_kid = false;            // multi-GPU (name kept): the inverted index holds the lists of this rank's share of the table: slot s belongs to
+                                          // rank (s / 32) mod G and is list ((s / 32) / G) * 32 + s mod 32 there (hga_owner_of_slot / hga_list_of_slot)
+    uint32_t index_keys = 0;              // number of lists in the inverted index: n_slots, or the owner's share of them with a communicator
     uint32_t index_key_div = 0;           // (unused)
 
     // inverted index
     DevBuf d_inv_off;                     // u32[index_keys + 1] (the incidence held by one GPU has < 2^32 entries)
     DevBuf d_inv_row;                     // u32[inc_entries]: ROW numbers (0-based), ascending inside a list
     DevBuf d_sort_a, d_sort_b, d_sort_tmp;
+    DevBuf d_index_tmp, d_index_goff;     // rows sorted by slot group, group offsets (index_local_sort_kernel)
     bool have_index = false;
 
     // pairs
@@ -350,6 +359,7 @@ int hga_table_build(hga_handle *h, const uint64_t *host_kmers);
 int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, const char *h_bases);
 int hga_scan_finish_positions(hga_handle *h);
 int hga_index_run(hga_handle *h);
+int hga_build_lists(hga_handle *h, const uint32_t *d_keys, const uint32_t *d_rows, uint64_t E, uint32_t n_keys);
 int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
 int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold);
 int hga_cc_run(hga_handle *h, int min_size);
@@ -389,6 +399,37 @@ struct StageTimer {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, a, b);
         *slot = ms;
+    }
+};
+
+// HGA_TRACE=1: sub-stage times on stderr (CUDA events on the stage's stream; the dump synchronises, so a traced run is for reading,
+// not for quoting)
+struct Trace {
+    bool on;
+    cudaStream_t s;
+    std::vector<std::pair<const char *, cudaEvent_t>> ev;
+    explicit Trace(hga_handle *h) : on(getenv("HGA_TRACE") != nullptr), s(h->stream) { mark("begin"); }
+    void mark(const char *name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.emplace_back(name, e);
+    }
+    void dump(const char *stage, int rank) {
+        if (!on || ev.empty()) return;
+        cudaEventSynchronize(ev.back().second);
+        std::string line = "[hga trace r" + std::to_string(rank) + " " + stage + "]";
+        for (size_t i = 1; i < ev.size(); i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+            char buf[96];
+            snprintf(buf, sizeof(buf), " %s=%.2f", ev[i].first, ms);
+            line += buf;
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+        for (auto &p : ev) cudaEventDestroy(p.second);
+        ev.clear();
     }
 };
 

@@ -546,6 +546,29 @@ __global__ void row_minhash_kernel(const uint64_t *__restrict__ row_off, const u
     }
 }
 
+// Pivot order, second form: label(r) = smallest row that shares a (sampled) k-mer with r. Inverted lists are ascending, so the label
+// every list hands to its rows is its first entry; one atomicMin per list entry. All reads overlapping a read m whose id is the
+// smallest in its neighbourhood get the label m: groups of ~coverage reads around one locus, whatever the error rate (the min-hash
+// order needs ONE particular k-mer to survive in both reads). Sorting the pivots by label makes the rows in flight share their
+// lists (and the inv_off sectors of those lists) in L2.
+__global__ void row_label_init_kernel(uint32_t *__restrict__ label, uint32_t *__restrict__ row, uint64_t n_rows) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_rows; i += (uint64_t) gridDim.x * blockDim.x) { label[i] = (uint32_t) i; row[i] = (uint32_t) i; }
+}
+__global__ void row_neighbor_min_kernel(const uint32_t *__restrict__ inv_off, const uint32_t *__restrict__ inv_row, uint32_t n_keys, uint32_t stride,
+                                        uint32_t *__restrict__ label) {
+    const uint64_t n_samples = ((uint64_t) n_keys + stride - 1) / stride;
+    for (uint64_t t = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; t < n_samples; t += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t s = (uint32_t) (t * stride);
+        const uint32_t lo = __ldg(&inv_off[s]), hi = __ldg(&inv_off[s + 1]);
+        if (hi - lo < 2) continue;
+        const uint32_t m = __ldg(&inv_row[lo]);
+        for (uint32_t i = lo + 1; i < hi; i++) {
+            const uint32_t y = __ldg(&inv_row[i]);
+            if (y != m) atomicMin(&label[y], m);
+        }
+    }
+}
+
 __global__ void flag_min_score_kernel(const uint32_t *__restrict__ score, uint64_t n, uint32_t min_score, uint8_t *flag) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) flag[i] = score[i] >= min_score;
 }
@@ -615,20 +638,54 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
         p.mode = PAIR_MODE_SUBSET;
     }
 
+    // experiment hook: a pivot order read from a file (HGA_PAIR_ORDER=3 + HGA_PAIR_ORDER_FILE = u32 rows), loaded before the stage timer
+    const uint32_t *file_order = nullptr;
+    if (const char *e = getenv("HGA_PAIR_ORDER")) {
+        const char *order_file = getenv("HGA_PAIR_ORDER_FILE");
+        if (atoi(e) == 3 && order_file && !pivots && n_rows > 4096) {
+            std::vector<uint32_t> ord(n_rows);
+            FILE *f = fopen(order_file, "rb");
+            if (!f || fread(ord.data(), 4, n_rows, f) != n_rows) { if (f) fclose(f); hga_set_error("HGA_PAIR_ORDER_FILE: cannot read %llu rows", (unsigned long long) n_rows); return HGA_E_ARG; }
+            fclose(f);
+            HGA_TRY(h->d_pivot_order.ensure((n_rows + 1) * 4 * 4));
+            HGA_CUDA(cudaMemcpyAsync(h->d_pivot_order.p, ord.data(), n_rows * 4, cudaMemcpyHostToDevice, h->stream));
+            HGA_CUDA(cudaStreamSynchronize(h->stream));
+            file_order = h->d_pivot_order.as<uint32_t>();
+        }
+    }
+
     StageTimer timer(h, &h->metrics.pair_ms);
-    bool minhash_order = !multi && !pivots && n_rows > 4096;
-    if (const char *e = getenv("HGA_PAIR_ORDER")) minhash_order = minhash_order && atoi(e) != 0;
-    if (minhash_order) {
+    Trace tr(h);
+    // pivot order (a performance hint only: the pairs are sorted into canonical order afterwards). 0: row order, 1: min-hash of the
+    // row's k-mers, 2: smallest neighbouring row (row_neighbor_min_kernel), 3: read from HGA_PAIR_ORDER_FILE (experiments: the true
+    // genome order of a synthetic input as the upper bound of what an order can buy)
+    int order_mode = (!pivots && n_rows > 4096) ? 1 : 0;
+    if (const char *e = getenv("HGA_PAIR_ORDER")) { if (!pivots && n_rows > 4096) order_mode = atoi(e); }
+    if (order_mode == 3) { order_mode = 0; if (file_order) p.pivot_rows = file_order; }
+    if (order_mode == 1 || order_mode == 2) {
         HGA_TRY(h->d_pivot_order.ensure((n_rows + 1) * 4 * 4));
         uint32_t *k_in = h->d_pivot_order.as<uint32_t>(), *r_in = k_in + (n_rows + 1), *k_out = r_in + (n_rows + 1), *r_out = k_out + (n_rows + 1);
-        row_minhash_kernel<<<(int) std::min<uint64_t>((n_rows * 32 + 255) / 256, (uint64_t) h->sm_count * 32), 256, 0, h->stream>>>(p.row_off, p.row_slot, n_rows, k_in, r_in);
+        if (order_mode == 1) {
+            row_minhash_kernel<<<(int) std::min<uint64_t>((n_rows * 32 + 255) / 256, (uint64_t) h->sm_count * 32), 256, 0, h->stream>>>(p.row_off, p.row_slot, n_rows, k_in, r_in);
+        } else {
+            // ~48 sampled lists per row on average
+            uint64_t stride = h->inc_entries / (48 * std::max<uint64_t>(n_rows, 1));
+            if (const char *e = getenv("HGA_PAIR_ORDER_STRIDE")) stride = (uint64_t) atoi(e);
+            stride = std::min<uint64_t>(std::max<uint64_t>(stride, 1), 256);
+            const uint64_t n_samples = ((uint64_t) h->index_keys + stride - 1) / stride;
+            row_label_init_kernel<<<(int) std::min<uint64_t>((n_rows + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(k_in, r_in, n_rows);
+            row_neighbor_min_kernel<<<(int) std::max<uint64_t>(1, std::min<uint64_t>((n_samples + 255) / 256, (uint64_t) h->sm_count * 32)), 256, 0, h->stream>>>(
+                p.inv_off, p.inv_row, h->index_keys, (uint32_t) stride, k_in);
+            h->metrics.kernel_launches++;
+        }
+        const int label_bits = order_mode == 1 ? 32 : (int) std::max<uint32_t>(hga_ceil_log2(n_rows + 1), 1);
         size_t tmp_bytes = 0;
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, r_in, r_out, n_rows, 0, 32, h->stream));
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, r_in, r_out, n_rows, 0, label_bits, h->stream));
         HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp_bytes, k_in, k_out, r_in, r_out, n_rows, 0, 32, h->stream));
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp_bytes, k_in, k_out, r_in, r_out, n_rows, 0, label_bits, h->stream));
         h->metrics.kernel_launches += 6;
         HGA_CUDA(cudaGetLastError());
-        p.pivot_rows = r_out;        // all rows, TAIL mode, in min-hash order
+        p.pivot_rows = r_out;        // all rows, TAIL mode, in that order
     }
     uint64_t capacity = std::max<uint64_t>(h->pair_capacity, std::max<uint64_t>(64 * n_rows, 1ull << 20));
     int occ_w = 0, occ_c = 0;
@@ -640,7 +697,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     if (occ_w < 1) occ_w = 1;
     if (occ_c < 1) occ_c = 1;
     const int grid_w = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) h->sm_count * occ_w, (p.n_pivots + PW_WARPS - 1) / PW_WARPS));
-    p.single_pass = multi ? 1 : 0;
+    p.single_pass = 0;
     if (const char *e = getenv("HGA_PAIR_SINGLE_PASS")) p.single_pass = atoi(e) != 0;
     const int grid_s = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) h->sm_count * occ_r, (p.n_pivots + PW_WARPS - 1) / PW_WARPS));
     PairScalars sc;
@@ -700,7 +757,9 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     }
     h->pair_capacity = capacity;
     uint64_t P = sc.cursor;
-    if (multi) HGA_TRY(hga_comm_exchange_partials(h, P, &P));     // partial (x, y, score) -> owner(x); received into d_pair_key / d_pair_score
+    tr.mark("kernels");
+    if (multi) HGA_TRY(hga_comm_exchange_partials(h, P, &P));
+    tr.mark("exchange");     // partial (x, y, score) -> owner(x); received into d_pair_key / d_pair_score
 
     // canonical physical order: sort by (x_row, y_row)
     HGA_TRY(h->d_pair_key2.ensure((P + 1) * 8));
@@ -723,6 +782,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
         std::swap(h->d_pair_key, h->d_pair_key2);          // from here on the sorted arrays are the secondary ones (swapped back below)
         std::swap(h->d_pair_score, h->d_pair_score2);
     }
+    tr.mark("sort");
     if (multi && P > 0) {
         // one record per contributing rank and pair, now adjacent: segmented sum -> final scores (back in d_pair_key / d_pair_score), then
         // the min_score filter the single-GPU kernels apply when they flush a row
@@ -760,6 +820,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     std::swap(h->d_pair_key, h->d_pair_key2);
     std::swap(h->d_pair_score, h->d_pair_score2);
     h->n_pairs = P;
+    tr.mark("reduce");
 
     {   // work measure
         HGA_CUDA(cudaMemsetAsync(&d_sc->increments, 0, 8, h->stream));
@@ -769,6 +830,8 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         h->n_increments = sc.increments;
     }
+    tr.mark("increments");
+    tr.dump("pairs", hga_comm_rank(h));
     timer.stop();
     h->metrics.n_pairs = h->n_pairs; h->metrics.n_increments = h->n_increments;
     h->have_pairs = true;

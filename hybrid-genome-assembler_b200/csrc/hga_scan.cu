@@ -41,10 +41,13 @@
 #define SCAN_Q 256                               // candidate ring (power of two, >= 31 + 32 * SCAN_UNROLL)
 #define SCAN_BND 32                              // read boundaries of a tile staged in shared memory (more: global search)
 #define SCAN_TR_STRIDE (SCAN_LANE + 1)            // row stride of the transposition buffer in entries (odd: conflict free)
+#define SCAN_CHUNK 2048                          // hit-buffer entries a warp reserves per atomic (a tile holds ~32 hits at config 4); 256 when the scan runs as many launches
+#define SCAN_TICKETS 4                           // consecutive tiles per ticket
 
 struct ScanScalars {
     unsigned long long ticket;
     unsigned long long total;        // hits appended so far (= all hits when the kernel ends)
+    unsigned long long alloc;        // hit-buffer entries handed out to warps (chunks of SCAN_CHUNK; >= total)
     unsigned long long candidates;   // windows that passed the filter (diagnostic: filter false positives = candidates - hits)
     unsigned int overflow;
     unsigned int pad;
@@ -69,6 +72,8 @@ struct ScanParams {
     uint64_t n_tiles;                 // tickets of this launch
     uint64_t tile_begin;              // first tile of this launch (chunked launches while the bases are still arriving)
     uint64_t tile_stride;             // > 0: sampling mode (count only, tile = tile_begin + ticket * stride)
+    uint32_t chunk;                   // hit-buffer entries a warp reserves per atomic
+    unsigned long long *warp_chunks;  // chunked launches: every warp's open chunk [pos, end) survives from one launch to the next (nullptr: one launch)
     int diag;                         // HGA_SCAN_DIAG experiment: 1 = no key probes (results are WRONG)
 };
 
@@ -79,6 +84,8 @@ struct WarpTile {
     uint32_t exc[SCAN_SPAN / 32 + 2];// bit p: staged base p is not one of ACGT (written as u16 halves, one per lane)
     uint16_t q[SCAN_Q];              // candidate windows: staged index | 0x8000 when the window holds a non-ACGT byte
     int32_t bnd[SCAN_BND];           // staged index of the first base of reads r_lo, r_lo + 1, ... (n_bnd of them)
+    unsigned long long chunk[2];     // the warp's open chunk of the hit buffer: [pos, end) (lane 0 only; kept out of the registers)
+    unsigned long long tk[2];        // the warp's current batch of tile tickets: [next, end)
 };
 
 // entry of staged window index i in the transposition buffer
@@ -241,15 +248,13 @@ __device__ __forceinline__ void drain_queue(QueueState &qs, uint32_t n, int lane
             if (probe_sector(t.keys, base_slot, sec + step, key, pol_first, slot)) open = false;
             else if (step == HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1) {
                 open = false;
-                if (t.n_over) {           // bucket full: the key, if present, lives in the overflow region
-                    const uint32_t mask = t.n_over - 1;
-                    uint32_t q = hga_plain_hash(key) & mask;
-                    for (;;) {
-                        const unsigned long long v = __ldg(t.keys + t.n_main + q);
-                        if (v == key) { slot = t.n_main + q; break; }
-                        if (v == HGA_EMPTY_KEY) break;
-                        q = (q + 1) & mask;
+                if (t.n_over_keys) {      // bucket full: the key, if present, lives in the overflow region (sorted: bisection)
+                    uint32_t lo = 0, hi = t.n_over_keys;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldg(t.keys + t.n_main + mid) < key) lo = mid + 1; else hi = mid;
                     }
+                    if (lo < t.n_over_keys && __ldg(t.keys + t.n_main + lo) == key) slot = t.n_main + lo;
                 }
             }
         }
@@ -384,12 +389,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
     __syncwarp();
 
     const uint64_t pol_stream = l2_policy_evict_first();               // the base stream passes through L2 once
-    unsigned long long next_ticket = 0;
-    if (lane == 0) next_ticket = atomicAdd(&p.scalars->ticket, 1ull);
+    // a ticket = SCAN_TICKETS consecutive tiles (one atomic per batch, the next one requested while this batch is processed); the
+    // hit buffer is handed out in chunks of SCAN_CHUNK entries, so a tile's segment costs no atomic round trip of its own (r2r: the
+    // two per-tile atomics were 9 % of the stall samples). scan_reorder_kernel closes the gaps the chunks leave.
+    unsigned long long next_batch = 0;
+    if (lane == 0) {
+        const size_t warp_id = (size_t) blockIdx.x * SCAN_WARPS + warp;
+        T.chunk[0] = p.warp_chunks ? p.warp_chunks[2 * warp_id] : 0ull;
+        T.chunk[1] = p.warp_chunks ? p.warp_chunks[2 * warp_id + 1] : 0ull;
+        T.tk[0] = T.tk[1] = 0;
+        next_batch = atomicAdd(&p.scalars->ticket, 1ull);
+    }
     for (;;) {
-        const unsigned long long ticket = __shfl_sync(0xFFFFFFFFu, next_ticket, 0);
+        unsigned long long ticket = 0;
+        if (lane == 0) {
+            ticket = T.tk[0];
+            if (ticket == T.tk[1]) {                                   // batch used up: on to the one requested a batch ago, request the next
+                ticket = next_batch * SCAN_TICKETS;
+                if (ticket < p.n_tiles) next_batch = atomicAdd(&p.scalars->ticket, 1ull);
+                T.tk[1] = min((unsigned long long) p.n_tiles, ticket + SCAN_TICKETS);
+            }
+            T.tk[0] = ticket + 1;
+        }
+        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
         if (ticket >= p.n_tiles) break;
-        if (lane == 0) next_ticket = atomicAdd(&p.scalars->ticket, 1ull);               // in flight while this tile is processed
+        {
         const uint64_t tile = p.tile_begin + (p.tile_stride ? ticket * p.tile_stride : ticket);
         // frame coordinate u = stream position + lead; the tile's window ends are u in [480 tile, 480 tile + 480); staged index 0 is u = 480 tile - 32
         const int64_t ubase = (int64_t) (tile * SCAN_TILE) - 32;
@@ -463,9 +487,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
         }
         unsigned long long tile_off = 0;
         if (lane == 0) {
-            tile_off = atomicAdd(&p.scalars->total, (unsigned long long) total);
+            unsigned long long chunk_pos = T.chunk[0], chunk_end = T.chunk[1];
+            if (chunk_end - chunk_pos < total) {                       // new chunk (what is left of the old one stays unused)
+                const unsigned long long want = max((unsigned long long) p.chunk, (unsigned long long) total);
+                chunk_pos = atomicAdd(&p.scalars->alloc, want);
+                chunk_end = chunk_pos + want;
+                if (chunk_end > p.capacity) { p.scalars->overflow = 1; chunk_end = chunk_pos; }     // nothing fits any more
+                T.chunk[1] = chunk_end;
+            }
+            tile_off = chunk_pos;
+            const bool fits = chunk_end - chunk_pos >= total;
+            if (fits) chunk_pos += total; else tile_off = ~0ull;
+            T.chunk[0] = chunk_pos;
+            if (total) atomicAdd(&p.scalars->total, (unsigned long long) total);                   // no return value: a reduction, nobody waits for it
             p.tile_tmp_off[tile] = tile_off; p.tile_cnt[tile] = total;
-            if (tile_off + total > p.capacity) p.scalars->overflow = 1;
         }
         tile_off = __shfl_sync(0xFFFFFFFFu, tile_off, 0);
         // rows starting in this tile: number of tile hits whose window ends before the read's first base
@@ -478,7 +513,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
                 p.row_off[rr] = lo;       // tile-local; scan_fix_rows_kernel adds the tile's final offset
             }
         }
-        if (tile_off + total <= p.capacity) {
+        if (tile_off != ~0ull) {
             for (uint32_t i = lane; i < total; i += 32) {
                 const uint2 hit = T.tr[i];
                 const int e = (int) hit.y;
@@ -487,6 +522,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
             }
         }
         __syncwarp();
+      }
+    }
+    if (lane == 0 && p.warp_chunks) {
+        const size_t warp_id = (size_t) blockIdx.x * SCAN_WARPS + warp;
+        p.warp_chunks[2 * warp_id] = T.chunk[0]; p.warp_chunks[2 * warp_id + 1] = T.chunk[1];
     }
     if (lane == 0 && n_cand) atomicAdd(&p.scalars->candidates, (unsigned long long) n_cand);
 }
@@ -505,16 +545,26 @@ __global__ void scan_tile_dir_kernel(const uint64_t *__restrict__ read_off, uint
     }
 }
 
-// tile segments (completion order) -> stream order; one warp per tile
+// tile segments (completion order, with the gaps the chunked allocation leaves) -> stream order. A warp takes 32 consecutive tiles: their
+// directory entries arrive in three coalesced loads (one tile per lane) and are handed round with shuffles; the 32 destinations are
+// one contiguous range. (One warp per tile with three dependent scalar loads each: 3.1 ms at config 4, r2q.)
 // (one array per launch: the slots are needed by the very next stage, the positions only by hga_get_hits, which moves them on demand)
 __global__ void scan_reorder_kernel(const uint32_t *__restrict__ tmp, const unsigned long long *__restrict__ tile_tmp_off, const uint32_t *__restrict__ tile_cnt,
                                     const unsigned long long *__restrict__ tile_off, uint64_t n_tiles, uint32_t *out) {
     const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
     const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    for (uint64_t t = w; t < n_tiles; t += warps) {
-        const unsigned long long src = tile_tmp_off[t], dst = tile_off[t], n = tile_cnt[t];
-        for (unsigned long long i = lane; i < n; i += 32) __stcs(&out[dst + i], __ldcs(&tmp[src + i]));
+    for (uint64_t t0 = w * 32; t0 < n_tiles; t0 += warps * 32) {
+        const uint64_t t = t0 + lane;
+        unsigned long long src = 0, dst = 0;
+        uint32_t n = 0;
+        if (t < n_tiles) { src = tile_tmp_off[t]; dst = tile_off[t]; n = tile_cnt[t]; }
+        #pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            const unsigned long long s = __shfl_sync(0xFFFFFFFFu, src, j), d = __shfl_sync(0xFFFFFFFFu, dst, j);
+            const uint32_t m = __shfl_sync(0xFFFFFFFFu, n, j);
+            for (uint32_t i = lane; i < m; i += 32) __stcs(&out[d + i], __ldcs(&tmp[s + i]));
+        }
     }
 }
 
@@ -555,7 +605,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     h->n_reads = n_reads; h->n_bases = n_bases; h->n_hits = 0;
     if (n_reads >= (1ull << 32) - 1) { hga_set_error("hga_scan: more than 2^32-2 reads per GPU"); return HGA_E_ARG; }
     HGA_TRY(h->d_row_off.ensure((n_reads + 1) * 8));
-    HGA_TRY(h->d_scan_scalars.ensure(sizeof(ScanScalars)));
+    HGA_TRY(h->d_scan_scalars.ensure(sizeof(ScanScalars) + (size_t) h->sm_count * 8 * SCAN_WARPS * 16));   // + the warps' open chunks (chunked launches)
     ScanScalars *d_sc = h->d_scan_scalars.as<ScanScalars>();
     const uint32_t lead = (uint32_t) (reinterpret_cast<uintptr_t>(d_bases) & 15);   // the kernel loads aligned 16 B pieces: frame = the bases aligned down
     const uint64_t n_tiles = (n_reads == 0 || n_bases == 0) ? 0 : (lead + n_bases + SCAN_TILE - 1) / SCAN_TILE;
@@ -593,6 +643,16 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     ScanScalars sc;
     memset(&sc, 0, sizeof(sc));
     uint64_t capacity = 0, E = 0;
+    // Hit-buffer sizes. Warps reserve chunks, so the buffer holds gaps: what is left of a chunk when the next tile does not fit (less
+    // than one tile's hits, <= SCAN_TILE) and every warp's last chunk. `expected` sizes the first attempt from an estimate of the hit
+    // count (an overflow is detected and the scan reruns), `certain` is the bound that cannot overflow for an exact count.
+    const uint64_t warps_full = (uint64_t) grid_full * SCAN_WARPS;
+    auto expected = [&](double hits, double margin, uint64_t launches, uint32_t chunk) {
+        return (uint64_t) (hits * (margin + 0.05)) + launches * warps_full * chunk + (1ull << 20);
+    };
+    auto certain = [&](uint64_t hits, uint64_t launches, uint32_t chunk) {
+        return hits + hits * SCAN_TILE / (chunk - SCAN_TILE + 1) + launches * warps_full * chunk + 1024;
+    };
     // Host source (hga_scan): the bases travel in chunks on a second stream and every chunk is scanned as soon as it has
     // landed (a tile only needs bases at or before its own end, so chunk c can run while chunk c + 1 is in flight).
     uint64_t chunk_mb = 256;                                                      // bases per chunk; HGA_SCAN_CHUNK_MB lets the tests reach this path with small inputs
@@ -638,13 +698,14 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             const double est = (double) sc.total * (double) n_tiles / (double) n_sample;
-            capacity = std::min<uint64_t>(n_bases, (uint64_t) (est * 1.15) + (1ull << 20));
+            capacity = std::min<uint64_t>(certain(n_bases, 1, SCAN_CHUNK), expected(est, 1.15, 1, SCAN_CHUNK));
         }
         HGA_TRY(h->d_sort_a.ensure((capacity + 1) * 4));
         HGA_TRY(h->d_pos_tmp.ensure((capacity + 1) * 4));
         p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_pos_tmp.as<uint32_t>();
-        p.capacity = capacity; p.tile_stride = 0;
-        HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
+        p.capacity = capacity; p.tile_stride = 0; p.chunk = SCAN_CHUNK;
+        p.warp_chunks = reinterpret_cast<unsigned long long *>(d_sc + 1);
+        HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars) + warps_full * 16, h->stream));
         for (uint64_t c = 0; c < n_chunks; c++) {
             HGA_CUDA(cudaStreamWaitEvent(h->stream, landed[c], 0));
             p.tile_begin = c * chunk_tiles; p.n_tiles = std::min<uint64_t>(chunk_tiles, n_tiles - p.tile_begin);
@@ -660,17 +721,17 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         for (cudaEvent_t e : landed) cudaEventDestroy(e);
         cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
         E = sc.total;
-        p.tile_begin = 0;
-        if (!sc.overflow) done = true; else capacity = E;     // the bases are resident now: one plain rerun with the exact size
+        p.tile_begin = 0; p.warp_chunks = nullptr;
+        if (!sc.overflow) done = true; else capacity = certain(E, 1, SCAN_CHUNK);     // the bases are resident now: one plain rerun with the exact count
     } else if (n_tiles > 0) {
         // capacity of the hit arrays: exact upper bound for small inputs, otherwise estimated from a strided
         // count-only sample (1 tile in 64)
         const uint64_t small_limit = 32ull << 20;
         if (n_bases <= small_limit) {
-            capacity = n_bases;
+            capacity = certain(n_bases, 1, SCAN_CHUNK);
         } else if (h->scan_density > 0) {
-            // this handle has scanned before: size from the hit density it saw (a denser input overflows and reruns with the exact size below)
-            capacity = std::min<uint64_t>(n_bases, (uint64_t) ((double) n_bases * h->scan_density * 1.25) + (1ull << 20));
+            // this handle has scanned before: size from the hit density it saw (a denser input overflows and reruns with the exact count below)
+            capacity = std::min<uint64_t>(certain(n_bases, 1, SCAN_CHUNK), expected((double) n_bases * h->scan_density, 1.25, 1, SCAN_CHUNK));
         } else {
             const uint64_t stride = 64;
             const uint64_t n_sample = (n_tiles + stride - 1) / stride;
@@ -682,8 +743,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
             HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
             HGA_CUDA(cudaStreamSynchronize(h->stream));
             const double est = (double) sc.total * (double) n_tiles / (double) n_sample;
-            capacity = (uint64_t) (est * 1.10) + (1ull << 20);
-            if (capacity > n_bases) capacity = n_bases;
+            capacity = std::min<uint64_t>(certain(n_bases, 1, SCAN_CHUNK), expected(est, 1.10, 1, SCAN_CHUNK));
         }
     }
 
@@ -691,7 +751,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         HGA_TRY(h->d_sort_a.ensure((capacity + 1) * 4));      // temporary slots (reused by the index sort later)
         HGA_TRY(h->d_pos_tmp.ensure((capacity + 1) * 4));     // temporary positions (kept until hga_get_hits asks for them)
         p.out_slot = h->d_sort_a.as<uint32_t>(); p.out_pos = h->d_pos_tmp.as<uint32_t>();
-        p.capacity = capacity; p.n_tiles = n_tiles; p.tile_begin = 0; p.tile_stride = 0;
+        p.capacity = capacity; p.n_tiles = n_tiles; p.tile_begin = 0; p.tile_stride = 0; p.chunk = SCAN_CHUNK;
         HGA_CUDA(cudaMemsetAsync(d_sc, 0, sizeof(ScanScalars), h->stream));
         HGA_TRY(launch_scan(h, p, grid_full));
         HGA_CUDA(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
@@ -699,7 +759,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         E = sc.total;
         if (!sc.overflow) break;
         if (attempt == 1) { hga_set_error("scan: hit buffer overflow after exact resize (internal error)"); return HGA_E_OVERFLOW; }
-        capacity = E;   // exact; rerun once
+        capacity = certain(E, 1, SCAN_CHUNK);   // cannot overflow; rerun once
     }
 
     HGA_TRY(h->d_hit_slot.ensure((E + 1) * 4));
@@ -709,7 +769,7 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
         HGA_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, tile_cnt, tile_off, cub::Sum(), 0ull, n_tiles + 1, h->stream));   // 64-bit accumulator
         HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
         HGA_CUDA(cub::DeviceScan::ExclusiveScan(h->d_sort_tmp.p, tmp_bytes, tile_cnt, tile_off, cub::Sum(), 0ull, n_tiles + 1, h->stream));
-        const int blocks = (int) std::min<uint64_t>((n_tiles * 32 + 255) / 256, (uint64_t) h->sm_count * 16);
+        const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + 255) / 256, (uint64_t) h->sm_count * 16));
         scan_reorder_kernel<<<blocks, 256, 0, h->stream>>>(h->d_sort_a.as<uint32_t>(), tile_tmp_off, tile_cnt, tile_off, n_tiles, h->d_hit_slot.as<uint32_t>());
         const int rblocks = (int) std::min<uint64_t>((n_reads + 256) / 256, 2048);
         scan_fix_rows_kernel<<<rblocks, 256, 0, h->stream>>>(d_read_off, n_reads, n_bases, lead, tile_off, n_tiles, p.row_off);
@@ -735,7 +795,7 @@ int hga_scan_finish_positions(hga_handle *h) {
     unsigned long long *tile_tmp_off = h->d_tile_state.as<unsigned long long>();
     unsigned long long *tile_off = tile_tmp_off + (n_tiles + 2);
     uint32_t *tile_cnt = reinterpret_cast<uint32_t *>(tile_off + (n_tiles + 2));
-    const int blocks = (int) std::min<uint64_t>((n_tiles * 32 + 255) / 256, (uint64_t) h->sm_count * 16);
+    const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + 255) / 256, (uint64_t) h->sm_count * 16));
     scan_reorder_kernel<<<blocks, 256, 0, h->stream>>>(h->d_pos_tmp.as<uint32_t>(), tile_tmp_off, tile_cnt, tile_off, n_tiles, h->d_hit_pos.as<uint32_t>());
     HGA_CUDA(cudaGetLastError());
     h->metrics.kernel_launches++;
