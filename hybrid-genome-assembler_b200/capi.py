@@ -69,7 +69,7 @@ class Metrics(C.Structure):
 EXPORTS = ["hga_last_error", "hga_version", "hga_device_count", "hga_init", "hga_host_alloc", "hga_host_free", "hga_create", "hga_destroy", "hga_set_stream",
            "hga_scan", "hga_scan_device", "hga_get_hits", "hga_build_index", "hga_get_index", "hga_pair_count", "hga_get_pairs", "hga_select_edges",
            "hga_get_selection", "hga_components", "hga_get_components", "hga_enrich", "hga_enrich_ex", "hga_enrich_full", "hga_get_tail_block", "hga_count_kmers", "hga_free_kmer_counts", "hga_host_sdk_merge", "hga_host_sdk_specificity", "hga_host_sdk_select", "hga_get_enrichment", "hga_get_purged_index", "hga_get_core_kmers", "hga_spectral_clustering", "hga_host_tail_connections", "hga_host_sym_eigen",
-           "hga_metrics", "hga_comm_unique_id", "hga_comm_init"]
+           "hga_metrics", "hga_comm_unique_id", "hga_comm_init", "hga_comm_gather_root"]
 
 
 def library_path():
@@ -111,6 +111,7 @@ def load_library():
         lib.hga_metrics.argtypes = [C.c_void_p, C.POINTER(Metrics)]
         lib.hga_comm_unique_id.argtypes = [C.c_void_p]
         lib.hga_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64]
+        lib.hga_comm_gather_root.argtypes = [C.c_void_p]
         lib.hga_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         lib.hga_host_free.argtypes = [C.c_void_p]
         lib.hga_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -296,6 +297,10 @@ class Handle:
     def comm_init(self, unique_id: bytes, rank, nranks, n_reads_total):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         _check(self.lib.hga_comm_init(self._h, buf, int(rank), int(nranks), int(n_reads_total)))
+
+    def comm_gather_root(self):
+        """collective: rank 0's handle becomes a complete single-GPU handle (hga_enrich* then runs there)"""
+        _check(self.lib.hga_comm_gather_root(self._h))
 
     # -- stages ------------------------------------------------------------------------------------------
     def scan(self, bases, read_off, read_id_base=1):

@@ -58,7 +58,8 @@ void usage() {
                  "  --spectral_dims arg       Number of dimensions for spectral embedding\n"
                  "  -s [ --spectral ]         Forces the usage of spectral clustering on the entire dataset\n"
                  "  -d [ --debug ]            Debug flag. Treat read files as separate haplotype reads.\n"
-                 "  -t [ --threads ] arg      Number of threads to use\n";
+                 "  -t [ --threads ] arg      Number of threads to use\n"
+                 "  --gpus arg (=1)           hga_b200: GPUs for the hot path (devices --device .. --device + N - 1, NCCL)\n";
 }
 
 struct Timer {
@@ -78,6 +79,64 @@ void check(int rc, const char *what) {
     }
 }
 
+// --gpus N: the hot path (scan -> index -> pair count -> edge selection -> union-find) on N GPUs, one rank thread per GPU: reads shard by
+// contiguous id ranges balanced by bases, the inverted index is partitioned by k-mer owner, partial pair scores are reduced at the owner of
+// x (hga_comm.cu). hga_comm_gather_root then leaves a complete single-GPU handle on the first GPU, and the rest of run_clustering
+// (ReadClusteringEngine.cpp:764-794) goes on there as with one GPU. Returns rank 0's handle; the stage lines are printed from rank 0's clock.
+hga_handle *run_hot_path_multi(const hga_host::KmerSet &ks, const hga_host::SequenceRecords &reads, const Config &config, int device, int gpus) {
+    const uint64_t n_reads = reads.n_reads();
+    const uint64_t total = reads.seq_off[n_reads];
+    std::vector<uint64_t> bound(gpus + 1, n_reads);
+    bound[0] = 0;
+    for (int r = 1; r < gpus; r++)
+        bound[r] = (uint64_t) (std::lower_bound(reads.seq_off.begin(), reads.seq_off.begin() + (ptrdiff_t) n_reads, total / gpus * r) - reads.seq_off.begin());
+    unsigned char id[128];
+    check(hga_comm_unique_id(id), "hga_comm_unique_id");
+    std::vector<hga_handle *> hs(gpus, nullptr);
+    std::vector<std::string> errors(gpus);
+    std::vector<double> stamp(6, 0.0);                        // rank 0: create, scan, index, pairs + select, components, gather
+    std::vector<std::thread> workers;
+    for (int r = 0; r < gpus; r++) {
+        workers.emplace_back([&, r] {
+            auto fail = [&](int rc, const char *what) {
+                if (rc == HGA_OK) return false;
+                errors[r] = std::string(what) + " failed (" + std::to_string(rc) + "): " + hga_last_error();
+                return true;
+            };
+            auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            const uint64_t lo = bound[r], hi = bound[r + 1];
+            std::vector<uint64_t> off(hi - lo + 1);
+            for (uint64_t i = lo; i <= hi; i++) off[i - lo] = reads.seq_off[i] - reads.seq_off[lo];
+            double t = now();
+            auto lap = [&](int i) { const double n2 = now(); if (r == 0) stamp[i] = n2 - t; t = n2; };
+            if (fail(hga_create(device + r, ks.k, ks.kmers.data(), ks.kmers.size(), &hs[r]), "hga_create")) return;
+            if (fail(hga_comm_init(hs[r], id, r, gpus, n_reads), "hga_comm_init")) return;
+            lap(0);
+            if (fail(hga_scan(hs[r], reads.bases_data + reads.seq_off[lo], off.data(), hi - lo, (uint32_t) (lo + 1)), "hga_scan")) return;
+            lap(1);
+            if (fail(hga_build_index(hs[r]), "hga_build_index")) return;
+            lap(2);
+            if (fail(hga_pair_count(hs[r], 1, nullptr, 0), "hga_pair_count")) return;
+            if (fail(hga_select_edges(hs[r], config.scaffold_forming_fraction, 0), "hga_select_edges")) return;
+            lap(3);
+            if (fail(hga_components(hs[r], config.scaffold_component_min_size), "hga_components")) return;
+            lap(4);
+            if (fail(hga_comm_gather_root(hs[r]), "hga_comm_gather_root")) return;
+            lap(5);
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int r = 0; r < gpus; r++)
+        if (!errors[r].empty()) { std::cerr << "categorization: rank " << r << ": " << errors[r] << "\n"; std::exit(2); }
+    std::cout << "Index construction took " << (long long) (stamp[0] + stamp[1] + stamp[2]) << "ms\n";
+    std::cout << "Calculation of connections between reads took " << (long long) stamp[3] << "ms\n";
+    std::cout << "Union-find took " << (long long) stamp[4] << "ms\n";
+    std::fprintf(stderr, "hga_b200: %d GPUs, wall ms on rank 0: create (CUDA context + table + NCCL) %.0f, scan (H2D inside) %.0f, index %.0f, pairs + select %.0f, "
+                         "components %.0f, gather to GPU %d %.0f\n", gpus, stamp[0], stamp[1], stamp[2], stamp[3], stamp[4], device, stamp[5]);
+    for (int r = 1; r < gpus; r++) hga_destroy(hs[r]);
+    return hs[0];
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -85,13 +144,13 @@ int main(int argc, char **argv) {
     std::string kmer_path, output_folder_path;
     Config config;
     bool debug = false, parse_only = false, dump_kmers = false, scaffolds_only = false, load_only = false, export_test = false, tail_block = true;
-    int device = 0;
+    int device = 0, gpus = 1;
 
     // boost::program_options' default style (read_clustering.cpp:60-66): --name=value and --name value, -k value and -kvalue,
     // and unambiguous prefixes of long names (--kmer for --kmers)
     static const char *long_names[] = {"--help", "--read_paths", "--kmers", "--output", "--sc_max_size", "--sc_min_size", "--sc_fraction", "--sc_score",
                                        "--tail_amplification", "--core_enrichment", "--spectral_dims", "--spectral", "--debug", "--threads",
-                                       "--parse-only", "--dump-kmers", "--scaffolds-only", "--load-only", "--export-test", "--device", "--tail-block", "--no-tail-block"};
+                                       "--parse-only", "--dump-kmers", "--scaffolds-only", "--load-only", "--export-test", "--device", "--tail-block", "--no-tail-block", "--gpus"};
     std::vector<std::string> args;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -143,6 +202,7 @@ int main(int argc, char **argv) {
         else if (a == "--load-only") load_only = true;
         else if (a == "--export-test") export_test = true;
         else if (a == "--device") device = std::atoi(need(i));
+        else if (a == "--gpus") gpus = std::max(1, std::atoi(need(i)));
         else if (a == "--tail-block") tail_block = true;
         else if (a == "--no-tail-block") tail_block = false;
         else if (a.size() > 1 && a[0] == '-') throw std::invalid_argument("unrecognised option '" + a + "'");
@@ -200,8 +260,16 @@ int main(int argc, char **argv) {
         return 3;
     }
 
+    if (gpus > 1 && (config.force_spectral || config.scaffold_forming_score > 0 || reads.n_reads() < (size_t) gpus)) {
+        std::cerr << "categorization: --gpus " << gpus << " applies to the default path (all reads as pivots, --sc_fraction); --spectral / --sc_score and inputs with "
+                     "fewer reads than GPUs run on one GPU\n";
+        gpus = 1;
+    }
     hga_handle *h = nullptr;
-    {
+    if (gpus > 1) {
+        if (cuda_start.joinable()) cuda_start.join();
+        h = run_hot_path_multi(ks, reads, config, device, gpus);
+    } else {
         Timer t("Index construction");               // table build + scan + inverted index = construct_indices (:234-299)
         if (cuda_start.joinable()) cuda_start.join();
         const auto w0 = std::chrono::steady_clock::now();
@@ -265,7 +333,7 @@ int main(int argc, char **argv) {
         hga_destroy(h);
         return 0;
     }
-    {
+    if (gpus == 1) {
         Timer t("Calculation of connections between reads");
         if (config.scaffold_forming_score > 0) {
             // pivots = components with at least sc_score discriminative k-mers (:750-752)
@@ -283,11 +351,13 @@ int main(int argc, char **argv) {
         t.done();
     }
     hga_components_t comp;
-    {
+    if (gpus == 1) {
         Timer t("Union-find");
         check(hga_components(h, config.scaffold_component_min_size), "hga_components");
         check(hga_get_components(h, &comp), "hga_get_components");
         t.done();
+    } else {
+        check(hga_get_components(h, &comp), "hga_get_components");
     }
 
     // export_components (:804-826): one file per component, records in input order; reads of no component are dropped

@@ -23,6 +23,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -86,19 +88,34 @@ int load_nccl() {
         }                                                                                                               \
     } while (0)
 
-// record = list number at the owner << 32 | global row; one warp per row
-__global__ void pack_records_kernel(const uint64_t *__restrict__ row_off, uint64_t n_rows, uint32_t row_base, const uint32_t *__restrict__ slot,
-                                    uint32_t G, uint64_t *__restrict__ rec, uint8_t *__restrict__ owner) {
+// per hit: list number at the owner + owner; per row and owner: the number of the row's hits that go there (cnt[g * n_rows + r]).
+// One warp per row. The rows themselves do not travel: a source sends its list numbers in row order and one count per row, and the
+// owner rebuilds the row offsets from the counts of all sources in rank order = global row order.
+__global__ void pack_lists_kernel(const uint64_t *__restrict__ row_off, uint64_t n_rows, const uint32_t *__restrict__ slot, uint32_t G,
+                                  uint32_t *__restrict__ list, uint8_t *__restrict__ owner, uint32_t *__restrict__ cnt) {
     const uint64_t warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
     const uint64_t w = (blockIdx.x * (uint64_t) blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     for (uint64_t r = w; r < n_rows; r += warps) {
         const uint64_t a = row_off[r], b = row_off[r + 1];
-        for (uint64_t i = a + lane; i < b; i += 32) {
-            const uint32_t s = slot[i];
-            rec[i] = ((uint64_t) hga_list_of_slot(s, G) << 32) | ((uint32_t) r + row_base);
-            owner[i] = (uint8_t) hga_owner_of_slot(s, G);
+        uint32_t mine = 0;                                  // lane g: hits of this row owned by rank g, g + 32 (G <= 62)
+        uint32_t mine_hi = 0;
+        for (uint64_t i0 = a; i0 < b; i0 += 32) {
+            const uint64_t i = i0 + lane;
+            uint32_t o = 0xFFu;
+            if (i < b) {
+                const uint32_t s = slot[i];
+                o = hga_owner_of_slot(s, G);
+                list[i] = hga_list_of_slot(s, G);
+                owner[i] = (uint8_t) o;
+            }
+            for (uint32_t g = 0; g < G; g++) {
+                const uint32_t c = __popc(__ballot_sync(0xFFFFFFFFu, o == g));
+                if ((g & 31) == (uint32_t) lane) { if (g < 32) mine += c; else mine_hi += c; }
+            }
         }
+        if ((uint32_t) lane < G) cnt[(size_t) lane * n_rows + r] = mine;
+        if ((uint32_t) lane + 32 < G) cnt[(size_t) (lane + 32) * n_rows + r] = mine_hi;
     }
 }
 
@@ -133,6 +150,32 @@ __global__ void field_offsets_kernel(const uint64_t *__restrict__ rec, uint64_t 
     }
 }
 
+// partial pair (key = x << 32 | y, score) -> ONE 64-bit record x | y | score (rb bits per row, sb = 64 - 2 rb bits of score) + destination
+// owner(x) = x mod G; a score that does not fit raises the flag (every rank then takes the unpacked path together)
+__global__ void pack_partials_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ score, uint64_t n, int rb, int sb, uint32_t G,
+                                     uint64_t *__restrict__ rec, uint8_t *__restrict__ dest, unsigned long long *flag) {
+    bool bad = false;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t k = key[i];
+        const uint32_t x = (uint32_t) (k >> 32), y = (uint32_t) k, sc = score[i];
+        if (sb < 32 && (sc >> sb)) bad = true;
+        rec[i] = ((uint64_t) x << (rb + sb)) | ((uint64_t) y << sb) | sc;
+        dest[i] = (uint8_t) (x % G);
+    }
+    if (bad) atomicExch(flag, 1ull);
+}
+
+struct UnpackPairKey {
+    int rb, sb;
+    __host__ __device__ __forceinline__ uint64_t operator()(const uint64_t &r) const {
+        return ((r >> (rb + sb)) << 32) | ((r >> sb) & ((1ull << rb) - 1));
+    }
+};
+struct UnpackPairScore {
+    uint64_t mask;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint64_t &r) const { return (uint32_t) (r & mask); }
+};
+
 __global__ void pair_dest_kernel(const uint64_t *__restrict__ key, uint64_t n, uint32_t G, uint8_t *__restrict__ dest) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) dest[i] = (uint8_t) ((uint32_t) (key[i] >> 32) % G);
 }
@@ -143,6 +186,7 @@ int hga_comm_rank(const hga_handle *h) { return h->comm ? h->comm->rank : 0; }
 int hga_comm_size(const hga_handle *h) { return h->comm ? h->comm->size : 1; }
 
 void hga_comm_destroy(hga_handle *h) {
+    if (!h->comm && h->comm_parked) { h->comm = h->comm_parked; h->comm_parked = nullptr; }
     if (!h->comm) return;
     if (h->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm->comm);
     h->comm->d_small.release();
@@ -235,27 +279,34 @@ int hga_comm_build_owner_index(hga_handle *h) {
     double comm_ms = 0, part_ms = 0;
     Trace tr(h);
 
-    // 1. packed records partitioned by owner (ONE stable radix pass: every owner segment keeps global row order)
+    // 1. list numbers partitioned by owner (ONE stable radix pass: every owner segment keeps row order) + per-row counts per owner
     const int owner_bits = (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) G), 1);
-    HGA_TRY(h->d_sort_a.ensure((E_loc + 1) * 8));      // packed records, partitioned
-    HGA_TRY(h->d_sort_b.ensure((E_loc + 1) * 8));      // packed records, stream order
-    HGA_TRY(h->d_x_row.ensure((E_loc + 1) * 2));       // owner per record: in | out
+    const uint64_t R_loc = h->n_reads;
+    HGA_TRY(h->d_sort_a.ensure((E_loc + 1) * 4));      // list numbers, partitioned
+    HGA_TRY(h->d_sort_b.ensure((E_loc + 1) * 4));      // list numbers, stream order
+    HGA_TRY(h->d_x_row.ensure((E_loc + 1) * 2));       // owner per hit: in | out
+    HGA_TRY(h->comm->d_rows.ensure(((size_t) G * R_loc + R_all + 2) * 4));   // my rows' counts per owner | all rows' counts for my lists
     uint8_t *own_in = h->d_x_row.as<uint8_t>(), *own_out = own_in + (E_loc + 1);
-    uint64_t *rec_in = h->d_sort_b.as<uint64_t>(), *rec_out = h->d_sort_a.as<uint64_t>();
+    uint32_t *list_in = h->d_sort_b.as<uint32_t>(), *list_out = h->d_sort_a.as<uint32_t>();
+    uint32_t *cnt_send = h->comm->d_rows.as<uint32_t>(), *cnt_recv = cnt_send + (size_t) G * R_loc;
+    if (R_loc) {
+        const int blocks = (int) std::min<uint64_t>((R_loc * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
+        pack_lists_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), R_loc, h->d_hit_slot.as<uint32_t>(), (uint32_t) G, list_in, own_in, cnt_send);
+        h->metrics.kernel_launches++;
+        HGA_CUDA(cudaGetLastError());
+    }
     if (E_loc) {
-        const int blocks = (int) std::min<uint64_t>((h->n_reads * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
-        pack_records_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->n_reads, row_base, h->d_hit_slot.as<uint32_t>(), (uint32_t) G, rec_in, own_in);
         size_t tmp = 0;
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, own_in, own_out, rec_in, rec_out, E_loc, 0, owner_bits, h->stream));
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, own_in, own_out, list_in, list_out, E_loc, 0, owner_bits, h->stream));
         HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp, own_in, own_out, rec_in, rec_out, E_loc, 0, owner_bits, h->stream));
-        h->metrics.kernel_launches += 4;
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp, own_in, own_out, list_in, list_out, E_loc, 0, owner_bits, h->stream));
+        h->metrics.kernel_launches += 3;
         HGA_CUDA(cudaGetLastError());
     }
     HGA_TRY(h->comm->d_small.ensure((size_t) (G + 2) * 8 * (G + 2)));
     unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + (G + 2);
     dest_counts_kernel<<<1, 64, 0, h->stream>>>(own_out, E_loc, G, d_cnt);
-    const unsigned long long my_rows = h->n_reads;                                  // rides along: the shard layout check below needs every rank's row count
+    const unsigned long long my_rows = R_loc;                                       // rides along: the receive layout needs every rank's row count
     HGA_CUDA(cudaMemcpyAsync(d_cnt + G, &my_rows, 8, cudaMemcpyHostToDevice, h->stream));
     h->metrics.kernel_launches++;
     HGA_CUDA(cudaGetLastError());
@@ -264,28 +315,31 @@ int hga_comm_build_owner_index(hga_handle *h) {
     HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, cnt_all));                         // the only host synchronisation of the stage
     tr.mark("counts");
     const size_t CS = (size_t) G + 1;
-    {   // shards must be contiguous read-id ranges in rank order: the row stream of source s must lie in s's range
-        uint64_t rows_before = 0, tot = 0;
-        for (int g = 0; g < G; g++) { if (g < me) rows_before += cnt_all[g * CS + G]; tot += cnt_all[g * CS + G]; }
-        if (rows_before != row_base) { hga_set_error("hga_build_index: shards must be contiguous read-id ranges in rank order (rank %d starts at row %u, expected %llu)", me, row_base, (unsigned long long) rows_before); return HGA_E_ARG; }
-        if (tot != R_all) { hga_set_error("hga_build_index: the ranks scanned %llu reads, hga_comm_init said %llu", (unsigned long long) tot, (unsigned long long) R_all); return HGA_E_ARG; }
-    }
+    std::vector<uint64_t> rows_off(G + 1, 0);
+    for (int g = 0; g < G; g++) rows_off[g + 1] = rows_off[g] + cnt_all[g * CS + G];
+    // shards must be contiguous read-id ranges in rank order: the row stream of source s must lie in s's range
+    if (rows_off[me] != row_base) { hga_set_error("hga_build_index: shards must be contiguous read-id ranges in rank order (rank %d starts at row %u, expected %llu)", me, row_base, (unsigned long long) rows_off[me]); return HGA_E_ARG; }
+    if (rows_off[G] != R_all) { hga_set_error("hga_build_index: the ranks scanned %llu reads, hga_comm_init said %llu", (unsigned long long) rows_off[G], (unsigned long long) R_all); return HGA_E_ARG; }
 
-    // 2. all-to-all: the records of my lists from every rank, in rank order = global row order
+    // 2. all-to-all: the list numbers of my lists from every rank, in rank order = global row order, and the sources' per-row counts
     uint64_t E_own = 0;
     std::vector<uint64_t> recv_off(G + 1, 0), send_off(G + 1, 0);
     for (int src = 0; src < G; src++) { recv_off[src] = E_own; E_own += cnt_all[src * CS + me]; }
     for (int g = 0; g < G; g++) send_off[g + 1] = send_off[g] + cnt_all[me * CS + g];
     if (E_own >= (1ull << 32)) { hga_set_error("this rank's share of the incidence (%llu entries) exceeds the 32-bit per-GPU limit", (unsigned long long) E_own); return HGA_E_OVERFLOW; }
-    HGA_TRY(h->d_x_slot.ensure((E_own + 1) * 8));       // received records
-    uint64_t *rx = h->d_x_slot.as<uint64_t>();
+    HGA_TRY(h->d_g_kid.ensure((E_own + 1) * 4));        // the by-row incidence of all rows restricted to my lists: list number per hit
+    HGA_TRY(h->d_g_row_off.ensure((R_all + 2) * 8));
+    uint32_t *rx = h->d_g_kid.as<uint32_t>();
     {
         StageTimer xt(h, &part_ms, true);
         HGA_NCCL(g_nccl.GroupStart());
         for (int g = 0; g < G; g++) {
             const uint64_t sc = cnt_all[me * CS + g], rc = cnt_all[g * CS + me];
-            if (sc) HGA_NCCL(g_nccl.Send(rec_out + send_off[g], sc, ncclUint64, g, h->comm->comm, h->stream));
-            if (rc) HGA_NCCL(g_nccl.Recv(rx + recv_off[g], rc, ncclUint64, g, h->comm->comm, h->stream));
+            const uint64_t rows_g = cnt_all[g * CS + G];
+            if (sc) HGA_NCCL(g_nccl.Send(list_out + send_off[g], sc, ncclUint32, g, h->comm->comm, h->stream));
+            if (rc) HGA_NCCL(g_nccl.Recv(rx + recv_off[g], rc, ncclUint32, g, h->comm->comm, h->stream));
+            if (R_loc) HGA_NCCL(g_nccl.Send(cnt_send + (size_t) g * R_loc, R_loc, ncclUint32, g, h->comm->comm, h->stream));
+            if (rows_g) HGA_NCCL(g_nccl.Recv(cnt_recv + rows_off[g], rows_g, ncclUint32, g, h->comm->comm, h->stream));
         }
         HGA_NCCL(g_nccl.GroupEnd());
         xt.stop();
@@ -293,20 +347,17 @@ int hga_comm_build_owner_index(hga_handle *h) {
     }
     tr.mark("alltoall");
 
-    // by-row incidence = the received stream (list numbers in row order + row offsets from the run boundaries); inverted lists = the
-    // single-GPU list builder over (list number, row)
-    HGA_TRY(h->d_g_row_off.ensure((R_all + 2) * 8));
-    HGA_TRY(h->d_g_kid.ensure((E_own + 1) * 4));
-    HGA_TRY(h->d_sort_b.ensure((E_own + 1) * 4));       // rows in stream order (scratch of the list builder)
+    // row offsets of the by-row incidence = exclusive sum of the counts (64-bit accumulator); inverted lists = the single-GPU list builder
     {
-        const int blocks = (int) std::min<uint64_t>((E_own + 256) / 256, (uint64_t) h->sm_count * 16);
-        field_offsets_kernel<uint64_t, 0><<<blocks, 256, 0, h->stream>>>(rx, E_own, R_all, h->d_g_row_off.as<uint64_t>());
-        if (E_own) unpack_records_kernel<<<blocks, 256, 0, h->stream>>>(rx, E_own, h->d_g_kid.as<uint32_t>(), h->d_sort_b.as<uint32_t>());
+        HGA_CUDA(cudaMemsetAsync(cnt_recv + R_all, 0, 4, h->stream));
+        size_t tmp = 0;
+        HGA_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp, cnt_recv, h->d_g_row_off.as<unsigned long long>(), cub::Sum(), 0ull, R_all + 1, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+        HGA_CUDA(cub::DeviceScan::ExclusiveScan(h->d_sort_tmp.p, tmp, cnt_recv, h->d_g_row_off.as<unsigned long long>(), cub::Sum(), 0ull, R_all + 1, h->stream));
         h->metrics.kernel_launches += 2;
-        HGA_CUDA(cudaGetLastError());
     }
-    tr.mark("unpack");
-    HGA_TRY(hga_build_lists(h, h->d_g_kid.as<uint32_t>(), h->d_sort_b.as<uint32_t>(), E_own, n_lists));
+    tr.mark("offsets");
+    HGA_TRY(hga_build_lists(h, h->d_g_kid.as<uint32_t>(), h->d_g_row_off.as<uint64_t>(), R_all, E_own, n_lists));
     tr.mark("lists");
     h->inc_rows = R_all;
     h->inc_row_first_id = 1;
@@ -385,6 +436,204 @@ int hga_comm_exchange_partials(hga_handle *h, uint64_t n, uint64_t *out_n) {
     tr.mark("alltoall");
     if (tr.on) fprintf(stderr, "[hga trace r%d partials] sent=%llu received=%llu\n", me, (unsigned long long) n, (unsigned long long) n_recv);
     tr.dump("partials", me);
+    return HGA_OK;
+}
+
+// Step 4, the usual way: the n partial records travel PACKED (one u64: x | y | partial score) - one partition pass, 8 instead of 12 bytes
+// per record on the wire, one keys-only sort over the 2 x row_bits key bits at the receiver - and are summed per (x, y) there. On return
+// *reduced = true and the final pairs (sorted by (x, y), scores summed, *out_n of them) are in h->d_pair_key / h->d_pair_score; when
+// the rows or a partial score do not fit 64 bits, *reduced = false and nothing has been exchanged (the caller takes the unpacked path).
+int hga_comm_reduce_partials_packed(hga_handle *h, uint64_t n, uint64_t *out_n, bool *reduced) {
+    const int G = h->comm->size, me = h->comm->rank;
+    *reduced = false;
+    const int rb = (int) std::max<uint32_t>(hga_ceil_log2(h->inc_rows + 1), 1), sb = 64 - 2 * rb;
+    if (getenv("HGA_PARTIALS_UNPACKED")) return HGA_OK;
+    if (sb < 12) return HGA_OK;                         // (the same on every rank: inc_rows is global)
+    const int owner_bits = (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) G), 1);
+    double part_ms = 0;
+    Trace tr(h);
+    HGA_TRY(h->d_x_row.ensure((n + 1) * 2));
+    HGA_TRY(h->d_pair_key2.ensure((n + 1) * 8));
+    HGA_TRY(h->d_x_slot.ensure((n + 1) * 8));
+    uint8_t *d_in = h->d_x_row.as<uint8_t>(), *d_out = d_in + (n + 1);
+    uint64_t *rec_in = h->d_x_slot.as<uint64_t>(), *rec_part = h->d_pair_key2.as<uint64_t>();
+    HGA_TRY(h->comm->d_small.ensure((size_t) (G + 2) * 8 * (G + 2)));
+    unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + (G + 2);
+    HGA_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t) (G + 1) * 8, h->stream));
+    if (n) {
+        pack_partials_kernel<<<(int) std::min<uint64_t>((n + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), h->d_pair_score.as<uint32_t>(), n, rb, sb,
+                                                                                                                           (uint32_t) G, rec_in, d_in, d_cnt + G);
+        size_t t1 = 0;
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, d_in, d_out, rec_in, rec_part, n, 0, owner_bits, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(t1 + 16));
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t1, d_in, d_out, rec_in, rec_part, n, 0, owner_bits, h->stream));
+        h->metrics.kernel_launches += 4;
+        HGA_CUDA(cudaGetLastError());
+    }
+    dest_counts_kernel<<<1, 64, 0, h->stream>>>(d_out, n, G, d_cnt);
+    h->metrics.kernel_launches++;
+    HGA_CUDA(cudaGetLastError());
+    tr.mark("pack+partition");
+    std::vector<unsigned long long> cnt_all;
+    HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, cnt_all));
+    tr.mark("counts");
+    const size_t CS = (size_t) G + 1;
+    for (int g = 0; g < G; g++) if (cnt_all[g * CS + G]) return HGA_OK;           // a score did not fit somewhere: everybody falls back
+    uint64_t n_recv = 0;
+    std::vector<uint64_t> recv_off(G + 1, 0), send_off(G + 1, 0);
+    for (int src = 0; src < G; src++) { recv_off[src] = n_recv; n_recv += cnt_all[src * CS + me]; }
+    for (int g = 0; g < G; g++) send_off[g + 1] = send_off[g] + cnt_all[me * CS + g];
+    HGA_TRY(h->d_x_slot.ensure((n_recv + 1) * 8 * 2));                            // received | sorted (rec_in is dead by now)
+    uint64_t *rx = h->d_x_slot.as<uint64_t>(), *rx_sorted = rx + (n_recv + 1);
+    {
+        StageTimer xt(h, &part_ms, true);
+        HGA_NCCL(g_nccl.GroupStart());
+        for (int g = 0; g < G; g++) {
+            const uint64_t sc = cnt_all[me * CS + g], rc = cnt_all[g * CS + me];
+            if (sc) HGA_NCCL(g_nccl.Send(rec_part + send_off[g], sc, ncclUint64, g, h->comm->comm, h->stream));
+            if (rc) HGA_NCCL(g_nccl.Recv(rx + recv_off[g], rc, ncclUint64, g, h->comm->comm, h->stream));
+        }
+        HGA_NCCL(g_nccl.GroupEnd());
+        xt.stop();
+        h->metrics.exchange_ms += part_ms;
+    }
+    tr.mark("alltoall");
+    uint64_t runs_h = 0;
+    HGA_TRY(h->d_pair_key.ensure((n_recv + 1) * 8));
+    HGA_TRY(h->d_pair_score.ensure((n_recv + 1) * 4));
+    if (n_recv) {
+        size_t t1 = 0, t2 = 0;
+        HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, t1, rx, rx_sorted, n_recv, sb, 64, h->stream));
+        cub::TransformInputIterator<uint64_t, UnpackPairKey, const uint64_t *> kit(rx_sorted, UnpackPairKey{rb, sb});
+        cub::TransformInputIterator<uint32_t, UnpackPairScore, const uint64_t *> vit(rx_sorted, UnpackPairScore{sb >= 64 ? ~0ull : ((1ull << sb) - 1)});
+        unsigned long long *d_runs = d_cnt;                                          // a free scalar
+        HGA_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, t2, kit, h->d_pair_key.as<uint64_t>(), vit, h->d_pair_score.as<uint32_t>(), d_runs, cub::Sum(), n_recv, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
+        HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, t1, rx, rx_sorted, n_recv, sb, 64, h->stream));
+        tr.mark("sort");
+        HGA_CUDA(cub::DeviceReduce::ReduceByKey(h->d_sort_tmp.p, t2, kit, h->d_pair_key.as<uint64_t>(), vit, h->d_pair_score.as<uint32_t>(), d_runs, cub::Sum(), n_recv, h->stream));
+        unsigned long long runs = 0;
+        HGA_CUDA(cudaMemcpyAsync(&runs, d_runs, 8, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+        runs_h = runs;
+        h->metrics.kernel_launches += (uint64_t) (2 * rb + 7) / 8 + 5;
+        tr.mark("reduce");
+    }
+    if (tr.on) fprintf(stderr, "[hga trace r%d partials] packed sent=%llu received=%llu final=%llu\n", me, (unsigned long long) n, (unsigned long long) n_recv, (unsigned long long) runs_h);
+    tr.dump("partials", me);
+    *out_n = runs_h;
+    *reduced = true;
+    return HGA_OK;
+}
+
+namespace {
+// row offsets of source s (local, starting at 0) -> global: out[rows_before + i] = local[i] + hits_before, i < n_rows
+__global__ void rebase_offsets_kernel(const uint64_t *__restrict__ local, uint64_t n_rows, uint64_t rows_before, uint64_t hits_before, uint64_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_rows; i += (uint64_t) gridDim.x * blockDim.x) out[rows_before + i] = local[i] + hits_before;
+}
+}  // namespace
+
+// The stages after the scaffold union_find (merge_components, tails, spectral clustering, enrichment: ReadClusteringEngine.cpp:764-794)
+// run on ONE GPU: their work is a small fraction of the hot path and their host parts are sequential. This collective turns rank 0's
+// handle into a complete single-GPU handle: the hits of all ranks (shards are contiguous id ranges in rank order, slots mean the same
+// k-mer on every rank: concatenation IS the single-GPU hit list), the selected edges of all ranks in (x, y) order, the component labels
+// (already replicated), and the by-slot inverted index rebuilt from the gathered hits. The communicator is detached from rank 0's
+// handle (kept for hga_destroy); the other ranks' handles keep their state and must not enter another collective.
+extern "C" int hga_comm_gather_root(hga_handle *h) {
+    if (!h) { hga_set_error("NULL handle"); return HGA_E_ARG; }
+    if (!h->comm || h->comm->size < 2) return HGA_OK;
+    if (!h->have_scan || !h->have_selection || !h->have_components) { hga_set_error("hga_comm_gather_root: needs hga_scan ... hga_components on every rank"); return HGA_E_STATE; }
+    HGA_CUDA(cudaSetDevice(h->device));
+    const int G = h->comm->size, me = h->comm->rank;
+    HGA_TRY(hga_scan_finish_positions(h));
+    // (reads, hits, selected edges) of every rank
+    HGA_TRY(h->comm->d_small.ensure((size_t) (G + 2) * 8 * (G + 2)));
+    unsigned long long *d_mine = h->comm->d_small.as<unsigned long long>(), *d_all = d_mine + 4;
+    const unsigned long long mine[3] = {h->n_reads, h->n_hits, h->n_selected};
+    HGA_CUDA(cudaMemcpyAsync(d_mine, mine, 24, cudaMemcpyHostToDevice, h->stream));
+    HGA_NCCL(g_nccl.AllGather(d_mine, d_all, 3, ncclUint64, h->comm->comm, h->stream));
+    std::vector<unsigned long long> all((size_t) 3 * G);
+    HGA_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t) 3 * G * 8, cudaMemcpyDeviceToHost, h->stream));
+    HGA_CUDA(cudaStreamSynchronize(h->stream));
+    uint64_t R = 0, E = 0, M = 0;
+    std::vector<uint64_t> r0(G + 1, 0), e0(G + 1, 0), m0(G + 1, 0);
+    for (int g = 0; g < G; g++) { r0[g + 1] = r0[g] + all[3 * g]; e0[g + 1] = e0[g] + all[3 * g + 1]; m0[g + 1] = m0[g] + all[3 * g + 2]; }
+    R = r0[G]; E = e0[G]; M = m0[G];
+    if (E >= (1ull << 32)) { hga_set_error("hga_comm_gather_root: %llu hits do not fit one GPU's 32-bit incidence", (unsigned long long) E); return HGA_E_OVERFLOW; }
+
+    DevBuf g_off_local, g_off, g_slot, g_pos, g_key, g_score, g_key2, g_score2;
+    if (me == 0) {
+        HGA_TRY(g_off_local.ensure((R + G + 1) * 8)); HGA_TRY(g_off.ensure((R + 2) * 8));
+        HGA_TRY(g_slot.ensure((E + 1) * 4)); HGA_TRY(g_pos.ensure((E + 1) * 4));
+        HGA_TRY(g_key.ensure((M + 1) * 8)); HGA_TRY(g_score.ensure((M + 1) * 4));
+        HGA_TRY(g_key2.ensure((M + 1) * 8)); HGA_TRY(g_score2.ensure((M + 1) * 4));
+    }
+    HGA_NCCL(g_nccl.GroupStart());
+    if (me != 0) {
+        HGA_NCCL(g_nccl.Send(h->d_row_off.p, h->n_reads + 1, ncclUint64, 0, h->comm->comm, h->stream));
+        if (h->n_hits) {
+            HGA_NCCL(g_nccl.Send(h->d_hit_slot.p, h->n_hits, ncclUint32, 0, h->comm->comm, h->stream));
+            HGA_NCCL(g_nccl.Send(h->d_hit_pos.p, h->n_hits, ncclUint32, 0, h->comm->comm, h->stream));
+        }
+        if (h->n_selected) {
+            HGA_NCCL(g_nccl.Send(h->d_sel_key.p, h->n_selected, ncclUint64, 0, h->comm->comm, h->stream));
+            HGA_NCCL(g_nccl.Send(h->d_sel_score.p, h->n_selected, ncclUint32, 0, h->comm->comm, h->stream));
+        }
+    } else {
+        for (int g = 1; g < G; g++) {
+            const uint64_t nr = all[3 * g], nh = all[3 * g + 1], ns = all[3 * g + 2];
+            HGA_NCCL(g_nccl.Recv(g_off_local.as<uint64_t>() + r0[g] + g, nr + 1, ncclUint64, g, h->comm->comm, h->stream));
+            if (nh) {
+                HGA_NCCL(g_nccl.Recv(g_slot.as<uint32_t>() + e0[g], nh, ncclUint32, g, h->comm->comm, h->stream));
+                HGA_NCCL(g_nccl.Recv(g_pos.as<uint32_t>() + e0[g], nh, ncclUint32, g, h->comm->comm, h->stream));
+            }
+            if (ns) {
+                HGA_NCCL(g_nccl.Recv(g_key.as<uint64_t>() + m0[g], ns, ncclUint64, g, h->comm->comm, h->stream));
+                HGA_NCCL(g_nccl.Recv(g_score.as<uint32_t>() + m0[g], ns, ncclUint32, g, h->comm->comm, h->stream));
+            }
+        }
+    }
+    HGA_NCCL(g_nccl.GroupEnd());
+    if (me != 0) { HGA_CUDA(cudaStreamSynchronize(h->stream)); return HGA_OK; }
+
+    // rank 0: its own part, then the global row offsets, the selection in (x, y) order, and the handle's new state
+    HGA_CUDA(cudaMemcpyAsync(g_off_local.p, h->d_row_off.p, (h->n_reads + 1) * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->n_hits) {
+        HGA_CUDA(cudaMemcpyAsync(g_slot.p, h->d_hit_slot.p, h->n_hits * 4, cudaMemcpyDeviceToDevice, h->stream));
+        HGA_CUDA(cudaMemcpyAsync(g_pos.p, h->d_hit_pos.p, h->n_hits * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (h->n_selected) {
+        HGA_CUDA(cudaMemcpyAsync(g_key.p, h->d_sel_key.p, h->n_selected * 8, cudaMemcpyDeviceToDevice, h->stream));
+        HGA_CUDA(cudaMemcpyAsync(g_score.p, h->d_sel_score.p, h->n_selected * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    for (int g = 0; g < G; g++) {
+        const uint64_t nr = all[3 * g];
+        if (nr) rebase_offsets_kernel<<<(int) std::min<uint64_t>((nr + 255) / 256, 2048), 256, 0, h->stream>>>(g_off_local.as<uint64_t>() + r0[g] + g, nr, r0[g], e0[g], g_off.as<uint64_t>());
+    }
+    HGA_CUDA(cudaMemcpyAsync(g_off.as<uint64_t>() + R, &E, 8, cudaMemcpyHostToDevice, h->stream));
+    if (M) {
+        size_t tmp = 0;
+        const int bits = 32 + (int) std::max<uint32_t>(hga_ceil_log2(R + 1), 1);
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, g_key.as<uint64_t>(), g_key2.as<uint64_t>(), g_score.as<uint32_t>(), g_score2.as<uint32_t>(), M, 0, bits, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp, g_key.as<uint64_t>(), g_key2.as<uint64_t>(), g_score.as<uint32_t>(), g_score2.as<uint32_t>(), M, 0, bits, h->stream));
+    }
+    HGA_CUDA(cudaGetLastError());
+    HGA_CUDA(cudaStreamSynchronize(h->stream));
+    h->d_row_off.release(); h->d_row_off = g_off;
+    h->d_hit_slot.release(); h->d_hit_slot = g_slot;
+    h->d_hit_pos.release(); h->d_hit_pos = g_pos;
+    h->d_sel_key.release(); h->d_sel_key = g_key2;
+    h->d_sel_score.release(); h->d_sel_score = g_score2;
+    g_off_local.release(); g_key.release(); g_score.release();
+    h->n_reads = R; h->n_hits = E; h->n_selected = M; h->read_id_base = 1;
+    h->pos_pending = false; h->scan_tiles = 0;
+    h->metrics.n_reads = R; h->metrics.n_hits = E; h->metrics.n_selected = M;
+    h->comm_parked = h->comm; h->comm = nullptr;           // from here on a single-GPU handle
+    h->have_index = false; h->have_pairs = false;
+    const bool had_selection = h->have_selection, had_components = h->have_components;
+    HGA_TRY(hga_index_run(h));                               // by-slot index over all reads (clears the later stages' flags)
+    h->have_selection = had_selection; h->have_components = had_components;
     return HGA_OK;
 }
 

@@ -155,10 +155,18 @@ __global__ void __launch_bounds__(IDX_WARPS * 32) index_local_sort_kernel(const 
 
 }  // namespace
 
-// Inverted lists from (key, row) pairs that arrive in row order: keys u32 < n_keys (a multiple of 32, or L = 0 is used), rows u32. On return
-// h->d_inv_off[0 .. n_keys] / h->d_inv_row hold the lists, rows ascending inside a list. d_keys is left untouched (the pair counter walks
-// it as the by-row incidence); d_rows is scratch.
-int hga_build_lists(hga_handle *h, const uint32_t *d_keys, const uint32_t *d_rows, uint64_t E, uint32_t n_keys) {
+// Inverted lists from the by-row incidence (CSR: d_row_off u64[n_rows + 1], d_keys u32[E], keys < n_keys, n_keys a multiple of 32 or L = 0
+// is used). On return h->d_inv_off[0 .. n_keys] / h->d_inv_row hold the lists, rows ascending inside a list. d_keys is left untouched (the
+// pair counter walks it as the by-row incidence).
+int hga_build_lists(hga_handle *h, const uint32_t *d_keys, const uint64_t *d_row_off, uint64_t n_rows, uint64_t E, uint32_t n_keys) {
+    HGA_TRY(h->d_sort_b.ensure((E + 1) * 4));     // the row of every pair, expanded from the row offsets
+    uint32_t *d_rows = h->d_sort_b.as<uint32_t>();
+    if (E > 0) {
+        const int blocks = (int) std::min<uint64_t>((n_rows * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
+        expand_rows_kernel<<<blocks, 256, 0, h->stream>>>(d_row_off, n_rows, d_rows);
+        h->metrics.kernel_launches++;
+        HGA_CUDA(cudaGetLastError());
+    }
     HGA_TRY(h->d_inv_off.ensure(((size_t) n_keys + 2) * 4));
     HGA_TRY(h->d_inv_row.ensure((E + 4) * 4));
     HGA_TRY(h->d_sort_a.ensure((E + 1) * 4));     // sorted keys
@@ -219,14 +227,7 @@ int hga_index_run(hga_handle *h) {
     if (E >= (1ull << 32)) { hga_set_error("incidence of %llu entries exceeds the 32-bit per-GPU limit", (unsigned long long) E); return HGA_E_OVERFLOW; }
 
     StageTimer timer(h, &h->metrics.index_ms);
-    HGA_TRY(h->d_sort_b.ensure((E + 1) * 4));
-    if (E > 0) {
-        const int blocks = (int) std::min<uint64_t>((h->inc_rows * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
-        expand_rows_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), h->inc_rows, h->d_sort_b.as<uint32_t>());
-        h->metrics.kernel_launches++;
-        HGA_CUDA(cudaGetLastError());
-    }
-    HGA_TRY(hga_build_lists(h, h->d_hit_slot.as<uint32_t>(), h->d_sort_b.as<uint32_t>(), E, n_slots));
+    HGA_TRY(hga_build_lists(h, h->d_hit_slot.as<uint32_t>(), h->d_row_off.as<uint64_t>(), h->inc_rows, E, n_slots));
     timer.stop();
     h->have_index = true;
     return HGA_OK;

@@ -350,6 +350,7 @@ struct hga_handle {
 
     hga_metrics_t metrics;
     hga_comm *comm = nullptr;
+    hga_comm *comm_parked = nullptr;      // rank 0 after hga_comm_gather_root: the communicator, detached (destroyed with the handle)
     uint64_t n_reads_total = 0;           // over all ranks (== n_reads without a comm)
 };
 
@@ -359,7 +360,7 @@ int hga_table_build(hga_handle *h, const uint64_t *host_kmers);
 int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint64_t n_bases, const char *h_bases);
 int hga_scan_finish_positions(hga_handle *h);
 int hga_index_run(hga_handle *h);
-int hga_build_lists(hga_handle *h, const uint32_t *d_keys, const uint32_t *d_rows, uint64_t E, uint32_t n_keys);
+int hga_build_lists(hga_handle *h, const uint32_t *d_keys, const uint64_t *d_row_off, uint64_t n_rows, uint64_t E, uint32_t n_keys);
 int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
 int hga_select_run(hga_handle *h, double fraction, uint32_t score_threshold);
 int hga_cc_run(hga_handle *h, int min_size);
@@ -371,6 +372,7 @@ int hga_export_index(hga_handle *h, const uint32_t *d_off, const uint32_t *d_row
 // multi-GPU hooks (hga_comm.cu); all are no-ops / never called without a communicator
 int hga_comm_build_owner_index(hga_handle *h);
 int hga_comm_exchange_partials(hga_handle *h, uint64_t n, uint64_t *out_n);
+int hga_comm_reduce_partials_packed(hga_handle *h, uint64_t n, uint64_t *out_n, bool *reduced);
 int hga_comm_allgather_u64(hga_handle *h, uint64_t mine, std::vector<uint64_t> &all);
 int hga_comm_allgatherv(hga_handle *h, const void *d_mine, void *d_all, const std::vector<uint64_t> &counts, int elem_bytes);
 int hga_comm_allreduce_u64_sum(hga_handle *h, uint64_t *d_buf, size_t n);

@@ -758,13 +758,18 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     h->pair_capacity = capacity;
     uint64_t P = sc.cursor;
     tr.mark("kernels");
-    if (multi) HGA_TRY(hga_comm_exchange_partials(h, P, &P));
-    tr.mark("exchange");     // partial (x, y, score) -> owner(x); received into d_pair_key / d_pair_score
+    // multi-GPU: partial (x, y, score) -> owner(x). Packed records are exchanged, sorted and summed in hga_comm.cu; when they do not fit
+    // 64 bits the records travel as (key, score) and the sort / segmented sum below run on them
+    bool reduced = false;
+    if (multi) HGA_TRY(hga_comm_reduce_partials_packed(h, P, &P, &reduced));
+    if (multi && !reduced) HGA_TRY(hga_comm_exchange_partials(h, P, &P));     // received into d_pair_key / d_pair_score
+    tr.mark("exchange");
 
     // canonical physical order: sort by (x_row, y_row)
     HGA_TRY(h->d_pair_key2.ensure((P + 1) * 8));
     HGA_TRY(h->d_pair_score2.ensure((P + 1) * 4));
-    if (P > 0) {
+    unsigned long long *d_runs = &d_sc->heavy_ticket;      // a free scalar
+    if (P > 0 && !reduced) {
         // key = x << 32 | y with x, y < 2^row_bits: two stable sorts over the bits that vary (y, then x) instead of one over all 32 + row_bits
         // (config 4: 3 + 3 passes instead of 7); the second one lands in the primary arrays again
         const int row_bits = (int) std::max<uint32_t>(hga_ceil_log2(h->inc_rows + 1), 1);
@@ -779,46 +784,45 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
         HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t2, h->d_pair_key2.as<uint64_t>(), h->d_pair_key.as<uint64_t>(),
                                                  h->d_pair_score2.as<uint32_t>(), h->d_pair_score.as<uint32_t>(), P, 32, 32 + row_bits, h->stream));
         h->metrics.kernel_launches += 2 * ((uint64_t) (row_bits + 7) / 8 + 2);
-        std::swap(h->d_pair_key, h->d_pair_key2);          // from here on the sorted arrays are the secondary ones (swapped back below)
-        std::swap(h->d_pair_score, h->d_pair_score2);
     }
     tr.mark("sort");
-    if (multi && P > 0) {
-        // one record per contributing rank and pair, now adjacent: segmented sum -> final scores (back in d_pair_key / d_pair_score), then
-        // the min_score filter the single-GPU kernels apply when they flush a row
-        unsigned long long *d_runs = &d_sc->heavy_ticket;      // a free scalar
+    if (multi && P > 0 && !reduced) {
+        // one record per contributing rank and pair, now adjacent: segmented sum -> final scores (primary -> secondary -> swapped back into the primary arrays)
         size_t tmp_bytes = 0;
-        HGA_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp_bytes, h->d_pair_key2.as<uint64_t>(), h->d_pair_key.as<uint64_t>(), h->d_pair_score2.as<uint32_t>(),
-                                                h->d_pair_score.as<uint32_t>(), d_runs, cub::Sum(), P, h->stream));
+        HGA_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp_bytes, h->d_pair_key.as<uint64_t>(), h->d_pair_key2.as<uint64_t>(), h->d_pair_score.as<uint32_t>(),
+                                                h->d_pair_score2.as<uint32_t>(), d_runs, cub::Sum(), P, h->stream));
         HGA_TRY(h->d_sort_tmp.ensure(tmp_bytes + 16));
-        HGA_CUDA(cub::DeviceReduce::ReduceByKey(h->d_sort_tmp.p, tmp_bytes, h->d_pair_key2.as<uint64_t>(), h->d_pair_key.as<uint64_t>(), h->d_pair_score2.as<uint32_t>(),
-                                                h->d_pair_score.as<uint32_t>(), d_runs, cub::Sum(), P, h->stream));
+        HGA_CUDA(cub::DeviceReduce::ReduceByKey(h->d_sort_tmp.p, tmp_bytes, h->d_pair_key.as<uint64_t>(), h->d_pair_key2.as<uint64_t>(), h->d_pair_score.as<uint32_t>(),
+                                                h->d_pair_score2.as<uint32_t>(), d_runs, cub::Sum(), P, h->stream));
         unsigned long long runs = 0;
         HGA_CUDA(cudaMemcpyAsync(&runs, d_runs, 8, cudaMemcpyDeviceToHost, h->stream));
         HGA_CUDA(cudaStreamSynchronize(h->stream));
         P = runs;
         h->metrics.kernel_launches += 3;
-        if (min_score > 1 && P > 0) {
-            HGA_TRY(h->d_pivot_flag.ensure(P + 1));
-            uint8_t *flag = h->d_pivot_flag.as<uint8_t>();
-            flag_min_score_kernel<<<(int) std::min<uint64_t>((P + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(h->d_pair_score.as<uint32_t>(), P, min_score, flag);
-            size_t t1 = 0, t2 = 0;
-            HGA_CUDA(cub::DeviceSelect::Flagged(nullptr, t1, h->d_pair_key.as<uint64_t>(), flag, h->d_pair_key2.as<uint64_t>(), d_runs, P, h->stream));
-            HGA_CUDA(cub::DeviceSelect::Flagged(nullptr, t2, h->d_pair_score.as<uint32_t>(), flag, h->d_pair_score2.as<uint32_t>(), d_runs, P, h->stream));
-            HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
-            HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, t1, h->d_pair_key.as<uint64_t>(), flag, h->d_pair_key2.as<uint64_t>(), d_runs, P, h->stream));
-            HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, t2, h->d_pair_score.as<uint32_t>(), flag, h->d_pair_score2.as<uint32_t>(), d_runs, P, h->stream));
-            HGA_CUDA(cudaMemcpyAsync(&runs, d_runs, 8, cudaMemcpyDeviceToHost, h->stream));
-            HGA_CUDA(cudaStreamSynchronize(h->stream));
-            P = runs;
-            h->metrics.kernel_launches += 5;
-        } else {
-            std::swap(h->d_pair_key, h->d_pair_key2);      // the swap below puts the reduced arrays back in place
-            std::swap(h->d_pair_score, h->d_pair_score2);
-        }
+        std::swap(h->d_pair_key, h->d_pair_key2);
+        std::swap(h->d_pair_score, h->d_pair_score2);
     }
-    std::swap(h->d_pair_key, h->d_pair_key2);
-    std::swap(h->d_pair_score, h->d_pair_score2);
+    if (multi && min_score > 1 && P > 0) {
+        // the min_score filter the single-GPU kernels apply when they flush a row
+        HGA_TRY(h->d_pair_key2.ensure((P + 1) * 8));
+        HGA_TRY(h->d_pair_score2.ensure((P + 1) * 4));
+        HGA_TRY(h->d_pivot_flag.ensure(P + 1));
+        uint8_t *flag = h->d_pivot_flag.as<uint8_t>();
+        flag_min_score_kernel<<<(int) std::min<uint64_t>((P + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(h->d_pair_score.as<uint32_t>(), P, min_score, flag);
+        size_t t1 = 0, t2 = 0;
+        HGA_CUDA(cub::DeviceSelect::Flagged(nullptr, t1, h->d_pair_key.as<uint64_t>(), flag, h->d_pair_key2.as<uint64_t>(), d_runs, P, h->stream));
+        HGA_CUDA(cub::DeviceSelect::Flagged(nullptr, t2, h->d_pair_score.as<uint32_t>(), flag, h->d_pair_score2.as<uint32_t>(), d_runs, P, h->stream));
+        HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
+        HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, t1, h->d_pair_key.as<uint64_t>(), flag, h->d_pair_key2.as<uint64_t>(), d_runs, P, h->stream));
+        HGA_CUDA(cub::DeviceSelect::Flagged(h->d_sort_tmp.p, t2, h->d_pair_score.as<uint32_t>(), flag, h->d_pair_score2.as<uint32_t>(), d_runs, P, h->stream));
+        unsigned long long runs = 0;
+        HGA_CUDA(cudaMemcpyAsync(&runs, d_runs, 8, cudaMemcpyDeviceToHost, h->stream));
+        HGA_CUDA(cudaStreamSynchronize(h->stream));
+        P = runs;
+        h->metrics.kernel_launches += 5;
+        std::swap(h->d_pair_key, h->d_pair_key2);
+        std::swap(h->d_pair_score, h->d_pair_score2);
+    }
     h->n_pairs = P;
     tr.mark("reduce");
 

@@ -270,7 +270,8 @@ int hga_metrics(hga_handle *h, hga_metrics_t *out);
 
 /* Multi-GPU (one handle per rank/GPU). The 128-byte id comes from hga_comm_unique_id on rank 0 and is
  * distributed by the caller (torch.distributed broadcast, a file, ...). After hga_comm_init:
- *   hga_build_index   routes (kmer, read) incidences to the k-mer's owner rank, kmer_id mod nranks (all-to-all); nothing is replicated:
+ *   hga_build_index   routes (kmer, read) incidences to the k-mer's owner rank (whole buckets of the k-mer table dealt round robin; the table
+ *                     layout is a function of the k-mer array, the same on every rank) with one all-to-all; nothing is replicated:
  *                     hga_get_index on a rank returns the lists of ITS k-mers (every other list empty),
  *   hga_pair_count    counts partial scores over the owned lists and reduces them at the owner of x, x mod nranks (all-to-all):
  *                     every unordered pair ends up on exactly one rank,
@@ -279,6 +280,12 @@ int hga_metrics(hga_handle *h, hga_metrics_t *out);
  * n_reads_total = number of reads over all ranks (rows are global: rank shards are contiguous id ranges). */
 int hga_comm_unique_id(void *id128);
 int hga_comm_init(hga_handle *h, const void *id128, int rank, int nranks, uint64_t n_reads_total);
+/* Collective, after hga_components on every rank: rank 0's handle becomes a complete single-GPU handle (hits and selected edges of all
+ * ranks gathered over NCCL, by-slot inverted index rebuilt, communicator detached), on which hga_enrich / hga_enrich_ex / hga_enrich_full
+ * and every hga_get_* except hga_get_pairs work as on one GPU: the stages after the scaffold union_find (run_clustering,
+ * ReadClusteringEngine.cpp:764-794) run on rank 0. The other ranks' handles are left as they are and must not enter another collective.
+ * Without a communicator: no-op. */
+int hga_comm_gather_root(hga_handle *h);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,30 @@ def main():
         h.components(min_size=min_size)
         comp = h.get_components()
         m = h.metrics()
+        # the stages after the scaffold union_find run on rank 0 after hga_comm_gather_root: the gathered handle must behave as a single-GPU
+        # handle that scanned everything (hits, by-slot index, selection, components) and hga_enrich_full on it must give the single-GPU result
+        h.comm_gather_root()
+        if rank == 0:
+            allb = b"".join(seqs)
+            alloff = np.zeros(len(seqs) + 1, dtype=np.uint64)
+            np.cumsum(lens, out=alloff[1:])
+            h1 = hga_b200.Handle(kmers, k, device=local)
+            h1.scan(allb, alloff, read_id_base=1)
+            h1.build_index(); h1.pair_count(min_score=1); h1.select_edges(fraction=0.15); h1.components(min_size=min_size)
+            for a1, a2 in zip(h.get_hits(), h1.get_hits()):
+                assert np.array_equal(a1, a2), f"case {case}: gathered hits differ from the single-GPU hits"
+            for a1, a2 in zip(h.get_index(), h1.get_index()):
+                assert np.array_equal(a1, a2), f"case {case}: index rebuilt on rank 0 differs from the single-GPU index"
+            s0, s1 = h.get_selection(), h1.get_selection()
+            for key in ("x", "y", "score"):
+                assert np.array_equal(s0[key], s1[key]), f"case {case}: gathered selection differs ({key})"
+            for hh in (h, h1):
+                hh.enrich_full(alloff, min_size=min_size, enrichment_min_score=5, tail_amplification_min_score=10, spectral_dims=8)
+            e0, e1 = h.get_enrichment(), h1.get_enrichment()
+            for key in ("core_id", "core_off", "core_read", "conn_x", "conn_y", "conn_score", "final_id", "final_off", "final_read", "assignment"):
+                assert np.array_equal(e0[key], e1[key]), f"case {case}: enrichment on the gathered handle differs from the single-GPU run ({key})"
+            print(f"gathered handle ok: case {case}, {len(e0['core_id'])} cores, {len(e0['final_id'])} final components")
+            h1.close()
         h.close()
 
         mine = dict(row_off=row_off, kid=kid, pos=pos, x=x, y=y, s=s, sx=sel["x"], sy=sel["y"], ss=sel["score"], n_directed=sel["n_directed"],
