@@ -87,25 +87,15 @@ __global__ void __launch_bounds__(IDX_WARPS * 32) index_local_sort_kernel(const 
         }
         cnt[lane] = 0;
         __syncwarp();
+        // counts: one shared-memory increment per entry (the hardware serialises equal slots)
         if (in_regs) {
             #pragma unroll
-            for (int u = 0; u < IDX_REG; u++) {
-                if ((uint32_t) u * 32 < n) {                                           // warp uniform
-                    const uint32_t peers = same_key_lanes(kk[u]);
-                    if (kk[u] < 32u && (peers & lt) == 0) cnt[kk[u]] += __popc(peers);  // the first lane of every key adds its step's count
-                    __syncwarp();
-                }
-            }
+            for (int u = 0; u < IDX_REG; u++)
+                if (kk[u] < 32u) atomicAdd(&cnt[kk[u]], 1u);
         } else {
-            for (uint32_t base = lo; base < hi; base += 32) {
-                const uint32_t i = base + lane;
-                const bool valid = i < hi;
-                const uint32_t k = valid ? (__ldg(&keys[i]) & mask) : 32u + lane;
-                const uint32_t peers = same_key_lanes(k);
-                if (valid && (peers & lt) == 0) cnt[k] += __popc(peers);
-                __syncwarp();
-            }
+            for (uint32_t i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[__ldg(&keys[i]) & mask], 1u);
         }
+        __syncwarp();
         // exclusive prefix over the group's slots -> list offsets
         const uint32_t c = cnt[lane];
         uint32_t incl = c;

@@ -161,39 +161,21 @@ __device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, 
     // lane one contiguous block of the row's entries instead of the interleaved lane, lane + 32, ... was 27 % slower (r3v):
     // neighbouring lanes walking neighbouring lists is what coalesces the list loads.)
     uint64_t j = a + lane;
-    uint32_t cur_lo = 0, cur_i = 0, n1_lo = 0, n1_hi = 0, n2_lo = 0, n2_hi = 0;
-    bool have1 = j < b, have2 = j + 32 < b;
+    uint32_t cur_lo = 0, cur_i = 0, n1_lo = 0, n1_hi = 0, n2_lo = 0, n2_hi = 0, slot3 = 0;
+    bool have1 = j < b, have2 = j + 32 < b, have3 = j + 64 < b;
+    // three lists in flight per lane: list j is walked, the bounds of list j + 32 are known (its last chunk prefetched), and the SLOT of
+    // list j + 64 is on its way, so that no load is issued with an address that has to be waited for (r2z: 13 % of the stall samples sat
+    // on the slot -> offset chain)
     if (have1) { const uint32_t slot = __ldg(&p.row_slot[j]); n1_lo = __ldg(&p.inv_off[slot]); n1_hi = __ldg(&p.inv_off[slot + 1]); }
     if (have2) { const uint32_t slot = __ldg(&p.row_slot[j + 32]); n2_lo = __ldg(&p.inv_off[slot]); n2_hi = __ldg(&p.inv_off[slot + 1]); }
+    if (have3) slot3 = __ldg(&p.row_slot[j + 64]);
+    // One loop body for all 32 lanes, predicated rather than branched (r2q: with one branch per list entry - fast path, probe loop, not
+    // in range - the warp ran with 10 of 32 lanes per instruction on average): a lane that has finished its list switches to the next
+    // one and goes straight on to that list's first chunk; the four entries of a chunk take the fast path together (partner already at
+    // its home slot: one predicated shared-memory increment each); the entries that missed are resolved afterwards in a probe loop the
+    // whole warp steps through together, one probe per lane and step.
     while (__any_sync(0xFFFFFFFFu, have1 || cur_i > cur_lo)) {
-        if (cur_i > cur_lo) {
-            // four list entries per step (one aligned 16 B load), walked from the end of the list
-            const uint32_t q = (cur_i - 1) >> 2, cb = q << 2;
-            const uint4 c = __ldg(reinterpret_cast<const uint4 *>(p.inv_row) + q);
-            const uint32_t ys[4] = {c.x, c.y, c.z, c.w};
-            // the four accumulator probes are issued together (four independent shared-memory loads), then resolved: the
-            // common case - partner already present - is one plain read and one atomic add per entry (r4a: 71.1 -> 64.0 ms;
-            // two chunks = eight probes per step needs 62 registers and was slower, 77.5 ms, r4b)
-            bool ok[4], stop = false;
-            uint32_t hh[4], kk[4];
-            #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const uint32_t idx = cb + e;
-                const bool inr = idx < cur_i && idx >= cur_lo;
-                stop |= inr && tail && ys[e] <= x;                    // ascending list: nothing further down can be > x
-                ok[e] = inr && keep_candidate(x, ys[e], p.mode, p.pivot_flag);
-                hh[e] = hash_row(ys[e]) >> cshift;
-            }
-            #pragma unroll
-            for (int e = 0; e < 4; e++) kk[e] = ok[e] ? *reinterpret_cast<volatile uint32_t *>(&A.key[hh[e]]) : 0u;
-            #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                if (!ok[e]) continue;
-                if (kk[e] == ys[e]) atomicAdd(&A.val[hh[e]], 1u);
-                else acc_add(A, ys[e], 1u, cmask, cshift, limit);
-            }
-            cur_i = stop ? cur_lo : max(cb, cur_lo);
-        } else if (have1) {
+        if (cur_i <= cur_lo && have1) {
             cur_lo = n1_lo; cur_i = n1_hi;
             if (cur_i - cur_lo > PW_LONG) {                           // long list: leave it to the whole warp
                 const uint32_t at = atomicAdd(&A.n_defer, 1u);
@@ -201,10 +183,69 @@ __device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, 
             }
             j += 32;
             have1 = have2; n1_lo = n2_lo; n1_hi = n2_hi;
-            if (have1 && n1_hi > n1_lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.inv_row + (((size_t) n1_hi - 1) & ~(size_t) 3)));
-            have2 = j + 32 < b;
-            if (have2) { const uint32_t slot = __ldg(&p.row_slot[j + 32]); n2_lo = __ldg(&p.inv_off[slot]); n2_hi = __ldg(&p.inv_off[slot + 1]); }
+            if (have1 && n1_hi > n1_lo) {
+                // (into L1 instead: no change; the sector below the current chunk as well: 53.5 -> 62.3 ms, r3a)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p.inv_row + (((size_t) n1_hi - 1) & ~(size_t) 3)));
+            }
+            have2 = have3;
+            if (have2) { n2_lo = __ldg(&p.inv_off[slot3]); n2_hi = __ldg(&p.inv_off[slot3 + 1]); }
+            have3 = j + 64 < b;
+            if (have3) slot3 = __ldg(&p.row_slot[j + 64]);
         }
+        // four list entries per step (one aligned 16 B load), walked from the end of the list
+        const bool act = cur_i > cur_lo;
+        uint32_t cb = 0;
+        uint4 c = make_uint4(0u, 0u, 0u, 0u);
+        if (act) {
+            const uint32_t q = (cur_i - 1) >> 2;
+            cb = q << 2;
+            c = __ldg(reinterpret_cast<const uint4 *>(p.inv_row) + q);
+        }
+        const uint32_t ys[4] = {c.x, c.y, c.z, c.w};
+        bool ok[4], stop = false;
+        uint32_t hh[4], kk[4];
+        #pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t idx = cb + e;
+            const bool inr = act && idx < cur_i && idx >= cur_lo;
+            stop |= inr && tail && ys[e] <= x;                    // ascending list: nothing further down can be > x
+            ok[e] = inr && keep_candidate(x, ys[e], p.mode, p.pivot_flag);
+            hh[e] = hash_row(ys[e]) >> cshift;
+        }
+        #pragma unroll
+        for (int e = 0; e < 4; e++) kk[e] = ok[e] ? *reinterpret_cast<volatile uint32_t *>(&A.key[hh[e]]) : 0u;
+        uint32_t pend = 0;
+        #pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const bool fast = ok[e] && kk[e] == ys[e];
+            if (fast) atomicAdd(&A.val[hh[e]], 1u);
+            if (ok[e] && !fast) pend |= 1u << e;
+        }
+        if (__any_sync(0xFFFFFFFFu, pend != 0)) {                  // warp uniform
+            uint32_t y = 0, hsl = 0;
+            bool busy = false;
+            for (;;) {
+                if (!busy && pend) {
+                    const int e = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    y = e == 0 ? ys[0] : e == 1 ? ys[1] : e == 2 ? ys[2] : ys[3];
+                    hsl = e == 0 ? hh[0] : e == 1 ? hh[1] : e == 2 ? hh[2] : hh[3];
+                    busy = true;
+                }
+                if (!__any_sync(0xFFFFFFFFu, busy)) break;
+                if (busy) {
+                    uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&A.key[hsl]);
+                    if (cur == PC_EMPTY) {
+                        cur = atomicCAS(&A.key[hsl], PC_EMPTY, y);
+                        if (cur == PC_EMPTY) { if (atomicAdd(&A.distinct, 1u) >= limit) A.overflow = 1; cur = y; }
+                    }
+                    if (cur == y) { atomicAdd(&A.val[hsl], 1u); busy = false; }
+                    else if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) { busy = false; pend = 0; }
+                    else hsl = (hsl + 1) & cmask;
+                }
+            }
+        }
+        if (act) cur_i = stop ? cur_lo : max(cb, cur_lo);
         if (*reinterpret_cast<volatile uint32_t *>(&A.overflow)) { cur_i = cur_lo; have1 = false; }
     }
     __syncwarp();
@@ -261,8 +302,8 @@ __device__ __forceinline__ void flush_table(WarpAcc<CMAX> &A, const PairParams &
 // 4 / 6 CTAs per SM -> 359 / 186 / 130 / 102 / 75 ms), and the accumulator is what limits them. The first pass therefore runs with
 // a 512-entry accumulator (17 KB per CTA: 11 CTAs = 44 warps per SM); the rows whose partner set does not fit it are listed and
 // redone by a second pass with 1024 entries (6 CTAs per SM), and only what overflows that goes on to tier 2.
-template<int CMAX, bool REDO>
-__global__ void __launch_bounds__(PW_THREADS) pair_count_warp_kernel(const __grid_constant__ PairParams p) {
+template<int CMAX, bool REDO, int MINB = 1>
+__global__ void __launch_bounds__(PW_THREADS, MINB) pair_count_warp_kernel(const __grid_constant__ PairParams p) {
     __shared__ WarpAcc<CMAX> s_acc[PW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpAcc<CMAX> &A = s_acc[warp];
@@ -690,7 +731,18 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     uint64_t capacity = std::max<uint64_t>(h->pair_capacity, std::max<uint64_t>(64 * n_rows, 1ull << 20));
     int occ_w = 0, occ_c = 0;
     int occ_r = 0;
-    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel<PW_CMAX_FIRST, false>, PW_THREADS, 0));
+    int pair_occ = 0;                        // experiment switch: 12 = the first pass compiled for 12 CTAs per SM (40 registers)
+    if (const char *e = getenv("HGA_PAIR_OCC")) pair_occ = atoi(e);
+    size_t pad_smem = 0;                     // experiment switch: cap the first pass at HGA_PAIR_CTAS CTAs per SM with unused dynamic shared memory
+    if (const char *e = getenv("HGA_PAIR_CTAS")) {
+        const int want = std::max(1, atoi(e));
+        const size_t per = (size_t) (227 * 1024) / want;
+        const size_t stat = sizeof(WarpAcc<PW_CMAX_FIRST>) * PW_WARPS + 1024;
+        if (per > stat) pad_smem = std::min<size_t>(per - stat, (size_t) 200 * 1024);
+        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pad_smem));
+    }
+    if (pair_occ == 12) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel<PW_CMAX_FIRST, false, 12>, PW_THREADS, 0));
+    else HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel<PW_CMAX_FIRST, false>, PW_THREADS, pad_smem));
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, pair_count_redo_kernel, PW_THREADS, 0));
     if (occ_r < 1) occ_r = 1;
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pair_count_kernel, PC_THREADS, 0));
@@ -711,7 +763,8 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
             // multi-GPU: the index is keyed by kmer_id there, neighbouring hits of a read do not have neighbouring lists, and the
             // extra warps of the 512-entry pass only add random DRAM traffic (r3z, 2 GPUs: 50.6 ms against 45.2 ms single pass)
             if (p.single_pass) pair_count_warp_kernel<PW_CMAX, false><<<grid_s, PW_THREADS, 0, h->stream>>>(p);
-            else pair_count_warp_kernel<PW_CMAX_FIRST, false><<<grid_w, PW_THREADS, 0, h->stream>>>(p);
+            else if (pair_occ == 12) pair_count_warp_kernel<PW_CMAX_FIRST, false, 12><<<grid_w, PW_THREADS, 0, h->stream>>>(p);
+            else pair_count_warp_kernel<PW_CMAX_FIRST, false><<<grid_w, PW_THREADS, pad_smem, h->stream>>>(p);
             h->metrics.kernel_launches++;
             HGA_CUDA(cudaGetLastError());
         }

@@ -539,8 +539,14 @@ __global__ void scan_tile_dir_kernel(const uint64_t *__restrict__ read_off, uint
         uint64_t lo = 0, hi = n_reads;        // lower bound over read_off[0 .. n_reads]
         while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (read_off[mid] < pos) lo = mid + 1; else hi = mid; }
         const uint64_t first = lo;
-        lo = 0; hi = n_reads - 1;
-        while (lo < hi) { const uint64_t mid = (lo + hi + 1) >> 1; if (read_off[mid] <= pos) lo = mid; else hi = mid - 1; }
+        // the read holding pos: the one before `first`, unless a read starts exactly at pos (then the LAST read that starts there: empty reads
+        // share their offset with their successor)
+        if (first < n_reads && read_off[first] == pos) {
+            lo = first; hi = n_reads - 1;
+            while (lo < hi) { const uint64_t mid = (lo + hi + 1) >> 1; if (read_off[mid] <= pos) lo = mid; else hi = mid - 1; }
+        } else {
+            lo = first > 0 ? std::min<uint64_t>(first, n_reads) - 1 : 0;
+        }
         dir[t] = make_uint2((uint32_t) first, (uint32_t) lo);
     }
 }
