@@ -121,6 +121,9 @@ int hga_create(int device, int k, const uint64_t *kmers, uint64_t n_kmers, hga_h
     cudaDeviceProp prop;
     HGA_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { hga_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return HGA_E_CUDA; }
+    if (const char *eg = getenv("HGA_L2_FETCH")) {       // experiment switch: DRAM fetch granularity of L2 misses (32 / 64 / 128 B), a device-wide limit
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) atoi(eg)) != cudaSuccess) cudaGetLastError();
+    }
     hga_handle *h = new hga_handle();
     memset(&h->metrics, 0, sizeof(h->metrics));
     h->device = device; h->k = k; h->n_kmers = n_kmers; h->sm_count = prop.multiProcessorCount;
@@ -142,7 +145,7 @@ void hga_destroy(hga_handle *h) {
     hga_comm_destroy(h);
     DevBuf *dev[] = {&h->d_keys, &h->d_slot_kid, &h->d_kid_slot, &h->d_filter, &h->d_bases, &h->d_read_off, &h->d_row_off, &h->d_hit_slot, &h->d_hit_pos, &h->d_pos_tmp,
                      &h->d_tile_state, &h->d_tile_dir, &h->d_scan_scalars, &h->d_x_slot, &h->d_x_row, &h->d_hit_kid, &h->d_g_kid, &h->d_g_row_off, &h->d_inv_off, &h->d_inv_row, &h->d_sort_a,
-                     &h->d_sort_b, &h->d_sort_tmp, &h->d_pair_key, &h->d_pair_score, &h->d_pair_key2, &h->d_pair_score2, &h->d_pair_scalars,
+                     &h->d_index_tmp, &h->d_index_goff, &h->d_sort_b, &h->d_sort_tmp, &h->d_pair_key, &h->d_pair_score, &h->d_pair_key2, &h->d_pair_score2, &h->d_pair_scalars,
                      &h->d_heavy_list, &h->d_mid_list, &h->d_redo_list, &h->d_heavy_tab, &h->d_pivot_flag, &h->d_pivot_order, &h->d_hist, &h->d_sel_key, &h->d_sel_score, &h->d_sel_scalars, &h->d_parent,
                      &h->d_comp_size, &h->d_comp_label, &h->d_comp_scalars, &h->d_export_a, &h->d_export_b, &h->d_export_c, &h->d_enr_parent, &h->d_enr_core_of,
                      &h->d_enr_surv, &h->d_enr_R, &h->d_enr_scalars, &h->d_enr_keys, &h->d_enr_keys2, &h->d_enr_core_koff, &h->d_purged_off, &h->d_purged_row, &h->d_purged2_off, &h->d_purged2_row};

@@ -733,6 +733,8 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     int occ_r = 0;
     int pair_occ = 0;                        // experiment switch: 12 = the first pass compiled for 12 CTAs per SM (40 registers)
     if (const char *e = getenv("HGA_PAIR_OCC")) pair_occ = atoi(e);
+    if (const char *e = getenv("HGA_PAIR_CARVEOUT"))   // experiment switch: shared-memory carve-out of the first pass in percent (the rest of the 228 KB is L1)
+        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     size_t pad_smem = 0;                     // experiment switch: cap the first pass at HGA_PAIR_CTAS CTAs per SM with unused dynamic shared memory
     if (const char *e = getenv("HGA_PAIR_CTAS")) {
         const int want = std::max(1, atoi(e));

@@ -74,7 +74,7 @@ struct ScanParams {
     uint64_t tile_stride;             // > 0: sampling mode (count only, tile = tile_begin + ticket * stride)
     uint32_t chunk;                   // hit-buffer entries a warp reserves per atomic
     unsigned long long *warp_chunks;  // chunked launches: every warp's open chunk [pos, end) survives from one launch to the next (nullptr: one launch)
-    int diag;                         // HGA_SCAN_DIAG experiment: 1 = no key probes (results are WRONG)
+    int diag;                         // HGA_SCAN_DIAG experiment: 1 = no key probes (results are WRONG), 2 = metrics.n_candidates counts sector probes
 };
 
 // shared memory of one warp
@@ -136,7 +136,10 @@ __device__ __forceinline__ uint32_t ldg_u32_policy(const uint32_t *a, uint64_t p
     return v;
 }
 
-// one 32 B sector of the key table
+// one 32 B sector of the key table: one 256-bit load (LDG.E.256), evict-first in L2. Measured (r3i - r3k, ncu, config 4): L1TEX asks for ONE sector
+// per probe, but the L2 turns a missing sector into a 64 - 128 B DRAM fetch: 2.5 sectors per probe arrive (4 without the evict-first hint);
+// two 128-bit loads, L1::no_allocate and cudaLimitMaxL2FetchGranularity = 32 change nothing. 1.0 G probes x 2.5 x 32 B = the 78 GB that the
+// kernel reads from DRAM beyond the 10 GB of bases.
 __device__ __forceinline__ void load_sector(const uint64_t *sp, uint64_t pol, unsigned long long &a, unsigned long long &b, unsigned long long &d, unsigned long long &e) {
     asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(d), "=l"(e) : "l"(sp), "l"(pol));
 }
@@ -204,7 +207,7 @@ __device__ __forceinline__ bool probe_sector(const uint64_t *keys, uint32_t base
     return slot != SCAN_NONE || a == HGA_EMPTY_KEY || b == HGA_EMPTY_KEY || d == HGA_EMPTY_KEY || e == HGA_EMPTY_KEY;
 }
 
-struct QueueState { uint32_t head, tail, st_count; };     // warp uniform
+struct QueueState { uint32_t head, tail, st_count, probes; };     // warp uniform (probes: per lane, HGA_SCAN_DIAG=2 only)
 
 // n (<= 32) queued candidates starting at ring position head: check the window against the read boundaries, rebuild the canonical
 // k-mer, probe the key table; hits are appended to the staging area in position order
@@ -245,6 +248,7 @@ __device__ __forceinline__ void drain_queue(QueueState &qs, uint32_t n, int lane
     const uint64_t pol_first = l2_policy_evict_first();
     for (int step = 0; __any_sync(0xFFFFFFFFu, open); step++) {
         if (open) {
+            if (p.diag & 2) qs.probes++;
             if (probe_sector(t.keys, base_slot, sec + step, key, pol_first, slot)) open = false;
             else if (step == HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS - 1) {
                 open = false;
@@ -335,7 +339,7 @@ __device__ __forceinline__ uint32_t phase_c(const TileCtx &c, int lane, uint32_t
     const uint32_t n_blocks = p.t.n_blocks, lane_lt = (1u << lane) - 1;
     const uint32_t *filter = p.t.filter;
     const int filter_k = p.t.filter_k;
-    QueueState qs = {0, 0, 0};
+    QueueState qs = {0, 0, 0, 0};
     #pragma unroll 1
     for (int s0 = 0; s0 <= SCAN_SPAN / 32; s0 += SCAN_UNROLL) {
         const bool last = s0 >= SCAN_SPAN / 32;                     // one more round that only empties the queue
@@ -368,7 +372,7 @@ __device__ __forceinline__ uint32_t phase_c(const TileCtx &c, int lane, uint32_t
             __syncwarp();
         }
     }
-    n_cand += qs.tail;
+    n_cand += (p.diag & 2) ? __reduce_add_sync(0xFFFFFFFFu, qs.probes) : qs.tail;     // HGA_SCAN_DIAG=2: sector probes instead of candidates
     return qs.st_count;
 }
 
