@@ -346,6 +346,8 @@ def test_count_kmers_orchestration_on_host(host_count_kmers, k, chunk):
 # forest, the glue around the host stages, the second merge, the enrichment connections and the final merge.
 FAKE_CUDA_MORE = r"""
 typedef void *cudaEvent_t;
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
