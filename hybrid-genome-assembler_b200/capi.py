@@ -339,7 +339,10 @@ class Handle:
             _check(self.lib.hga_pair_count(self._h, int(min_score), None, 0))
         else:
             pv = np.ascontiguousarray(pivots, dtype=np.uint32)
-            _check(self.lib.hga_pair_count(self._h, int(min_score), pv.ctypes.data_as(C.c_void_p), pv.shape[0]))
+            n = pv.shape[0]
+            if n == 0:                     # the empty subset: a non-NULL pointer with n = 0 (NULL would mean "all reads")
+                pv = np.zeros(1, dtype=np.uint32)
+            _check(self.lib.hga_pair_count(self._h, int(min_score), pv.ctypes.data_as(C.c_void_p), n))
 
     def get_pairs(self):
         out = _Pairs()

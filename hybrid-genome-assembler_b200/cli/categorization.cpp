@@ -342,7 +342,8 @@ int main(int argc, char **argv) {
             std::vector<uint32_t> pivots;
             for (uint64_t r = 0; r < hits.n_reads; r++)
                 if (hits.row_off[r + 1] - hits.row_off[r] >= config.scaffold_forming_score) pivots.push_back((uint32_t) (r + 1));
-            check(hga_pair_count(h, (uint32_t) config.scaffold_forming_score, pivots.data(), pivots.size()), "hga_pair_count");
+            const uint32_t none = 0;       // no read reaches the threshold: the EMPTY subset (a NULL pointer would mean "all reads")
+            check(hga_pair_count(h, (uint32_t) config.scaffold_forming_score, pivots.empty() ? &none : pivots.data(), pivots.size()), "hga_pair_count");
             check(hga_select_edges(h, 0.0, (uint32_t) config.scaffold_forming_score), "hga_select_edges");
         } else {
             check(hga_pair_count(h, 1, nullptr, 0), "hga_pair_count");

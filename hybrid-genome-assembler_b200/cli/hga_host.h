@@ -58,7 +58,7 @@ struct MappedFile {
     MappedFile() = default;
     MappedFile(const MappedFile &) = delete;
     MappedFile &operator=(const MappedFile &) = delete;
-    MappedFile(MappedFile &&o) noexcept : data(o.data), size(o.size), fd(o.fd) { o.data = nullptr; o.size = 0; o.fd = -1; }
+    MappedFile(MappedFile &&o) noexcept : data(o.data), size(o.size), fd(o.fd), owned(o.owned) { o.data = nullptr; o.size = 0; o.fd = -1; o.owned = nullptr; }
     bool open(const std::string &path) {
         fd = ::open(path.c_str(), O_RDONLY);
         if (fd < 0) return false;

@@ -319,7 +319,7 @@ struct hga_handle {
     // pairs
     uint64_t n_pairs = 0, n_increments = 0;
     DevBuf d_pair_key, d_pair_score;      // u64 key = (x_row << 32 | y_row), u32 score; sorted by key
-    DevBuf d_pair_key2, d_pair_score2, d_pair_scalars, d_heavy_list, d_mid_list, d_redo_list, d_heavy_tab, d_pivot_flag, d_pivot_order;
+    DevBuf d_pair_key2, d_pair_score2, d_pair_scalars, d_heavy_list, d_mid_list, d_redo_list, d_heavy_tab, d_pivot_flag, d_pivot_order, d_pivot_rows;
     uint64_t pair_capacity = 0;
     uint64_t pair_rows = 0;               // rows of the by-read incidence the pair counter walks (this rank's pivots with a communicator)
     uint32_t pair_pivot_mul = 1, pair_pivot_add = 0;   // local row t is global row t * mul + add (rank, rank + G, ...)

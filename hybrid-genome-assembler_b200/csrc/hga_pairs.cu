@@ -654,7 +654,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     p.heavy_tab = nullptr; p.heavy_cap = 0;
     p.sc = d_sc;
 
-    DevBuf d_pivots;
+    DevBuf &d_pivots = h->d_pivot_rows;      // (a member: released with the handle)
     if (pivots) {
         // caller passes read ids; rows are id - first id
         std::vector<uint32_t> rows(n_pivots);

@@ -24,7 +24,9 @@
  *     (thread-local). The reference signals errors by uncaught C++ exceptions (std::terminate).
  *   - plain pointers and sizes only. Inputs are caller-owned HOST buffers unless the name says _device.
  *   - results stay in HBM between stages; hga_get_* copies them into library-owned pinned host buffers that
- *     remain valid until the next call that produces the same result, or hga_destroy.
+ *     remain valid until the next call that produces the same result, or hga_destroy. hga_enrich / hga_enrich_ex / hga_enrich_full and
+ *     hga_comm_gather_root use the same buffers as scratch: they invalidate what hga_get_hits, hga_get_index and hga_get_selection
+ *     returned before (call those again afterwards if their results are still needed).
  *   - read ids are 1-based and global (SequenceRecordIterator.h:82): row r of a scan has id read_id_base + r.
  *   - kmer_id = index into the array given to hga_create (the reference's KmerID is an arbitrary bijection,
  *     so parity is by k-mer VALUE).
@@ -104,7 +106,8 @@ int hga_get_index(hga_handle *h, hga_index *out);
 
 /* score(x,y) = sum_k mult_x(k) * mult_y(k) for every unordered read pair sharing a k-mer.
  * pivots == NULL: all reads (get_all_connections); else only pairs with at least one endpoint in pivots
- * (get_connections over a component list). Pairs with score < min_score are dropped. */
+ * (get_connections over a component list). A non-NULL pointer with n_pivots == 0 is the EMPTY subset: no pairs, as get_connections({}).
+ * Pairs with score < min_score are dropped. */
 int hga_pair_count(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uint64_t n_pivots);
 typedef struct {
     uint64_t n_pairs;          /* unordered pairs, x < y, ordered by (x, y) */

@@ -270,6 +270,15 @@ def test_pivot_subset_and_min_score(oracle):
             x, y, s, _ = h.get_pairs()
         got = {(a_, b_): c_ for a_, b_, c_ in zip(x.tolist(), y.tolist(), s.tolist())}
         assert got == want
+    # the EMPTY subset (get_connections({}) in the reference: no connections) is not "all reads"
+    with hga_b200.Handle(kmers, 19) as h:
+        h.scan(bases, off)
+        h.build_index()
+        h.pair_count(min_score=1, pivots=np.zeros(0, dtype=np.uint32))
+        x, y, s, _ = h.get_pairs()
+        assert x.shape[0] == 0 and y.shape[0] == 0
+        h.pair_count(min_score=1)
+        assert h.get_pairs()[0].shape[0] > 0
 
 
 def test_score_threshold_mode(oracle):
