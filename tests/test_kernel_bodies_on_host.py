@@ -49,6 +49,7 @@ def host_kernels(tmp_path_factory):
     parts = [PRELUDE,
              re.search(r"^constexpr unsigned long long COUNT_SENTINEL.*$", count, flags=re.M).group(0),
              _cut(count, r"^__device__ __forceinline__ int count_base_code"),
+             _cut(count, r"^__device__ __forceinline__ unsigned long long count_window_key"),
              _cut(count, r"^__global__ void count_emit_kernel"),
              _cut(count, r"^__global__ void count_flag_kernel"),
              _cut(enrich, r"^__global__ void enr_merge2_keys_kernel"),
@@ -198,6 +199,8 @@ static inline const char *cudaGetErrorString(cudaError_t) { return "fake"; }
 static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 2; return 0; }
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void *p) { std::free(p); return 0; }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
@@ -353,9 +356,7 @@ static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFreeHost(void *p) { std::free(p); return 0; }
-static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
 static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned) (((unsigned long long) a * b) >> 32); }
 static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }
 """

@@ -34,13 +34,35 @@ def test_cuda_kmer_counts_are_exact(k):
     km1, ct1 = hga_b200.capi.count_kmers(seq, off, k, min_count=1)
     wk1, wc1 = exact_counts(seq, off, k, 1)
     assert np.array_equal(km1, wk1) and np.array_equal(ct1, wc1) and int(ct1.sum()) == int(wc1.sum())
-    # the multi-chunk path (partial runs of several chunks merged by sort + reduce-by-key), forced with a tiny chunk
+    # the key-range passes of large inputs (quantiles from a sample, one pass per range, overflowing ranges split), forced with a tiny budget
     os.environ["HGA_COUNT_CHUNK"] = "4096"
     try:
         km2, ct2 = hga_b200.capi.count_kmers(seq, off, k, min_count=2)
     finally:
         del os.environ["HGA_COUNT_CHUNK"]
     assert np.array_equal(km2, wk) and np.array_equal(ct2, wc)
+
+
+def test_key_range_passes_equal_the_single_pass_on_a_larger_input():
+    """40 Mbases with a budget of 2^22 keys per pass (~15 key ranges; the range holding the poly-A k-mer overflows and is halved down to that
+    single value, whose count is then the number of matches) against the single pass of the same input: identical k-mers and counts, ascending"""
+    import hga_b200
+    rng = np.random.default_rng(77)
+    g = datagen.random_genome(400000, 501)
+    g[1000:51000] = 0                                             # 50 kb of poly-A at 100x: ONE k-mer with ~5 M occurrences, more than a whole budget
+    reads = datagen.sample_reads(g, 4000, 10000, 502, error_rate=0.02, length_sigma=0.3, max_len=60000)
+    seq = b"".join(datagen.to_ascii(r).encode() for r in reads)
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    assert off[-1] > 30_000_000
+    km, ct = hga_b200.capi.count_kmers(seq, off, 19, min_count=2)
+    os.environ["HGA_COUNT_CHUNK"] = str(1 << 22)
+    try:
+        km2, ct2 = hga_b200.capi.count_kmers(seq, off, 19, min_count=2)
+    finally:
+        del os.environ["HGA_COUNT_CHUNK"]
+    assert len(km) > 100000 and np.all(km[1:] > km[:-1]) and km[0] == 0 and ct[0] > (1 << 22)
+    assert np.array_equal(km, km2) and np.array_equal(ct, ct2)
 
 
 def test_cli_jf_occurrences_exports_the_kmers_file(oracle, tmp_path):
