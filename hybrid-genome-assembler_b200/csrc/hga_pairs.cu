@@ -10,8 +10,8 @@
 //      (and their random offset look-ups) in flight; a lane that finishes a list picks up the row's next entry without
 //      waiting for the others, and the offsets of its next list are prefetched while it walks the current one. Lists are
 //      sorted by row, so with all rows as pivots the walk runs from the END of the list and stops at the first row <= pivot:
-//      only the half of every list that can produce a (pivot < partner) pair is read (four entries per aligned 16 B load, their
-//      four accumulator probes issued together), and every unordered pair is produced exactly once. Lists longer than PW_LONG
+//      only the half of every list that can produce a (pivot < partner) pair is read (eight entries = one aligned 32 B sector per
+//      step, their accumulator probes issued together, one predicated loop body for all 32 lanes), and every unordered pair is produced exactly once. Lists longer than PW_LONG
 //      are walked by the whole warp with coalesced loads. The kernel is LATENCY bound (time inversely proportional to the
 //      resident warps up to 24 per SM), so the first pass runs with 512-entry accumulators (44 warps per SM) and the few rows
 //      whose partner set does not fit are redone by pair_count_redo_kernel (a CTA per row, four warps on quarter ranges with
@@ -152,7 +152,7 @@ __device__ __forceinline__ void acc_add(WarpAcc<CMAX> &A, uint32_t y, uint32_t c
 }
 
 // The walk of one pivot row's incidence entries [a, b) by one warp into its accumulator A.
-template<int CMAX>
+template<int CMAX, int EPS = 4>
 __device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, uint32_t x, uint64_t a, uint64_t b, bool tail, uint32_t cmask, int cshift,
                                          uint32_t limit, int lane) {
     // every lane: one list at a time, two lists ahead in flight: the bounds of list j + 64 are being loaded while the
@@ -192,20 +192,25 @@ __device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, 
             have3 = j + 64 < b;
             if (have3) slot3 = __ldg(&p.row_slot[j + 64]);
         }
-        // four list entries per step (one aligned 16 B load), walked from the end of the list
+        // EPS (4 or 8) list entries per step (one aligned 16 / 32 B piece), walked from the end of the list
         const bool act = cur_i > cur_lo;
         uint32_t cb = 0;
-        uint4 c = make_uint4(0u, 0u, 0u, 0u);
-        if (act) {
-            const uint32_t q = (cur_i - 1) >> 2;
-            cb = q << 2;
-            c = __ldg(reinterpret_cast<const uint4 *>(p.inv_row) + q);
-        }
-        const uint32_t ys[4] = {c.x, c.y, c.z, c.w};
-        bool ok[4], stop = false;
-        uint32_t hh[4], kk[4];
+        uint32_t ys[EPS];
         #pragma unroll
-        for (int e = 0; e < 4; e++) {
+        for (int e = 0; e < EPS; e++) ys[e] = 0u;
+        if (act) {
+            const uint32_t q = (cur_i - 1) / EPS;
+            cb = q * EPS;
+            #pragma unroll
+            for (int v = 0; v < EPS / 4; v++) {
+                const uint4 c = __ldg(reinterpret_cast<const uint4 *>(p.inv_row) + (size_t) q * (EPS / 4) + v);
+                ys[4 * v] = c.x; ys[4 * v + 1] = c.y; ys[4 * v + 2] = c.z; ys[4 * v + 3] = c.w;
+            }
+        }
+        bool ok[EPS], stop = false;
+        uint32_t hh[EPS], kk[EPS];
+        #pragma unroll
+        for (int e = 0; e < EPS; e++) {
             const uint32_t idx = cb + e;
             const bool inr = act && idx < cur_i && idx >= cur_lo;
             stop |= inr && tail && ys[e] <= x;                    // ascending list: nothing further down can be > x
@@ -213,10 +218,10 @@ __device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, 
             hh[e] = hash_row(ys[e]) >> cshift;
         }
         #pragma unroll
-        for (int e = 0; e < 4; e++) kk[e] = ok[e] ? *reinterpret_cast<volatile uint32_t *>(&A.key[hh[e]]) : 0u;
+        for (int e = 0; e < EPS; e++) kk[e] = ok[e] ? *reinterpret_cast<volatile uint32_t *>(&A.key[hh[e]]) : 0u;
         uint32_t pend = 0;
         #pragma unroll
-        for (int e = 0; e < 4; e++) {
+        for (int e = 0; e < EPS; e++) {
             const bool fast = ok[e] && kk[e] == ys[e];
             if (fast) atomicAdd(&A.val[hh[e]], 1u);
             if (ok[e] && !fast) pend |= 1u << e;
@@ -228,8 +233,8 @@ __device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, 
                 if (!busy && pend) {
                     const int e = __ffs(pend) - 1;
                     pend &= pend - 1;
-                    y = e == 0 ? ys[0] : e == 1 ? ys[1] : e == 2 ? ys[2] : ys[3];
-                    hsl = e == 0 ? hh[0] : e == 1 ? hh[1] : e == 2 ? hh[2] : hh[3];
+                    #pragma unroll
+                    for (int f = 0; f < EPS; f++) if (e == f) { y = ys[f]; hsl = hh[f]; }
                     busy = true;
                 }
                 if (!__any_sync(0xFFFFFFFFu, busy)) break;
@@ -302,7 +307,7 @@ __device__ __forceinline__ void flush_table(WarpAcc<CMAX> &A, const PairParams &
 // 4 / 6 CTAs per SM -> 359 / 186 / 130 / 102 / 75 ms), and the accumulator is what limits them. The first pass therefore runs with
 // a 512-entry accumulator (17 KB per CTA: 11 CTAs = 44 warps per SM); the rows whose partner set does not fit it are listed and
 // redone by a second pass with 1024 entries (6 CTAs per SM), and only what overflows that goes on to tier 2.
-template<int CMAX, bool REDO, int MINB = 1>
+template<int CMAX, bool REDO, int MINB = 1, int EPS = 4>
 __global__ void __launch_bounds__(PW_THREADS, MINB) pair_count_warp_kernel(const __grid_constant__ PairParams p) {
     __shared__ WarpAcc<CMAX> s_acc[PW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(PW_THREADS, MINB) pair_count_warp_kernel(const
             if (lane == 0) { A.distinct = 0; A.overflow = 0; A.n_defer = 0; }
             __syncwarp();
 
-            walk_row<CMAX>(A, p, x, a, b, tail, cmask, cshift, limit, lane);
+            walk_row<CMAX, EPS>(A, p, x, a, b, tail, cmask, cshift, limit, lane);
             if (!*reinterpret_cast<volatile uint32_t *>(&A.overflow)) {
                 flush_table<CMAX>(A, p, x, C, lane);
                 break;
@@ -731,20 +736,25 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     uint64_t capacity = std::max<uint64_t>(h->pair_capacity, std::max<uint64_t>(64 * n_rows, 1ull << 20));
     int occ_w = 0, occ_c = 0;
     int occ_r = 0;
-    int pair_occ = 0;                        // experiment switch: 12 = the first pass compiled for 12 CTAs per SM (40 registers)
+    int pair_occ = 0;                        // experiment switch, see first_pass below
     if (const char *e = getenv("HGA_PAIR_OCC")) pair_occ = atoi(e);
     if (const char *e = getenv("HGA_PAIR_CARVEOUT"))   // experiment switch: shared-memory carve-out of the first pass in percent (the rest of the 228 KB is L1)
-        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     size_t pad_smem = 0;                     // experiment switch: cap the first pass at HGA_PAIR_CTAS CTAs per SM with unused dynamic shared memory
     if (const char *e = getenv("HGA_PAIR_CTAS")) {
         const int want = std::max(1, atoi(e));
         const size_t per = (size_t) (227 * 1024) / want;
         const size_t stat = sizeof(WarpAcc<PW_CMAX_FIRST>) * PW_WARPS + 1024;
         if (per > stat) pad_smem = std::min<size_t>(per - stat, (size_t) 200 * 1024);
-        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pad_smem));
+        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pad_smem));
     }
-    if (pair_occ == 12) HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel<PW_CMAX_FIRST, false, 12>, PW_THREADS, 0));
-    else HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, pair_count_warp_kernel<PW_CMAX_FIRST, false>, PW_THREADS, pad_smem));
+    // first-pass kernel: (CTAs per SM the registers are limited for, list entries per step). Default (9, 8): 55 registers, eight entries = one 32 B sector per
+    // step. r3p / r3q, config 4: (1, 4) 56 registers 55.5 ms, (1, 8) 75 registers 53.7, (8, 8) 59 registers 49.8, (9, 8) 48.7, (10, 8) 47 registers 48.7,
+    // (8, 16) 60.3, (6, 16) 65.0. HGA_PAIR_OCC=4 selects the four-entry kernel for A/B runs.
+    typedef void (*pair_kernel_t)(const PairParams);
+    pair_kernel_t first_pass = pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8>;
+    if (pair_occ == 4) first_pass = pair_count_warp_kernel<PW_CMAX_FIRST, false, 1, 4>;
+    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, first_pass, PW_THREADS, pad_smem));
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, pair_count_redo_kernel, PW_THREADS, 0));
     if (occ_r < 1) occ_r = 1;
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, pair_count_kernel, PC_THREADS, 0));
@@ -765,8 +775,7 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
             // multi-GPU: the index is keyed by kmer_id there, neighbouring hits of a read do not have neighbouring lists, and the
             // extra warps of the 512-entry pass only add random DRAM traffic (r3z, 2 GPUs: 50.6 ms against 45.2 ms single pass)
             if (p.single_pass) pair_count_warp_kernel<PW_CMAX, false><<<grid_s, PW_THREADS, 0, h->stream>>>(p);
-            else if (pair_occ == 12) pair_count_warp_kernel<PW_CMAX_FIRST, false, 12><<<grid_w, PW_THREADS, 0, h->stream>>>(p);
-            else pair_count_warp_kernel<PW_CMAX_FIRST, false><<<grid_w, PW_THREADS, pad_smem, h->stream>>>(p);
+            else first_pass<<<grid_w, PW_THREADS, pad_smem, h->stream>>>(p);
             h->metrics.kernel_launches++;
             HGA_CUDA(cudaGetLastError());
         }

@@ -44,7 +44,7 @@ def test_cuda_kmer_counts_are_exact(k):
 
 
 def test_key_range_passes_equal_the_single_pass_on_a_larger_input():
-    """40 Mbases with a budget of 2^22 keys per pass (~15 key ranges; the range holding the poly-A k-mer overflows and is halved down to that
+    """40 Mbases with a budget of 2^21 keys per pass (~30 key ranges; the range holding the poly-A k-mer overflows and is halved down to that
     single value, whose count is then the number of matches) against the single pass of the same input: identical k-mers and counts, ascending"""
     import hga_b200
     rng = np.random.default_rng(77)
@@ -56,12 +56,12 @@ def test_key_range_passes_equal_the_single_pass_on_a_larger_input():
     np.cumsum([len(r) for r in reads], out=off[1:])
     assert off[-1] > 30_000_000
     km, ct = hga_b200.capi.count_kmers(seq, off, 19, min_count=2)
-    os.environ["HGA_COUNT_CHUNK"] = str(1 << 22)
+    os.environ["HGA_COUNT_CHUNK"] = str(1 << 21)
     try:
         km2, ct2 = hga_b200.capi.count_kmers(seq, off, 19, min_count=2)
     finally:
         del os.environ["HGA_COUNT_CHUNK"]
-    assert len(km) > 100000 and np.all(km[1:] > km[:-1]) and km[0] == 0 and ct[0] > (1 << 22)
+    assert len(km) > 100000 and np.all(km[1:] > km[:-1]) and km[0] == 0 and ct[0] > (1 << 21)
     assert np.array_equal(km, km2) and np.array_equal(ct, ct2)
 
 
