@@ -152,9 +152,12 @@ __device__ __forceinline__ void acc_add(WarpAcc<CMAX> &A, uint32_t y, uint32_t c
 }
 
 // The walk of one pivot row's incidence entries [a, b) by one warp into its accumulator A.
-template<int CMAX, int EPS = 4>
-__device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, uint32_t x, uint64_t a, uint64_t b, bool tail, uint32_t cmask, int cshift,
+// TAILONLY: the mode is PAIR_MODE_TAIL at compile time (all rows are pivots: the first-pass kernel of the hot path), so the candidate test is y > x and nothing else
+template<int CMAX, int EPS = 4, bool TAILONLY = false>
+__device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, uint32_t x, uint64_t a, uint64_t b, bool tail_rt, uint32_t cmask, int cshift,
                                          uint32_t limit, int lane) {
+    const bool tail = TAILONLY ? true : tail_rt;
+    const int mode = TAILONLY ? PAIR_MODE_TAIL : p.mode;
     // every lane: one list at a time, two lists ahead in flight: the bounds of list j + 64 are being loaded while the
     // last 16 B chunk of list j + 32 (bounds known by now) is prefetched into L2 and list j is walked. (Requesting
     // every chunk one step before it is used - a register double buffer - was measured 14 % SLOWER (r1t). Giving every
@@ -214,7 +217,7 @@ __device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, 
             const uint32_t idx = cb + e;
             const bool inr = act && idx < cur_i && idx >= cur_lo;
             stop |= inr && tail && ys[e] <= x;                    // ascending list: nothing further down can be > x
-            ok[e] = inr && keep_candidate(x, ys[e], p.mode, p.pivot_flag);
+            ok[e] = inr && keep_candidate(x, ys[e], mode, p.pivot_flag);
             hh[e] = hash_row(ys[e]) >> cshift;
         }
         #pragma unroll
@@ -262,7 +265,7 @@ __device__ __forceinline__ void walk_row(WarpAcc<CMAX> &A, const PairParams &p, 
             if (go) {
                 const uint32_t y = __ldg(&p.inv_row[i]);
                 if (tail && y <= x) go = false;
-                else if (keep_candidate(x, y, p.mode, p.pivot_flag)) acc_add(A, y, 1u, cmask, cshift, limit);
+                else if (keep_candidate(x, y, mode, p.pivot_flag)) acc_add(A, y, 1u, cmask, cshift, limit);
             }
             if (!__any_sync(0xFFFFFFFFu, go)) break;
         }
@@ -307,7 +310,7 @@ __device__ __forceinline__ void flush_table(WarpAcc<CMAX> &A, const PairParams &
 // 4 / 6 CTAs per SM -> 359 / 186 / 130 / 102 / 75 ms), and the accumulator is what limits them. The first pass therefore runs with
 // a 512-entry accumulator (17 KB per CTA: 11 CTAs = 44 warps per SM); the rows whose partner set does not fit it are listed and
 // redone by a second pass with 1024 entries (6 CTAs per SM), and only what overflows that goes on to tier 2.
-template<int CMAX, bool REDO, int MINB = 1, int EPS = 4>
+template<int CMAX, bool REDO, int MINB = 1, int EPS = 4, bool TAILONLY = false>
 __global__ void __launch_bounds__(PW_THREADS, MINB) pair_count_warp_kernel(const __grid_constant__ PairParams p) {
     __shared__ WarpAcc<CMAX> s_acc[PW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(PW_THREADS, MINB) pair_count_warp_kernel(const
             if (lane == 0) { A.distinct = 0; A.overflow = 0; A.n_defer = 0; }
             __syncwarp();
 
-            walk_row<CMAX, EPS>(A, p, x, a, b, tail, cmask, cshift, limit, lane);
+            walk_row<CMAX, EPS, TAILONLY>(A, p, x, a, b, tail, cmask, cshift, limit, lane);
             if (!*reinterpret_cast<volatile uint32_t *>(&A.overflow)) {
                 flush_table<CMAX>(A, p, x, C, lane);
                 break;
@@ -739,21 +742,23 @@ int hga_pairs_run(hga_handle *h, uint32_t min_score, const uint32_t *pivots, uin
     int pair_occ = 0;                        // experiment switch, see first_pass below
     if (const char *e = getenv("HGA_PAIR_OCC")) pair_occ = atoi(e);
     if (const char *e = getenv("HGA_PAIR_CARVEOUT"))   // experiment switch: shared-memory carve-out of the first pass in percent (the rest of the 228 KB is L1)
-        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     size_t pad_smem = 0;                     // experiment switch: cap the first pass at HGA_PAIR_CTAS CTAs per SM with unused dynamic shared memory
     if (const char *e = getenv("HGA_PAIR_CTAS")) {
         const int want = std::max(1, atoi(e));
         const size_t per = (size_t) (227 * 1024) / want;
         const size_t stat = sizeof(WarpAcc<PW_CMAX_FIRST>) * PW_WARPS + 1024;
         if (per > stat) pad_smem = std::min<size_t>(per - stat, (size_t) 200 * 1024);
-        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pad_smem));
+        HGA_CUDA(cudaFuncSetAttribute(pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pad_smem));
     }
     // first-pass kernel: (CTAs per SM the registers are limited for, list entries per step). Default (9, 8): 55 registers, eight entries = one 32 B sector per
     // step. r3p / r3q, config 4: (1, 4) 56 registers 55.5 ms, (1, 8) 75 registers 53.7, (8, 8) 59 registers 49.8, (9, 8) 48.7, (10, 8) 47 registers 48.7,
     // (8, 16) 60.3, (6, 16) 65.0. HGA_PAIR_OCC=4 selects the four-entry kernel for A/B runs.
     typedef void (*pair_kernel_t)(const PairParams);
-    pair_kernel_t first_pass = pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8>;
+    pair_kernel_t first_pass = pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8, true>;
+    if (p.mode != PAIR_MODE_TAIL) first_pass = pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8, false>;
     if (pair_occ == 4) first_pass = pair_count_warp_kernel<PW_CMAX_FIRST, false, 1, 4>;
+    if (pair_occ == 98) first_pass = pair_count_warp_kernel<PW_CMAX_FIRST, false, 9, 8, false>;
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, first_pass, PW_THREADS, pad_smem));
     HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, pair_count_redo_kernel, PW_THREADS, 0));
     if (occ_r < 1) occ_r = 1;
