@@ -6,14 +6,16 @@
 //   1. the table layout is a function of the k-mer array (hga_table.cu), so a slot number means the same k-mer on every rank: whole
 //      32-slot buckets are dealt round robin, owner(slot) = (slot / 32) mod G, list number at the owner = (slot / 32) / G * 32 + slot mod 32
 //      (the hits of a minimizer run keep neighbouring list numbers: the pair counter's locality survives the partition);
-//   2. ALL-TO-ALL 1 (grouped ncclSend / ncclRecv): (list number, global row) records go to their owner. Every source sends in
-//      row order and the sources arrive in rank order = global row order, so the received stream IS the owner's by-row
-//      incidence (row offsets from run boundaries, no sort), and one stable sort by list number gives its inverted lists with
-//      rows ascending. Nothing is replicated: a rank holds E / G incidence entries whatever G is;
+//   2. ALL-TO-ALL 1 (grouped ncclSend / ncclRecv): the u32 list numbers of a source's hits go to their owners in row order, together
+//      with one count per row and owner; the rows themselves do not travel. The sources arrive in rank order = global row order, so
+//      the owner's by-row incidence is the received stream + an exclusive scan of the counts, and the single-GPU list builder
+//      (hga_build_lists) gives its inverted lists with rows ascending. Nothing is replicated: a rank holds E / G incidence entries;
 //   3. every rank runs the single-GPU pair kernels over ALL rows as pivots, each row restricted to the hits of the rank's own
-//      k-mers (y > x, list tails only): PARTIAL scores, work = the increments of the owned lists = 1 / G of the total;
-//   4. ALL-TO-ALL 2: partial (x, y, score) records go to owner(x) = x mod G, where one radix sort by (x, y) and a segmented sum
-//      give the final scores: every unordered pair ends up on exactly one rank, in canonical order.
+//      lists (y > x, list tails only): PARTIAL scores, work = the increments of the owned lists = 1 / G of the total;
+//   4. ALL-TO-ALL 2: partial (x, y, score) records, packed into one u64 when they fit, go to owner(x) = x mod G, where one radix sort
+//      by (x, y) and a segmented sum give the final scores: every unordered pair ends up on exactly one rank, in canonical order;
+//   5. hga_comm_gather_root: for the stages after the scaffold union_find, rank 0 gathers every rank's hits and selected edges and
+//      becomes a complete single-GPU handle.
 // Edge selection needs two small all-reduces (score histograms) and an all-gather of the tie keys; components iterate
 // union-find with all-reduce(min) over the replicated label array.
 //

@@ -10,17 +10,15 @@
 //      (and their random offset look-ups) in flight; a lane that finishes a list picks up the row's next entry without
 //      waiting for the others, and the offsets of its next list are prefetched while it walks the current one. Lists are
 //      sorted by row, so with all rows as pivots the walk runs from the END of the list and stops at the first row <= pivot:
-//      only the half of every list that can produce a (pivot < partner) pair is read (eight entries = one aligned 32 B sector per
-//      step, their accumulator probes issued together, one predicated loop body for all 32 lanes), and every unordered pair is produced exactly once. Lists longer than PW_LONG
-//      are walked by the whole warp with coalesced loads. The kernel is LATENCY bound (time inversely proportional to the
-//      resident warps up to 24 per SM), so the first pass runs with 512-entry accumulators (44 warps per SM) and the few rows
-//      whose partner set does not fit are redone by pair_count_redo_kernel (a CTA per row, four warps on quarter ranges with
-//      1024-entry accumulators that are merged at the end). On one GPU the pivots take their tickets in min-hash order
-//      (row_minhash_kernel): overlapping reads run close together and find each other's lists in L2. With a communicator
-//      (index keyed by kmer_id: neighbouring hits have unrelated lists) the first pass is skipped: one pass with 1024 entries.
-//      Measured and dropped: __match_any_sync merging of equal candidates (5 % slower), a flattened one-entry-per-lane walk
-//      (29 % fewer instructions, 3 % slower), eight probes per step (62 registers, slower), a blocked lane-to-entry mapping
-//      (27 % slower), longest rows first (no change); profiles/r03p_pair_count_memory_bound.md, DESIGN.md 3.4.
+//      only the half of every list that can produce a (pivot < partner) pair is read, eight entries = one aligned 32 B sector per
+//      step, and every unordered pair is produced exactly once. The loop body is ONE predicated path for all 32 lanes (round 1 ran
+//      with 10 of 32 lanes per instruction): list switch, the step's eight probes issued together, a predicated shared-memory
+//      increment for the partners found at their home slot, and a probe loop the warp steps through together for the misses. Lists
+//      longer than PW_LONG are walked by the whole warp with coalesced loads. The first pass runs with 512-entry accumulators
+//      (55 registers, 9 CTAs per SM) and the few rows whose partner set does not fit are redone by pair_count_redo_kernel (a CTA
+//      per row, four warps on quarter ranges with 1024-entry accumulators that are merged at the end). The pivots take their tickets
+//      in min-hash order (row_minhash_kernel); with a communicator the lists are partitioned by whole table buckets, so neighbouring
+//      hits still have neighbouring lists and the same kernels run there. What was measured and dropped: DESIGN.md 3.4.
 //   2. pair_count_kernel: rows whose partner set overflowed tier 1; one CTA per row, 4096-entry accumulator.
 //   3. pair_count_heavy_kernel: rows that overflow tier 2; per-CTA accumulator in HBM.
 // Output: (key = min_row << 32 | max_row, score) appended through one atomic cursor bump per row, then one
