@@ -380,7 +380,10 @@ __device__ __forceinline__ uint32_t phase_c(const TileCtx &c, int lane, uint32_t
 // is inlined so that nothing lives in local memory.
 // MINB = resident CTAs per SM the register allocation aims at (4: 64 registers = 32 warps, 5: 48 registers = 40 warps, 3: 80
 // registers = 24 warps; experiment switch HGA_SCAN_OCC)
-template<int MINB>
+// TMA (experiment, HGA_SCAN_TMA=1): the tile's 512 bytes arrive by a 1-D bulk copy (cp.async.bulk, evict-first in L2) into a per-warp double buffer and
+// complete on an mbarrier; the copy of the NEXT tile is in flight while the current one is processed, so phase A never waits for HBM.
+#define SCAN_STAGE_BYTES (2 * SCAN_SPAN + 16)    // two tile buffers + two mbarriers per warp
+template<int MINB, bool TMA>
 __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -404,19 +407,64 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
         T.tk[0] = T.tk[1] = 0;
         next_batch = atomicAdd(&p.scalars->ticket, 1ull);
     }
-    for (;;) {
-        unsigned long long ticket = 0;
-        if (lane == 0) {
-            ticket = T.tk[0];
-            if (ticket == T.tk[1]) {                                   // batch used up: on to the one requested a batch ago, request the next
-                ticket = next_batch * SCAN_TICKETS;
-                if (ticket < p.n_tiles) next_batch = atomicAdd(&p.scalars->ticket, 1ull);
-                T.tk[1] = min((unsigned long long) p.n_tiles, ticket + SCAN_TICKETS);
-            }
-            T.tk[0] = ticket + 1;
+    // lane 0: the next tile ticket of this warp (>= n_tiles: none left)
+    auto take_ticket = [&]() -> unsigned long long {
+        unsigned long long t = T.tk[0];
+        if (t == T.tk[1]) {                                        // batch used up: on to the one requested a batch ago, request the next
+            t = next_batch * SCAN_TICKETS;
+            if (t < p.n_tiles) next_batch = atomicAdd(&p.scalars->ticket, 1ull);
+            T.tk[1] = min((unsigned long long) p.n_tiles, t + SCAN_TICKETS);
         }
-        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+        T.tk[0] = t + 1;
+        return t;
+    };
+    // TMA path: stage buffers and mbarriers of this warp, and the bulk copy of one tile into a buffer (lane 0)
+    unsigned char *stage = s_raw + SCAN_WARPS * sizeof(WarpTile) + (size_t) warp * SCAN_STAGE_BYTES;
+    const uint32_t stage_sa = (uint32_t) __cvta_generic_to_shared(stage), mbar_sa = stage_sa + 2 * SCAN_SPAN;
+    const int64_t u_end_all = (int64_t) p.lead + (int64_t) p.n_bases;
+    auto issue_tile = [&](unsigned long long t, int buf) {
+        const uint64_t tl = p.tile_begin + (p.tile_stride ? t * p.tile_stride : t);
+        const int64_t ub = (int64_t) (tl * SCAN_TILE) - 32;
+        const int64_t lo = max(ub, (int64_t) 0), hi = min(ub + SCAN_SPAN, (u_end_all + 15) & ~(int64_t) 15);
+        const uint32_t bytes = hi > lo ? (uint32_t) (hi - lo) : 0u;
+        const uint32_t mb = mbar_sa + 8 * buf;
+        if (bytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         :: "r"(stage_sa + buf * SCAN_SPAN + (uint32_t) (lo - ub)), "l"(p.frame + lo), "r"(bytes), "r"(mb), "l"(pol_stream) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mb) : "memory");
+        }
+    };
+    unsigned long long cur = 0;
+    uint32_t parity = 0;                                                // bit b: phase parity of buffer b's mbarrier
+    int buf = 0;
+    if (TMA) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_sa));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_sa + 8));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        cur = take_ticket();
+        if (TMA && cur < p.n_tiles) issue_tile(cur, 0);
+    }
+    for (;;) {
+        const unsigned long long ticket = __shfl_sync(0xFFFFFFFFu, cur, 0);
         if (ticket >= p.n_tiles) break;
+        const int my_buf = buf;
+        if (lane == 0) {
+            cur = take_ticket();                                        // the tile after this one: its bytes travel while this one is processed
+            if (TMA && cur < p.n_tiles) issue_tile(cur, buf ^ 1);
+        }
+        if (TMA) {
+            const uint32_t mb = mbar_sa + 8 * my_buf, ph = (parity >> my_buf) & 1u;
+            asm volatile("{\n.reg .pred p;\nSCAN_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra SCAN_DONE;\nbra SCAN_WAIT;\nSCAN_DONE:\n}" :: "r"(mb), "r"(ph) : "memory");
+            parity ^= 1u << my_buf;
+            buf ^= 1;
+        }
         {
         const uint64_t tile = p.tile_begin + (p.tile_stride ? ticket * p.tile_stride : ticket);
         // frame coordinate u = stream position + lead; the tile's window ends are u in [480 tile, 480 tile + 480); staged index 0 is u = 480 tile - 32
@@ -430,8 +478,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_probe_kernel(const __
             const int64_t u = ubase + SCAN_LANE * lane;
             uint32_t v[4];
             if (u >= 0 && u < u_end) {
-                asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p.frame + u), "l"(pol_stream));
+                if (TMA) {
+                    const uint4 c = *reinterpret_cast<const uint4 *>(stage + my_buf * SCAN_SPAN + SCAN_LANE * lane);
+                    v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w;
+                } else {
+                    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p.frame + u), "l"(pol_stream));
+                }
             } else {
                 #pragma unroll
                 for (int i = 0; i < 4; i++) v[i] = 0x41414141u;                        // outside the stream: 'A' (never inside a valid window)
@@ -591,18 +644,28 @@ __global__ void scan_fix_rows_kernel(const uint64_t *__restrict__ read_off, uint
     }
 }
 
-const size_t kScanSmem = SCAN_WARPS * sizeof(WarpTile);
-
 int scan_occ_variant() {
     static int v = 0;
     if (!v) { const char *e = getenv("HGA_SCAN_OCC"); v = e ? atoi(e) : 4; if (v != 3 && v != 5) v = 4; }
     return v;
 }
+bool scan_tma_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("HGA_SCAN_TMA"); v = e && atoi(e) != 0 ? 1 : 0; }
+    return v != 0;
+}
+
+typedef void (*scan_kernel_t)(const ScanParams);
+scan_kernel_t scan_kernel() {
+    if (scan_tma_variant()) return scan_probe_kernel<4, true>;
+    if (scan_occ_variant() == 3) return scan_probe_kernel<3, false>;
+    if (scan_occ_variant() == 5) return scan_probe_kernel<5, false>;
+    return scan_probe_kernel<4, false>;
+}
+size_t scan_smem_bytes() { return SCAN_WARPS * sizeof(WarpTile) + (scan_tma_variant() ? (size_t) SCAN_WARPS * SCAN_STAGE_BYTES : 0); }
 
 int launch_scan(hga_handle *h, const ScanParams &p, int grid) {
-    if (scan_occ_variant() == 3) scan_probe_kernel<3><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
-    else if (scan_occ_variant() == 5) scan_probe_kernel<5><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
-    else scan_probe_kernel<4><<<grid, SCAN_THREADS, kScanSmem, h->stream>>>(p);
+    scan_kernel()<<<grid, SCAN_THREADS, scan_smem_bytes(), h->stream>>>(p);
     HGA_CUDA(cudaGetLastError());
     h->metrics.kernel_launches++;
     return HGA_OK;
@@ -636,16 +699,8 @@ int hga_scan_run(hga_handle *h, const char *d_bases, const uint64_t *d_read_off,
     if (const char *e = getenv("HGA_SCAN_DIAG")) p.diag = atoi(e);
 
     int occ = 0;
-    if (scan_occ_variant() == 3) {
-        HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
-        HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<3>, SCAN_THREADS, kScanSmem));
-    } else if (scan_occ_variant() == 5) {
-        HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
-        HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<5>, SCAN_THREADS, kScanSmem));
-    } else {
-        HGA_CUDA(cudaFuncSetAttribute(scan_probe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem));
-        HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_probe_kernel<4>, SCAN_THREADS, kScanSmem));
-    }
+    HGA_CUDA(cudaFuncSetAttribute(scan_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scan_smem_bytes()));
+    HGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel(), SCAN_THREADS, scan_smem_bytes()));
     if (occ < 1) occ = 1;
     const int grid_full = (int) std::min<uint64_t>((uint64_t) h->sm_count * occ, std::max<uint64_t>((n_tiles + SCAN_WARPS - 1) / SCAN_WARPS, 1));
 
