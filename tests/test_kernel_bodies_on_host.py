@@ -627,3 +627,102 @@ def test_enrich_on_host_same_handle_again(host_enrich, oracle):
     e3, t3 = _emu_collect(host_enrich)
     compare.check_enrichment(c["ref"], e3, c["kmers"])
     assert t3["ran"] and all(np.array_equal(a, b) for a, b in zip(t1["clusters"], t3["clusters"]))
+
+
+# ---- the k-mer table build (csrc/hga_table.cu) on the host --------------------------------------------------------------------------
+# The table layout is a function of the k-mer array (bucket sort, one thread per bucket, sorted overflow region); the scan's lookup relies on three
+# invariants nothing checks at run time: (i) a key sits in its home bucket and every SECTOR between its start sector and its own sector (going round the
+# bucket) is full, so a lookup that goes sector by sector and stops at a sector with an empty slot never stops early; (ii) a key that is not in its
+# bucket sits in the overflow region, which is sorted (bisection); (iii) the filter word of every key has the key's bits set.
+TABLE_HARNESS = r"""
+extern "C" int emu_table(int k, const uint64_t *kmers, uint64_t n, double load, uint64_t *stats) {
+    static hga_handle hh;
+    hga_handle *h = &hh;
+    h->k = k; h->n_kmers = n; h->sm_count = 2; h->stream = nullptr;
+    char buf[32];
+    snprintf(buf, sizeof buf, "%g", load);
+    if (load > 0) setenv("HGA_TABLE_LOAD", buf, 1); else unsetenv("HGA_TABLE_LOAD");
+    int rc = hga_table_build(h, kmers);
+    unsetenv("HGA_TABLE_LOAD");
+    if (rc != HGA_OK) return rc;
+    const KmerTable &t = h->table;
+    uint64_t in_main = 0, in_over = 0, bad = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t key = kmers[i];
+        const uint32_t s = t.kid_slot[i];
+        if (s >= t.n_slots || t.keys[s] != key || t.slot_kid[s] != (uint32_t) i) { bad |= 1; continue; }
+        const uint32_t hb = hga_bits_hash(key, t.geom);
+        const uint32_t B = hga_locality_from_min(hga_minimizer(key, hb, t.geom));
+        if ((t.filter[(size_t) hga_scale(B, t.n_blocks) * 8 + hga_bits_word(hb)] & hga_bits_mask(hb, t.filter_k)) != hga_bits_mask(hb, t.filter_k)) bad |= 2;
+        const uint32_t home = hga_scale(B, t.n_buckets) * HGA_BUCKET_SLOTS, start_sec = hga_start_sector(B, hb, t.sector_by_min);
+        const uint32_t n_sec = HGA_BUCKET_SLOTS / HGA_SECTOR_SLOTS;
+        if (s < t.n_main) {
+            in_main++;
+            if (s / HGA_BUCKET_SLOTS != home / HGA_BUCKET_SLOTS) { bad |= 4; continue; }
+            const uint32_t my_sec = (s - home) / HGA_SECTOR_SLOTS;
+            for (uint32_t step = 0; (start_sec + step) % n_sec != my_sec; step++)            // every sector before the key's own is full
+                for (uint32_t j = 0; j < HGA_SECTOR_SLOTS; j++)
+                    if (t.keys[home + ((start_sec + step) % n_sec) * HGA_SECTOR_SLOTS + j] == HGA_EMPTY_KEY) bad |= 8;
+        } else {
+            in_over++;
+            for (uint32_t j = 0; j < HGA_BUCKET_SLOTS; j++) if (t.keys[home + j] == HGA_EMPTY_KEY) bad |= 16;   // its bucket is full
+            const uint32_t q = s - t.n_main;
+            if (q >= t.n_over_keys) bad |= 32;
+        }
+    }
+    for (uint32_t q = 1; q < t.n_over_keys; q++) if (t.keys[t.n_main + q - 1] >= t.keys[t.n_main + q]) bad |= 64;   // sorted, no duplicates
+    for (uint32_t q = t.n_over_keys; q < t.n_over; q++) if (t.keys[t.n_main + q] != HGA_EMPTY_KEY) bad |= 128;
+    uint64_t used = 0;
+    for (uint32_t s = 0; s < t.n_slots; s++) used += t.keys[s] != HGA_EMPTY_KEY;
+    if (used != n) bad |= 256;
+    if (t.n_slots % HGA_BUCKET_SLOTS) bad |= 512;
+    stats[0] = in_main; stats[1] = in_over; stats[2] = bad; stats[3] = t.n_slots; stats[4] = t.n_over_keys;
+    return HGA_OK;
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def host_table(tmp_path_factory):
+    internal = open(os.path.join(CSRC, "hga_internal.cuh")).read()
+    internal = internal.replace("#include <cuda_runtime.h>\n", "").replace("#pragma once\n", "")
+    internal = internal.replace('#include "../../include/hga_b200.h"', '#include "hga_b200.h"')
+    text = open(os.path.join(CSRC, "hga_table.cu")).read()
+    text = re.sub(r'#include\s+"hga_internal.cuh"\n', "", text)
+    text = re.sub(r"#include\s+<cub/[^>]+>\n", "", text)
+    text = re.sub(r"<<<[^;]*?>>>", "", text)
+    fake = FAKE_CUDA.replace("void hga_set_error(const char *fmt, ...) {", "void hga_set_error_unused(const char *fmt, ...) {")
+    more = FAKE_CUDA_MORE + r"""
+static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
+static inline int atomicOr(int *p, int v) { int o = *p; *p |= v; return o; }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
+"""
+    d = tmp_path_factory.mktemp("host_table")
+    src, so = str(d / "table_host.cpp"), str(d / "table_host.so")
+    open(src, "w").write(PRELUDE + "#include <string>\n" + fake + more + internal + text + TABLE_HARNESS)
+    err = str(d / "err.cpp")
+    open(err, "w").write('#include <cstdarg>\n#include <cstdio>\nstatic char g[512];\nvoid hga_set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g, sizeof g, fmt, ap); va_end(ap); }\n'
+                         'extern "C" const char *emu_last_error() { return g; }\n')
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", so, src, err], check=True)
+    lib = C.CDLL(so)
+    lib.emu_last_error.restype = C.c_char_p
+    return lib
+
+
+@pytest.mark.parametrize("k,load", [(19, 0.0), (19, 0.9), (15, 0.9), (31, 0.9), (8, 0.0)])
+def test_table_layout_invariants_on_host(host_table, k, load):
+    """load 0.9 (HGA_TABLE_LOAD) fills buckets, so that start sectors wrap round, sectors fill up and keys spill into the overflow region"""
+    g1 = datagen.random_genome(60000, 600 + k)
+    g2 = datagen.mutate(g1, 0.03, 700 + k)
+    kmers = np.ascontiguousarray(datagen.discriminative_kmers([g1, g2], k), dtype=np.uint64)
+    assert len(kmers) > 100
+    stats = np.zeros(8, dtype=np.uint64)
+    try:
+        rc = host_table.emu_table(k, _p(kmers), C.c_uint64(len(kmers)), C.c_double(load), _p(stats))
+    finally:
+        os.environ.pop("HGA_TABLE_LOAD", None)
+    assert rc == 0, host_table.emu_last_error()
+    assert int(stats[2]) == 0, f"table invariants violated (bit mask {int(stats[2])})"
+    assert int(stats[0]) + int(stats[1]) == len(kmers)
+    if load >= 0.9 and k >= 15:
+        assert int(stats[1]) > 0, "the dense table was meant to exercise the overflow region"
