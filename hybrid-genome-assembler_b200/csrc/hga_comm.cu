@@ -257,15 +257,33 @@ int hga_comm_allgatherv(hga_handle *h, const void *d_mine, void *d_all, const st
     return HGA_OK;
 }
 
-// counts all-to-all: every rank's G send counts + one extra value (device array of G + 1) -> the G x (G + 1) matrix on the host
-// (cnt_all[src * (G + 1) + dst], extra at [src * (G + 1) + G])
-static int exchange_counts(hga_handle *h, const unsigned long long *d_send_cnt, unsigned long long *d_all, std::vector<unsigned long long> &cnt_all) {
-    const int G = h->comm->size;
-    cnt_all.assign((size_t) G * (G + 1), 0);
-    HGA_NCCL(g_nccl.AllGather(d_send_cnt, d_all, G + 1, ncclUint64, h->comm->comm, h->stream));
-    HGA_CUDA(cudaMemcpyAsync(cnt_all.data(), d_all, (size_t) G * (G + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+// Count matrix of an exchange: every rank contributes G send counts, two extra values and its STATUS (the return code of the local phase that
+// produced the counts); the all-gather of these G + 3 values is the stage's one host synchronisation. A rank whose local phase failed still takes
+// part (with zero counts), so that nobody is left waiting in NCCL: every rank sees every status and they all leave the stage together, the failed
+// rank with its own error, the others with HGA_E_NCCL. cnt_all[src * HGA_CS(G) + dst], extras at + G and + G + 1.
+#define HGA_CS(G) ((size_t) (G) + 3)
+static int exchange_counts(hga_handle *h, unsigned long long *d_send_cnt, unsigned long long *d_all, int local_rc, const char *stage, std::vector<unsigned long long> &cnt_all) {
+    const int G = h->comm->size, me = h->comm->rank;
+    const size_t CS = HGA_CS(G);
+    cnt_all.assign((size_t) G * CS, 0);
+    const unsigned long long status = (unsigned long long) (local_rc == HGA_OK ? 0 : (unsigned) -local_rc + 1u);
+    if (local_rc != HGA_OK) HGA_CUDA(cudaMemsetAsync(d_send_cnt, 0, (CS - 1) * 8, h->stream));
+    HGA_CUDA(cudaMemcpyAsync(d_send_cnt + G + 2, &status, 8, cudaMemcpyHostToDevice, h->stream));
+    HGA_NCCL(g_nccl.AllGather(d_send_cnt, d_all, CS, ncclUint64, h->comm->comm, h->stream));
+    HGA_CUDA(cudaMemcpyAsync(cnt_all.data(), d_all, (size_t) G * CS * 8, cudaMemcpyDeviceToHost, h->stream));
     HGA_CUDA(cudaStreamSynchronize(h->stream));
+    if (local_rc != HGA_OK) return local_rc;                         // (the error text of the local phase stands)
+    for (int g = 0; g < G; g++)
+        if (cnt_all[g * CS + G + 2]) { hga_set_error("%s: rank %d failed before the exchange (rank %d leaves the stage with it)", stage, g, me); return HGA_E_NCCL; }
     return HGA_OK;
+}
+
+// test hook: HGA_FAULT="<stage>:<rank>" makes that rank's local phase of the stage fail (tests/multi_gpu_parity.py: nobody may hang)
+static bool fault_injected(const hga_handle *h, const char *stage) {
+    const char *e = getenv("HGA_FAULT");
+    if (!e) return false;
+    const size_t n = strlen(stage);
+    return strncmp(e, stage, n) == 0 && e[n] == ':' && atoi(e + n + 1) == h->comm->rank;
 }
 
 // Steps 1-2 of the header comment. On return h->d_inv_off / h->d_inv_row hold the inverted lists of THIS rank's k-mers (list number
@@ -277,58 +295,71 @@ int hga_comm_build_owner_index(hga_handle *h) {
     const uint32_t n_buckets_all = h->table.n_slots / HGA_BUCKET_SLOTS;                         // n_slots is a multiple of 32
     const uint32_t n_lists = (n_buckets_all + G - 1) / G * HGA_BUCKET_SLOTS;                    // of the fullest owner; a multiple of 32
     const uint32_t row_base = h->read_id_base - 1;
-    if (E_loc >= (1ull << 32)) { hga_set_error("local incidence of %llu entries exceeds the 32-bit per-GPU limit", (unsigned long long) E_loc); return HGA_E_OVERFLOW; }
     double comm_ms = 0, part_ms = 0;
     Trace tr(h);
 
-    // 1. list numbers partitioned by owner (ONE stable radix pass: every owner segment keeps row order) + per-row counts per owner
+    // 1. list numbers partitioned by owner (ONE stable radix pass: every owner segment keeps row order) + per-row counts per owner.
+    // The local phase: whatever goes wrong in it is reported through the count matrix, not by leaving early (exchange_counts).
     const int owner_bits = (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) G), 1);
     const uint64_t R_loc = h->n_reads;
-    HGA_TRY(h->d_sort_a.ensure((E_loc + 1) * 4));      // list numbers, partitioned
-    HGA_TRY(h->d_sort_b.ensure((E_loc + 1) * 4));      // list numbers, stream order
-    HGA_TRY(h->d_x_row.ensure((E_loc + 1) * 2));       // owner per hit: in | out
-    HGA_TRY(h->comm->d_rows.ensure(((size_t) G * R_loc + R_all + 2) * 4));   // my rows' counts per owner | all rows' counts for my lists
-    uint8_t *own_in = h->d_x_row.as<uint8_t>(), *own_out = own_in + (E_loc + 1);
-    uint32_t *list_in = h->d_sort_b.as<uint32_t>(), *list_out = h->d_sort_a.as<uint32_t>();
-    uint32_t *cnt_send = h->comm->d_rows.as<uint32_t>(), *cnt_recv = cnt_send + (size_t) G * R_loc;
-    if (R_loc) {
-        const int blocks = (int) std::min<uint64_t>((R_loc * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
-        pack_lists_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), R_loc, h->d_hit_slot.as<uint32_t>(), (uint32_t) G, list_in, own_in, cnt_send);
+    unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + HGA_CS(G) + 1;     // (sized by hga_comm_init)
+    uint32_t *list_out = nullptr, *cnt_send = nullptr, *cnt_recv = nullptr;
+    auto local_phase = [&]() -> int {
+        if (fault_injected(h, "index")) { hga_set_error("hga_build_index: injected fault (HGA_FAULT)"); return HGA_E_NOMEM; }
+        if (E_loc >= (1ull << 32)) { hga_set_error("local incidence of %llu entries exceeds the 32-bit per-GPU limit", (unsigned long long) E_loc); return HGA_E_OVERFLOW; }
+        HGA_TRY(h->d_sort_a.ensure((E_loc + 1) * 4));      // list numbers, partitioned
+        HGA_TRY(h->d_sort_b.ensure((E_loc + 1) * 4));      // list numbers, stream order
+        HGA_TRY(h->d_x_row.ensure((E_loc + 1) * 2));       // owner per hit: in | out
+        HGA_TRY(h->comm->d_rows.ensure(((size_t) G * R_loc + R_all + 2) * 4));   // my rows' counts per owner | all rows' counts for my lists
+        uint8_t *own_in = h->d_x_row.as<uint8_t>(), *own_out = own_in + (E_loc + 1);
+        uint32_t *list_in = h->d_sort_b.as<uint32_t>();
+        list_out = h->d_sort_a.as<uint32_t>();
+        cnt_send = h->comm->d_rows.as<uint32_t>(); cnt_recv = cnt_send + (size_t) G * R_loc;
+        if (R_loc) {
+            const int blocks = (int) std::min<uint64_t>((R_loc * 32 + 255) / 256, (uint64_t) h->sm_count * 32);
+            pack_lists_kernel<<<blocks, 256, 0, h->stream>>>(h->d_row_off.as<uint64_t>(), R_loc, h->d_hit_slot.as<uint32_t>(), (uint32_t) G, list_in, own_in, cnt_send);
+            h->metrics.kernel_launches++;
+            HGA_CUDA(cudaGetLastError());
+        }
+        if (E_loc) {
+            size_t tmp = 0;
+            HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, own_in, own_out, list_in, list_out, E_loc, 0, owner_bits, h->stream));
+            HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+            HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp, own_in, own_out, list_in, list_out, E_loc, 0, owner_bits, h->stream));
+            h->metrics.kernel_launches += 3;
+            HGA_CUDA(cudaGetLastError());
+        }
+        dest_counts_kernel<<<1, 64, 0, h->stream>>>(own_out, E_loc, G, d_cnt);
+        const unsigned long long extra[2] = {R_loc, row_base};                          // ride along: the receive layout and the shard-layout check need them from every rank
+        HGA_CUDA(cudaMemcpyAsync(d_cnt + G, extra, 16, cudaMemcpyHostToDevice, h->stream));
         h->metrics.kernel_launches++;
         HGA_CUDA(cudaGetLastError());
-    }
-    if (E_loc) {
-        size_t tmp = 0;
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, own_in, own_out, list_in, list_out, E_loc, 0, owner_bits, h->stream));
-        HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, tmp, own_in, own_out, list_in, list_out, E_loc, 0, owner_bits, h->stream));
-        h->metrics.kernel_launches += 3;
-        HGA_CUDA(cudaGetLastError());
-    }
-    HGA_TRY(h->comm->d_small.ensure((size_t) (G + 2) * 8 * (G + 2)));
-    unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + (G + 2);
-    dest_counts_kernel<<<1, 64, 0, h->stream>>>(own_out, E_loc, G, d_cnt);
-    const unsigned long long my_rows = R_loc;                                       // rides along: the receive layout needs every rank's row count
-    HGA_CUDA(cudaMemcpyAsync(d_cnt + G, &my_rows, 8, cudaMemcpyHostToDevice, h->stream));
-    h->metrics.kernel_launches++;
-    HGA_CUDA(cudaGetLastError());
+        return HGA_OK;
+    };
+    const int local_rc = local_phase();
     tr.mark("pack+partition");
     std::vector<unsigned long long> cnt_all;
-    HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, cnt_all));                         // the only host synchronisation of the stage
+    HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, local_rc, "hga_build_index", cnt_all));   // the only host synchronisation of the stage
     tr.mark("counts");
-    const size_t CS = (size_t) G + 1;
+    const size_t CS = HGA_CS(G);
     std::vector<uint64_t> rows_off(G + 1, 0);
     for (int g = 0; g < G; g++) rows_off[g + 1] = rows_off[g] + cnt_all[g * CS + G];
-    // shards must be contiguous read-id ranges in rank order: the row stream of source s must lie in s's range
-    if (rows_off[me] != row_base) { hga_set_error("hga_build_index: shards must be contiguous read-id ranges in rank order (rank %d starts at row %u, expected %llu)", me, row_base, (unsigned long long) rows_off[me]); return HGA_E_ARG; }
+    // shards must be contiguous read-id ranges in rank order: the row stream of source s must lie in s's range. Every rank checks EVERY rank's layout and share
+    // (the matrix holds them all), so they all come to the same verdict.
+    for (int g = 0; g < G; g++)
+        if (rows_off[g] != cnt_all[g * CS + G + 1]) { hga_set_error("hga_build_index: shards must be contiguous read-id ranges in rank order (rank %d starts at row %llu, expected %llu)", g, (unsigned long long) cnt_all[g * CS + G + 1], (unsigned long long) rows_off[g]); return HGA_E_ARG; }
     if (rows_off[G] != R_all) { hga_set_error("hga_build_index: the ranks scanned %llu reads, hga_comm_init said %llu", (unsigned long long) rows_off[G], (unsigned long long) R_all); return HGA_E_ARG; }
+    for (int g = 0; g < G; g++) {
+        uint64_t share = 0;
+        for (int src = 0; src < G; src++) share += cnt_all[src * CS + g];
+        if (share >= (1ull << 32)) { hga_set_error("rank %d's share of the incidence (%llu entries) exceeds the 32-bit per-GPU limit", g, (unsigned long long) share); return HGA_E_OVERFLOW; }
+    }
 
     // 2. all-to-all: the list numbers of my lists from every rank, in rank order = global row order, and the sources' per-row counts
     uint64_t E_own = 0;
     std::vector<uint64_t> recv_off(G + 1, 0), send_off(G + 1, 0);
     for (int src = 0; src < G; src++) { recv_off[src] = E_own; E_own += cnt_all[src * CS + me]; }
     for (int g = 0; g < G; g++) send_off[g + 1] = send_off[g] + cnt_all[me * CS + g];
-    if (E_own >= (1ull << 32)) { hga_set_error("this rank's share of the incidence (%llu entries) exceeds the 32-bit per-GPU limit", (unsigned long long) E_own); return HGA_E_OVERFLOW; }
     HGA_TRY(h->d_g_kid.ensure((E_own + 1) * 4));        // the by-row incidence of all rows restricted to my lists: list number per hit
     HGA_TRY(h->d_g_row_off.ensure((R_all + 2) * 8));
     uint32_t *rx = h->d_g_kid.as<uint32_t>();
@@ -381,36 +412,43 @@ int hga_comm_exchange_partials(hga_handle *h, uint64_t n, uint64_t *out_n) {
     const int owner_bits = (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) G), 1);
     double part_ms = 0;
     Trace tr(h);
-    HGA_TRY(h->d_x_row.ensure((n + 1) * 2));
-    HGA_TRY(h->d_pair_key2.ensure((n + 1) * 8));
-    HGA_TRY(h->d_pair_score2.ensure((n + 1) * 4));
-    uint8_t *d_in = h->d_x_row.as<uint8_t>(), *d_out = d_in + (n + 1);
-    uint64_t *key_part = h->d_pair_key2.as<uint64_t>();
-    uint32_t *score_part = h->d_pair_score2.as<uint32_t>();
-    if (n) {
-        pair_dest_kernel<<<(int) std::min<uint64_t>((n + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), n, (uint32_t) G, d_in);
-        size_t t1 = 0, t2 = 0;
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, d_in, d_out, h->d_pair_key.as<uint64_t>(), key_part, n, 0, owner_bits, h->stream));
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t2, d_in, d_out, h->d_pair_score.as<uint32_t>(), score_part, n, 0, owner_bits, h->stream));
-        HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
-        // two stable passes with the same keys: the same permutation for both value arrays
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t1, d_in, d_out, h->d_pair_key.as<uint64_t>(), key_part, n, 0, owner_bits, h->stream));
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t2, d_in, d_out, h->d_pair_score.as<uint32_t>(), score_part, n, 0, owner_bits, h->stream));
-        h->metrics.kernel_launches += 7;
+    unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + HGA_CS(G) + 1;
+    uint64_t *key_part = nullptr;
+    uint32_t *score_part = nullptr;
+    auto local_phase = [&]() -> int {
+        if (fault_injected(h, "partials")) { hga_set_error("hga_pair_count: injected fault (HGA_FAULT)"); return HGA_E_NOMEM; }
+        HGA_TRY(h->d_x_row.ensure((n + 1) * 2));
+        HGA_TRY(h->d_pair_key2.ensure((n + 1) * 8));
+        HGA_TRY(h->d_pair_score2.ensure((n + 1) * 4));
+        uint8_t *d_in = h->d_x_row.as<uint8_t>(), *d_out = d_in + (n + 1);
+        key_part = h->d_pair_key2.as<uint64_t>();
+        score_part = h->d_pair_score2.as<uint32_t>();
+        if (n) {
+            pair_dest_kernel<<<(int) std::min<uint64_t>((n + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), n, (uint32_t) G, d_in);
+            size_t t1 = 0, t2 = 0;
+            HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, d_in, d_out, h->d_pair_key.as<uint64_t>(), key_part, n, 0, owner_bits, h->stream));
+            HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t2, d_in, d_out, h->d_pair_score.as<uint32_t>(), score_part, n, 0, owner_bits, h->stream));
+            HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
+            // two stable passes with the same keys: the same permutation for both value arrays
+            HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t1, d_in, d_out, h->d_pair_key.as<uint64_t>(), key_part, n, 0, owner_bits, h->stream));
+            HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t2, d_in, d_out, h->d_pair_score.as<uint32_t>(), score_part, n, 0, owner_bits, h->stream));
+            h->metrics.kernel_launches += 7;
+            HGA_CUDA(cudaGetLastError());
+        }
+        dest_counts_kernel<<<1, 64, 0, h->stream>>>(d_out, n, G, d_cnt);
+        HGA_CUDA(cudaMemsetAsync(d_cnt + G, 0, 16, h->stream));
+        h->metrics.kernel_launches++;
         HGA_CUDA(cudaGetLastError());
-    }
-    HGA_TRY(h->comm->d_small.ensure((size_t) (G + 2) * 8 * (G + 2)));
-    unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + (G + 2);
-    dest_counts_kernel<<<1, 64, 0, h->stream>>>(d_out, n, G, d_cnt);
-    h->metrics.kernel_launches++;
-    HGA_CUDA(cudaGetLastError());
+        return HGA_OK;
+    };
+    const int local_rc = local_phase();
     tr.mark("partition");
     std::vector<unsigned long long> cnt_all;
-    HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, cnt_all));
+    HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, local_rc, "hga_pair_count", cnt_all));
     tr.mark("counts");
     uint64_t n_recv = 0;
     std::vector<uint64_t> recv_off(G + 1, 0), send_off(G + 1, 0);
-    const size_t CS = (size_t) G + 1;
+    const size_t CS = HGA_CS(G);
     for (int src = 0; src < G; src++) { recv_off[src] = n_recv; n_recv += cnt_all[src * CS + me]; }
     for (int g = 0; g < G; g++) send_off[g + 1] = send_off[g] + cnt_all[me * CS + g];
     // the receive buffers: the (now free) primary pair arrays
@@ -454,32 +492,38 @@ int hga_comm_reduce_partials_packed(hga_handle *h, uint64_t n, uint64_t *out_n, 
     const int owner_bits = (int) std::max<uint32_t>(hga_ceil_log2((uint64_t) G), 1);
     double part_ms = 0;
     Trace tr(h);
-    HGA_TRY(h->d_x_row.ensure((n + 1) * 2));
-    HGA_TRY(h->d_pair_key2.ensure((n + 1) * 8));
-    HGA_TRY(h->d_x_slot.ensure((n + 1) * 8));
-    uint8_t *d_in = h->d_x_row.as<uint8_t>(), *d_out = d_in + (n + 1);
-    uint64_t *rec_in = h->d_x_slot.as<uint64_t>(), *rec_part = h->d_pair_key2.as<uint64_t>();
-    HGA_TRY(h->comm->d_small.ensure((size_t) (G + 2) * 8 * (G + 2)));
-    unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + (G + 2);
-    HGA_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t) (G + 1) * 8, h->stream));
-    if (n) {
-        pack_partials_kernel<<<(int) std::min<uint64_t>((n + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), h->d_pair_score.as<uint32_t>(), n, rb, sb,
-                                                                                                                           (uint32_t) G, rec_in, d_in, d_cnt + G);
-        size_t t1 = 0;
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, d_in, d_out, rec_in, rec_part, n, 0, owner_bits, h->stream));
-        HGA_TRY(h->d_sort_tmp.ensure(t1 + 16));
-        HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t1, d_in, d_out, rec_in, rec_part, n, 0, owner_bits, h->stream));
-        h->metrics.kernel_launches += 4;
+    unsigned long long *d_cnt = h->comm->d_small.as<unsigned long long>(), *d_cnt_all = d_cnt + HGA_CS(G) + 1;
+    uint64_t *rec_part = nullptr;
+    auto local_phase = [&]() -> int {
+        if (fault_injected(h, "partials")) { hga_set_error("hga_pair_count: injected fault (HGA_FAULT)"); return HGA_E_NOMEM; }
+        HGA_TRY(h->d_x_row.ensure((n + 1) * 2));
+        HGA_TRY(h->d_pair_key2.ensure((n + 1) * 8));
+        HGA_TRY(h->d_x_slot.ensure((n + 1) * 8));
+        uint8_t *d_in = h->d_x_row.as<uint8_t>(), *d_out = d_in + (n + 1);
+        uint64_t *rec_in = h->d_x_slot.as<uint64_t>();
+        rec_part = h->d_pair_key2.as<uint64_t>();
+        HGA_CUDA(cudaMemsetAsync(d_cnt, 0, HGA_CS(G) * 8, h->stream));
+        if (n) {
+            pack_partials_kernel<<<(int) std::min<uint64_t>((n + 255) / 256, (uint64_t) h->sm_count * 16), 256, 0, h->stream>>>(h->d_pair_key.as<uint64_t>(), h->d_pair_score.as<uint32_t>(), n, rb, sb,
+                                                                                                                               (uint32_t) G, rec_in, d_in, d_cnt + G);
+            size_t t1 = 0;
+            HGA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, d_in, d_out, rec_in, rec_part, n, 0, owner_bits, h->stream));
+            HGA_TRY(h->d_sort_tmp.ensure(t1 + 16));
+            HGA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp.p, t1, d_in, d_out, rec_in, rec_part, n, 0, owner_bits, h->stream));
+            h->metrics.kernel_launches += 4;
+            HGA_CUDA(cudaGetLastError());
+        }
+        dest_counts_kernel<<<1, 64, 0, h->stream>>>(d_out, n, G, d_cnt);
+        h->metrics.kernel_launches++;
         HGA_CUDA(cudaGetLastError());
-    }
-    dest_counts_kernel<<<1, 64, 0, h->stream>>>(d_out, n, G, d_cnt);
-    h->metrics.kernel_launches++;
-    HGA_CUDA(cudaGetLastError());
+        return HGA_OK;
+    };
+    const int local_rc = local_phase();
     tr.mark("pack+partition");
     std::vector<unsigned long long> cnt_all;
-    HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, cnt_all));
+    HGA_TRY(exchange_counts(h, d_cnt, d_cnt_all, local_rc, "hga_pair_count", cnt_all));
     tr.mark("counts");
-    const size_t CS = (size_t) G + 1;
+    const size_t CS = HGA_CS(G);
     for (int g = 0; g < G; g++) if (cnt_all[g * CS + G]) return HGA_OK;           // a score did not fit somewhere: everybody falls back
     uint64_t n_recv = 0;
     std::vector<uint64_t> recv_off(G + 1, 0), send_off(G + 1, 0);
@@ -662,6 +706,7 @@ extern "C" int hga_comm_init(hga_handle *h, const void *id128, int rank, int nra
     memcpy(&id, id128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
     if (r != ncclSuccess) { hga_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); delete c; return HGA_E_NCCL; }
+    if (c->d_small.ensure((size_t) (nranks + 4) * 8 * (nranks + 4)) != HGA_OK) { g_nccl.CommDestroy(c->comm); delete c; return HGA_E_NOMEM; }   // count matrices: never allocated inside a stage
     h->comm = c;
     h->n_reads_total = n_reads_total;
     return HGA_OK;

@@ -131,6 +131,45 @@ def main():
             print(f"multi-GPU parity ok: case {case}, {world} ranks, {len(seqs)} reads, {len(ux)} pairs, {len(want)} selected, {len(wantc)} components, "
                   f"exchange {max(r['exchange_ms'] for r in box):.3f} ms")
         dist.barrier()
+
+    # a rank whose local phase fails before an exchange (HGA_FAULT test hook) must not leave the others waiting in NCCL: every rank leaves the stage with an
+    # error (the failing one with its own, the others with "rank r failed before the exchange"), and the same handles' communicator is still usable afterwards
+    a = datagen.random_genome(20000, 900)
+    b = datagen.mutate(a, 0.02, 901)
+    reads = datagen.sample_reads(a, 100, 1000, 31) + datagen.sample_reads(b, 100, 1000, 32)
+    seqs = [datagen.to_ascii(r).encode() for r in reads]
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    kmers = datagen.discriminative_kmers([a, b], 19)
+    bounds = parallel.shard_bounds(lens, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    off = np.zeros(hi - lo + 1, dtype=np.uint64)
+    np.cumsum(lens[lo:hi], out=off[1:])
+    h = hga_b200.Handle(kmers, 19, device=local)
+    uid = parallel.broadcast_unique_id(dist, rank, hga_b200.capi.comm_unique_id)
+    h.comm_init(uid, rank, world, len(seqs))
+    for stage in ("index", "partials"):
+        os.environ["HGA_FAULT"] = f"{stage}:{world - 1}"
+        h.scan(b"".join(seqs[lo:hi]), off, read_id_base=lo + 1)
+        failed = None
+        try:
+            h.build_index()
+            h.pair_count(min_score=1)
+        except hga_b200.capi.HgaError as e:
+            failed = str(e)
+        finally:
+            del os.environ["HGA_FAULT"]
+        assert failed is not None, f"rank {rank}: the injected {stage} fault went unnoticed"
+        assert ("injected fault" in failed) == (rank == world - 1), (rank, failed)
+    # ... and without the fault the same handles still work
+    h.scan(b"".join(seqs[lo:hi]), off, read_id_base=lo + 1)
+    h.build_index(); h.pair_count(min_score=1); h.select_edges(fraction=0.15); h.components(min_size=5)
+    n_pairs = torch.tensor([h.get_pairs()[0].shape[0]], device=torch.device("cuda", local))
+    dist.all_reduce(n_pairs)
+    assert int(n_pairs.item()) > 0
+    h.close()
+    if rank == 0:
+        print(f"fault injection ok: {world} ranks left the index and the partial-pair exchange together")
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -19,6 +19,7 @@ def test_two_rank_parity():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("multi-GPU parity ok") == 2
     assert r.stdout.count("gathered handle ok") == 2
+    assert r.stdout.count("fault injection ok") == 1
 
 
 @pytest.mark.gpu
