@@ -268,6 +268,12 @@ int main(int argc, char **argv) {
     hga_handle *h = nullptr;
     if (gpus > 1) {
         if (cuda_start.joinable()) cuda_start.join();
+        int n_dev = 0;
+        check(hga_device_count(&n_dev), "hga_device_count");
+        if (device < 0 || device + gpus > n_dev) {            // checked here: a rank thread that cannot create its handle would leave the others waiting in ncclCommInitRank
+            std::cerr << "categorization: --gpus " << gpus << " from --device " << device << " needs devices " << device << " .. " << device + gpus - 1 << ", this machine has " << n_dev << "\n";
+            return 2;
+        }
         h = run_hot_path_multi(ks, reads, config, device, gpus);
     } else {
         Timer t("Index construction");               // table build + scan + inverted index = construct_indices (:234-299)
