@@ -24,6 +24,8 @@
 #include <filesystem>
 #include <iostream>
 #include <map>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "hga_b200.h"
@@ -96,11 +98,28 @@ hga_handle *run_hot_path_multi(const hga_host::KmerSet &ks, const hga_host::Sequ
     std::vector<std::string> errors(gpus);
     std::vector<double> stamp(6, 0.0);                        // rank 0: create, scan, index, pairs + select, components, gather
     std::vector<std::thread> workers;
+    // the rank threads meet after every stage: a rank that failed in a purely local stage (hga_create, hga_scan) must not leave the others waiting in the
+    // next stage's collective
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0, generation = 0;
+    bool any_failed = false;
+    auto meet = [&](bool ok) {
+        std::unique_lock<std::mutex> lk(mu);
+        if (!ok) any_failed = true;
+        const int gen = generation;
+        if (++arrived == gpus) { arrived = 0; generation++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return generation != gen; });
+        return !any_failed;
+    };
     for (int r = 0; r < gpus; r++) {
         workers.emplace_back([&, r] {
+            bool alive = true;
             auto fail = [&](int rc, const char *what) {
+                if (!alive) return true;
                 if (rc == HGA_OK) return false;
                 errors[r] = std::string(what) + " failed (" + std::to_string(rc) + "): " + hga_last_error();
+                alive = false;
                 return true;
             };
             auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -109,25 +128,36 @@ hga_handle *run_hot_path_multi(const hga_host::KmerSet &ks, const hga_host::Sequ
             for (uint64_t i = lo; i <= hi; i++) off[i - lo] = reads.seq_off[i] - reads.seq_off[lo];
             double t = now();
             auto lap = [&](int i) { const double n2 = now(); if (r == 0) stamp[i] = n2 - t; t = n2; };
-            if (fail(hga_create(device + r, ks.k, ks.kmers.data(), ks.kmers.size(), &hs[r]), "hga_create")) return;
-            if (fail(hga_comm_init(hs[r], id, r, gpus, n_reads), "hga_comm_init")) return;
+            // every stage is entered by all ranks or by none
+            alive = !fail(hga_create(device + r, ks.k, ks.kmers.data(), ks.kmers.size(), &hs[r]), "hga_create");
+            if (!meet(alive)) return;
+            alive = !fail(hga_comm_init(hs[r], id, r, gpus, n_reads), "hga_comm_init");
+            if (!meet(alive)) return;
             lap(0);
-            if (fail(hga_scan(hs[r], reads.bases_data + reads.seq_off[lo], off.data(), hi - lo, (uint32_t) (lo + 1)), "hga_scan")) return;
+            alive = !fail(hga_scan(hs[r], reads.bases_data + reads.seq_off[lo], off.data(), hi - lo, (uint32_t) (lo + 1)), "hga_scan");
+            if (!meet(alive)) return;
             lap(1);
-            if (fail(hga_build_index(hs[r]), "hga_build_index")) return;
+            alive = !fail(hga_build_index(hs[r]), "hga_build_index");
+            if (!meet(alive)) return;
             lap(2);
-            if (fail(hga_pair_count(hs[r], 1, nullptr, 0), "hga_pair_count")) return;
-            if (fail(hga_select_edges(hs[r], config.scaffold_forming_fraction, 0), "hga_select_edges")) return;
+            alive = !fail(hga_pair_count(hs[r], 1, nullptr, 0), "hga_pair_count");
+            if (!meet(alive)) return;
+            alive = !fail(hga_select_edges(hs[r], config.scaffold_forming_fraction, 0), "hga_select_edges");
+            if (!meet(alive)) return;
             lap(3);
-            if (fail(hga_components(hs[r], config.scaffold_component_min_size), "hga_components")) return;
+            alive = !fail(hga_components(hs[r], config.scaffold_component_min_size), "hga_components");
+            if (!meet(alive)) return;
             lap(4);
-            if (fail(hga_comm_gather_root(hs[r]), "hga_comm_gather_root")) return;
+            alive = !fail(hga_comm_gather_root(hs[r]), "hga_comm_gather_root");
+            if (!meet(alive)) return;
             lap(5);
         });
     }
     for (auto &w : workers) w.join();
+    bool failed = false;
     for (int r = 0; r < gpus; r++)
-        if (!errors[r].empty()) { std::cerr << "categorization: rank " << r << ": " << errors[r] << "\n"; std::exit(2); }
+        if (!errors[r].empty()) { std::cerr << "categorization: rank " << r << ": " << errors[r] << "\n"; failed = true; }
+    if (failed) std::exit(2);
     std::cout << "Index construction took " << (long long) (stamp[0] + stamp[1] + stamp[2]) << "ms\n";
     std::cout << "Calculation of connections between reads took " << (long long) stamp[3] << "ms\n";
     std::cout << "Union-find took " << (long long) stamp[4] << "ms\n";
