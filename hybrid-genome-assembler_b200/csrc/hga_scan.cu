@@ -3,29 +3,30 @@
 // Replaces the per-read half of ReadClusteringEngine::construct_indices
 // (clustering/ReadClusteringEngine.cpp:246-277) and KmerIterator (common/KmerIterator.cpp:23-76).
 //
-// Work decomposition (B200: 148 SMs x 24 resident warps, every WARP is an independent worker, nothing synchronises two warps):
-//   * the concatenated base stream is cut into tiles of SCAN_TILE (992) window-end positions; a warp takes a tile ticket (the
-//     next ticket is requested while the current tile is processed);
-//   * phase A: every lane loads ONE 32 B sector of ASCII bases with a single 256-bit load (LDG.256, sm_100) - 31 lanes hold
-//     the tile, lane 0 the 32 bases before it - and packs them into two words of forward codes (first base most significant)
-//     and two words of complement codes (first base least significant). Bytes outside {A,C,G,T} get code 0 in BOTH streams -
-//     the reference's rule (KmerIterator.cpp:56,62: unordered_map::operator[] default-inserts 0 in both tables) - and a bit in
-//     an exception bitmap (validity = one PRMT lookup of the expected byte per 4 bases); the previous lane's words come over
-//     with four shuffles;
-//   * phase B, lane-sequential: a lane owns 32 CONSECUTIVE window ends. With its 64 bases in registers every piece is a funnel
-//     shift with a compile-time register index: the forward and reverse strand's last 16 bases and the 16 before, the two
-//     hashed m-mers (one IMAD each: the multiplier shifts out everything above the m-mer), the sliding minimum over the last
-//     W symmetric hashes (VIMNMX3, two instructions, no shuffles) and the strand-symmetric bit hash g(F) + g(R). No canonical
-//     VALUE and no 64-bit compare is needed (hga_internal.cuh). (minimizer, bit hash) go to shared memory;
+// Work decomposition (B200: 148 SMs x 32 resident warps, every WARP is an independent worker, nothing synchronises two warps):
+//   * the concatenated base stream is cut into tiles of SCAN_TILE (480) window-end positions; a warp takes tickets of SCAN_TICKETS
+//     consecutive tiles (one atomic per ticket, the next one requested while the current is processed);
+//   * phase A: every lane loads 16 bytes of ASCII bases (30 lanes hold the tile, lanes 0 and 1 the 32 bases before it) and packs
+//     them into one word of forward codes (first base most significant) and one word of complement codes (first base least
+//     significant). Bytes outside {A,C,G,T} get code 0 in BOTH streams - the reference's rule (KmerIterator.cpp:56,62:
+//     unordered_map::operator[] default-inserts 0 in both tables) - and a bit in an exception bitmap (validity = one PRMT lookup
+//     of the expected byte per 4 bases); the two previous lanes' words come over with four shuffles. (The same 512 bytes as a
+//     1-D bulk copy into a double buffer, cp.async.bulk + mbarrier: template variant TMA, HGA_SCAN_TMA=1, measured slower.)
+//   * phase B, lane-sequential: a lane owns SCAN_LANE (16) CONSECUTIVE window ends. With its 48 bases in registers every piece
+//     is a funnel shift with a compile-time register index: the forward and reverse strand's last 16 bases and the 16 before,
+//     the two hashed m-mers (one IMAD each: the multiplier shifts out everything above the m-mer), the sliding minimum over the
+//     last W symmetric hashes (VIMNMX3, two instructions, no shuffles) and the strand-symmetric bit hash g(F) + g(R). No
+//     canonical VALUE and no 64-bit compare is needed (hga_internal.cuh). (minimizer, bit hash) go to shared memory;
 //   * phase C, lane-parallel: the 32 lanes take 32 ADJACENT windows from shared memory (a transposition through an 8-byte-
 //     entry buffer with an odd row stride, conflict free both ways), so that the ~3.5 consecutive windows that share a
 //     minimizer hit the same 32 B filter block and a warp's 32 probes coalesce into ~9 sectors. Windows that pass are queued;
 //   * drain, dense, 32 candidates per warp instruction: validity against the read boundaries, the forward k-mer re-extracted
 //     from the packed words, its reverse complement, the canonical minimum (KmerIterator.cpp:69), and ONE 256-bit load of the
-//     key sector the bit hash points at (a warp-uniform loop goes round the bucket for the few that need more);
-//   * hits are staged in position order (in the already consumed part of the transposition buffer); a tile's hits are
-//     appended with ONE atomicAdd on a global cursor and a copy kernel moves the tile segments into stream order (exclusive
-//     scan over the tile counts). CSR row offsets are produced per tile and fixed up with the tile's final offset;
+//     key sector the bit hash points at (a warp-uniform loop goes round the bucket for the few that need more, then the sorted
+//     overflow region by bisection);
+//   * hits are staged in position order (in the already consumed part of the transposition buffer); a warp reserves the hit
+//     buffer in chunks (one atomic per ~64 tiles) and a copy kernel moves the tile segments into stream order (exclusive scan
+//     over the tile counts). CSR row offsets are produced per tile and fixed up with the tile's final offset;
 //   * windows that contain a non-ACGT byte skip the filter; the drain rebuilds their reverse strand by the reference's rule and
 //     takes minimizer and bit hash from the k-mer value; tiles without such bytes never pay for the check.
 #include "hga_internal.cuh"
@@ -376,7 +377,7 @@ __device__ __forceinline__ uint32_t phase_c(const TileCtx &c, int lane, uint32_t
     return qs.st_count;
 }
 
-// 24 independent warps per SM (3 CTAs of 8; 9.3 KB of shared memory per warp). The parameters are __grid_constant__ and every helper
+// 32 independent warps per SM (4 CTAs of 8; 5.2 KB of shared memory per warp). The parameters are __grid_constant__ and every helper
 // is inlined so that nothing lives in local memory.
 // MINB = resident CTAs per SM the register allocation aims at (4: 64 registers = 32 warps, 5: 48 registers = 40 warps, 3: 80
 // registers = 24 warps; experiment switch HGA_SCAN_OCC)
