@@ -193,6 +193,30 @@ __global__ void enr_filter_kernel(const uint64_t *__restrict__ run_key, const ui
     }
 }
 
+// ---- tail amplification (amplify_component -> get_connections(tail, min), ReadClusteringEngine.cpp:583-592, :301-333) on the GPU ---------------------------
+// A pivot = one tail vertex. Its k-mer list is, as in the engine state after the first merge: the unique union U_c for a survivor, the read's own hits
+// (duplicates included) for every other id. amp_list_kernel flattens the lists of all pivots into keys (pivot index << 32 | slot); the enrichment's
+// enr_emit_len / enr_emit kernels, a sort and a run-length encode turn them into (pivot, partner, count); amp_filter_kernel keeps count >= min, partner != pivot.
+__global__ void amp_list_kernel(const unsigned long long *__restrict__ key_off, const unsigned long long *__restrict__ src_begin, const uint8_t *__restrict__ from_union,
+                                uint64_t n_pivots, uint64_t n_keys, const uint32_t *__restrict__ hit_slot, const uint64_t *__restrict__ ukeys, uint64_t *__restrict__ out) {
+    for (uint64_t j = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; j < n_keys; j += (uint64_t) gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = n_pivots - 1;                       // the pivot whose key range holds j: last pi with key_off[pi] <= j
+        while (lo < hi) { const uint64_t mid = (lo + hi + 1) >> 1; if (key_off[mid] <= j) lo = mid; else hi = mid - 1; }
+        const uint64_t at = src_begin[lo] + (j - key_off[lo]);
+        const uint32_t slot = from_union[lo] ? (uint32_t) ukeys[at] : hit_slot[at];
+        out[j] = (lo << 32) | slot;
+    }
+}
+
+__global__ void amp_filter_kernel(const uint64_t *__restrict__ run_key, const uint32_t *__restrict__ run_len, uint64_t n_runs, const uint32_t *__restrict__ pivot_row,
+                                  uint32_t min_score, uint32_t first_id, uint64_t *out, unsigned long long *count) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_runs; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t k = run_key[i];
+        const uint32_t y = (uint32_t) k;
+        if (y != pivot_row[k >> 32] && run_len[i] >= min_score) out[atomicAdd(count, 1ull)] = (k & 0xFFFFFFFF00000000ull) | (y + first_id);
+    }
+}
+
 // sort keys of the connection list, read through the current permutation. STAGE 0: x (and perm = identity); 1: min << 32 | max;
 // 2: ~score
 template<int STAGE>
@@ -300,7 +324,109 @@ struct PhaseClock {
     }
 };
 
+// The GPU side of hga_host_tail_connections_impl's amplification callback (hga_tails.cpp): the state hga_enrich_run holds after the first merge
+struct AmplifyCtx {
+    hga_handle *h;
+    const std::vector<int32_t> *core_of;          // row -> core (or -1)
+    const std::vector<uint32_t> *surv_row;        // core -> surviving row
+    const uint64_t *row_off;                      // HOST row offsets of the hits (hga_get_hits)
+    uint32_t first_id;
+    uint64_t C;
+    const uint64_t *d_u;                          // sorted unique (core << 32 | slot)
+    const unsigned long long *d_core_koff;        // core -> first key of its union in d_u
+    const uint32_t *d_poff, *d_prow;              // purged index by slot
+    unsigned long long *d_count;
+};
+
+int gpu_tail_amplify(void *vctx, const uint32_t *pivot_id, uint64_t n_pivots, uint32_t min_score, std::vector<std::pair<uint32_t, uint32_t>> &out) {
+    AmplifyCtx &c = *static_cast<AmplifyCtx *>(vctx);
+    hga_handle *h = c.h;
+    if (n_pivots == 0) return HGA_OK;
+    if (n_pivots >= (1ull << 32)) { hga_set_error("tail amplification: too many tail vertices"); return HGA_E_OVERFLOW; }
+    std::vector<unsigned long long> koff(c.C + 1, 0);
+    HGA_CUDA(cudaMemcpyAsync(koff.data(), c.d_core_koff, (c.C + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    HGA_CUDA(cudaStreamSynchronize(h->stream));
+    // per pivot: where its k-mer list lives (the union of its core for a survivor, its own hits otherwise) and where its keys go
+    std::vector<unsigned long long> key_off(n_pivots + 1, 0), src_begin(n_pivots, 0);
+    std::vector<uint8_t> from_union(n_pivots, 0);
+    std::vector<uint32_t> pivot_row(n_pivots, 0);
+    for (uint64_t i = 0; i < n_pivots; i++) {
+        const uint32_t r = pivot_id[i] - c.first_id;
+        pivot_row[i] = r;
+        const int32_t core = (*c.core_of)[r];
+        uint64_t len;
+        if (core >= 0 && (*c.surv_row)[core] == r) { from_union[i] = 1; src_begin[i] = koff[core]; len = koff[core + 1] - koff[core]; }
+        else { src_begin[i] = c.row_off[r]; len = c.row_off[r + 1] - c.row_off[r]; }
+        key_off[i + 1] = key_off[i] + len;
+    }
+    const uint64_t n_keys = key_off[n_pivots];
+    if (n_keys == 0) return HGA_OK;
+    DevBuf b_desc, b_keys, b_len, b_emit, b_sorted, b_runlen, b_out;
+    struct Release { DevBuf *b[7]; ~Release() { for (DevBuf *x : b) x->release(); } } rel{{&b_desc, &b_keys, &b_len, &b_emit, &b_sorted, &b_runlen, &b_out}};
+    HGA_TRY(b_desc.ensure((n_pivots + 1) * (8 + 8 + 4 + 1) + 64));
+    unsigned long long *d_key_off = b_desc.as<unsigned long long>(), *d_src = d_key_off + (n_pivots + 1);
+    uint32_t *d_pivot_row = reinterpret_cast<uint32_t *>(d_src + n_pivots);
+    uint8_t *d_from = reinterpret_cast<uint8_t *>(d_pivot_row + n_pivots);
+    HGA_CUDA(cudaMemcpyAsync(d_key_off, key_off.data(), (n_pivots + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    HGA_CUDA(cudaMemcpyAsync(d_src, src_begin.data(), n_pivots * 8, cudaMemcpyHostToDevice, h->stream));
+    HGA_CUDA(cudaMemcpyAsync(d_pivot_row, pivot_row.data(), n_pivots * 4, cudaMemcpyHostToDevice, h->stream));
+    HGA_CUDA(cudaMemcpyAsync(d_from, from_union.data(), n_pivots, cudaMemcpyHostToDevice, h->stream));
+    HGA_TRY(b_keys.ensure((n_keys + 1) * 8));
+    HGA_TRY(b_len.ensure((n_keys + 2) * 8 * 2));
+    uint64_t *d_keys = b_keys.as<uint64_t>();
+    unsigned long long *d_len = b_len.as<unsigned long long>(), *d_at = d_len + (n_keys + 2);
+    amp_list_kernel<<<grid_for(h, n_keys), 256, 0, h->stream>>>(d_key_off, d_src, d_from, n_pivots, n_keys, h->d_hit_slot.as<uint32_t>(), c.d_u, d_keys);
+    enr_emit_len_kernel<<<grid_for(h, n_keys), 256, 0, h->stream>>>(d_keys, n_keys, c.d_poff, d_len);
+    HGA_CUDA(cudaMemsetAsync(d_len + n_keys, 0, 8, h->stream));
+    size_t tmp = 0;
+    HGA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_len, d_at, n_keys + 1, h->stream));
+    HGA_TRY(h->d_sort_tmp.ensure(tmp + 16));
+    HGA_CUDA(cub::DeviceScan::ExclusiveSum(h->d_sort_tmp.p, tmp, d_len, d_at, n_keys + 1, h->stream));
+    unsigned long long n_emit = 0;
+    HGA_CUDA(cudaMemcpyAsync(&n_emit, d_at + n_keys, 8, cudaMemcpyDeviceToHost, h->stream));
+    HGA_CUDA(cudaStreamSynchronize(h->stream));
+    h->metrics.kernel_launches += 4;
+    if (n_emit == 0) return HGA_OK;
+    HGA_TRY(b_emit.ensure((n_emit + 1) * 8));
+    HGA_TRY(b_sorted.ensure((n_emit + 1) * 8));
+    HGA_TRY(b_runlen.ensure((n_emit + 1) * 4));
+    uint64_t *d_emit = b_emit.as<uint64_t>(), *d_sorted = b_sorted.as<uint64_t>();
+    uint32_t *d_run_len = b_runlen.as<uint32_t>();
+    enr_emit_kernel<<<grid_for(h, n_keys), 256, 0, h->stream>>>(d_keys, n_keys, c.d_poff, c.d_prow, d_at, d_emit);
+    const int bits = 32 + (int) std::max<uint32_t>(hga_ceil_log2(n_pivots + 1), 1);
+    size_t t1 = 0, t2 = 0;
+    HGA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, t1, d_emit, d_sorted, n_emit, 0, bits, h->stream));
+    HGA_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, t2, d_sorted, d_emit, d_run_len, c.d_count, n_emit, h->stream));
+    HGA_TRY(h->d_sort_tmp.ensure(std::max(t1, t2) + 16));
+    HGA_CUDA(cub::DeviceRadixSort::SortKeys(h->d_sort_tmp.p, t1, d_emit, d_sorted, n_emit, 0, bits, h->stream));
+    HGA_CUDA(cub::DeviceRunLengthEncode::Encode(h->d_sort_tmp.p, t2, d_sorted, d_emit, d_run_len, c.d_count, n_emit, h->stream));   // run keys in d_emit
+    unsigned long long n_runs = 0;
+    HGA_CUDA(cudaMemcpyAsync(&n_runs, c.d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+    HGA_CUDA(cudaStreamSynchronize(h->stream));
+    HGA_TRY(b_out.ensure((n_runs + 1) * 8));
+    HGA_CUDA(cudaMemsetAsync(c.d_count, 0, 8, h->stream));
+    amp_filter_kernel<<<grid_for(h, n_runs), 256, 0, h->stream>>>(d_emit, d_run_len, n_runs, d_pivot_row, min_score, c.first_id, b_out.as<uint64_t>(), c.d_count);
+    h->metrics.kernel_launches += (uint64_t) (bits + 7) / 8 + 5;
+    HGA_CUDA(cudaGetLastError());
+    unsigned long long n_out = 0;
+    HGA_CUDA(cudaMemcpyAsync(&n_out, c.d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+    HGA_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<uint64_t> got(n_out);
+    if (n_out) HGA_CUDA(cudaMemcpy(got.data(), b_out.p, n_out * 8, cudaMemcpyDeviceToHost));
+    out.reserve(out.size() + n_out);
+    for (uint64_t v : got) out.push_back({(uint32_t) (v >> 32), (uint32_t) v});
+    return HGA_OK;
+}
+
 }  // namespace
+
+// hga_tails.cpp
+typedef int (*hga_tail_amplify_fn)(void *ctx, const uint32_t *pivot_id, uint64_t n_pivots, uint32_t min_score, std::vector<std::pair<uint32_t, uint32_t>> &out);
+int hga_host_tail_connections_impl(uint64_t n_reads, const uint64_t *row_off, const uint32_t *kmer_id, const uint32_t *pos, const uint32_t *read_len,
+                                   uint64_t avg_read_length, uint32_t read_id_first, uint64_t n_comp, const uint64_t *comp_off,
+                                   const uint32_t *comp_member, const uint64_t *tree_off, const uint32_t *tree_x, const uint32_t *tree_y,
+                                   const uint64_t *purged_off, const uint32_t *purged_read, uint32_t amplification_min_score, uint32_t *out_x,
+                                   uint32_t *out_y, uint64_t *out_score, uint64_t *out_n, hga_tail_amplify_fn amplify_fn, void *amplify_ctx);
 
 int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score, const TailParams *tail) {
     if (!h->have_selection || !h->have_index || !h->have_scan) { hga_set_error("hga_enrich: needs hga_scan, hga_build_index and hga_select_edges"); return HGA_E_STATE; }
@@ -521,8 +647,7 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
         hga_hits hits;
         HGA_TRY(hga_get_hits(h, 1, &hits));
         if (hits.n_reads != n) { hga_set_error("hga_enrich_full: the scan covers %llu reads, the index %llu rows", (unsigned long long) hits.n_reads, (unsigned long long) n); return HGA_E_STATE; }
-        hga_index pidx;
-        HGA_TRY(hga_export_index(h, d_poff, d_prow, n_purged, &pidx));
+        // (the purged index stays on the GPU: the one step that reads it, the tail amplification, runs there - gpu_tail_amplify)
         std::vector<uint32_t> read_len(n + 1);
         for (uint64_t r = 0; r < n; r++) read_len[r] = (uint32_t) (tail->read_off[r + 1] - tail->read_off[r]);
         const uint64_t avg_read_length = n ? (tail->read_off[n] - tail->read_off[0]) / n : 0;      // SequenceRecordIterator.cpp:64
@@ -545,9 +670,10 @@ int hga_enrich_run(hga_handle *h, int min_size, int max_size, uint32_t min_score
         const uint64_t cap = (uint64_t) C * (C - 1) / 2;
         res.tconn_x.resize(cap); res.tconn_y.resize(cap); res.tconn_score.resize(cap);
         uint64_t n_t = 0;
-        HGA_TRY(hga_host_tail_connections(n, hits.row_off, hits.kmer_id, hits.pos, read_len.data(), avg_read_length, first_id, C, comp_off.data(), comp_member.data(),
-                                          tree_off.data(), tree_x.data(), tree_y.data(), pidx.off, pidx.read_id, tail->amplification_min_score,
-                                          res.tconn_x.data(), res.tconn_y.data(), res.tconn_score.data(), &n_t));
+        AmplifyCtx actx{h, &core_of, &surv_row, hits.row_off, first_id, C, d_u, d_core_koff, d_poff, d_prow, d_count};
+        HGA_TRY(hga_host_tail_connections_impl(n, hits.row_off, hits.kmer_id, hits.pos, read_len.data(), avg_read_length, first_id, C, comp_off.data(), comp_member.data(),
+                                               tree_off.data(), tree_x.data(), tree_y.data(), nullptr, nullptr, tail->amplification_min_score,
+                                               res.tconn_x.data(), res.tconn_y.data(), res.tconn_score.data(), &n_t, gpu_tail_amplify, &actx));
         res.tconn_x.resize(n_t); res.tconn_y.resize(n_t); res.tconn_score.resize(n_t);
         pc.mark("  tail connections (host)", 1);
         uint64_t n_strong = 0;                                                                      // :770 score > 5; the list is score-descending

@@ -21,9 +21,11 @@
 // differ. Canonical choice, imposed on the reference too (oracle/shim/tsl/robin_map.h orders that one map): the first sweep starts
 // at the SMALLEST vertex id; distance ties go to the smallest id. The arithmetic is the reference's, wrap-around included.
 //
-// Small host arithmetic (a few hundred tree vertices per component): sequential in the reference, sequential here. The
-// amplification walks purged lists on the host in this first version; its GPU form is hga_enrich's connection kernel with the
-// tails as pivots.
+// Small host arithmetic (a few hundred tree vertices per component): sequential in the reference, sequential here - except the
+// amplification (get_connections(tail, min) through the purged index, :583-592), which is the one data-parallel step: inside
+// hga_enrich_full it runs on the GPU (hga_enrich.cu hands hga_host_tail_connections_impl a callback that counts the partners of ALL
+// tail vertices of all components in one go, with the enrichment's emit / sort / run-length kernels); the plain C entry point walks
+// the purged lists on the host.
 #include <algorithm>
 #include <cstdint>
 #include <map>
@@ -83,12 +85,16 @@ struct TailState {
 
 }  // namespace
 
-extern "C" int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_off, const uint32_t *kmer_id, const uint32_t *pos, const uint32_t *read_len,
-                                         uint64_t avg_read_length, uint32_t read_id_first, uint64_t n_comp, const uint64_t *comp_off,
-                                         const uint32_t *comp_member, const uint64_t *tree_off, const uint32_t *tree_x, const uint32_t *tree_y,
-                                         const uint64_t *purged_off, const uint32_t *purged_read, uint32_t amplification_min_score, uint32_t *out_x,
-                                         uint32_t *out_y, uint64_t *out_score, uint64_t *out_n) {
-    if (!row_off || !comp_off || !tree_off || !purged_off || !out_n || (n_comp > 1 && (!out_x || !out_y || !out_score))) {
+// amplification callback: for every pivot id (n_pivots of them, in tail order) the ids it reaches through the purged index with at least
+// min_score shared k-mers (duplicates of the pivot's list count, the pivot itself excluded): appends (pivot index, partner id) to out
+typedef int (*hga_tail_amplify_fn)(void *ctx, const uint32_t *pivot_id, uint64_t n_pivots, uint32_t min_score, std::vector<std::pair<uint32_t, uint32_t>> &out);
+
+int hga_host_tail_connections_impl(uint64_t n_reads, const uint64_t *row_off, const uint32_t *kmer_id, const uint32_t *pos, const uint32_t *read_len,
+                                   uint64_t avg_read_length, uint32_t read_id_first, uint64_t n_comp, const uint64_t *comp_off,
+                                   const uint32_t *comp_member, const uint64_t *tree_off, const uint32_t *tree_x, const uint32_t *tree_y,
+                                   const uint64_t *purged_off, const uint32_t *purged_read, uint32_t amplification_min_score, uint32_t *out_x,
+                                   uint32_t *out_y, uint64_t *out_score, uint64_t *out_n, hga_tail_amplify_fn amplify_fn, void *amplify_ctx) {
+    if (!row_off || !comp_off || !tree_off || (!purged_off && !amplify_fn) || !out_n || (n_comp > 1 && (!out_x || !out_y || !out_score))) {
         hga_set_error("hga_host_tail_connections: NULL argument");
         return HGA_E_ARG;
     }
@@ -107,7 +113,7 @@ extern "C" int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_o
     }
     const uint64_t tail_length = avg_read_length * 2;                       // :543
 
-    std::map<uint32_t, std::pair<std::vector<uint32_t>, std::vector<uint32_t>>> tails;   // survivor -> (k-mers of one end, of the other)
+    std::vector<std::pair<uint32_t, std::pair<std::vector<uint32_t>, std::vector<uint32_t>>>> comp_tails;   // (survivor, (tail vertices of one end, of the other)), components ascending
     for (uint64_t c = 0; c < n_comp; c++) {
         // adjacency with the approximate overlap as edge attribute (:511-516)
         std::map<uint32_t, std::vector<std::pair<uint32_t, int>>> adj;
@@ -150,34 +156,54 @@ extern "C" int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_o
         const auto far_left = farthest(d_left);
         for (const auto &d : d_left) if (d.second + tail_length > far_left.second) end_b.push_back(d.first);
 
-        // amplify_component (:583-592): the tail plus both endpoints of every connection a tail vertex has with score >= min
-        auto amplify = [&](const std::vector<uint32_t> &tail) {
-            std::vector<uint32_t> ids(tail);
-            std::unordered_map<uint32_t, uint64_t> count;
-            for (uint32_t pivot : tail) {
-                count.clear();
-                const uint32_t *pl;
-                size_t nl;
-                S.list_of(pivot, pl, nl);
-                for (size_t i = 0; i < nl; i++)                             // duplicates of the pivot's list count (:311-316)
-                    for (uint64_t j = purged_off[pl[i]]; j < purged_off[pl[i] + 1]; j++) count[purged_read[j]]++;
-                count.erase(pivot);                                          // :317
-                for (const auto &cn : count) if (cn.second >= amplification_min_score) ids.push_back(cn.first);
-            }
-            std::sort(ids.begin(), ids.end());
-            ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-            return ids;
-        };
-        // accumulate_kmer_ids (:340-346): sorted unique union of the components' current lists
-        auto kmers_of = [&](const std::vector<uint32_t> &ids) {
-            std::vector<uint32_t> u;
-            for (uint32_t id : ids) { const uint32_t *pl; size_t nl; S.list_of(id, pl, nl); u.insert(u.end(), pl, pl + nl); }
-            std::sort(u.begin(), u.end());
-            u.erase(std::unique(u.begin(), u.end()), u.end());
-            return u;
-        };
-        tails[comp_member[comp_off[c]]] = {kmers_of(amplify(end_b)), kmers_of(amplify(end_a))};
+        comp_tails.push_back({comp_member[comp_off[c]], {std::move(end_b), std::move(end_a)}});
     }
+
+    // amplify_component (:583-592) for ALL tails at once: the tail plus every id a tail vertex reaches with score >= min
+    std::vector<uint32_t> pivot_id;                                         // the tail vertices, tail by tail
+    std::vector<uint64_t> tail_first;                                       // tail t = pivots [tail_first[t], tail_first[t + 1])
+    for (const auto &ct : comp_tails)
+        for (const std::vector<uint32_t> *tl : {&ct.second.first, &ct.second.second}) {
+            tail_first.push_back(pivot_id.size());
+            pivot_id.insert(pivot_id.end(), tl->begin(), tl->end());
+        }
+    tail_first.push_back(pivot_id.size());
+    std::vector<std::pair<uint32_t, uint32_t>> reached;                    // (pivot index, partner id)
+    if (amplify_fn) {
+        const int rc = amplify_fn(amplify_ctx, pivot_id.data(), pivot_id.size(), amplification_min_score, reached);
+        if (rc != HGA_OK) return rc;
+    } else {
+        std::unordered_map<uint32_t, uint64_t> count;
+        for (size_t pi = 0; pi < pivot_id.size(); pi++) {
+            const uint32_t pivot = pivot_id[pi];
+            count.clear();
+            const uint32_t *pl;
+            size_t nl;
+            S.list_of(pivot, pl, nl);
+            for (size_t i = 0; i < nl; i++)                                 // duplicates of the pivot's list count (:311-316)
+                for (uint64_t j = purged_off[pl[i]]; j < purged_off[pl[i] + 1]; j++) count[purged_read[j]]++;
+            count.erase(pivot);                                              // :317
+            for (const auto &cn : count) if (cn.second >= amplification_min_score) reached.push_back({(uint32_t) pi, cn.first});
+        }
+    }
+    std::vector<std::vector<uint32_t>> amplified(tail_first.size() - 1);
+    for (size_t t = 0; t + 1 < tail_first.size(); t++) amplified[t].assign(pivot_id.begin() + (ptrdiff_t) tail_first[t], pivot_id.begin() + (ptrdiff_t) tail_first[t + 1]);
+    for (const auto &pr : reached) {
+        const size_t t = (size_t) (std::upper_bound(tail_first.begin(), tail_first.end(), (uint64_t) pr.first) - tail_first.begin()) - 1;
+        amplified[t].push_back(pr.second);
+    }
+    // accumulate_kmer_ids (:340-346): sorted unique union of the components' current lists
+    auto kmers_of = [&](std::vector<uint32_t> &ids) {
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        std::vector<uint32_t> u;
+        for (uint32_t id : ids) { const uint32_t *pl; size_t nl; S.list_of(id, pl, nl); u.insert(u.end(), pl, pl + nl); }
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        return u;
+    };
+    std::map<uint32_t, std::pair<std::vector<uint32_t>, std::vector<uint32_t>>> tails;   // survivor -> (k-mers of one end, of the other)
+    for (size_t i = 0; i < comp_tails.size(); i++) tails[comp_tails[i].first] = {kmers_of(amplified[2 * i]), kmers_of(amplified[2 * i + 1])};
 
     // :621-640: for every pair of components the largest of the four tail-to-tail intersections; :650 keep score > 0. The reference
     // intersects the sorted unions pair by pair (S^2 / 2 pairs x 4 merges); the unions are sets, so |A n B| is the number of
@@ -217,4 +243,14 @@ extern "C" int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_o
     for (size_t i = 0; i < conns.size(); i++) { out_x[i] = conns[i].x; out_y[i] = conns[i].y; out_score[i] = conns[i].s; }
     *out_n = conns.size();
     return HGA_OK;
+}
+
+extern "C" int hga_host_tail_connections(uint64_t n_reads, const uint64_t *row_off, const uint32_t *kmer_id, const uint32_t *pos, const uint32_t *read_len,
+                                         uint64_t avg_read_length, uint32_t read_id_first, uint64_t n_comp, const uint64_t *comp_off,
+                                         const uint32_t *comp_member, const uint64_t *tree_off, const uint32_t *tree_x, const uint32_t *tree_y,
+                                         const uint64_t *purged_off, const uint32_t *purged_read, uint32_t amplification_min_score, uint32_t *out_x,
+                                         uint32_t *out_y, uint64_t *out_score, uint64_t *out_n) {
+    if (!purged_off) { hga_set_error("hga_host_tail_connections: NULL argument"); return HGA_E_ARG; }
+    return hga_host_tail_connections_impl(n_reads, row_off, kmer_id, pos, read_len, avg_read_length, read_id_first, n_comp, comp_off, comp_member, tree_off, tree_x, tree_y,
+                                          purged_off, purged_read, amplification_min_score, out_x, out_y, out_score, out_n, nullptr, nullptr);
 }

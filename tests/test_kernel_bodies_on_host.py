@@ -392,6 +392,9 @@ extern "C" int emu_enrich(uint64_t n_reads, uint64_t n_kmers, const uint64_t *ro
     h->have_scan = h->have_index = h->have_selection = true;
     g_emu.row_off.assign(row_off, row_off + n_reads + 1); g_emu.kid.assign(kid, kid + row_off[n_reads]); g_emu.pos.assign(pos, pos + row_off[n_reads]);
     if (h->d_inv_off.ensure((n_kmers + 1) * 4) || h->d_inv_row.ensure((inv_off[n_kmers] + 1) * 4) || h->d_sel_key.ensure((M + 1) * 8) || h->d_sel_score.ensure((M + 1) * 4)) return -1;
+    if (h->d_row_off.ensure((n_reads + 1) * 8) || h->d_hit_slot.ensure((row_off[n_reads] + 1) * 4)) return -1;      // the hits by read (slot == kmer_id): the tail amplification reads them
+    std::memcpy(h->d_row_off.p, row_off, (n_reads + 1) * 8);
+    std::memcpy(h->d_hit_slot.p, kid, row_off[n_reads] * 4);
     for (uint64_t k = 0; k <= n_kmers; k++) h->d_inv_off.as<uint32_t>()[k] = (uint32_t) inv_off[k];
     for (uint64_t i = 0; i < inv_off[n_kmers]; i++) h->d_inv_row.as<uint32_t>()[i] = inv_read[i] - 1;
     for (uint64_t i = 0; i < M; i++) { h->d_sel_key.as<uint64_t>()[i] = ((uint64_t) (sel_x[i] - 1) << 32) | (sel_y[i] - 1); h->d_sel_score.as<uint32_t>()[i] = sel_score[i]; }
