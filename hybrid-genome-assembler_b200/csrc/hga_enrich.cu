@@ -5,8 +5,8 @@
 //   :785-794  get_connections(core_component_ids, enrichment_connections_min_score), union_find(conns, restricted = cores,
 //             2, -1), merge_components, get_component_ids(scaffold_component_min_size)
 // The tail / spectral block in between (:768-777) runs when the caller asks for it (hga_enrich_full -> `tail`): the
-// state after the scaffold merge goes to the host stages hga_host_tail_connections / hga_spectral_clustering and the clusters they
-// return are merged by a SECOND merge_components on the GPU (enr_merge2_keys_kernel, enr_purge2_kernel; rule at the kernels).
+// state after the scaffold merge goes to the host stages hga_host_tail_connections / hga_spectral_clustering (the tail amplification
+// comes back to the GPU: gpu_tail_amplify) and the clusters they return are merged by a SECOND merge_components on the GPU (enr_merge2_keys_kernel, enr_purge2_kernel; rule at the kernels).
 // Without it (hga_enrich, hga_enrich_ex) what runs here is the reference's own path when it has at most two scaffold components
 // or finds no strong tail connection.
 //

@@ -178,8 +178,9 @@ int hga_get_core_kmers(hga_handle *h, hga_core_kmers_t *out);
 
 /* The same INCLUDING the tail / spectral block (run_clustering :768-777), i.e. everything run_clustering does after
  * the scaffold union_find. When the scaffold merge leaves more than two cores: the engine state after the merge (hits, spanning
- * trees of the replayed union_find, purged index) goes to the host stages hga_host_tail_connections and, for the connections
- * with score > 5 (:770), hga_spectral_clustering; the clusters are merged by a SECOND merge_components on the GPU (unique unions
+ * trees of the replayed union_find) goes to the host stages of hga_host_tail_connections - whose amplification step
+ * (get_connections(tail, min) through the purged index) runs on the GPU, the purged index stays there - and, for the connections
+ * with score > 5 (:770), to hga_spectral_clustering; the clusters are merged by a SECOND merge_components on the GPU (unique unions
  * of the members' merged k-mer lists, second purge of the already purged index with the same truncation rule: the removal list
  * of a k-mer holds every member of a multi-member cluster that lists it plus the cluster's survivor); enrichment, restricted
  * union_find and the final merge then run on that state. With at most two cores, or no strong tail connection, the result is
