@@ -212,10 +212,16 @@ class ReadClusteringEngine:
     """GPU-backed stand-in for the reference engine's hot-path stages. Component ids are read ids, as in the
     reference before any merge (ReadComponent ctor, ReadClusteringEngine.h:38-43)."""
 
-    def __init__(self, reader: SequenceRecords, config: ReadClusteringConfig = None, device=0):
+    def __init__(self, reader: SequenceRecords, config: ReadClusteringConfig = None, device=0, dist=None):
+        """dist: an initialised torch.distributed module (one rank per GPU) or None. With it every rank holds the SAME reader and k-mer set; the hot path
+        (construct_indices ... union_find) runs on this rank's contiguous shard of the reads with the exchanges of hga_comm.cu, hga_comm_gather_root then
+        leaves a complete single-GPU state on rank 0, and the rest of run_clustering runs there (what `categorization --gpus N` does with rank threads)."""
         self.reader = reader
         self.config = config or ReadClusteringConfig()
         self.device = device
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
         self.handle = None
         self.kmers = None
 
@@ -229,7 +235,17 @@ class ReadClusteringEngine:
         self.close()
         self.kmers = np.unique(np.asarray(discriminative_kmers, dtype=np.uint64))
         self.handle = capi.Handle(self.kmers, k, device=self.device)
-        self.handle.scan(self.reader.bases, self.reader.seq_off, read_id_base=1)
+        if self.world > 1:
+            from . import parallel
+            off = np.asarray(self.reader.seq_off, dtype=np.uint64)
+            bounds = parallel.shard_bounds(np.diff(off.astype(np.int64)), self.world)
+            lo, hi = bounds[self.rank], bounds[self.rank + 1]
+            uid = parallel.broadcast_unique_id(self.dist, self.rank, capi.comm_unique_id)
+            self.handle.comm_init(uid, self.rank, self.world, self.reader.n_reads)
+            bases = self.reader.bases[int(off[lo]):int(off[hi])]
+            self.handle.scan(bases, off[lo:hi + 1] - off[lo], read_id_base=lo + 1)
+        else:
+            self.handle.scan(self.reader.bases, self.reader.seq_off, read_id_base=1)
         self.handle.build_index()
         return 0
 
@@ -288,6 +304,8 @@ class ReadClusteringEngine:
     def run_clustering(self, discriminative_kmers, k, tail_block=True):
         cfg = self.config
         self.construct_indices(discriminative_kmers, k)
+        if self.world > 1 and cfg.force_spectral:
+            raise NotImplementedError("--spectral needs every pair on one GPU: single-GPU only")
         if cfg.force_spectral:
             # :739-746: get_all_connections(5) on the GPU, spectral clustering of the whole data set on the host (an S x S
             # eigen-problem over all connected reads, as in the reference: small inputs only), merge_components, ids with >= min size
@@ -297,7 +315,24 @@ class ReadClusteringEngine:
             for fid, members in self.final_components.items():
                 self.assignment[members - 1] = fid
             return list(self.final_components)
+        if self.world > 1 and cfg.scaffold_forming_score > 0:
+            raise NotImplementedError("--sc_score (a pivot subset) is single-GPU only")
         self._select_scaffold_edges()
+        if self.world > 1:
+            # the stages after the scaffold union_find run on rank 0 (hga_comm_gather_root); every rank gets the result
+            self.handle.components(min_size=cfg.scaffold_component_min_size)
+            self.handle.comm_gather_root()
+            box = [None]
+            if self.rank == 0:
+                self._merge_and_enrich(tail_block)
+                box = [(self.final_components, self.assignment)]
+            self.dist.broadcast_object_list(box, src=0)
+            self.final_components, self.assignment = box[0]
+            return [int(v) for v in self.final_components]
+        return self._merge_and_enrich(tail_block)
+
+    def _merge_and_enrich(self, tail_block):
+        cfg = self.config
         if tail_block:
             self.handle.enrich_full(self.reader.seq_off, min_size=cfg.scaffold_component_min_size, enrichment_min_score=cfg.enrichment_connections_min_score,
                                     max_size=cfg.scaffold_component_max_size, tail_amplification_min_score=cfg.tail_amplification_min_score,

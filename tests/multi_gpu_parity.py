@@ -169,6 +169,28 @@ def main():
     h.close()
     if rank == 0:
         print(f"fault injection ok: {world} ranks left the index and the partial-pair exchange together")
+
+    # the Python mirror of the engine with dist = torch.distributed: every rank runs run_clustering, all get rank 0's final components,
+    # and they are the single-GPU engine's
+    import tempfile
+    from hga_b200 import engine
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, f"reads_rank{rank}.fa")
+        datagen.write_fasta(fa, reads, prefix="r")
+        cfg = engine.ReadClusteringConfig(scaffold_component_min_size=5, enrichment_connections_min_score=5, tail_amplification_min_score=10, spectral_dims=8)
+        eng = engine.ReadClusteringEngine(engine.SequenceRecords([fa]), cfg, device=local, dist=dist)
+        ids = eng.run_clustering(kmers, 19)
+        comps = {int(k_): np.asarray(v) for k_, v in eng.final_components.items()}
+        eng.close()
+        if rank == 0:
+            one = engine.ReadClusteringEngine(engine.SequenceRecords([fa]), cfg, device=local)
+            ids1 = one.run_clustering(kmers, 19)
+            assert sorted(ids) == sorted(ids1) and len(ids1) > 0, (ids, ids1)
+            for fid in ids1:
+                assert np.array_equal(comps[fid], one.final_components[fid]), f"final component {fid} differs between {world} GPUs and one"
+            assert np.array_equal(eng.assignment, one.assignment)
+            one.close()
+            print(f"engine mirror ok: {world} ranks, {len(ids1)} final components")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -20,6 +20,7 @@ def test_two_rank_parity():
     assert r.stdout.count("multi-GPU parity ok") == 2
     assert r.stdout.count("gathered handle ok") == 2
     assert r.stdout.count("fault injection ok") == 1
+    assert r.stdout.count("engine mirror ok") == 1
 
 
 @pytest.mark.gpu
