@@ -121,14 +121,6 @@ __global__ void pack_lists_kernel(const uint64_t *__restrict__ row_off, uint64_t
     }
 }
 
-__global__ void unpack_records_kernel(const uint64_t *__restrict__ rec, uint64_t n, uint32_t *__restrict__ hi, uint32_t *__restrict__ lo) {
-    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
-        const uint64_t v = rec[i];
-        if (hi) hi[i] = (uint32_t) (v >> 32);
-        if (lo) lo[i] = (uint32_t) v;
-    }
-}
-
 // send counts of a partitioned array: cnt[g] = number of elements whose (sorted) destination byte is g, g = 0 .. G - 1
 __global__ void dest_counts_kernel(const uint8_t *__restrict__ sorted_dest, uint64_t n, int G, unsigned long long *cnt) {
     const int g = threadIdx.x;
@@ -138,18 +130,6 @@ __global__ void dest_counts_kernel(const uint8_t *__restrict__ sorted_dest, uint
     uint64_t lo2 = lo, hi2 = n;
     while (lo2 < hi2) { const uint64_t mid = (lo2 + hi2) >> 1; if (sorted_dest[mid] <= g) lo2 = mid + 1; else hi2 = mid; }
     cnt[g] = lo2 - lo;
-}
-
-// off[s] = first position of the ascending values (field of a 64-bit record) with value >= s, s = 0 .. count
-template<typename OFF, int SHIFT>
-__global__ void field_offsets_kernel(const uint64_t *__restrict__ rec, uint64_t n, uint64_t count, OFF *__restrict__ off) {
-    uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x;
-    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    for (; i <= n; i += stride) {
-        const int64_t cur = (i < n) ? (int64_t) (uint32_t) (rec[i] >> SHIFT) : (int64_t) count;    // sentinel closes the tail
-        const int64_t prev = (i == 0) ? -1 : (int64_t) (uint32_t) (rec[i - 1] >> SHIFT);
-        for (int64_t s = prev + 1; s <= cur && s <= (int64_t) count; s++) off[s] = (OFF) i;
-    }
 }
 
 // partial pair (key = x << 32 | y, score) -> ONE 64-bit record x | y | score (rb bits per row, sb = 64 - 2 rb bits of score) + destination
@@ -399,7 +379,6 @@ int hga_comm_build_owner_index(hga_handle *h) {
     h->pair_pivot_mul = 1; h->pair_pivot_add = 0;
     h->index_by_kid = true;
     h->index_keys = n_lists;
-    h->index_key_div = 0;
     h->metrics.exchange_ms = comm_ms;       // NCCL payload calls only (the sorts between them belong to index_ms)
     tr.dump("index", me);
     return HGA_OK;

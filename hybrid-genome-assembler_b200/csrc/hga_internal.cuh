@@ -216,13 +216,6 @@ __host__ __device__ __forceinline__ uint32_t hga_mix_bits(uint32_t hb) { return 
 __host__ __device__ __forceinline__ uint32_t hga_owner_of_slot(uint32_t slot, uint32_t G) { return (slot / HGA_BUCKET_SLOTS) % G; }
 __host__ __device__ __forceinline__ uint32_t hga_list_of_slot(uint32_t slot, uint32_t G) { return (slot / HGA_BUCKET_SLOTS) / G * HGA_BUCKET_SLOTS + slot % HGA_BUCKET_SLOTS; }
 
-// plain k-mer hash (unused by the table since the overflow region became a sorted array; kept for experiments)
-__host__ __device__ __forceinline__ uint32_t hga_plain_hash(uint64_t kmer) {
-    uint32_t h = (uint32_t) kmer * HGA_C2 + (uint32_t) (kmer >> 32) * HGA_C1;
-    h ^= h >> 16;
-    return h * HGA_C3;
-}
-
 // hashed m-mer: x = any word whose LOW 2m bits are the m-mer (cm shifts the rest out)
 __host__ __device__ __forceinline__ uint32_t hga_mmer_hash(uint32_t x, uint32_t cm) { return x * cm + HGA_C4; }
 
@@ -302,12 +295,10 @@ struct hga_handle {
     uint32_t inc_row_first_id = 1;        // read id of row 0
     uint64_t inc_entries = 0;             // entries of the inverted index
     DevBuf d_x_slot, d_x_row;             // exchange staging (multi-GPU)
-    DevBuf d_hit_kid;                     // (unused)
     DevBuf d_g_kid, d_g_row_off;          // multi-GPU: by-row incidence of ALL rows restricted to this rank's k-mers (list number per hit, u64 row offsets)
     bool index_by_kid = false;            // multi-GPU (name kept): the inverted index holds the lists of this rank's share of the table: slot s belongs to
                                           // rank (s / 32) mod G and is list ((s / 32) / G) * 32 + s mod 32 there (hga_owner_of_slot / hga_list_of_slot)
     uint32_t index_keys = 0;              // number of lists in the inverted index: n_slots, or the owner's share of them with a communicator
-    uint32_t index_key_div = 0;           // (unused)
 
     // inverted index
     DevBuf d_inv_off;                     // u32[index_keys + 1] (the incidence held by one GPU has < 2^32 entries)
